@@ -1,0 +1,251 @@
+// extern "C" entry points of libiadmm_b200.so (declared in include/iadmm.h) and the per-iteration
+// orchestration of the unrolled solve (main.py:874-887 x models/lstm.py:47-96 x utils.py:68-71).
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace iadmm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// implemented in the other translation units
+int pack_weights_impl(const float* const W[4], const float* const U[4], const float* const b[4], const float* W_h,
+                      const float* b_h, const float* rho, const float* alpha, int h, int length, void* packed,
+                      cudaStream_t st);
+size_t ruiz_ws_floats(int B, int n, int m, int* R_out, int* cq_out, int* ca_out);
+int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, const float* zu, float* Qs, float* ps,
+              float* A0s, float* zls, float* zus, float* d, float* e, float* c, int B, int n, int m, int iterations,
+              void* workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, const float* x, const float* y,
+                           const KktScratch& s, cudaStream_t st);
+int launch_build_kkt(int B, int n, int m, int num_ineq, const float* Q, const float* p, const float* A0,
+                     const float* x, const float* y, const float* z, const Sched* sched_t, float sigma, float* K,
+                     float* rhs, float* rho_vec, cudaStream_t st);
+
+static int check_device() {
+  int dev = 0, major = 0;
+  IADMM_CUDA(cudaGetDevice(&dev));
+  IADMM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) IADMM_FAIL(IADMM_EARCH, "device %d has compute capability %d.x; libiadmm_b200 needs sm_100 (B200)", dev, major);
+  return IADMM_OK;
+}
+
+struct SolveWs {
+  KktDims d;
+  KktScratch s;
+  float* head_part;       // [tiles][rows]
+  float* h_alt;           // SIMT: second fp32 H buffer [rows,h]
+  TcState tc;             // TC: fp16 hi/lo ping-pong
+  int tiles;
+  size_t bytes;
+};
+
+static int is_tc(int mode) { return mode == IADMM_GATES_TC_3XFP16 || mode == IADMM_GATES_TC_1XFP16; }
+
+static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, void* base, SolveWs* ws) {
+  if (mode != IADMM_GATES_SIMT_FP32 && !is_tc(mode)) IADMM_FAIL(IADMM_EMODE, "unknown gate mode %d", mode);
+  if (is_tc(mode) && (h % 8 != 0)) IADMM_FAIL(IADMM_EMODE, "tensor-core gate modes need hidden_dim %% 8 == 0 (got %d)", h);
+  ws->d = make_kkt_dims(B, n, m, num_ineq);
+  const size_t rows = (size_t)B * (n + m);
+  ws->tiles = is_tc(mode) ? tc_gate_tiles(h) : simt_gate_tiles(h);
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return base ? p + o : nullptr; };
+  float* kkt = reinterpret_cast<float*>(take(kkt_scratch_floats(ws->d) * sizeof(float)));
+  if (base) kkt_scratch_carve(ws->d, kkt, &ws->s);
+  ws->head_part = reinterpret_cast<float*>(take((size_t)ws->tiles * rows * sizeof(float)));
+  ws->h_alt = nullptr;
+  memset(&ws->tc, 0, sizeof(ws->tc));
+  if (is_tc(mode)) {
+    const size_t hb = rows * (size_t)h * sizeof(__half);
+    for (int i = 0; i < 2; ++i) {
+      ws->tc.h_hi[i] = reinterpret_cast<__half*>(take(hb));
+      ws->tc.h_lo[i] = reinterpret_cast<__half*>(take(hb));
+    }
+  } else {
+    ws->h_alt = reinterpret_cast<float*>(take(rows * (size_t)h * sizeof(float)));
+  }
+  ws->bytes = off;
+  return IADMM_OK;
+}
+
+}  // namespace iadmm
+
+using namespace iadmm;
+
+extern "C" {
+
+int iadmm_abi_version(void) { return IADMM_ABI_VERSION; }
+const char* iadmm_last_error(void) { return g_err; }
+int iadmm_device_check(void) { return check_device(); }
+
+int iadmm_weights_bytes(int h, int length, size_t* bytes) {
+  if (h <= 0 || length <= 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "weights_bytes: h=%d length=%d", h, length);
+  *bytes = weight_layout(h, length).total;
+  return IADMM_OK;
+}
+
+int iadmm_pack_weights(const float* W_i, const float* U_i, const float* b_i, const float* W_f, const float* U_f,
+                       const float* b_f, const float* W_o, const float* U_o, const float* b_o, const float* W_u,
+                       const float* U_u, const float* b_u, const float* W_h, const float* b_h, const float* rho,
+                       const float* alpha, int h, int length, void* packed, void* stream) {
+  if (h <= 0 || length <= 0) IADMM_FAIL(IADMM_ESHAPE, "pack_weights: h=%d length=%d", h, length);
+  const float* W[4] = {W_i, W_f, W_o, W_u};
+  const float* U[4] = {U_i, U_f, U_o, U_u};
+  const float* b[4] = {b_i, b_f, b_o, b_u};
+  for (int g = 0; g < 4; ++g)
+    if (!W[g] || !U[g] || !b[g]) IADMM_FAIL(IADMM_EALIGN, "pack_weights: NULL gate parameter %d", g);
+  if (!W_h || !b_h || !rho || !alpha || !packed) IADMM_FAIL(IADMM_EALIGN, "pack_weights: NULL pointer");
+  if (!aligned16(packed)) IADMM_FAIL(IADMM_EALIGN, "pack_weights: packed buffer not 16-byte aligned");
+  int rc = check_device();
+  if (rc) return rc;
+  return pack_weights_impl(W, U, b, W_h, b_h, rho, alpha, h, length, packed, static_cast<cudaStream_t>(stream));
+}
+
+int iadmm_ruiz_workspace_bytes(int B, int n, int m, size_t* bytes) {
+  if (B <= 0 || n <= 0 || m < 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "ruiz_workspace_bytes: B=%d n=%d m=%d", B, n, m);
+  *bytes = ruiz_ws_floats(B, n, m, nullptr, nullptr, nullptr) * sizeof(float);
+  return IADMM_OK;
+}
+
+int iadmm_ruiz(const float* Q, const float* p, const float* A0, const float* zl, const float* zu, float* Qs, float* ps,
+               float* A0s, float* zls, float* zus, float* d, float* e, float* c, int B, int n, int m, int iterations,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n <= 0 || m < 0 || iterations < 0) IADMM_FAIL(IADMM_ESHAPE, "ruiz: B=%d n=%d m=%d ites=%d", B, n, m, iterations);
+  if (B > 65535) IADMM_FAIL(IADMM_ESHAPE, "ruiz: batch %d > 65535 per call", B);
+  if (!Q || !p || !Qs || !ps || !d || !c || !workspace) IADMM_FAIL(IADMM_EALIGN, "ruiz: NULL pointer");
+  if (m > 0 && (!A0 || !zl || !zu || !A0s || !zls || !zus || !e)) IADMM_FAIL(IADMM_EALIGN, "ruiz: NULL constraint pointer");
+  if (Q == Qs || (m > 0 && A0 == A0s)) IADMM_FAIL(IADMM_EALIGN, "ruiz: outputs must not alias inputs");
+  int rc = check_device();
+  if (rc) return rc;
+  return ruiz_impl(Q, p, A0, zl, zu, Qs, ps, A0s, zls, zus, d, e, c, B, n, m, iterations, workspace, workspace_bytes,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int iadmm_solve_workspace_bytes(int B, int n, int m, int h, int mode, size_t* bytes) {
+  if (B <= 0 || n <= 0 || m < 0 || h <= 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "solve_workspace_bytes: B=%d n=%d m=%d h=%d", B, n, m, h);
+  SolveWs ws;
+  int rc = plan_workspace(B, n, m, 0, h, mode, nullptr, &ws);
+  if (rc) return rc;
+  *bytes = ws.bytes;
+  return IADMM_OK;
+}
+
+int iadmm_solve(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
+                const float* zu, const float* sd, const float* se, const float* sc, float* x, float* y, float* z,
+                float* xv, float* H, float* C, float* pri_trace, float* dual_trace, float* pri_trace_u,
+                float* dual_trace_u, int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
+                float sigma, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+  const int m = num_ineq + num_eq;
+  if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || K < 0 || t0 < 0)
+    IADMM_FAIL(IADMM_ESHAPE, "solve: B=%d n=%d ineq=%d eq=%d h=%d t0=%d K=%d", B, n, num_ineq, num_eq, h, t0, K);
+  if (t0 + K > length) IADMM_FAIL(IADMM_ESHAPE, "solve: iterations %d..%d exceed the schedule length %d (lstm.py:60)", t0, t0 + K - 1, length);
+  if (B > 65535) IADMM_FAIL(IADMM_ESHAPE, "solve: batch %d > 65535 per call; shard the batch", B);
+  if (!packed_weights || !Q || !p || !x || !xv || !H || !C || !workspace) IADMM_FAIL(IADMM_EALIGN, "solve: NULL pointer");
+  if (m > 0 && (!A0 || !zl || !zu || !y || !z)) IADMM_FAIL(IADMM_EALIGN, "solve: NULL constraint pointer");
+  if ((pri_trace_u || dual_trace_u) && (!sd || !sc || (m > 0 && !se)))
+    IADMM_FAIL(IADMM_EALIGN, "solve: un-scaled traces need the Ruiz diagonals d, e, c");
+  if (!aligned16(H) || !aligned16(C) || !aligned16(workspace) || !aligned16(packed_weights))
+    IADMM_FAIL(IADMM_EALIGN, "solve: H, C, workspace and packed weights must be 16-byte aligned");
+  int rc = check_device();
+  if (rc) return rc;
+  SolveWs ws;
+  rc = plan_workspace(B, n, m, num_ineq, h, mode, workspace, &ws);
+  if (rc) return rc;
+  if (ws.bytes > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "solve: workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
+  if (K == 0) return IADMM_OK;
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const WeightLayout L = weight_layout(h, length);
+  const char* wbase = static_cast<const char*>(packed_weights);
+  const Sched* sched = reinterpret_cast<const Sched*>(wbase + L.off_sched);
+  const float* b_h = reinterpret_cast<const float*>(wbase + L.off_bh);
+  const long rows = (long)B * (n + m);
+  const bool tc = is_tc(mode);
+  const int nprod = (mode == IADMM_GATES_TC_3XFP16) ? 3 : 1;
+  const bool want_trace = pri_trace || dual_trace || pri_trace_u || dual_trace_u;
+
+  float* hbuf[2] = {H, ws.h_alt};
+  int cur = 0;
+  if (tc) {
+    if (flags & IADMM_F_ZERO_STATE) rc = launch_zero_state(ws.tc.h_hi[0], ws.tc.h_lo[0], rows * h, st);
+    else                            rc = launch_split_state(H, ws.tc.h_hi[0], ws.tc.h_lo[0], rows * h, st);
+    if (rc) return rc;
+  }
+  for (int k = 0; k < K; ++k) {
+    const Sched* sk = sched + (t0 + k);
+    if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
+    if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, sk, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
+                                  dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st))) return rc;
+    if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st))) return rc;
+    if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st))) return rc;
+    if (tc) {
+      rc = launch_gates_tc(packed_weights, L, xv, ws.s.g, ws.tc.h_hi[cur], ws.tc.h_lo[cur], ws.tc.h_hi[cur ^ 1],
+                           ws.tc.h_lo[cur ^ 1], (k == K - 1) ? H : nullptr, C, ws.head_part, rows, h, nprod, st);
+    } else {
+      rc = launch_gates_simt(packed_weights, L, xv, ws.s.g, hbuf[cur], hbuf[cur ^ 1], C, ws.head_part, rows, h, st);
+    }
+    if (rc) return rc;
+    cur ^= 1;
+    if ((rc = launch_tail(ws.d, ws.head_part, ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st))) return rc;
+  }
+  if (!tc && cur == 1)
+    IADMM_CUDA(cudaMemcpyAsync(H, ws.h_alt, (size_t)rows * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (want_trace && !(flags & IADMM_F_SKIP_FINAL_RESID)) {
+    if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
+    if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, nullptr, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
+                                  dual_trace_u, sd, se, sc, K - 1, 1, st))) return rc;
+  }
+  return IADMM_OK;
+}
+
+int iadmm_residuals_workspace_bytes(int B, int n, int m, size_t* bytes) {
+  if (B <= 0 || n <= 0 || m < 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "residuals_workspace_bytes: B=%d n=%d m=%d", B, n, m);
+  *bytes = kkt_scratch_floats(make_kkt_dims(B, n, m, 0)) * sizeof(float);
+  return IADMM_OK;
+}
+
+int iadmm_residuals(const float* x, const float* y, const float* z, const float* Q, const float* p, const float* A0,
+                    float* pri, float* dual, int B, int n, int m, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  if (B <= 0 || n <= 0 || m < 0) IADMM_FAIL(IADMM_ESHAPE, "residuals: B=%d n=%d m=%d", B, n, m);
+  if (B > 65535) IADMM_FAIL(IADMM_ESHAPE, "residuals: batch %d > 65535 per call", B);
+  if (!x || !Q || !p || !pri || !dual || !workspace) IADMM_FAIL(IADMM_EALIGN, "residuals: NULL pointer");
+  if (m > 0 && (!y || !z || !A0)) IADMM_FAIL(IADMM_EALIGN, "residuals: NULL constraint pointer");
+  int rc = check_device();
+  if (rc) return rc;
+  const KktDims d = make_kkt_dims(B, n, m, 0);
+  if (kkt_scratch_floats(d) * sizeof(float) > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "residuals: workspace too small");
+  KktScratch s;
+  kkt_scratch_carve(d, static_cast<float*>(workspace), &s);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = launch_kkt_pass1_plain(d, Q, A0, x, y, s, st))) return rc;
+  return launch_kkt_combine1(d, p, nullptr, x, y, z, nullptr, 0.f, s, pri, dual, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, 0, 1, st);
+}
+
+int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* x,
+                    const float* y, const float* z, float* Kmat, float* rhs, float* rho_vec, int B, int n,
+                    int num_ineq, int num_eq, int h, int length, int t, float sigma, void* stream) {
+  const int m = num_ineq + num_eq;
+  if (B <= 0 || n <= 0 || m < 0 || t < 0 || t >= length) IADMM_FAIL(IADMM_ESHAPE, "build_kkt: B=%d n=%d m=%d t=%d length=%d", B, n, m, t, length);
+  if (B > 65535 || n + m > 65535) IADMM_FAIL(IADMM_ESHAPE, "build_kkt: B and n+m must be <= 65535");
+  if (!packed_weights || !Q || !p || !x || !Kmat || !rhs) IADMM_FAIL(IADMM_EALIGN, "build_kkt: NULL pointer");
+  int rc = check_device();
+  if (rc) return rc;
+  const WeightLayout L = weight_layout(h, length);
+  const Sched* sched = reinterpret_cast<const Sched*>(static_cast<const char*>(packed_weights) + L.off_sched) + t;
+  return launch_build_kkt(B, n, m, num_ineq, Q, p, A0, x, y, z, sched, sigma, Kmat, rhs, rho_vec,
+                          static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// Shared device helpers and the internal (non-ABI) kernel launch interface of libiadmm_b200.
+// sm_100a only.  Nothing here is visible through include/iadmm.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/iadmm.h"
+
+namespace iadmm {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (thread-local last-error string, set by IADMM_FAIL / IADMM_CUDA)
+// ------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define IADMM_FAIL(code, ...)                      \
+  do {                                             \
+    ::iadmm::set_error(__VA_ARGS__);               \
+    return (code);                                 \
+  } while (0)
+
+#define IADMM_CUDA(expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::iadmm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return IADMM_ECUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define IADMM_LAUNCH_CHECK(name)                                                               \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) {                                                                   \
+      ::iadmm::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));             \
+      return IADMM_ECUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int    cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline bool   aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+// packed weights (layout computed on the host from (h, length); see pack.cu)
+// ------------------------------------------------------------------------------------------------
+constexpr int   kHShift = 14;   // H is stored as fp16 hi/lo of H * 2^14 (|H| < 1 for an LSTM state)
+constexpr int   kSchedStride = 6;   // floats per schedule row, see Sched below
+
+struct WeightLayout {
+  int    h, length;
+  size_t off_u32;     // fp32 [h][4h]   column 4*j+g  (g: 0=i 1=f 2=o 3=u)
+  size_t off_wc;      // fp32 [2][4h]   W rows, same column order
+  size_t off_bias;    // fp32 [4h]
+  size_t off_wh;      // fp32 [h]
+  size_t off_bh;      // fp32 [1] (+pad)
+  size_t off_sched;   // fp32 [length][6]: rho_ineq, rho_eq, 1/rho_ineq, 1/rho_eq, alpha, 1-alpha
+  size_t off_scale;   // fp32 [4]: u_scale (power of two applied to U before the fp16 split),
+                      //           dequant = 1/(u_scale*2^14), |U|max, unused
+  size_t off_uhi;     // fp16 [4h][h]   row 4*j+g, K-major (k = input unit): tcgen05 B operand, hi part
+  size_t off_ulo;     // fp16 [4h][h]   lo part
+  size_t total;
+};
+WeightLayout weight_layout(int h, int length);
+
+struct Sched {  // one schedule row, already in fp32 exactly as models/lstm.py:60-63 rounds it
+  float rho_ineq, rho_eq, inv_rho_ineq, inv_rho_eq, alpha, one_minus_alpha;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// streaming 128-bit load: read-only path, do not allocate in L1 (matrix data is touched once per pass)
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+// same, through the coherent path (for buffers that are rewritten in place by the same kernel)
+__device__ __forceinline__ float4 ld_stream4_coherent(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+  return v;
+}
+
+// Transpose-reduce: every lane holds NV partial values; afterwards lane l holds the warp-wide total of
+// value (l * NV) >> 5  (i.e. 32/NV consecutive lanes hold the same value index).  NV in {1,2,4,8,16,32}.
+// NV shuffles + log2(32/NV) more instead of 5*NV.  Fixed order => deterministic.
+template <int NV, bool IS_MAX = false>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[NV], int lane) {
+  int bit = 16;
+#pragma unroll
+  for (int half = NV / 2; half >= 1; half >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      const float got  = __shfl_xor_sync(kFullMask, send, bit);
+      v[i] = IS_MAX ? fmaxf(keep, got) : keep + got;
+    }
+    bit >>= 1;
+  }
+  float r = v[0];
+#pragma unroll
+  for (; bit >= 1; bit >>= 1) {
+    const float got = __shfl_xor_sync(kFullMask, r, bit);
+    r = IS_MAX ? fmaxf(r, got) : r + got;
+  }
+  return r;
+}
+
+// 1/(1+exp(-x)) the way torch's CUDA sigmoid evaluates it (fp32 expf, IEEE divide)
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// internal launchers (each enqueues on `st`; returns IADMM_OK or an error code with message set)
+// ------------------------------------------------------------------------------------------------
+struct KktDims {
+  int B, n, m, num_ineq;
+  int rows_per_chunk;          // R: rows of Q / A0 one CTA streams (multiple of 8)
+  int chunks_q, chunks_a;      // ceil(n/R), ceil(m/R)
+};
+KktDims make_kkt_dims(int B, int n, int m, int num_ineq);
+
+struct KktScratch {            // all [B, ...] fp32, carved from the solve workspace
+  float* qxt;   // [B,n]   Q  x~          (pass 1)
+  float* qx;    // [B,n]   Q  x           (pass 1, residual of the previous iterate)
+  float* axt;   // [B,m]   A0 x~
+  float* ax;    // [B,m]   A0 x
+  float* aw1;   // [B,m]   A0 w1          (pass 2)
+  float* part_a;  // [B, chunks_a, 2, n]  column partials of A0^T {v | y} (pass 1) / A0^T w2 (pass 2, slot 0)
+  float* part_q;  // [B, chunks_q, n]     column partials of Q^T w1     (pass 2)
+  float* w;     // [B, n+m]  K xv - rhs
+  float* g;     // [B, n+m]  K^T w
+};
+size_t kkt_scratch_floats(const KktDims& d);
+void   kkt_scratch_carve(const KktDims& d, float* base, KktScratch* s);
+
+// pass 1: qxt,qx,axt,ax and column partials of A0^T v, A0^T y
+int launch_kkt_pass1(const KktDims& d, const float* Q, const float* A0, const float* xv, const float* x,
+                     const float* y, const KktScratch& s, cudaStream_t st);
+// combine 1: w = K xv - rhs ; residual norms of (x,y,z) into trace row `trace_row` (skipped when < 0)
+int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const float* x, const float* y,
+                        const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
+                        float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
+                        const float* sd, const float* se, const float* sc, int trace_row, int residual_only,
+                        cudaStream_t st);
+// pass 2: column partials of Q^T w1, A0^T w2 and rows A0 w1
+int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st);
+// combine 2: g = K^T w
+int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, const KktScratch& s, cudaStream_t st);
+
+// LSTM cell on every coordinate (fp32 SIMT path): reads H_in, writes H_out, updates C in place,
+// writes per-unit-tile partial sums of the output head into head_part [tiles][rows].
+int  simt_gate_tiles(int h);
+int  launch_gates_simt(const void* packed, const WeightLayout& L, const float* xv, const float* g,
+                       const float* H_in, float* H_out, float* C, float* head_part, long rows, int h,
+                       cudaStream_t st);
+
+// tensor-core path (gate_tc.cu)
+struct TcState {               // fp16 hi/lo images of H * 2^14, ping-pong
+  __half* h_hi[2];
+  __half* h_lo[2];
+};
+int  tc_gate_tiles(int h);
+size_t tc_state_bytes(long rows, int h);
+int  launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g,
+                     const __half* Hin_hi, const __half* Hin_lo, __half* Hout_hi, __half* Hout_lo,
+                     float* H_out_f32 /* may be NULL */, float* C, float* head_part, long rows, int h,
+                     int nprod, cudaStream_t st);
+int  launch_split_state(const float* H, __half* hi, __half* lo, long count, cudaStream_t st);
+int  launch_zero_state(__half* hi, __half* lo, long count, cudaStream_t st);
+
+// O(N) tail: xv -= head ; x,z,y updates (models/lstm.py:82-94)
+int launch_tail(const KktDims& d, const float* head_part, int tiles, const float* b_h, const Sched* sched_t,
+                const float* zl, const float* zu, float* x, float* y, float* z, float* xv, cudaStream_t st);
+
+}  // namespace iadmm

@@ -1,0 +1,552 @@
+// KKT passes of one I-ADMM-LSTM iteration, never forming the KKT matrix.
+//
+// Reference: models/lstm.py:67-72 builds K = [[Q+sigma I, A0^T],[A0, -diag(1/rho)]] (16 MB per instance
+// at n=m=1000, every iteration) and evaluates g = K^T (K xv - rhs) with two dense bmm's.  Here the same
+// expression is evaluated block-wise from Q and A0 directly:
+//     pass 1   w1 = Q x~ + sigma x~ + A0^T v - (sigma x - p)        w2 = A0 x~ - v/rho - (z - y/rho)
+//     pass 2   g1 = Q^T w1 + sigma w1 + A0^T w2                     g2 = A0 w1 - w2/rho
+// Each pass streams Q and A0 from HBM exactly once (the two passes are data dependent, so twice per
+// iteration is the algorithmic minimum: 8(n^2+mn) bytes).  Pass 1 carries the previous iterate (x, y)
+// as extra right-hand sides, so Q x, A0 x and A0^T y for primal_dual_loss (utils.py:68-71) come out of
+// the same read and the reference's third pass per iteration disappears.
+//
+// Work decomposition: one CTA streams R rows of one matrix of one instance.  Its 8 warps own disjoint
+// 128-column slabs (lane = one 128-bit column group), so "column" products (M^T s, accumulated over the
+// CTA's rows) stay in registers with no cross-warp traffic, and "row" products (M r) are reduced with a
+// transpose-reduce over the warp (2 shuffles per 128-bit load) and a small shared-memory sum over warps.
+// Column partials of different row chunks are summed in a fixed order by the combine kernels, so results
+// are bit-reproducible run to run.  HBM-bound by design: 8 independent 128-bit loads in flight per lane.
+#include "common.cuh"
+
+namespace iadmm {
+
+constexpr int kKktThreads = 256;
+constexpr int kKktWarps   = kKktThreads / 32;
+constexpr int kRowUnroll  = 8;
+constexpr int kSlabCols   = 128;                    // columns per warp per column chunk
+constexpr int kChunkCols  = kSlabCols * kKktWarps;  // 1024
+
+KktDims make_kkt_dims(int B, int n, int m, int num_ineq) {
+  KktDims d;
+  d.B = B; d.n = n; d.m = m; d.num_ineq = num_ineq;
+  // Aim for >= ~6 waves of 148 SMs x 3 resident CTAs; keep chunks >= 32 rows so the column-partial
+  // traffic (4n bytes per chunk and product) stays a few percent of the 4nR bytes streamed.
+  int R = 128;
+  const long target = 148L * 3 * 6;
+  while (R > 32 && (long)B * (cdiv(n, R) + cdiv(m, R)) < target) R /= 2;
+  d.rows_per_chunk = R;
+  d.chunks_q = cdiv(n, R);
+  d.chunks_a = cdiv(m, R);
+  return d;
+}
+
+size_t kkt_scratch_floats(const KktDims& d) {
+  const size_t B = d.B, n = d.n, m = d.m;
+  return 2 * B * n + 3 * B * m + B * (size_t)d.chunks_a * 2 * n + B * (size_t)d.chunks_q * n + 2 * B * (n + m) + 64;
+}
+
+void kkt_scratch_carve(const KktDims& d, float* base, KktScratch* s) {
+  const size_t B = d.B, n = d.n, m = d.m;
+  auto take = [&](size_t cnt) { float* p = base; base += (cnt + 3) / 4 * 4; return p; };
+  s->qxt = take(B * n);  s->qx = take(B * n);
+  s->axt = take(B * m);  s->ax = take(B * m);  s->aw1 = take(B * m);
+  s->part_a = take(B * d.chunks_a * 2 * n);
+  s->part_q = take(B * d.chunks_q * n);
+  s->w = take(B * (n + m));
+  s->g = take(B * (n + m));
+}
+
+// ------------------------------------------------------------------------------------------------
+// the streaming tile pass
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__device__ __forceinline__ float4 load_cols4(const float* __restrict__ rowp, int col, int n) {
+  if (VEC) return ldg_stream4(rowp + col);
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col + 0 < n) r.x = ldg_stream1(rowp + col + 0);
+  if (col + 1 < n) r.y = ldg_stream1(rowp + col + 1);
+  if (col + 2 < n) r.z = ldg_stream1(rowp + col + 2);
+  if (col + 3 < n) r.w = ldg_stream1(rowp + col + 3);
+  return r;
+}
+template <bool VEC>
+__device__ __forceinline__ float4 load_vec4(const float* __restrict__ v, int col, int n) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (VEC) {
+    if (col < n) r = __ldg(reinterpret_cast<const float4*>(v + col));
+    return r;
+  }
+  if (col + 0 < n) r.x = __ldg(v + col + 0);
+  if (col + 1 < n) r.y = __ldg(v + col + 1);
+  if (col + 2 < n) r.z = __ldg(v + col + 2);
+  if (col + 3 < n) r.w = __ldg(v + col + 3);
+  return r;
+}
+template <bool VEC>
+__device__ __forceinline__ void store_cols4(float* __restrict__ v, int col, int n, float4 a) {
+  if (VEC) {
+    if (col < n) *reinterpret_cast<float4*>(v + col) = a;
+    return;
+  }
+  if (col + 0 < n) v[col + 0] = a.x;
+  if (col + 1 < n) v[col + 1] = a.y;
+  if (col + 2 < n) v[col + 2] = a.z;
+  if (col + 3 < n) v[col + 3] = a.w;
+}
+
+struct TileArgs {
+  const float* mat;        // first element of the instance's matrix [rows_total, n]
+  int rows_total, n, r0, R;
+  const float* rrhs[2];    // NR vectors of length n      (row products  M r)
+  float*       rout[2];    // NR outputs of length rows_total
+  const float* crhs[2];    // NC vectors of length rows_total (column products M^T s)
+  float*       cpart[2];   // NC outputs of length n: this chunk's partial of M^T s
+};
+
+// smem: rowscal[2][R] | rowacc[R*2] | rowpart[warps][R*2]
+template <int NR, int NC, bool VEC>
+__device__ __forceinline__ void tile_pass(const TileArgs& a, float* smem) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = a.R, n = a.n;
+  float* rowscal = smem;
+  float* rowacc  = smem + 2 * R;
+  float* rowpart = smem + 4 * R;
+
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    for (int r = tid; r < R; r += kKktThreads) {
+      const int row = a.r0 + r;
+      rowscal[c * R + r] = (row < a.rows_total) ? __ldg(a.crhs[c] + row) : 0.f;
+    }
+  for (int i = tid; i < R * NR; i += kKktThreads) rowacc[i] = 0.f;
+  __syncthreads();
+
+  const int nchunk = (n + kChunkCols - 1) / kChunkCols;
+  for (int cc = 0; cc < nchunk; ++cc) {
+    const int  col    = cc * kChunkCols + warp * kSlabCols + lane * 4;
+    const bool active = col < n;
+    float4 rv[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) rv[k] = load_vec4<VEC>(a.rrhs[k], col, n);
+    float4 cacc[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cacc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int rg = 0; rg < R; rg += kRowUnroll) {
+      float4 v[kRowUnroll];
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) {
+        const int row = a.r0 + rg + u;
+        v[u] = (active && row < a.rows_total) ? load_cols4<VEC>(a.mat + (size_t)row * n, col, n)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (NC > 0) {
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const float s = rowscal[c * R + rg + u];
+            cacc[c].x = fmaf(v[u].x, s, cacc[c].x);
+            cacc[c].y = fmaf(v[u].y, s, cacc[c].y);
+            cacc[c].z = fmaf(v[u].z, s, cacc[c].z);
+            cacc[c].w = fmaf(v[u].w, s, cacc[c].w);
+          }
+        }
+      }
+      if (NR > 0) {
+        float rp[kRowUnroll * (NR > 0 ? NR : 1)];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+          for (int k = 0; k < NR; ++k) {
+            float t = v[u].x * rv[k].x;
+            t = fmaf(v[u].y, rv[k].y, t);
+            t = fmaf(v[u].z, rv[k].z, t);
+            t = fmaf(v[u].w, rv[k].w, t);
+            rp[u * NR + k] = t;
+          }
+        }
+        constexpr int NV = kRowUnroll * (NR > 0 ? NR : 1);
+        const float tot = warp_transpose_reduce<NV>(rp, lane);
+        constexpr int kGroup = 32 / NV;              // lanes holding the same value
+        if ((lane % kGroup) == 0) {
+          const int idx = lane / kGroup;             // = u*NR + k
+          rowpart[warp * (R * NR) + rg * NR + idx] = tot;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) store_cols4<VEC>(a.cpart[c], col, n, cacc[c]);
+
+    if (NR > 0) {
+      __syncthreads();
+      for (int i = tid; i < R * NR; i += kKktThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kKktWarps; ++w) s += rowpart[w * (R * NR) + i];
+        rowacc[i] += s;
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NR; ++k)
+    for (int r = tid; r < R; r += kKktThreads) {
+      const int row = a.r0 + r;
+      if (row < a.rows_total) a.rout[k][row] = rowacc[r * NR + k];
+    }
+}
+
+static size_t tile_smem_bytes(int R) { return (size_t)(4 * R + kKktWarps * R * 2) * sizeof(float); }
+
+// ------------------------------------------------------------------------------------------------
+// pass 1 / pass 2 kernels.  grid = (chunks_q + chunks_a, B)
+// ------------------------------------------------------------------------------------------------
+struct Pass1Args {
+  KktDims d;
+  const float *Q, *A0;
+  const float *xt; long xt_stride;   // x~  (first n entries of xv)
+  const float *v;  long v_stride;    // v   (last m entries of xv)
+  const float *x, *y;                // previous iterate [B,n], [B,m]
+  KktScratch s;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(kKktThreads) kkt_pass1_kernel(const Pass1Args P) {
+  extern __shared__ float smem[];
+  const KktDims& d = P.d;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const size_t n = d.n, m = d.m;
+  TileArgs a;
+  a.n = d.n; a.R = d.rows_per_chunk;
+  a.rrhs[0] = P.xt + (size_t)b * P.xt_stride;
+  a.rrhs[1] = P.x + b * n;
+  if (chunk < d.chunks_q) {
+    a.mat = P.Q + b * n * n; a.rows_total = d.n; a.r0 = chunk * a.R;
+    a.rout[0] = P.s.qxt + b * n; a.rout[1] = P.s.qx + b * n;
+    a.crhs[0] = a.crhs[1] = nullptr; a.cpart[0] = a.cpart[1] = nullptr;
+    tile_pass<2, 0, VEC>(a, smem);
+  } else {
+    const int ca = chunk - d.chunks_q;
+    a.mat = P.A0 + b * m * n; a.rows_total = d.m; a.r0 = ca * a.R;
+    a.rout[0] = P.s.axt + b * m; a.rout[1] = P.s.ax + b * m;
+    a.crhs[0] = P.v + (size_t)b * P.v_stride; a.crhs[1] = P.y + b * m;
+    float* part = P.s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
+    a.cpart[0] = part; a.cpart[1] = part + n;
+    tile_pass<2, 2, VEC>(a, smem);
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kKktThreads) kkt_pass2_kernel(const KktDims d, const float* __restrict__ Q,
+                                                                const float* __restrict__ A0, const KktScratch s) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const size_t n = d.n, m = d.m, N = n + m;
+  TileArgs a;
+  a.n = d.n; a.R = d.rows_per_chunk;
+  const float* w1 = s.w + b * N;
+  const float* w2 = w1 + n;
+  a.rrhs[1] = nullptr; a.rout[1] = nullptr; a.crhs[1] = nullptr; a.cpart[1] = nullptr;
+  if (chunk < d.chunks_q) {
+    a.mat = Q + b * n * n; a.rows_total = d.n; a.r0 = chunk * a.R;
+    a.rrhs[0] = nullptr; a.rout[0] = nullptr;
+    a.crhs[0] = w1; a.cpart[0] = s.part_q + ((size_t)b * d.chunks_q + chunk) * n;
+    tile_pass<0, 1, VEC>(a, smem);
+  } else {
+    const int ca = chunk - d.chunks_q;
+    a.mat = A0 + b * m * n; a.rows_total = d.m; a.r0 = ca * a.R;
+    a.rrhs[0] = w1; a.rout[0] = s.aw1 + b * m;
+    a.crhs[0] = w2; a.cpart[0] = s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
+    tile_pass<1, 1, VEC>(a, smem);
+  }
+}
+
+static bool can_vectorise(const KktDims& d, const void* Q, const void* A0) {
+  return (d.n % 4 == 0) && aligned16(Q) && aligned16(A0);
+}
+
+int launch_kkt_pass1(const KktDims& d, const float* Q, const float* A0, const float* xv, const float* x,
+                     const float* y, const KktScratch& s, cudaStream_t st) {
+  Pass1Args P;
+  P.d = d; P.Q = Q; P.A0 = A0;
+  P.xt = xv; P.xt_stride = d.n + d.m;
+  P.v = xv + d.n; P.v_stride = d.n + d.m;
+  P.x = x; P.y = y; P.s = s;
+  const dim3 grid(d.chunks_q + d.chunks_a, d.B);
+  const size_t smem = tile_smem_bytes(d.rows_per_chunk);
+  if (can_vectorise(d, Q, A0)) kkt_pass1_kernel<true><<<grid, kKktThreads, smem, st>>>(P);
+  else                         kkt_pass1_kernel<false><<<grid, kKktThreads, smem, st>>>(P);
+  IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
+  return IADMM_OK;
+}
+
+// primal_dual_loss on its own (utils.py:68-71): x plays x~ and y plays v, the second product pair is unused
+int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, const float* x, const float* y,
+                           const KktScratch& s, cudaStream_t st) {
+  Pass1Args P;
+  P.d = d; P.Q = Q; P.A0 = A0;
+  P.xt = x; P.xt_stride = d.n;
+  P.v = y; P.v_stride = d.m;
+  P.x = x; P.y = y; P.s = s;
+  const dim3 grid(d.chunks_q + d.chunks_a, d.B);
+  const size_t smem = tile_smem_bytes(d.rows_per_chunk);
+  if (can_vectorise(d, Q, A0)) kkt_pass1_kernel<true><<<grid, kKktThreads, smem, st>>>(P);
+  else                         kkt_pass1_kernel<false><<<grid, kKktThreads, smem, st>>>(P);
+  IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
+  return IADMM_OK;
+}
+
+int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st) {
+  const dim3 grid(d.chunks_q + d.chunks_a, d.B);
+  const size_t smem = tile_smem_bytes(d.rows_per_chunk);
+  if (can_vectorise(d, Q, A0)) kkt_pass2_kernel<true><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s);
+  else                         kkt_pass2_kernel<false><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s);
+  IADMM_LAUNCH_CHECK("kkt_pass2_kernel");
+  return IADMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// combine 1: w = K xv - rhs, and the residual norms of the previous iterate.  One CTA per instance.
+// Element order of every sum follows the reference expression (models/lstm.py:69,72; utils.py:69-70);
+// products and sums are rounded separately where the reference rounds them separately.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCombThreads = 512;
+
+struct Combine1Args {
+  KktDims d;
+  const float *p, *xt, *v, *x, *y, *z;
+  long xt_stride, v_stride;
+  const Sched* sched;           // device pointer to this iteration's schedule row (NULL when residual_only)
+  float sigma;
+  KktScratch s;
+  float *pri, *dual, *pri_u, *dual_u;   // trace rows (already offset to the row), may be NULL
+  const float *sd, *se, *sc;            // Ruiz diagonals, may be NULL
+  int residual_only;
+};
+
+__device__ __forceinline__ double block_sum_double(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < kCombThreads / 32; ++w) t += sh[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combine1Args A) {
+  __shared__ double sh[kCombThreads / 32];
+  const KktDims& d = A.d;
+  const int b = blockIdx.x;
+  const size_t n = d.n, m = d.m, N = n + m;
+  const float* part = A.s.part_a + (size_t)b * d.chunks_a * 2 * n;
+  const bool want_res = (A.pri != nullptr) || (A.dual != nullptr) || (A.pri_u != nullptr) || (A.dual_u != nullptr);
+  const bool unscaled = (A.sd != nullptr) && ((A.pri_u != nullptr) || (A.dual_u != nullptr));
+  float inv_ineq = 0.f, inv_eq = 0.f;
+  if (!A.residual_only) { inv_ineq = A.sched->inv_rho_ineq; inv_eq = A.sched->inv_rho_eq; }
+  const float cscale = unscaled ? A.sc[b] : 1.f;
+
+  double dual2 = 0.0, dual2u = 0.0, pri2 = 0.0, pri2u = 0.0;
+  for (int j = threadIdx.x; j < d.n; j += kCombThreads) {
+    float atv = 0.f, aty = 0.f;
+    for (int c = 0; c < d.chunks_a; ++c) {
+      atv += part[((size_t)c * 2 + 0) * n + j];
+      aty += part[((size_t)c * 2 + 1) * n + j];
+    }
+    const float pj = A.p[b * n + j];
+    if (!A.residual_only) {
+      const float xt  = A.xt[(size_t)b * A.xt_stride + j];
+      const float kxv = __fadd_rn(__fadd_rn(A.s.qxt[b * n + j], __fmul_rn(A.sigma, xt)), atv);
+      const float rhs = __fsub_rn(__fmul_rn(A.sigma, A.x[b * n + j]), pj);
+      A.s.w[b * N + j] = __fsub_rn(kxv, rhs);
+    }
+    if (want_res) {
+      const float r = __fadd_rn(__fadd_rn(A.s.qx[b * n + j], pj), aty);
+      dual2 += (double)r * (double)r;
+      if (unscaled) {
+        const float ru = r / (cscale * A.sd[b * n + j]);
+        dual2u += (double)ru * (double)ru;
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < d.m; i += kCombThreads) {
+    const float zi = A.z[b * m + i];
+    if (!A.residual_only) {
+      const float inv = (i < d.num_ineq) ? inv_ineq : inv_eq;
+      const float vi  = A.v[(size_t)b * A.v_stride + i];
+      const float kxv = __fsub_rn(A.s.axt[b * m + i], __fmul_rn(inv, vi));
+      const float rhs = __fsub_rn(zi, __fmul_rn(inv, A.y[b * m + i]));
+      A.s.w[b * N + n + i] = __fsub_rn(kxv, rhs);
+    }
+    if (want_res) {
+      const float r = __fsub_rn(A.s.ax[b * m + i], zi);
+      pri2 += (double)r * (double)r;
+      if (unscaled) {
+        const float ru = r / A.se[b * m + i];
+        pri2u += (double)ru * (double)ru;
+      }
+    }
+  }
+  if (want_res) {
+    pri2  = block_sum_double(pri2, sh);
+    dual2 = block_sum_double(dual2, sh);
+    if (unscaled) { pri2u = block_sum_double(pri2u, sh); dual2u = block_sum_double(dual2u, sh); }
+    if (threadIdx.x == 0) {
+      if (A.pri)  A.pri[b]  = (float)sqrt(pri2);
+      if (A.dual) A.dual[b] = (float)sqrt(dual2);
+      if (unscaled && A.pri_u)  A.pri_u[b]  = (float)sqrt(pri2u);
+      if (unscaled && A.dual_u) A.dual_u[b] = (float)sqrt(dual2u);
+    }
+  }
+}
+
+int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const float* x, const float* y,
+                        const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
+                        float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
+                        const float* sd, const float* se, const float* sc, int trace_row, int residual_only,
+                        cudaStream_t st) {
+  Combine1Args A;
+  A.d = d; A.p = p; A.x = x; A.y = y; A.z = z;
+  A.xt = xv; A.v = xv ? xv + d.n : nullptr; A.xt_stride = A.v_stride = d.n + d.m;
+  A.sched = sched_t; A.sigma = sigma; A.s = s;
+  const size_t off = trace_row >= 0 ? (size_t)trace_row * d.B : 0;
+  A.pri    = (trace_row >= 0 && pri_trace)    ? pri_trace + off    : nullptr;
+  A.dual   = (trace_row >= 0 && dual_trace)   ? dual_trace + off   : nullptr;
+  A.pri_u  = (trace_row >= 0 && pri_trace_u)  ? pri_trace_u + off  : nullptr;
+  A.dual_u = (trace_row >= 0 && dual_trace_u) ? dual_trace_u + off : nullptr;
+  A.sd = sd; A.se = se; A.sc = sc;
+  A.residual_only = residual_only;
+  kkt_combine1_kernel<<<d.B, kCombThreads, 0, st>>>(A);
+  IADMM_LAUNCH_CHECK("kkt_combine1_kernel");
+  return IADMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// combine 2: g = K^T w   (element-wise over B*(n+m))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kkt_combine2_kernel(const KktDims d, const Sched* __restrict__ sched,
+                                                           float sigma, const KktScratch s) {
+  const size_t n = d.n, m = d.m, N = n + m;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)d.B * N) return;
+  const size_t b = idx / N;
+  const int    r = (int)(idx - b * N);
+  if (r < d.n) {
+    float qtw = 0.f, atw = 0.f;
+    const float* pq = s.part_q + b * d.chunks_q * n + r;
+    for (int c = 0; c < d.chunks_q; ++c) qtw += pq[(size_t)c * n];
+    const float* pa = s.part_a + b * d.chunks_a * 2 * n + r;
+    for (int c = 0; c < d.chunks_a; ++c) atw += pa[(size_t)c * 2 * n];
+    const float w1 = s.w[b * N + r];
+    s.g[idx] = __fadd_rn(__fadd_rn(qtw, __fmul_rn(sigma, w1)), atw);
+  } else {
+    const int   i   = r - d.n;
+    const float inv = (i < d.num_ineq) ? sched->inv_rho_ineq : sched->inv_rho_eq;
+    s.g[idx] = __fsub_rn(s.aw1[b * m + i], __fmul_rn(inv, s.w[idx]));
+  }
+}
+
+int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, const KktScratch& s, cudaStream_t st) {
+  const size_t total = (size_t)d.B * (d.n + d.m);
+  kkt_combine2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, sched_t, sigma, s);
+  IADMM_LAUNCH_CHECK("kkt_combine2_kernel");
+  return IADMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// O(N) tail of the iteration (models/lstm.py:80-94): head bias, xv step, x relaxation, z projection,
+// dual update.  Every product/sum is rounded separately, in the reference's order: equality rows carry
+// rho ~ 500 and y + rho*(z~ - z) cancels catastrophically, so a contracted FMA here would show up as a
+// 1e-4-level difference in y.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tail_kernel(const KktDims d, const float* __restrict__ head_part, int tiles,
+                                                   const float* __restrict__ b_h, const Sched* __restrict__ sched,
+                                                   const float* __restrict__ zl, const float* __restrict__ zu,
+                                                   float* __restrict__ x, float* __restrict__ y, float* __restrict__ z,
+                                                   float* __restrict__ xv) {
+  const size_t n = d.n, m = d.m, N = n + m;
+  const size_t rows = (size_t)d.B * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows) return;
+  float head = 0.f;
+  for (int t = 0; t < tiles; ++t) head += head_part[(size_t)t * rows + idx];
+  head = __fadd_rn(head, b_h[0]);
+  const float xvn = __fsub_rn(xv[idx], head);
+  xv[idx] = xvn;
+  const size_t b = idx / N;
+  const int    r = (int)(idx - b * N);
+  if (r < d.n) {
+    const float a = sched->alpha, oma = sched->one_minus_alpha;
+    const size_t j = b * n + r;
+    x[j] = __fadd_rn(__fmul_rn(a, xvn), __fmul_rn(oma, x[j]));
+  } else {
+    const int    i   = r - d.n;
+    const size_t k   = b * m + i;
+    const bool   eq  = i >= d.num_ineq;
+    const float  rho = eq ? sched->rho_eq : sched->rho_ineq;
+    const float  inv = eq ? sched->inv_rho_eq : sched->inv_rho_ineq;
+    const float  yo = y[k], zo = z[k];
+    const float  zmid = __fadd_rn(zo, __fmul_rn(inv, __fsub_rn(xvn, yo)));
+    const float  zc   = fmaxf(fminf(__fadd_rn(zmid, __fmul_rn(inv, yo)), zu[k]), zl[k]);
+    z[k] = zc;
+    y[k] = __fadd_rn(yo, __fmul_rn(rho, __fsub_rn(zmid, zc)));
+  }
+}
+
+int launch_tail(const KktDims& d, const float* head_part, int tiles, const float* b_h, const Sched* sched_t,
+                const float* zl, const float* zu, float* x, float* y, float* z, float* xv, cudaStream_t st) {
+  const size_t rows = (size_t)d.B * (d.n + d.m);
+  tail_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, head_part, tiles, b_h, sched_t, zl, zu, x, y, z, xv);
+  IADMM_LAUNCH_CHECK("tail_kernel");
+  return IADMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense K / rhs / rho_vec materialisation for API compatibility (models/lstm.py:61-62,67-69)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_kkt_kernel(int B, int n, int m, int num_ineq, const float* __restrict__ Q,
+                                                        const float* __restrict__ p, const float* __restrict__ A0,
+                                                        const float* __restrict__ x, const float* __restrict__ y,
+                                                        const float* __restrict__ z, const Sched* __restrict__ sched,
+                                                        float sigma, float* __restrict__ K, float* __restrict__ rhs,
+                                                        float* __restrict__ rho_vec) {
+  const size_t N = (size_t)n + m;
+  const size_t b = blockIdx.z;
+  const int r = blockIdx.y;                       // row of K
+  const float rho_r = (r >= n) ? ((r - n < num_ineq) ? sched->rho_ineq : sched->rho_eq) : 0.f;
+  const float inv_r = (r >= n) ? ((r - n < num_ineq) ? sched->inv_rho_ineq : sched->inv_rho_eq) : 0.f;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < (int)N; c += gridDim.x * blockDim.x) {
+    float v;
+    if (r < n) {
+      if (c < n) { v = Q[(b * n + r) * n + c]; if (c == r) v = __fadd_rn(v, sigma); }
+      else       v = A0[(b * m + (c - n)) * n + r];
+    } else {
+      if (c < n) v = A0[(b * m + (r - n)) * n + c];
+      else       v = (c == r) ? -inv_r : -0.0f;     // -(1/rho) * 0 in the reference is -0.0
+    }
+    K[(b * N + r) * N + c] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (r < n) rhs[b * N + r] = __fsub_rn(__fmul_rn(sigma, x[b * n + r]), p[b * n + r]);
+    else {
+      const int i = r - n;
+      rhs[b * N + r] = __fsub_rn(z[b * m + i], __fmul_rn(inv_r, y[b * m + i]));
+      rho_vec[b * m + i] = rho_r;
+    }
+  }
+}
+
+int launch_build_kkt(int B, int n, int m, int num_ineq, const float* Q, const float* p, const float* A0,
+                     const float* x, const float* y, const float* z, const Sched* sched_t, float sigma,
+                     float* K, float* rhs, float* rho_vec, cudaStream_t st) {
+  const int N = n + m;
+  const dim3 grid(cdiv(N, 256) > 8 ? 8 : cdiv(N, 256), N, B);
+  build_kkt_kernel<<<grid, 256, 0, st>>>(B, n, m, num_ineq, Q, p, A0, x, y, z, sched_t, sigma, K, rhs, rho_vec);
+  IADMM_LAUNCH_CHECK("build_kkt_kernel");
+  return IADMM_OK;
+}
+
+}  // namespace iadmm

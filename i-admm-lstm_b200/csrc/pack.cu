@@ -1,0 +1,161 @@
+// Weight packing and the penalty schedule (models/lstm.py:21-41 parameters, :60-63 schedule).
+//
+// The 16 parameter tensors are re-laid once per weight update into what the kernels stream:
+//   * gate matrices interleaved per hidden unit (column 4*j+g, g = i,f,o,u) so one thread / one TMEM
+//     column group holds all four pre-activations of a unit;
+//   * an fp16 hi/lo split of U * 2^s (s chosen so max|U| * 2^s is in [2^12, 2^13)): the tensor-core
+//     path multiplies H_hi U_hi + H_lo U_hi + H_hi U_lo in fp32 accumulators, i.e. ~22-bit operands;
+//   * rho_t = sigmoid(rho[t]), 1e3 * rho_t, their reciprocals and alpha_t = 2 sigmoid(alpha[t]),
+//     rounded to fp32 after every operation exactly like the reference's tensor ops.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace iadmm {
+
+WeightLayout weight_layout(int h, int length) {
+  WeightLayout L;
+  L.h = h; L.length = length;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t H = (size_t)h;
+  L.off_u32   = take(H * 4 * H * sizeof(float));
+  L.off_wc    = take(2 * 4 * H * sizeof(float));
+  L.off_bias  = take(4 * H * sizeof(float));
+  L.off_wh    = take(H * sizeof(float));
+  L.off_bh    = take(4 * sizeof(float));
+  L.off_sched = take((size_t)length * kSchedStride * sizeof(float));
+  L.off_scale = take(4 * sizeof(float));
+  L.off_uhi   = take(4 * H * H * sizeof(__half));
+  L.off_ulo   = take(4 * H * H * sizeof(__half));
+  L.total = off;
+  return L;
+}
+
+struct PackSrc {
+  const float* W[4];
+  const float* U[4];
+  const float* b[4];
+  const float *W_h, *b_h, *rho, *alpha;
+};
+
+__global__ void __launch_bounds__(256) pack_small_kernel(PackSrc S, int h, int length, float* __restrict__ wc,
+                                                         float* __restrict__ bias, float* __restrict__ wh,
+                                                         float* __restrict__ bh, float* __restrict__ sched,
+                                                         float* __restrict__ scale) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = tid; i < 4 * h; i += stride) {
+    const int j = i >> 2, g = i & 3;
+    wc[i]         = S.W[g][j];
+    wc[4 * h + i] = S.W[g][h + j];
+    bias[i]       = S.b[g][j];
+  }
+  for (int j = tid; j < h; j += stride) wh[j] = S.W_h[j];
+  if (tid == 0) { bh[0] = S.b_h[0]; scale[2] = 0.f; }
+  for (int t = tid; t < length; t += stride) {
+    const float rho = sigmoid_ref(S.rho[t]);
+    const float rho_eq = __fmul_rn(rho, 1000.0f);
+    const float alpha = __fmul_rn(2.0f, sigmoid_ref(S.alpha[t]));
+    float* r = sched + (size_t)t * kSchedStride;
+    r[0] = rho;
+    r[1] = rho_eq;
+    r[2] = 1.0f / rho;
+    r[3] = 1.0f / rho_eq;
+    r[4] = alpha;
+    r[5] = __fsub_rn(1.0f, alpha);
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_absmax_kernel(PackSrc S, int h, float* __restrict__ scale) {
+  const size_t total = (size_t)4 * h * h;
+  float mx = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i / ((size_t)h * h));
+    const size_t r = i - (size_t)g * h * h;
+    const float v = fabsf(S.U[g][r]);
+    if (isfinite(v)) mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(scale + 2), __float_as_int(mx));  // mx >= 0
+}
+
+__global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __restrict__ u32, __half* __restrict__ uhi,
+                                                     __half* __restrict__ ulo, float* __restrict__ scale) {
+  const float mx = scale[2];
+  float us = 1.f;
+  if (mx > 0.f) us = exp2f((float)(12 - ilogbf(mx)));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scale[0] = us;
+    scale[1] = 1.0f / (us * (float)(1 << kHShift));
+  }
+  const size_t total = (size_t)4 * h * h;
+  // one thread per (column c = 4j+g, input unit k); consecutive threads -> consecutive c for the fp32
+  // image (row k of u32 is contiguous in c)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / (4 * (size_t)h));
+    const int c = (int)(i - (size_t)k * 4 * h);
+    const int j = c >> 2, g = c & 3;
+    const float v = S.U[g][(size_t)k * h + j];
+    u32[i] = v;
+    const float vs = v * us;
+    const __half hi = __float2half_rn(vs);
+    const __half lo = __float2half_rn(vs - __half2float(hi));
+    uhi[(size_t)c * h + k] = hi;
+    ulo[(size_t)c * h + k] = lo;
+  }
+}
+
+int pack_weights_impl(const float* const W[4], const float* const U[4], const float* const b[4], const float* W_h,
+                      const float* b_h, const float* rho, const float* alpha, int h, int length, void* packed,
+                      cudaStream_t st) {
+  const WeightLayout L = weight_layout(h, length);
+  char* base = static_cast<char*>(packed);
+  PackSrc S;
+  for (int g = 0; g < 4; ++g) { S.W[g] = W[g]; S.U[g] = U[g]; S.b[g] = b[g]; }
+  S.W_h = W_h; S.b_h = b_h; S.rho = rho; S.alpha = alpha;
+  float* scale = reinterpret_cast<float*>(base + L.off_scale);
+  pack_small_kernel<<<cdiv(4 * h > length ? 4 * h : length, 256), 256, 0, st>>>(
+      S, h, length, reinterpret_cast<float*>(base + L.off_wc), reinterpret_cast<float*>(base + L.off_bias),
+      reinterpret_cast<float*>(base + L.off_wh), reinterpret_cast<float*>(base + L.off_bh),
+      reinterpret_cast<float*>(base + L.off_sched), scale);
+  IADMM_LAUNCH_CHECK("pack_small_kernel");
+  const size_t total = (size_t)4 * h * h;
+  const int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+  pack_absmax_kernel<<<blocks, 256, 0, st>>>(S, h, scale);
+  IADMM_LAUNCH_CHECK("pack_absmax_kernel");
+  pack_u_kernel<<<blocks, 256, 0, st>>>(S, h, reinterpret_cast<float*>(base + L.off_u32),
+                                        reinterpret_cast<__half*>(base + L.off_uhi),
+                                        reinterpret_cast<__half*>(base + L.off_ulo), scale);
+  IADMM_LAUNCH_CHECK("pack_u_kernel");
+  return IADMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 <-> fp16 hi/lo images of the hidden state (tensor-core path)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_state_kernel(const float* __restrict__ H, __half* __restrict__ hi,
+                                                          __half* __restrict__ lo, size_t count) {
+  const float s = (float)(1 << kHShift);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = H[i] * s;
+    const __half a = __float2half_rn(v);
+    hi[i] = a;
+    lo[i] = __float2half_rn(v - __half2float(a));
+  }
+}
+
+int launch_split_state(const float* H, __half* hi, __half* lo, long count, cudaStream_t st) {
+  const long blocks = (count + 255) / 256;
+  split_state_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(H, hi, lo, (size_t)count);
+  IADMM_LAUNCH_CHECK("split_state_kernel");
+  return IADMM_OK;
+}
+
+int launch_zero_state(__half* hi, __half* lo, long count, cudaStream_t st) {
+  IADMM_CUDA(cudaMemsetAsync(hi, 0, (size_t)count * sizeof(__half), st));
+  IADMM_CUDA(cudaMemsetAsync(lo, 0, (size_t)count * sizeof(__half), st));
+  return IADMM_OK;
+}
+
+}  // namespace iadmm

@@ -1,0 +1,283 @@
+// Modified Ruiz equilibration with cost normalisation, O(n^2) streaming form.
+//
+// Reference: methods/scaling.py:50-119.  The reference multiplies by dense diag matrices (6 [n,n]x[n,n]
+// bmm per iteration).  Every one of those products has a diagonal factor, so each output entry is ONE
+// rounded product; we therefore apply the same products element-wise, in the same order,
+//     Q <- d_i * ((c_prev * Q_ij) * d_j)          A0 <- e_i * (A0_ij * d_j)
+// and reproduce the reference's fp32 values exactly (the only order-dependent quantity is the mean of
+// the n column norms in the cost scaling, accumulated here in double).  The cost factor c_t of
+// iteration k is applied lazily by the matrix pass of iteration k+1 (rounding commutes with the
+// column max because c_t > 0), so one iteration is one read+write pass: (1 + 2*ites + 1/2) * 4(n^2+mn)
+// bytes in total instead of O(n^3) flops.
+#include "common.cuh"
+
+namespace iadmm {
+
+constexpr int kRzThreads = 256;
+constexpr int kRzWarps   = 8;
+constexpr int kRzUnroll  = 8;
+constexpr int kRzChunkCols = 128 * kRzWarps;
+constexpr float kMinScaling = 1e-4f;   // scaling.py:12
+constexpr float kMaxScaling = 1e4f;    // scaling.py:13
+
+__device__ __forceinline__ float limit_scaling(float v) {   // scaling.py:31-38
+  float w = fminf(fmaxf(v, kMinScaling), kMaxScaling);
+  return (w == kMinScaling) ? 1.0f : w;
+}
+
+struct RuizWs {            // per-instance vectors, fp32
+  float* sd;               // [B,n] current D_temp diagonal
+  float* se;               // [B,m] current E_temp diagonal
+  float* cprev;            // [B]   cost factor of the previous iteration, not yet applied to Q
+  float* rowmax;           // [B,m] row inf-norms of the current A0
+  float* partq;            // [B,chunks_q,n] column inf-norm partials of the current (pre-cost) Q
+  float* parta;            // [B,chunks_a,n]
+  int R, chunks_q, chunks_a;
+};
+
+enum { kRzNorm = 0, kRzScale = 1, kRzCost = 2 };
+
+// grid = (chunks_q + chunks_a, B).  MODE kRzNorm: norms of src.  kRzScale: dst = scaled src + norms of
+// dst.  kRzCost (Q chunks only): dst = cprev * src.
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(kRzThreads)
+ruiz_pass_kernel(const float* Qsrc, const float* Asrc, float* Qdst, float* Adst, int n, int m, RuizWs W) {
+  // src may alias dst (in-place rescaling): every element is read and then written by the same thread,
+  // and the loads below are coherent (no .nc).
+  __shared__ float rowpart[kRzWarps][128];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const bool isQ = chunk < W.chunks_q;
+  if (MODE == kRzCost && !isQ) return;
+  const int ca = isQ ? chunk : chunk - W.chunks_q;
+  const int rows_total = isQ ? n : m;
+  const int R = W.R, r0 = ca * R;
+  const float* src = isQ ? Qsrc + (size_t)b * n * n : Asrc + (size_t)b * m * n;
+  float*       dst = isQ ? (Qdst ? Qdst + (size_t)b * n * n : nullptr) : (Adst ? Adst + (size_t)b * m * n : nullptr);
+  const float* sd = W.sd + (size_t)b * n;
+  const float* srow = isQ ? sd : W.se + (size_t)b * m;       // left diagonal factor
+  const float cprev = (MODE != kRzNorm && isQ) ? W.cprev[b] : 1.0f;
+  float* colpart = isQ ? W.partq + ((size_t)b * W.chunks_q + ca) * n : W.parta + ((size_t)b * W.chunks_a + ca) * n;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int nchunk = (n + kRzChunkCols - 1) / kRzChunkCols;
+  for (int cc = 0; cc < nchunk; ++cc) {
+    const int  col    = cc * kRzChunkCols + warp * 128 + lane * 4;
+    const bool active = col < n;
+    float sc[4] = {1.f, 1.f, 1.f, 1.f};
+    if (MODE == kRzScale) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (col + e < n) sc[e] = sd[col + e];
+    }
+    float cmax[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int rg = 0; rg < R; rg += kRzUnroll) {
+      float v[kRzUnroll][4];
+#pragma unroll
+      for (int u = 0; u < kRzUnroll; ++u) {
+        const int row = r0 + rg + u;
+        const bool ok = active && row < rows_total;
+        if (ok && VEC) {
+          const float4 t = ld_stream4_coherent(src + (size_t)row * n + col);
+          v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v[u][e] = (ok && col + e < n) ? src[(size_t)row * n + col + e] : 0.f;
+        }
+      }
+      float rmax[kRzUnroll];
+#pragma unroll
+      for (int u = 0; u < kRzUnroll; ++u) {
+        const int row = r0 + rg + u;
+        const bool ok = active && row < rows_total;
+        if (MODE == kRzScale) {
+          const float sr = (row < rows_total) ? srow[row] : 1.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float t = v[u][e];
+            if (isQ) t = __fmul_rn(cprev, t);            // lazily applied c_{k-1} (scaling.py:101)
+            t = __fmul_rn(t, sc[e]);                     // bmm(M, D_temp)       (scaling.py:80-81)
+            v[u][e] = __fmul_rn(sr, t);                  // bmm(D_temp|E_temp, .)
+          }
+        } else if (MODE == kRzCost) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[u][e] = __fmul_rn(cprev, v[u][e]);
+        }
+        if (MODE != kRzNorm && ok) {
+          float* drow = dst + (size_t)row * n + col;
+          if (VEC) *reinterpret_cast<float4*>(drow) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+          else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (col + e < n) drow[e] = v[u][e];
+          }
+        }
+        float rm = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = fabsf(v[u][e]);
+          cmax[e] = fmaxf(cmax[e], a);
+          rm = fmaxf(rm, a);
+        }
+        rmax[u] = rm;
+      }
+      if (MODE != kRzCost && !isQ) {
+        const float tot = warp_transpose_reduce<kRzUnroll, true>(rmax, lane);
+        if ((lane & 3) == 0) rowpart[warp][rg + (lane >> 2)] = tot;
+      }
+    }
+    if (MODE != kRzCost && active) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (col + e < n) colpart[col + e] = cmax[e];
+    }
+    if (MODE != kRzCost && !isQ) {
+      __syncthreads();
+      for (int r = tid; r < R; r += kRzThreads) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRzWarps; ++w) t = fmaxf(t, rowpart[w][r]);
+        const int row = r0 + r;
+        if (row < rows_total) {
+          float* rm = W.rowmax + (size_t)b * m + row;
+          *rm = (cc == 0) ? t : fmaxf(*rm, t);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One CTA per instance: finish iteration k-1 (cost normalisation, vector updates) and prepare the
+// diagonal factors of iteration k.
+constexpr int kRzVecThreads = 512;
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = sh[0];
+  for (int w = 1; w < kRzVecThreads / 32; ++w) t = fmaxf(t, sh[w]);
+  return t;
+}
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < kRzVecThreads / 32; ++w) t += sh[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(kRzVecThreads)
+ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, float* __restrict__ p, float* __restrict__ zl,
+                float* __restrict__ zu, float* __restrict__ d, float* __restrict__ e, float* __restrict__ c, RuizWs W) {
+  __shared__ float shf[kRzVecThreads / 32];
+  __shared__ double shd[kRzVecThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float* sd = W.sd + (size_t)b * n;
+  float* se = W.se + (size_t)b * m;
+  const float* partq = W.partq + (size_t)b * W.chunks_q * n;
+  const float* parta = W.parta + (size_t)b * W.chunks_a * n;
+  p += (size_t)b * n; d += (size_t)b * n;
+  zl += (size_t)b * m; zu += (size_t)b * m; e += (size_t)b * m;
+
+  float cprev = 1.0f;
+  if (finish_prev) {
+    // scaling.py:82-105 for the iteration whose matrix pass just ran
+    double colsum = 0.0;
+    float pmax = 0.f;
+    for (int j = tid; j < n; j += kRzVecThreads) {
+      float cq = 0.f;
+      for (int ch = 0; ch < W.chunks_q; ++ch) cq = fmaxf(cq, partq[(size_t)ch * n + j]);
+      colsum += (double)cq;
+      const float pj = __fmul_rn(sd[j], p[j]);
+      p[j] = pj;
+      pmax = fmaxf(pmax, fabsf(pj));
+      d[j] = __fmul_rn(sd[j], d[j]);
+    }
+    for (int i = tid; i < m; i += kRzVecThreads) {
+      zl[i] = __fmul_rn(se[i], zl[i]);
+      zu[i] = __fmul_rn(se[i], zu[i]);
+      e[i]  = __fmul_rn(se[i], e[i]);
+    }
+    colsum = block_sum_d(colsum, shd);
+    pmax = block_max(pmax, shf);
+    const float mean_col = (float)colsum / (float)n;
+    const float cost = limit_scaling(fmaxf(limit_scaling(pmax), mean_col));
+    cprev = 1.0f / cost;
+    for (int j = tid; j < n; j += kRzVecThreads) p[j] = __fmul_rn(cprev, p[j]);
+    if (tid == 0) { c[b] = __fmul_rn(cprev, c[b]); W.cprev[b] = cprev; }
+  } else {
+    for (int j = tid; j < n; j += kRzVecThreads) d[j] = 1.0f;
+    for (int i = tid; i < m; i += kRzVecThreads) e[i] = 1.0f;
+    if (tid == 0) { c[b] = 1.0f; W.cprev[b] = 1.0f; }
+  }
+  if (prepare_next) {
+    // scaling.py:66-69 on the matrix as it stands (Q carries the pending factor cprev)
+    for (int j = tid; j < n; j += kRzVecThreads) {
+      float cq = 0.f, ca = 0.f;
+      for (int ch = 0; ch < W.chunks_q; ++ch) cq = fmaxf(cq, partq[(size_t)ch * n + j]);
+      for (int ch = 0; ch < W.chunks_a; ++ch) ca = fmaxf(ca, parta[(size_t)ch * n + j]);
+      const float nrm = fmaxf(__fmul_rn(cprev, cq), ca);
+      sd[j] = 1.0f / sqrtf(limit_scaling(nrm));
+    }
+    const float* rowmax = W.rowmax + (size_t)b * m;
+    for (int i = tid; i < m; i += kRzVecThreads) se[i] = 1.0f / sqrtf(limit_scaling(rowmax[i]));
+  }
+}
+
+size_t ruiz_ws_floats(int B, int n, int m, int* R_out, int* cq_out, int* ca_out) {
+  const KktDims kd = make_kkt_dims(B, n, m, 0);
+  int R = kd.rows_per_chunk > 128 ? 128 : kd.rows_per_chunk;
+  const int cq = cdiv(n, R), ca = cdiv(m, R);
+  if (R_out) { *R_out = R; *cq_out = cq; *ca_out = ca; }
+  return (size_t)B * n + (size_t)B * m + B + (size_t)B * m + (size_t)B * cq * n + (size_t)B * ca * n + 64;
+}
+
+int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, const float* zu, float* Qs, float* ps,
+              float* A0s, float* zls, float* zus, float* d, float* e, float* c, int B, int n, int m, int iterations,
+              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  RuizWs W;
+  const size_t need = ruiz_ws_floats(B, n, m, &W.R, &W.chunks_q, &W.chunks_a) * sizeof(float);
+  if (workspace_bytes < need) IADMM_FAIL(IADMM_EWORK, "ruiz workspace too small: %zu < %zu", workspace_bytes, need);
+  float* base = static_cast<float*>(workspace);
+  auto take = [&](size_t cnt) { float* q = base; base += (cnt + 3) / 4 * 4; return q; };
+  W.sd = take((size_t)B * n); W.se = take((size_t)B * m); W.cprev = take(B); W.rowmax = take((size_t)B * m);
+  W.partq = take((size_t)B * W.chunks_q * n); W.parta = take((size_t)B * W.chunks_a * n);
+
+  IADMM_CUDA(cudaMemcpyAsync(ps, p, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (m > 0) {
+    IADMM_CUDA(cudaMemcpyAsync(zls, zl, (size_t)B * m * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    IADMM_CUDA(cudaMemcpyAsync(zus, zu, (size_t)B * m * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  const bool vec = (n % 4 == 0) && aligned16(Q) && aligned16(A0) && aligned16(Qs) && aligned16(A0s);
+  const dim3 grid(W.chunks_q + W.chunks_a, B);
+  if (iterations == 0) {
+    IADMM_CUDA(cudaMemcpyAsync(Qs, Q, (size_t)B * n * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (m > 0) IADMM_CUDA(cudaMemcpyAsync(A0s, A0, (size_t)B * m * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 0, ps, zls, zus, d, e, c, W);
+    IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+    return IADMM_OK;
+  }
+  if (vec) ruiz_pass_kernel<kRzNorm, true><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, W);
+  else     ruiz_pass_kernel<kRzNorm, false><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, W);
+  IADMM_LAUNCH_CHECK("ruiz_pass_kernel<norm>");
+  ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 1, ps, zls, zus, d, e, c, W);
+  IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+  for (int k = 0; k < iterations; ++k) {
+    const float* qsrc = (k == 0) ? Q : Qs;
+    const float* asrc = (k == 0) ? A0 : A0s;
+    if (vec) ruiz_pass_kernel<kRzScale, true><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, W);
+    else     ruiz_pass_kernel<kRzScale, false><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, W);
+    IADMM_LAUNCH_CHECK("ruiz_pass_kernel<scale>");
+    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 1, (k + 1 < iterations) ? 1 : 0, ps, zls, zus, d, e, c, W);
+    IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+  }
+  if (vec) ruiz_pass_kernel<kRzCost, true><<<grid, kRzThreads, 0, st>>>(Qs, A0s, Qs, A0s, n, m, W);
+  else     ruiz_pass_kernel<kRzCost, false><<<grid, kRzThreads, 0, st>>>(Qs, A0s, Qs, A0s, n, m, W);
+  IADMM_LAUNCH_CHECK("ruiz_pass_kernel<cost>");
+  return IADMM_OK;
+}
+
+}  // namespace iadmm

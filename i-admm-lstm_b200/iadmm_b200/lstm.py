@@ -1,0 +1,181 @@
+"""Drop-in for the reference's `models/lstm.py` (class `LSTM`), backed by libiadmm_b200.
+
+Same constructor, parameter names/shapes (the state_dict contract of models/lstm.py:21-41, so
+reference checkpoints load unchanged) and the same `forward(t, num_ineq, num_eq, x, y, z, xv, sigma,
+H_t, C_t, **kwargs)` 9-tuple.  `forward` runs ONE iteration through the same CUDA kernels as the fused
+`solve`, which runs K iterations and the per-iteration residual evaluation of utils.py:68-71 in one
+call with no host synchronisation.
+"""
+from ctypes import byref, c_size_t
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+PARAM_ORDER = ("W_i", "U_i", "b_i", "W_f", "U_f", "b_f", "W_o", "U_o", "b_o",
+               "W_u", "U_u", "b_u", "W_h", "b_h", "rho", "alpha")
+
+
+@dataclass
+class SolveResult:
+    x: torch.Tensor            # [B,n,1]
+    y: torch.Tensor            # [B,m,1]
+    z: torch.Tensor            # [B,m,1]
+    xv: torch.Tensor           # [B,n+m,1]
+    H: torch.Tensor            # [B,n+m,h]
+    C: torch.Tensor            # [B,n+m,h]
+    pri: Optional[torch.Tensor] = None           # [K,B] residuals on the data the solve ran on
+    dual: Optional[torch.Tensor] = None
+    pri_unscaled: Optional[torch.Tensor] = None  # [K,B] on the original data (needs `scaling`)
+    dual_unscaled: Optional[torch.Tensor] = None
+
+
+class LSTM(nn.Module):
+    def __init__(self, num_constr, input_dim, hidden_dim, length, device, gate_mode="tc_3xfp16"):
+        super(LSTM, self).__init__()
+        if input_dim != 2:
+            raise ValueError("the I-ADMM-LSTM cell takes [xv, grad] (input_dim=2, models/lstm.py:72)")
+        self.num_constr = num_constr
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.length = length
+        self.RHO_EQ_OVER_RHO_INEQ = 1e03
+        self.device = torch.device(device)
+        self.gate_mode = gate_mode
+        self.materialize_kkt = True      # forward() returns dense A_tild/b_tild like the reference
+        dev = self.device
+
+        def normal(*size):
+            return nn.Parameter(torch.normal(mean=0, std=0.01, size=size, device=dev), requires_grad=True)
+
+        def zeros(*size):
+            return nn.Parameter(torch.zeros(size, device=dev, dtype=torch.float32), requires_grad=True)
+
+        # same creation order as the reference so a given torch seed draws the same weights
+        for g in ("i", "f", "o", "u"):
+            setattr(self, f"W_{g}", normal(input_dim, hidden_dim))
+            setattr(self, f"U_{g}", normal(hidden_dim, hidden_dim))
+            setattr(self, f"b_{g}", zeros(hidden_dim))
+        self.W_h = normal(hidden_dim, 1)
+        self.b_h = zeros(1)
+        self.rho = normal(length, 1)
+        self.alpha = normal(length, 1)
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+
+    def name(self):
+        return 'lstm'
+
+    # -- packed weights ----------------------------------------------------------------------
+    def _mode(self):
+        mode = self.gate_mode
+        if isinstance(mode, str):
+            mode = _lib.GATE_MODES[mode]
+        if mode != _lib.GATES_SIMT_FP32 and self.hidden_dim % 8 != 0:
+            mode = _lib.GATES_SIMT_FP32    # the tcgen05 tiles need 16-byte rows of fp16
+        return mode
+
+    def packed_weights(self):
+        """Device buffer in the kernels' layout; re-packed when any parameter changed."""
+        prm = [getattr(self, k) for k in PARAM_ORDER]
+        key = tuple((p.data_ptr(), p._version) for p in prm)
+        if self._packed is None or key != self._packed_key:
+            L = _lib.lib()
+            dev = prm[0].device
+            nbytes = c_size_t()
+            _lib.check(L.iadmm_weights_bytes(self.hidden_dim, self.length, byref(nbytes)))
+            if self._packed is None or self._packed.numel() != nbytes.value or self._packed.device != dev:
+                self._packed = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            data = [_lib.f32(p.detach()) for p in prm]
+            with torch.cuda.device(dev):
+                _lib.check(L.iadmm_pack_weights(*[_lib.ptr(t) for t in data], self.hidden_dim, self.length,
+                                                _lib.ptr(self._packed), _lib.stream_ptr()))
+            self._packed_key = key
+        return self._packed
+
+    def _workspace(self, B, n, m, mode, dev):
+        nbytes = c_size_t()
+        _lib.check(_lib.lib().iadmm_solve_workspace_bytes(B, n, m, self.hidden_dim, mode, byref(nbytes)))
+        if self._ws is None or self._ws.numel() < nbytes.value or self._ws.device != dev:
+            self._ws = None
+            self._ws = _lib.workspace(nbytes.value, dev)
+        return self._ws
+
+    # -- K fused iterations -------------------------------------------------------------------
+    def solve(self, K, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state=None, t0=0, scaling=None,
+              traces=True, inplace=False):
+        """K iterations of `forward` (t = t0..t0+K-1) plus the residuals of utils.py:68-71 after each,
+        in one library call.  `state=(x,y,z,xv,H,C)` or None for the zero state of main.py:837-843.
+        `scaling` is the `Scaling` object that produced (Q,p,A0,zl,zu): with it the residuals of the
+        un-scaled iterates on the original data (main.py:922-955) are traced too."""
+        L = _lib.lib()
+        _lib.require_cuda(Q, p, A0, zl, zu, *[prm for prm in self.parameters()])
+        dev = Q.device
+        Q, p, A0, zl, zu = (_lib.f32(t, dev) for t in (Q, p, A0, zl, zu))
+        B, n = Q.shape[0], Q.shape[1]
+        m = num_ineq + num_eq
+        h = self.hidden_dim
+        if A0.shape != (B, m, n):
+            raise ValueError(f"A0 has shape {tuple(A0.shape)}, expected {(B, m, n)}")
+        flags = 0
+        if state is None:
+            x = torch.zeros((B, n, 1), device=dev); y = torch.zeros((B, m, 1), device=dev)
+            z = torch.zeros((B, m, 1), device=dev); xv = torch.zeros((B, n + m, 1), device=dev)
+            H = torch.zeros((B, n + m, h), device=dev); C = torch.zeros((B, n + m, h), device=dev)
+            flags |= _lib.F_ZERO_STATE
+        else:
+            x, y, z, xv, H, C = (_lib.f32(t, dev) if inplace else _lib.f32(t, dev).clone() for t in state)
+        mode = self._mode()
+        packed = self.packed_weights()
+        ws = self._workspace(B, n, m, mode, dev)
+        pri = dual = pri_u = dual_u = None
+        if traces and K > 0:
+            pri = torch.empty((K, B), device=dev); dual = torch.empty((K, B), device=dev)
+            if scaling is not None:
+                pri_u = torch.empty((K, B), device=dev); dual_u = torch.empty((K, B), device=dev)
+        sd = se = sc = None
+        if scaling is not None:
+            sd, se, sc = scaling.d, scaling.e, scaling.c_vec
+        with torch.cuda.device(dev):
+            _lib.check(L.iadmm_solve(_lib.ptr(packed), _lib.ptr(Q), _lib.ptr(p), _lib.ptr(A0), _lib.ptr(zl), _lib.ptr(zu),
+                                     _lib.ptr(sd), _lib.ptr(se), _lib.ptr(sc),
+                                     _lib.ptr(x), _lib.ptr(y), _lib.ptr(z), _lib.ptr(xv), _lib.ptr(H), _lib.ptr(C),
+                                     _lib.ptr(pri), _lib.ptr(dual), _lib.ptr(pri_u), _lib.ptr(dual_u),
+                                     B, n, int(num_ineq), int(num_eq), h, self.length, int(t0), int(K),
+                                     float(sigma), mode, flags, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return SolveResult(x, y, z, xv, H, C, pri, dual, pri_u, dual_u)
+
+    # -- the reference's per-iteration interface -------------------------------------------------
+    def forward(self, t, num_ineq, num_eq, x, y, z, xv, sigma, H_t, C_t, **kwargs):
+        """One iteration; returns (x, y, z, xv, H_t, C_t, A_tild, b_tild, rho_vec) like models/lstm.py:96.
+        `lb`/`ub` are accepted and ignored, as in the reference (lstm.py:89-90 is commented out)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("libiadmm_b200: forward() is the inference path; wrap it in torch.no_grad() "
+                                      "(truncated-BPTT training kernels are not part of this build)")
+        Q, p, A0, zl, zu = (kwargs[k] for k in ("Q", "p", "A0", "zl", "zu"))
+        if not (0 <= int(t) < self.length):
+            raise IndexError(f"index {t} is out of bounds for dimension 0 with size {self.length}")
+        L = _lib.lib()
+        _lib.require_cuda(Q, p, A0, zl, zu, x, y, z, xv, H_t, C_t)
+        dev = Q.device
+        B, n = Q.shape[0], Q.shape[1]
+        m = num_ineq + num_eq
+        A_tild = b_tild = rho_vec = None
+        if self.materialize_kkt:
+            N = n + m
+            A_tild = torch.empty((B, N, N), device=dev)
+            b_tild = torch.empty((B, N, 1), device=dev)
+            rho_vec = torch.empty((B, m, 1), device=dev)
+            Qc, pc, Ac, xc, yc, zc = (_lib.f32(v, dev) for v in (Q, p, A0, x, y, z))
+            with torch.cuda.device(dev):
+                _lib.check(L.iadmm_build_kkt(_lib.ptr(self.packed_weights()), _lib.ptr(Qc), _lib.ptr(pc), _lib.ptr(Ac),
+                                             _lib.ptr(xc), _lib.ptr(yc), _lib.ptr(zc), _lib.ptr(A_tild), _lib.ptr(b_tild),
+                                             _lib.ptr(rho_vec), B, n, int(num_ineq), int(num_eq), self.hidden_dim,
+                                             self.length, int(t), float(sigma), _lib.stream_ptr()))
+        r = self.solve(1, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state=(x, y, z, xv, H_t, C_t), t0=int(t),
+                       traces=False)
+        return r.x, r.y, r.z, r.xv, r.H, r.C, A_tild, b_tild, rho_vec

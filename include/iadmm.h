@@ -1,0 +1,142 @@
+/*
+ * iadmm.h -- C ABI of libiadmm_b200.so: the B200 (sm_100a) implementation of the I-ADMM-LSTM
+ * unrolled solve path.
+ *
+ * The reference (NetSysOpt/I-ADMM-LSTM) has no FFI layer; its boundary for this path is three Python
+ * call signatures.  Each entry point below names the reference interface it replaces (paths relative
+ * to the reference checkout).  INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 memory owned by the caller, 16-byte aligned
+ *     (torch allocations are 256-byte aligned); the library never allocates or frees caller-visible
+ *     memory and keeps no state between calls except the last error string (thread local);
+ *   - vectors are the reference's [B, dim, 1] columns, i.e. [B, dim] contiguous; matrices are
+ *     row-major [B, rows, cols]; rows of A0 are the num_ineq inequality rows, then the num_eq
+ *     equality rows (generate_data.py:74);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it and
+ *     nothing synchronises the device;
+ *   - return value 0 = success, negative = IADMM_E*; iadmm_last_error() describes the failure.
+ *     There is no CPU fallback: on a device that is not compute capability 10.x every compute
+ *     entry point fails with IADMM_EARCH.
+ */
+#ifndef IADMM_H_
+#define IADMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IADMM_ABI_VERSION 1
+
+enum {
+  IADMM_OK      = 0,
+  IADMM_ESHAPE  = -1,   /* negative / inconsistent sizes, t0+K > schedule length */
+  IADMM_EALIGN  = -2,   /* pointer not 16-byte aligned or NULL where required */
+  IADMM_EARCH   = -3,   /* current device is not sm_100 */
+  IADMM_ECUDA   = -4,   /* a CUDA runtime/driver call failed (message has the cudaError) */
+  IADMM_EWORK   = -5,   /* workspace too small */
+  IADMM_EMODE   = -6    /* unknown or unsupported mode for these sizes */
+};
+
+/* Gate-contraction arithmetic (models/lstm.py:74-77, the [B*N,h]x[h,4h] product H_t @ U_*). */
+enum {
+  IADMM_GATES_SIMT_FP32   = 0,  /* fp32 FMA on CUDA cores: bit-stable validation path                   */
+  IADMM_GATES_TC_3XFP16   = 1,  /* tcgen05, fp16 hi/lo split of both operands, 3 MMAs, fp32 accumulate: */
+                                /* ~22-bit operands, the default (parity <= 1e-4 after K=100)           */
+  IADMM_GATES_TC_1XFP16   = 2   /* tcgen05, single fp16 MMA (TF32-class operands): opt-in fast mode     */
+};
+
+/* Flags of iadmm_solve. */
+enum {
+  IADMM_F_ZERO_STATE = 1,       /* H (and the other state) is known to be all-zero on entry (main.py:837-843) */
+  IADMM_F_SKIP_FINAL_RESID = 2  /* do not run the trailing residual pass (traces row K-1 left untouched)      */
+};
+
+int         iadmm_abi_version(void);
+const char* iadmm_last_error(void);
+/* 0 if the CURRENT cuda device can run the kernels (compute capability 10.x), else IADMM_EARCH/ECUDA. */
+int         iadmm_device_check(void);
+
+/* ---- weights ------------------------------------------------------------------------------------
+ * Replaces: the 16 nn.Parameters of models/lstm.py:21-41 as consumed by LSTM.forward (:60-63, :74-80).
+ * Packs them once per weight update into the layouts the kernels read:
+ *   - U_{i,f,o,u} interleaved per hidden unit (column 4*j+g), as fp32 [h][4h] and as fp16 hi/lo
+ *     K-major [4*h_pad][h_pad] tiles for the tensor-core path,
+ *   - W rows, biases, W_h, b_h,
+ *   - the schedule rho_t = sigmoid(rho[t]), 1e3*rho_t, their reciprocals, alpha_t = 2*sigmoid(alpha[t]).
+ * `packed` must hold iadmm_weights_bytes(h, length) bytes.
+ */
+int iadmm_weights_bytes(int h, int length, size_t* bytes);
+int iadmm_pack_weights(const float* W_i, const float* U_i, const float* b_i,
+                       const float* W_f, const float* U_f, const float* b_f,
+                       const float* W_o, const float* U_o, const float* b_o,
+                       const float* W_u, const float* U_u, const float* b_u,
+                       const float* W_h, const float* b_h,
+                       const float* rho, const float* alpha,
+                       int h, int length, void* packed, void* stream);
+
+/* ---- Ruiz equilibration -------------------------------------------------------------------------
+ * Replaces: Scaling.scale_data, methods/scaling.py:50-119 (incl. _norm_KKT_cols :17-29 and
+ * _limit_scaling :31-46).  O(n^2) streaming passes on the diagonals instead of dense diag bmm's;
+ * element-wise products are rounded in the reference's order, so outputs match it bit-for-bit up to
+ * the summation order of one mean per iteration.
+ * In : Q [B,n,n], p [B,n], A0 [B,m,n], zl, zu [B,m]  (zl may hold -inf, zu +inf).
+ * Out: Qs, ps, A0s, zls, zus (same shapes, may NOT alias the inputs), d [B,n], e [B,m], c [B]
+ *      with D = diag(d), E = diag(e) (scaling.py:107-117).
+ */
+int iadmm_ruiz_workspace_bytes(int B, int n, int m, size_t* bytes);
+int iadmm_ruiz(const float* Q, const float* p, const float* A0, const float* zl, const float* zu,
+               float* Qs, float* ps, float* A0s, float* zls, float* zus,
+               float* d, float* e, float* c,
+               int B, int n, int m, int iterations,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the unrolled solve -------------------------------------------------------------------------
+ * Replaces: K consecutive calls of LSTM.forward (models/lstm.py:47-96) as driven by main.py:874-887
+ * (test), :338-347 (train forward) and :503-509 (validation), plus the residual evaluation
+ * primal_dual_loss (utils.py:68-71) main.py performs after every call (:346, :955).
+ *
+ * State x [B,n], y,z [B,m], xv [B,n+m], H,C [B,n+m,h] is updated IN PLACE (iterations t0..t0+K-1 of
+ * the schedule).  Traces are [K,B] row-major, optional (NULL to skip):
+ *   pri_trace/dual_trace     residuals on the data passed in                       (main.py:346)
+ *   pri_trace_u/dual_trace_u residuals of the un-scaled iterates on the original data, computed from
+ *                            the diagonals d,e,c of iadmm_ruiz (main.py:922-955); need d,e,c != NULL.
+ * mode: IADMM_GATES_*; flags: IADMM_F_*.
+ */
+int iadmm_solve_workspace_bytes(int B, int n, int m, int h, int mode, size_t* bytes);
+int iadmm_solve(const void* packed_weights,
+                const float* Q, const float* p, const float* A0, const float* zl, const float* zu,
+                const float* d, const float* e, const float* c,
+                float* x, float* y, float* z, float* xv, float* H, float* C,
+                float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
+                int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
+                float sigma, int mode, int flags,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- adjacent pieces of the reference interface ------------------------------------------------- */
+
+/* Replaces: primal_dual_loss, utils.py:68-71 (forward).  pri, dual: [B]. */
+int iadmm_residuals_workspace_bytes(int B, int n, int m, size_t* bytes);
+int iadmm_residuals(const float* x, const float* y, const float* z,
+                    const float* Q, const float* p, const float* A0,
+                    float* pri, float* dual, int B, int n, int m,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces: the A_tild / b_tild / rho_vec members of LSTM.forward's return tuple
+ * (models/lstm.py:61-62, :67-69, :96), which main.py:952 and the Stage-II solver (models/lu.py) read.
+ * The solve itself never forms them.  Kmat [B,n+m,n+m], rhs [B,n+m], rho_vec [B,m]; x,y,z are the
+ * iterates BEFORE iteration t. */
+int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, const float* A0,
+                    const float* x, const float* y, const float* z,
+                    float* Kmat, float* rhs, float* rho_vec,
+                    int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IADMM_H_ */

@@ -1,0 +1,93 @@
+"""CPU checks of the C-ABI boundary: the library builds, loads without a GPU, exports every symbol
+include/iadmm.h declares, sizes its workspaces, and fails loudly (no fallback) when no B200 is present."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    sys.path.insert(0, os.path.join(ROOT, "i-admm-lstm_b200"))
+    import build as iadmm_build
+    return iadmm_build.build()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "iadmm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(iadmm_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(libpath):
+    L = ctypes.CDLL(libpath)
+    names = declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/iadmm.h but not exported"
+
+
+def test_binding_covers_header(libpath):
+    from iadmm_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    assert _lib.lib().iadmm_abi_version() == 1
+
+
+def test_workspace_sizes(libpath):
+    from iadmm_b200 import _lib
+    L = _lib.lib()
+    n = ctypes.c_size_t()
+    assert L.iadmm_weights_bytes(800, 100, ctypes.byref(n)) == 0
+    assert n.value >= 4 * 800 * 800 * 4 + 2 * 4 * 800 * 800 * 2
+    assert L.iadmm_solve_workspace_bytes(256, 1000, 1000, 800, 0, ctypes.byref(n)) == 0
+    simt = n.value
+    assert L.iadmm_solve_workspace_bytes(256, 1000, 1000, 800, 1, ctypes.byref(n)) == 0
+    assert n.value > simt > 256 * 2000 * 800 * 4          # holds the second H buffer
+    assert L.iadmm_solve_workspace_bytes(4, 100, 100, 60, 1, ctypes.byref(n)) == -6   # h % 8 != 0 -> EMODE
+    assert b"hidden_dim" in L.iadmm_last_error()
+    assert L.iadmm_solve_workspace_bytes(0, 100, 100, 64, 0, ctypes.byref(n)) == -1   # ESHAPE
+    assert L.iadmm_ruiz_workspace_bytes(8, 100, 100, ctypes.byref(n)) == 0 and n.value > 0
+    assert L.iadmm_residuals_workspace_bytes(8, 100, 100, ctypes.byref(n)) == 0 and n.value > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(libpath):
+    """Without a B200 the product path raises; it never routes through the oracle or torch."""
+    import iadmm_b200 as ia
+    assert ia.lib().iadmm_device_check() != 0
+    model = ia.LSTM(None, 2, 8, 4, "cpu")
+    qp = {k: torch.zeros(s) for k, s in dict(Q=(1, 4, 4), p=(1, 4, 1), A0=(1, 2, 4), zl=(1, 2, 1), zu=(1, 2, 1)).items()}
+    with pytest.raises(ia.IadmmError):
+        with torch.no_grad():
+            model.solve(2, 1, 1, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 1e-6)
+    with pytest.raises(ia.IadmmError):
+        ia.Scaling(4, 2, 10, "cpu").scale_data(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"])
+    with pytest.raises(ia.IadmmError):
+        ia.primal_dual_loss(torch.zeros(1, 4, 1), torch.zeros(1, 2, 1), torch.zeros(1, 2, 1), qp["Q"], qp["p"], qp["A0"])
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "i-admm-lstm_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("no CPU or PyTorch fallback", ""), f"{f} mentions the oracle"
+
+
+def test_state_dict_contract():
+    """Parameter names, order and shapes match the reference (checkpoints load unchanged, lstm.py:21-41)."""
+    import numpy as np
+    import iadmm_b200 as ia
+    g = np.load(os.path.join(ROOT, "tests", "golden", "init_contract.npz"))
+    model = ia.LSTM(None, 2, 8, 5, "cpu")
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(g["keys"])
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(g["shape_" + k])
+    assert model.name() == "lstm"

@@ -1,0 +1,231 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) behind the reference's own Python
+interface, against (a) golden outputs of the reference modules (tests/golden/*.npz) and (b) the CPU
+oracle on seeded inputs.  Tolerance: north_star's fp32 bound, rel <= 1e-4 on x, y, z and the residuals
+after K=100; the fp32 CUDA-core path and Ruiz are held to much tighter bounds.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, golden_params, golden_qp, rel_err, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NORTH_STAR_TOL = 1e-4
+
+MODES = ["simt_fp32", "tc_3xfp16", "tc_1xfp16"]
+# per-mode tolerance for K<=100 trajectories at random-init-sized weights
+MODE_TOL = {"simt_fp32": 2e-5, "tc_3xfp16": 5e-5, "tc_1xfp16": 2e-3}
+
+
+def make_model(prm, h, K, mode):
+    import iadmm_b200 as ia
+    model = ia.LSTM(None, 2, h, K, DEV, gate_mode=mode)
+    with torch.no_grad():
+        for k, v in prm.items():
+            getattr(model, k).copy_(v.to(DEV))
+    return model.eval()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["step_small", "step_ineq_only", "step_eq_only"])
+def test_single_step_vs_reference(name, mode):
+    """LSTM.forward (models/lstm.py:47-96) from a random non-zero state, incl. A_tild/b_tild/rho_vec."""
+    g = load_golden(name)
+    B, n, mi, me, h, tt = (int(v) for v in g["meta"])
+    prm, qp = golden_params(g), golden_qp(g, device=DEV)
+    st = {k: t(g["in_" + k], device=DEV) for k in ("x", "y", "z", "xv", "H", "C")}
+    model = make_model(prm, h, 4, mode)
+    keep = {k: v.clone() for k, v in st.items()}
+    with torch.no_grad():
+        out = model(tt, mi, me, st["x"], st["y"], st["z"], st["xv"], float(g["sigma"]), st["H"], st["C"],
+                    Q=qp["Q"], p=qp["p"], A0=qp["A0"], lb=None, ub=None, zl=qp["zl"], zu=qp["zu"])
+    torch.cuda.synchronize()
+    for k in keep:                                   # pure-functional like the reference: inputs untouched
+        assert torch.equal(keep[k], st[k]), k
+    tol = {"simt_fp32": 5e-6, "tc_3xfp16": 2e-5, "tc_1xfp16": 2e-3}[mode]
+    for k, v in zip(("x", "y", "z", "xv", "H", "C"), out[:6]):
+        assert v.shape == g["out_" + k].shape
+        assert rel_err(v, g["out_" + k]) < tol, (k, rel_err(v, g["out_" + k]))
+    assert torch.equal(out[6].cpu(), t(g["out_K"]))
+    assert torch.equal(out[7].cpu(), t(g["out_rhs"]))
+    assert rel_err(out[8], g["out_rho_vec"]) < 1e-6
+    with pytest.raises(IndexError):
+        with torch.no_grad():
+            model(4, mi, me, st["x"], st["y"], st["z"], st["xv"], 1e-6, st["H"], st["C"], Q=qp["Q"], p=qp["p"],
+                  A0=qp["A0"], lb=None, ub=None, zl=qp["zl"], zu=qp["zu"])
+
+
+@pytest.mark.parametrize("name", ["ruiz_small", "ruiz_zero_rows", "ruiz_c1"])
+def test_ruiz_vs_reference(name):
+    """Scaling.scale_data (methods/scaling.py:50-119) incl. the -inf bounds and the 1e-4 clamp branch."""
+    import iadmm_b200 as ia
+    g = load_golden(name)
+    B, n, mi, me, ites = (int(v) for v in g["meta"])
+    qp = golden_qp(g, device=DEV)
+    sc = ia.Scaling(n, mi + me, ites, DEV)
+    Q, p, A0, zl, zu = sc.scale_data(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"])
+    torch.cuda.synchronize()
+    for k, v in dict(Q=Q, p=p, A0=A0, zl=zl, zu=zu).items():
+        assert v.shape == g["out_" + k].shape
+        assert rel_err(v, g["out_" + k]) < 1e-6, (k, rel_err(v, g["out_" + k]))
+    assert rel_err(sc.d, g["out_d"]) < 1e-6 and rel_err(sc.e, g["out_e"]) < 1e-6
+    assert rel_err(sc.c, g["out_c"]) < 1e-6 and rel_err(sc.cinv, g["out_cinv"]) < 1e-6
+    # the dense attributes main.py multiplies with (main.py:922,923,940)
+    assert sc.D.shape == (B, n, n) and sc.Einv.shape == (B, mi + me, mi + me)
+    assert rel_err(sc.D_inv.diagonal(dim1=1, dim2=2), g["out_dinv"]) < 1e-6
+    assert rel_err(sc.Einv.diagonal(dim1=1, dim2=2), g["out_einv"]) < 1e-6
+    assert np.array_equal(np.isinf(zl.cpu().numpy()), np.isinf(g["out_zl"]))
+
+
+def test_ruiz_bit_exact_matrices():
+    """Element-wise products are rounded in the reference's order, so Q and A0 agree to the last bit
+    whenever the per-iteration cost factor does (it depends on one fp32 mean)."""
+    import iadmm_b200 as ia
+    g = load_golden("ruiz_small")
+    B, n, mi, me, ites = (int(v) for v in g["meta"])
+    qp = golden_qp(g, device=DEV)
+    sc = ia.Scaling(n, mi + me, 1, DEV)
+    from oracle import iadmm_oracle as orc
+    cpu = golden_qp(g)
+    Qo, po, Ao, zlo, zuo, so = orc.ruiz_equilibrate(cpu["Q"], cpu["p"], cpu["A0"], cpu["zl"], cpu["zu"], 1)
+    Q, p, A0, zl, zu = sc.scale_data(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"])
+    assert torch.equal(A0.cpu(), Ao) and torch.equal(zl.cpu(), zlo) and torch.equal(zu.cpu(), zuo)
+    assert torch.equal(sc.d.cpu(), so.d) and torch.equal(sc.e.cpu(), so.e)
+    assert rel_err(Q, Qo) < 2e-7 and rel_err(p, po) < 2e-7
+
+
+@pytest.mark.parametrize("shape", [(3, 12, 5, 7), (2, 10, 6, 0), (2, 37, 11, 9), (2, 1100, 130, 70)])
+def test_primal_dual_loss_vs_oracle(shape):
+    """primal_dual_loss (utils.py:68-71); n=37 takes the unaligned path, n=1100 spans two column chunks."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me = shape
+    m = mi + me
+    qp = orc.qp_instances(B, n, mi, max(me, 0), seed=5) if me > 0 else orc.qp_instances(B, n, mi, 0, seed=5)
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn((B, n, 1), generator=gen); y = torch.randn((B, m, 1), generator=gen); z = torch.randn((B, m, 1), generator=gen)
+    Qd = qp["Q"] + 0.1 * torch.randn((B, n, n), generator=gen)          # dense, non-symmetric Q
+    pr, du, tot = orc.primal_dual_residuals(x.double(), y.double(), z.double(), Qd.double(), qp["p"].double(), qp["A0"].double())
+    gp, gd, gt = ia.primal_dual_loss(x.to(DEV), y.to(DEV), z.to(DEV), Qd.to(DEV), qp["p"].to(DEV), qp["A0"].to(DEV))
+    assert gp.shape == (B, 1, 1) and gd.shape == (B, 1, 1) and gt.shape == (B, 1, 1)
+    assert rel_err(gp, pr) < 2e-6 and rel_err(gd, du) < 2e-6 and rel_err(gt, tot) < 2e-6
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["solve_small", "solve_small_scaled", "solve_small_bigw", "solve_c1", "solve_c1_scaled"])
+def test_solve_vs_reference(name, mode):
+    """K unrolled iterations from the zero state vs the reference run (main.py:837-887 loop), config-1 size
+    included (n=100, 50+50, h=64, K=100).  x, y, z, xv, H, C and the residual traces."""
+    import iadmm_b200 as ia
+    g = load_golden(name)
+    B, n, mi, me, h, K, scaled = (int(v) for v in g["meta"])
+    prm, qp = golden_params(g), golden_qp(g, device=DEV)
+    model = make_model(prm, h, K, mode)
+    Q, p, A0, zl, zu = (qp[k] for k in ("Q", "p", "A0", "zl", "zu"))
+    sc = None
+    if scaled:
+        sc = ia.Scaling(n, mi + me, 10, DEV)
+        Q, p, A0, zl, zu = sc.scale_data(Q, p, A0, zl, zu)
+    with torch.no_grad():
+        r = model.solve(K, mi, me, Q, p, A0, zl, zu, float(g["sigma"]), scaling=sc)
+    torch.cuda.synchronize()
+    tol = MODE_TOL[mode] * (4.0 if "bigw" in name else 1.0)
+    if mode != "tc_1xfp16":
+        assert tol <= NORTH_STAR_TOL * 2
+    errs = {k: rel_err(getattr(r, k), g["f32_" + k]) for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual")}
+    if scaled:
+        errs["pri_u"] = rel_err(r.pri_unscaled, g["f32_pri_u"])
+        errs["dual_u"] = rel_err(r.dual_unscaled, g["f32_dual_u"])
+    print(name, mode, {k: f"{v:.1e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < tol, (k, v)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_step_by_step_equals_fused(mode):
+    """K calls of forward() == one solve(K): same kernels, state converted at the boundary each call."""
+    g = load_golden("solve_small")
+    B, n, mi, me, h, K, _ = (int(v) for v in g["meta"])
+    prm, qp = golden_params(g), golden_qp(g, device=DEV)
+    model = make_model(prm, h, K, mode)
+    model.materialize_kkt = False
+    m = mi + me
+    x = torch.zeros((B, n, 1), device=DEV); y = torch.zeros((B, m, 1), device=DEV); z = torch.zeros((B, m, 1), device=DEV)
+    xv = torch.zeros((B, n + m, 1), device=DEV); H = torch.zeros((B, n + m, h), device=DEV); C = torch.zeros((B, n + m, h), device=DEV)
+    with torch.no_grad():
+        for tt in range(5):
+            x, y, z, xv, H, C, _, _, _ = model(tt, mi, me, x, y, z, xv, float(g["sigma"]), H, C, Q=qp["Q"], p=qp["p"],
+                                               A0=qp["A0"], lb=None, ub=None, zl=qp["zl"], zu=qp["zu"])
+        r = model.solve(5, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], float(g["sigma"]))
+    tol = 0.0 if mode == "simt_fp32" else 1e-5
+    for a, b, k in ((x, r.x, "x"), (y, r.y, "y"), (z, r.z, "z"), (xv, r.xv, "xv"), (H, r.H, "H"), (C, r.C, "C")):
+        assert rel_err(a, b) <= tol, (k, rel_err(a, b))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_instance_sharding_is_bit_exact(mode):
+    """Size-independent property used by the multi-GPU path: solving two halves of a batch separately
+    gives bit-identical iterates to solving the whole batch (no cross-instance arithmetic anywhere)."""
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, K = 6, 64, 24, 24, 32, 8
+    qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=31).items()}
+    model = make_model(orc.lstm_parameters(h, K, seed=31), h, K, mode)
+    with torch.no_grad():
+        full = model.solve(K, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6)
+        parts = [model.solve(K, mi, me, *(qp[k][s].contiguous() for k in ("Q", "p", "A0", "zl", "zu")), 6e-6)
+                 for s in (slice(0, 3), slice(3, 6))]
+    for k in ("x", "y", "z", "xv", "H", "C"):
+        assert torch.equal(getattr(full, k), torch.cat([getattr(p_, k) for p_ in parts], 0)), k
+    assert torch.equal(full.pri, torch.cat([p_.pri for p_ in parts], 1))
+    # and run-to-run determinism
+    with torch.no_grad():
+        again = model.solve(K, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6)
+    assert torch.equal(full.x, again.x) and torch.equal(full.H, again.H) and torch.equal(full.dual, again.dual)
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_3xfp16"])
+def test_config2_shape_vs_oracle(mode):
+    """BASELINE config-2 dimensions (n=1000, 500+500, h=800, --scaling) at a batch/K the CPU oracle
+    finishes in seconds: Ruiz + K=4 iterations + residual traces."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    B, n, mi, me, h, K = 2, 1000, 500, 500, 800, 4
+    qp = orc.qp_instances(B, n, mi, me, seed=41)
+    prm = orc.lstm_parameters(h, K, seed=41)
+    Qs, ps, As, zls, zus, so = orc.ruiz_equilibrate(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 10)
+    ref = orc.solve(prm, K, mi, me, Qs, ps, As, zls, zus, 6e-6, h, scaling=so, original=(qp["Q"], qp["p"], qp["A0"]),
+                    form="block")
+    sc = ia.Scaling(n, mi + me, 10, DEV)
+    Q, p, A0, zl, zu = sc.scale_data(*(qp[k].to(DEV) for k in ("Q", "p", "A0", "zl", "zu")))
+    assert rel_err(Q, Qs) < 1e-6 and rel_err(A0, As) < 1e-6
+    model = make_model(prm, h, K, mode)
+    with torch.no_grad():
+        r = model.solve(K, mi, me, Q, p, A0, zl, zu, 6e-6, scaling=sc)
+    torch.cuda.synchronize()
+    errs = {k: rel_err(getattr(r, k), getattr(ref, k)) for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual")}
+    errs["pri_u"] = rel_err(r.pri_unscaled, ref.pri_unscaled)
+    errs["dual_u"] = rel_err(r.dual_unscaled, ref.dual_unscaled)
+    print("config2-shape", mode, {k: f"{v:.1e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < 2e-5, (k, v)
+
+
+def test_inf_bounds_and_odd_sizes():
+    """Ragged sizes (n, m not multiples of 4; h not a multiple of 8 falls back to the fp32 cell),
+    inequality-only rows with -inf lower bounds, one-sided +inf upper bounds."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, K = 3, 23, 9, 0, 12, 6
+    qp = orc.qp_instances(B, n, mi, me, seed=51)
+    qp["zu"][:, ::2] = float("inf")
+    qp["zl"][:, 1::2] = -0.5
+    prm = orc.lstm_parameters(h, K, seed=51, scale=5.0)
+    ref = orc.solve(prm, K, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6, h)
+    model = make_model(prm, h, K, "tc_3xfp16")
+    with torch.no_grad():
+        r = model.solve(K, mi, me, *(qp[k].to(DEV) for k in ("Q", "p", "A0", "zl", "zu")), 6e-6)
+    for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual"):
+        assert rel_err(getattr(r, k), getattr(ref, k)) < 1e-5, k
+    assert torch.isfinite(r.z).all()
