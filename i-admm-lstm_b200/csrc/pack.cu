@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(256) pack_small_kernel(PackSrc S, int h, int l
     float* r = sched + (size_t)t * kSchedStride;
     r[0] = rho;
     r[1] = rho_eq;
-    r[2] = 1.0f / rho;
-    r[3] = 1.0f / rho_eq;
+    r[2] = __frcp_rn(rho);
+    r[3] = __frcp_rn(rho_eq);
     r[4] = alpha;
     r[5] = __fsub_rn(1.0f, alpha);
   }

@@ -203,9 +203,9 @@ ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, float* __restri
     }
     colsum = block_sum_d(colsum, shd);
     pmax = block_max(pmax, shf);
-    const float mean_col = (float)colsum / (float)n;
+    const float mean_col = __fdiv_rn((float)colsum, (float)n);
     const float cost = limit_scaling(fmaxf(limit_scaling(pmax), mean_col));
-    cprev = 1.0f / cost;
+    cprev = __frcp_rn(cost);
     for (int j = tid; j < n; j += kRzVecThreads) p[j] = __fmul_rn(cprev, p[j]);
     if (tid == 0) { c[b] = __fmul_rn(cprev, c[b]); W.cprev[b] = cprev; }
   } else {
@@ -220,10 +220,10 @@ ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, float* __restri
       for (int ch = 0; ch < W.chunks_q; ++ch) cq = fmaxf(cq, partq[(size_t)ch * n + j]);
       for (int ch = 0; ch < W.chunks_a; ++ch) ca = fmaxf(ca, parta[(size_t)ch * n + j]);
       const float nrm = fmaxf(__fmul_rn(cprev, cq), ca);
-      sd[j] = 1.0f / sqrtf(limit_scaling(nrm));
+      sd[j] = __frcp_rn(__fsqrt_rn(limit_scaling(nrm)));   // reciprocal(sqrt(.)), two roundings like scaling.py:68-69
     }
     const float* rowmax = W.rowmax + (size_t)b * m;
-    for (int i = tid; i < m; i += kRzVecThreads) se[i] = 1.0f / sqrtf(limit_scaling(rowmax[i]));
+    for (int i = tid; i < m; i += kRzVecThreads) se[i] = __frcp_rn(__fsqrt_rn(limit_scaling(rowmax[i])));
   }
 }
 
