@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the I-ADMM-LSTM unrolled solve path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gate-mode M] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = the hot path over one batch of synthetic QPs: Ruiz equilibration (10 its) + K=100 unrolled
+I-ADMM-LSTM iterations + the per-iteration primal/dual residual traces, for `batch` instances per GPU of
+BASELINE config 2 (n=1000, 500 ineq + 500 eq, hidden_dim=800, --scaling).  The batch shards by instance
+across GPUs with no collective (weak scaling: every rank solves its own `batch` instances).
+
+Prints ONE JSON line (rank 0).  `value` = solves/s with inputs resident in HBM; `e2e` = the same through
+the public API with pinned HOST buffers, H2D/D2H copies inside the timed region; `roofline` = the gate
+kernel (tensor-bound) measured live with CUDA events through the library's profile hooks, plus
+`roofline_kkt` for the HBM-bound KKT phase; `cpu_baseline` = the oracle port of the reference's torch
+path on the host cores (bounded sample).  `--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "i-admm-lstm_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+N_VAR, N_INEQ, N_EQ, HIDDEN, K_ITERS, SIGMA, RUIZ_ITS = 1000, 500, 500, 800, 100, 6e-6, 10
+METRIC = "QP solves/sec (K=100, n=1000, m=1000)"
+UNIT = "solves/s"
+WORKLOAD = ("config2: dense QP n=1000, 500 ineq + 500 eq, hidden_dim=800, --scaling (10 Ruiz its), K=100 "
+            "unrolled iterations + per-iteration residual traces, random-init LSTM")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gate-mode", default="tc_3xfp16", choices=["tc_3xfp16", "tc_1xfp16", "simt_fp32"])
+    ap.add_argument("--batch", type=int, default=256, help="instances per GPU")
+    ap.add_argument("--iters", type=int, default=K_ITERS, help="unrolled iterations per solve (metric is quoted at 100)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic inputs: generate_data.py:67-76 restated on the device (main.py:718 doubles Q on load)
+# ---------------------------------------------------------------------------------------------------
+def device_qp_batch(B, n, mi, me, seed, dev):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    Q = torch.diag_embed(torch.rand((B, n), device=dev, generator=g))            # 2 * (0.5 * diag(U[0,1)))
+    p = torch.rand((B, n, 1), device=dev, generator=g)
+    A = torch.randn((B, me, n), device=dev, generator=g)
+    b = 2 * torch.rand((B, me, 1), device=dev, generator=g) - 1
+    G = torch.randn((B, mi, n), device=dev, generator=g)
+    c = torch.empty((B, mi, 1), device=dev)
+    for lo in range(0, B, 32):     # c = sum_j |G A^+|, A^+ = A^T (A A^T)^-1 for full row rank A
+        Ab, Gb = A[lo:lo + 32].double(), G[lo:lo + 32].double()
+        GAp = torch.linalg.solve(Ab @ Ab.mT, (Gb @ Ab.mT).mT).mT
+        c[lo:lo + 32] = GAp.abs().sum(dim=2, keepdim=True).float()
+    A0 = torch.cat((G, A), dim=1).contiguous()
+    zl = torch.cat((torch.full_like(c, float("-inf")), b), dim=1).contiguous()
+    zu = torch.cat((c, b), dim=1).contiguous()
+    return Q, p, A0, zl, zu
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, dev):
+        self.proc = None
+        self.path = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(dev).uuid)
+            self.gpu_id = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        except Exception:
+            self.gpu_id = str(torch.device(dev).index or 0)
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu_id, "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks, mx, reasons, power = [], None, set(), []
+        try:
+            for line in open(self.path):
+                f = [s.strip() for s in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    clocks.append(float(f[0])); mx = float(f[1]); power.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(self.NAMES, f[3:7]):
+                    if v == "Active":
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if clocks:
+            out.update(sm_mhz=statistics.median(clocks), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(clocks),
+                       power_w_max=max(power) if power else None)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference arm / cpu baseline: oracle port of the reference's torch CPU path
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_solves_per_s(steps, warmup, cpu_batch, iters):
+    from oracle import iadmm_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    qp = orc.qp_instances(cpu_batch, N_VAR, N_INEQ, N_EQ, seed=17)
+    prm = orc.lstm_parameters(HIDDEN, iters, seed=17)
+
+    def one_step():
+        # what main.py times: scale_data (:825-834) + the K model() calls (:881-890); residuals as in :955
+        Qs, ps, As, zls, zus, sc = orc.ruiz_equilibrate(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], RUIZ_ITS)
+        orc.solve(prm, iters, N_INEQ, N_EQ, Qs, ps, As, zls, zus, SIGMA, HIDDEN, scaling=sc,
+                  original=(qp["Q"], qp["p"], qp["A0"]), form="dense")
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            one_step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one_step()
+        dt = time.perf_counter() - t0
+    sample = (f"{steps} x ({cpu_batch} instance(s) of the same workload, Ruiz + K={iters}, dense-KKT form like "
+              f"models/lstm.py:67-72), torch {torch.__version__} CPU fp32, {cores} threads")
+    return cpu_batch * steps / dt, dt / steps * 1e3, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    val, ms, cores, sample = cpu_reference_solves_per_s(steps, warmup, args.cpu_batch, args.iters)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step": args.cpu_batch, "iters": args.iters},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+def ncu_traffic(kind, batch, mode):
+    """DRAM bytes per launch from the committed ncu --set full capture of this config, if any."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return d.get(f"{kind}:{mode}:B{batch}")
+        except Exception:
+            return None
+    return None
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import iadmm_b200 as ia
+    from ctypes import byref, c_double, c_int
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    B, n, mi, me, h, K = args.batch, N_VAR, N_INEQ, N_EQ, HIDDEN, args.iters
+    m, N = mi + me, N_VAR + N_INEQ + N_EQ
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    L = ia.lib()
+
+    torch.manual_seed(17)                                    # identical random-init weights on every rank
+    model = ia.LSTM(None, 2, h, K, dev, gate_mode=args.gate_mode).eval()
+    Q, p, A0, zl, zu = device_qp_batch(B, n, mi, me, 17 + rank, dev)
+    scaling = ia.Scaling(n, m, RUIZ_ITS, dev)
+
+    def hot_step():
+        Qs, ps, As, zls, zus = scaling.scale_data(Q, p, A0, zl, zu)
+        return model.solve(K, mi, me, Qs, ps, As, zls, zus, SIGMA, scaling=scaling)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            r = hot_step()
+        barrier()
+        sampler = ClockSampler(dev) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        ia._lib.check(L.iadmm_profile_begin(steps * K))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            r = hot_step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        kkt_ms, gate_ms, tail_ms, nit = c_double(), c_double(), c_double(), c_int()
+        ia._lib.check(L.iadmm_profile_end(byref(kkt_ms), byref(gate_ms), byref(tail_ms), byref(nit)))
+        clocks = sampler.stop() if sampler else None
+        finite = bool(torch.isfinite(r.x).all() and torch.isfinite(r.pri).all())
+
+        # ---- e2e: same step through the public API from pinned host buffers --------------------------
+        e2e = None
+        if not args.no_e2e:
+            host_in = [t.cpu().pin_memory() for t in (Q, p, A0, zl, zu)]
+            dev_in = [torch.empty_like(t) for t in (Q, p, A0, zl, zu)]
+            host_out = None
+
+            def e2e_step():
+                nonlocal host_out
+                for d_, h_ in zip(dev_in, host_in):
+                    d_.copy_(h_, non_blocking=True)
+                Qs, ps, As, zls, zus = scaling.scale_data(*dev_in)
+                rr = model.solve(K, mi, me, Qs, ps, As, zls, zus, SIGMA, scaling=scaling)
+                outs = (rr.x, rr.y, rr.z, rr.pri, rr.dual, rr.pri_unscaled, rr.dual_unscaled)
+                if host_out is None:
+                    host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+                for h_, o in zip(host_out, outs):
+                    h_.copy_(o, non_blocking=True)
+                return outs
+
+            for _ in range(2):
+                outs = e2e_step()
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(steps):
+                outs = e2e_step()
+            t1.record()
+            barrier()
+            e2e_ms = t0.elapsed_time(t1)
+            h2d = sum(t.numel() * t.element_size() for t in host_in)
+            d2h = sum(o.numel() * o.element_size() for o in outs)
+            e2e = (e2e_ms, h2d, d2h)
+
+    # max over ranks
+    times = torch.tensor([ms, e2e[0] if e2e else 0.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        hbm_gbs, tf_sus, tf_burst, peak_kind = measured_peaks()
+        rows = B * N
+        nit_v = max(1, nit.value)
+        gate_avg_ms = gate_ms.value / nit_v
+        kkt_avg_ms = kkt_ms.value / nit_v
+        gate_flops = 8.0 * rows * h * h                      # logical fp32 flops of H@U (no credit for the 3-way split)
+        gate_tflops = gate_flops / (gate_avg_ms * 1e-3) / 1e12 if gate_avg_ms > 0 else 0.0
+        kkt_bytes = 8.0 * B * (n * n + m * n)                # Q and A0 streamed once per pass, two passes
+        kkt_gbs = kkt_bytes / (kkt_avg_ms * 1e-3) / 1e9 if kkt_avg_ms > 0 else 0.0
+        iter_bytes = kkt_bytes + 16.0 * rows * h + 64.0 * rows       # SURVEY section 8(d) bytes per iteration
+        step_s = ms / steps * 1e-3
+        hbm_frac_whole = (iter_bytes * K / step_s / 1e9) / hbm_gbs
+        launches_per_step = K * 6 + 2 + (3 + 2 * RUIZ_ITS)
+        line = {
+            "metric": METRIC, "value": n_gpus * B * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "iters": K, "gate_mode": args.gate_mode,
+                       "gate_arithmetic": {"tc_3xfp16": "tcgen05 fp16 hi/lo split, 3 MMAs, fp32 accumulate",
+                                           "tc_1xfp16": "tcgen05 single fp16 MMA, fp32 accumulate",
+                                           "simt_fp32": "fp32 FMA"}[args.gate_mode],
+                       "cache": "inputs larger than L2: Q+A0 %.2f GB and LSTM state %.2f GB per GPU per iteration vs 126 MB L2"
+                                % (kkt_bytes / 2 / 1e9, 16.0 * rows * h / 1e9),
+                       "parallelism": "instances sharded over %d GPU(s), no collective" % n_gpus,
+                       "results_finite": finite},
+            "gpu_launches": steps * launches_per_step,
+            "roofline": {"kernel": "gates_tc_kernel" if args.gate_mode != "simt_fp32" else "gates_simt_kernel",
+                         "bound": "tensor", "achieved": gate_tflops, "peak": tf_sus, "unit": "TFLOP/s",
+                         "frac": gate_tflops / tf_sus, "traffic": ncu_traffic("gates", B, args.gate_mode),
+                         "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,
+                         "flops_per_launch": gate_flops, "ms_per_launch": gate_avg_ms,
+                         "share_of_step": gate_ms.value / ms,
+                         "note": "logical fp32 flops 8*rows*h^2; the 3xfp16 split issues 3x that on the tensor pipe "
+                                 "(issued rate %.1f TFLOP/s)" % (gate_tflops * (3 if args.gate_mode == "tc_3xfp16" else 1))},
+            "roofline_kkt": {"kernel": "kkt_pass1+combine1+pass2+combine2", "bound": "hbm", "achieved": kkt_gbs,
+                             "peak": hbm_gbs, "unit": "GB/s", "frac": kkt_gbs / hbm_gbs,
+                             "traffic": ncu_traffic("kkt", B, args.gate_mode),
+                             "bytes_per_iteration": kkt_bytes, "ms_per_iteration": kkt_avg_ms,
+                             "share_of_step": kkt_ms.value / ms, "peak_kind": "%s hbm_gbs" % peak_kind},
+            "hbm_roofline_frac_whole_path": hbm_frac_whole,
+            "phase_ms_per_iteration": {"kkt": kkt_avg_ms, "gates": gate_avg_ms, "tail": tail_ms.value / nit_v},
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = {"value": n_gpus * B * steps / (e2e_ms * 1e-3), "unit": UNIT,
+                           "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms / steps}
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            val, cms, cores, sample = cpu_reference_solves_per_s(1, 0, max(2, args.cpu_batch), K)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

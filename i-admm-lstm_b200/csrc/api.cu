@@ -49,6 +49,18 @@ struct SolveWs {
   size_t bytes;
 };
 
+// measurement hooks: events recorded around the phases of each iteration
+struct Profile {
+  bool on = false;
+  int cap = 0, used = 0;            // iterations
+  cudaEvent_t* ev = nullptr;        // 4 per iteration
+};
+static Profile g_prof;
+
+static inline void prof_record(int slot, cudaStream_t st) {
+  if (g_prof.on && g_prof.used < g_prof.cap) cudaEventRecord(g_prof.ev[(size_t)g_prof.used * 4 + slot], st);
+}
+
 static int is_tc(int mode) { return mode == IADMM_GATES_TC_3XFP16 || mode == IADMM_GATES_TC_1XFP16; }
 
 static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, void* base, SolveWs* ws) {
@@ -183,11 +195,13 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   }
   for (int k = 0; k < K; ++k) {
     const Sched* sk = sched + (t0 + k);
+    prof_record(0, st);
     if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, sk, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
                                   dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st))) return rc;
     if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st))) return rc;
+    prof_record(1, st);
     if (tc) {
       rc = launch_gates_tc(packed_weights, L, xv, ws.s.g, ws.tc.h_hi[cur], ws.tc.h_lo[cur], ws.tc.h_hi[cur ^ 1],
                            ws.tc.h_lo[cur ^ 1], (k == K - 1) ? H : nullptr, C, ws.head_part, rows, h, nprod, st);
@@ -195,8 +209,11 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
       rc = launch_gates_simt(packed_weights, L, xv, ws.s.g, hbuf[cur], hbuf[cur ^ 1], C, ws.head_part, rows, h, st);
     }
     if (rc) return rc;
+    prof_record(2, st);
     cur ^= 1;
     if ((rc = launch_tail(ws.d, ws.head_part, ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st))) return rc;
+    prof_record(3, st);
+    if (g_prof.on && g_prof.used < g_prof.cap) ++g_prof.used;
   }
   if (!tc && cur == 1)
     IADMM_CUDA(cudaMemcpyAsync(H, ws.h_alt, (size_t)rows * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -206,6 +223,41 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
                                   dual_trace_u, sd, se, sc, K - 1, 1, st))) return rc;
   }
   return IADMM_OK;
+}
+
+int iadmm_profile_begin(int max_iterations) {
+  if (max_iterations <= 0 || max_iterations > (1 << 20)) IADMM_FAIL(IADMM_ESHAPE, "profile_begin: max_iterations=%d", max_iterations);
+  if (g_prof.ev) IADMM_FAIL(IADMM_ESHAPE, "profile_begin: a profile is already open");
+  g_prof.ev = new cudaEvent_t[(size_t)max_iterations * 4];
+  for (size_t i = 0; i < (size_t)max_iterations * 4; ++i) IADMM_CUDA(cudaEventCreate(&g_prof.ev[i]));
+  g_prof.cap = max_iterations; g_prof.used = 0; g_prof.on = true;
+  return IADMM_OK;
+}
+
+int iadmm_profile_end(double* kkt_ms, double* gates_ms, double* tail_ms, int* iterations) {
+  if (!g_prof.ev) IADMM_FAIL(IADMM_ESHAPE, "profile_end: no open profile");
+  g_prof.on = false;
+  double k = 0, g = 0, t = 0;
+  int rc = IADMM_OK;
+  if (g_prof.used > 0) {
+    cudaError_t e = cudaEventSynchronize(g_prof.ev[(size_t)(g_prof.used - 1) * 4 + 3]);
+    if (e != cudaSuccess) { set_error("profile_end: %s", cudaGetErrorString(e)); rc = IADMM_ECUDA; }
+    for (int i = 0; i < g_prof.used && rc == IADMM_OK; ++i) {
+      float a = 0, b = 0, c = 0;
+      cudaEvent_t* ev = g_prof.ev + (size_t)i * 4;
+      cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
+      k += a; g += b; t += c;
+    }
+  }
+  for (size_t i = 0; i < (size_t)g_prof.cap * 4; ++i) cudaEventDestroy(g_prof.ev[i]);
+  delete[] g_prof.ev;
+  g_prof.ev = nullptr;
+  if (kkt_ms) *kkt_ms = k;
+  if (gates_ms) *gates_ms = g;
+  if (tail_ms) *tail_ms = t;
+  if (iterations) *iterations = g_prof.used;
+  g_prof.cap = g_prof.used = 0;
+  return rc;
 }
 
 int iadmm_residuals_workspace_bytes(int B, int n, int m, size_t* bytes) {

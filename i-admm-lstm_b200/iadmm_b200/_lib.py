@@ -35,6 +35,8 @@ SIGNATURES = {
     "iadmm_residuals_workspace_bytes": ([_I, _I, _I, POINTER(_Z)], c_int),
     "iadmm_residuals": ([_P] * 8 + [_I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_build_kkt": ([_P] * 10 + [_I] * 7 + [_F, _P], c_int),
+    "iadmm_profile_begin": ([_I], c_int),
+    "iadmm_profile_end": ([POINTER(ctypes.c_double)] * 3 + [POINTER(_I)], c_int),
 }
 
 

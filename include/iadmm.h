@@ -136,6 +136,16 @@ int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, 
                     int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
                     void* stream);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------
+ * The reference times its solve with time.time() around model() (main.py:881-890, no device sync).
+ * Between iadmm_profile_begin and iadmm_profile_end every iadmm_solve call records CUDA events on its
+ * own stream around the three phases of each iteration (KKT passes+combines | gate kernel | tail), up
+ * to max_iterations iterations in total.  iadmm_profile_end synchronises on the last event and returns
+ * the summed device time of each phase in milliseconds and the number of iterations recorded.
+ * Process-wide, not thread safe; recording costs four event records per iteration. */
+int iadmm_profile_begin(int max_iterations);
+int iadmm_profile_end(double* kkt_ms, double* gates_ms, double* tail_ms, int* iterations);
+
 #ifdef __cplusplus
 }
 #endif

