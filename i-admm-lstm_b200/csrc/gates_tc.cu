@@ -28,6 +28,7 @@
 #include "common.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <cuda.h>   // CUtensorMap (types only; the encode entry point is resolved at run time)
 
 namespace iadmm {
@@ -118,6 +119,46 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar_local) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_local),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, rows of 64 bytes, 64B swizzle (as written by TMA):
@@ -132,13 +173,37 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n_cols
-__device__ __forceinline__ uint32_t make_idesc_f16(int n_cols) {
+__device__ __forceinline__ uint32_t make_idesc_f16(int n_cols, int m_rows = kTcBM) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n_cols >> 3) << 17) |
-         ((uint32_t)(kTcBM >> 4) << 24);
+         ((uint32_t)(m_rows >> 4) << 24);
 }
 
-// accurate-enough transcendental pieces for the epilogue (errors ~1e-7, far below the gate-GEMM split error)
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// Transcendentals of the epilogue: MUFU ex2/rcp based, relative error ~2e-7 (measured against fp64 on the
+// host for the polynomial; the gate-GEMM split error and fp32 summation order are larger).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {            // 1 / (1 + 2^(-x log2 e))
+  return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f));
+}
+// tanh: odd minimax polynomial x + x^3 q(x^2) for |x| < 0.55 (rel err 1e-7 in fp32), 1 - 2/(e^{2x}+1) beyond;
+// both evaluated, selected without a branch.
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float t = x * x;
+  float q = fmaf(t, 0.016433170300270403f, -0.052669384762106176f);
+  q = fmaf(q, t, 0.133206865150314f);
+  q = fmaf(q, t, -0.33332945121698027f);
+  const float small = fmaf(x * t, q, x);
+  const float big = fmaf(-2.0f, rcp_approx(ex2_approx(x * 2.8853900817779268f) + 1.0f), 1.0f);
+  return (fabsf(x) < 0.55f) ? small : big;
+}
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
@@ -160,6 +225,121 @@ struct TcParams {
   long num_tiles;
 };
 
+// The fused LSTM-cell epilogue of one tile, executed by the 8 epilogue warps of a CTA (thread = one
+// accumulator lane = one coordinate row; a warp pair splits the tile's 8 column chunks of 8 hidden units).
+// Split in two so the C loads are in flight while the warp waits for the accumulator.
+constexpr int kChunksPerHalf = kTcBN / kTcChunk / 2;   // 4
+
+struct EpiRow {
+  long row;
+  bool row_ok;
+  float xr, gr;
+  float4 c_lo[kChunksPerHalf], c_hi[kChunksPerHalf];
+};
+
+__device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRow& R, int quarter, int half, int lane, int ut,
+                                                       long row_base) {
+  R.row = row_base + quarter * 32 + lane;
+  R.row_ok = R.row < P.rows;
+  R.xr = R.row_ok ? __ldg(P.xv + R.row) : 0.f;
+  R.gr = R.row_ok ? __ldg(P.g + R.row) : 0.f;
+#pragma unroll
+  for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+    const int unit0 = ut * kTcUnits + (half * kChunksPerHalf + cc) * 8;
+    if (R.row_ok && unit0 < P.h) {
+      const float* cp = P.C + (size_t)R.row * P.h + unit0;
+      R.c_lo[cc] = *reinterpret_cast<const float4*>(cp);
+      R.c_hi[cc] = *reinterpret_cast<const float4*>(cp + 4);
+    } else {
+      R.c_lo[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+      R.c_hi[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+template <int NPROD>
+__device__ __forceinline__ void lstm_epilogue_tile(const TcParams& P, const EpiRow& R, const float* sp, uint32_t tmem_base, int buf,
+                                                   int quarter, int half, int ut, float dequant) {
+  float hp = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+    const int chunk = half * kChunksPerHalf + cc;
+    const int unit0 = ut * kTcUnits + chunk * 8;          // first hidden unit of this chunk
+    uint32_t v[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kTcBN + chunk * kTcChunk);
+    tc_ld32(taddr, v);
+    tc_wait_ld();
+    if (R.row_ok && unit0 < P.h) {
+      const size_t o = (size_t)R.row * P.h + unit0;
+      const float cold[8] = {R.c_lo[cc].x, R.c_lo[cc].y, R.c_lo[cc].z, R.c_lo[cc].w,
+                             R.c_hi[cc].x, R.c_hi[cc].y, R.c_hi[cc].z, R.c_hi[cc].w};
+      float cnew[8], hnew[8];
+      const float4* w0 = reinterpret_cast<const float4*>(sp + chunk * kTcChunk);
+      const float4* w1 = reinterpret_cast<const float4*>(sp + kTcBN + chunk * kTcChunk);
+      const float4* bb = reinterpret_cast<const float4*>(sp + 2 * kTcBN + chunk * kTcChunk);
+      const float4* wh = reinterpret_cast<const float4*>(sp + 3 * kTcBN + chunk * 8);
+      const float4 wh0 = wh[0], wh1 = wh[1];
+      const float whv[8] = {wh0.x, wh0.y, wh0.z, wh0.w, wh1.x, wh1.y, wh1.z, wh1.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 a0 = w0[u], a1 = w1[u], ab = bb[u];
+        // pre_g = xv*W0 + grad*W1 + (H@U) + b   (models/lstm.py:74-77)
+        const float pi = fmaf(__uint_as_float(v[u * 4 + 0]), dequant, fmaf(R.gr, a1.x, fmaf(R.xr, a0.x, ab.x)));
+        const float pf = fmaf(__uint_as_float(v[u * 4 + 1]), dequant, fmaf(R.gr, a1.y, fmaf(R.xr, a0.y, ab.y)));
+        const float po = fmaf(__uint_as_float(v[u * 4 + 2]), dequant, fmaf(R.gr, a1.z, fmaf(R.xr, a0.z, ab.z)));
+        const float pu = fmaf(__uint_as_float(v[u * 4 + 3]), dequant, fmaf(R.gr, a1.w, fmaf(R.xr, a0.w, ab.w)));
+        const float gi = sigmoid_fast(pi);
+        const float gf = sigmoid_fast(pf);
+        const float go = sigmoid_fast(po);
+        const float gu = tanh_fast(pu);
+        const float cn = __fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, cold[u]));     // lstm.py:78
+        const float hn = __fmul_rn(go, tanh_fast(cn));                              // lstm.py:79
+        cnew[u] = cn;
+        hnew[u] = hn;
+        hp = fmaf(hn, whv[u], hp);                                                  // lstm.py:80 (partial)
+      }
+      *reinterpret_cast<float4*>(P.C + o)     = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
+      *reinterpret_cast<float4*>(P.C + o + 4) = make_float4(cnew[4], cnew[5], cnew[6], cnew[7]);
+      // fp16 hi/lo image of H * 2^14 for the next iteration's MMAs
+      const float hs = (float)(1 << kHShift);
+      __half2 hh[4], hl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float s0 = hnew[2 * u] * hs, s1 = hnew[2 * u + 1] * hs;
+        hh[u] = __floats2half2_rn(s0, s1);
+        const float2 back = __half22float2(hh[u]);
+        hl[u] = __floats2half2_rn(s0 - back.x, s1 - back.y);
+      }
+      *reinterpret_cast<uint4*>(P.hout_hi + o) = *reinterpret_cast<const uint4*>(hh);
+      if (NPROD == 3) *reinterpret_cast<uint4*>(P.hout_lo + o) = *reinterpret_cast<const uint4*>(hl);
+      if (P.hout_f32) {
+        *reinterpret_cast<float4*>(P.hout_f32 + o)     = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+        *reinterpret_cast<float4*>(P.hout_f32 + o + 4) = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
+      }
+    }
+  }
+  if (R.row_ok) P.head_part[((size_t)ut * 2 + half) * P.rows + R.row] = hp;
+}
+
+// stage this tile's W rows / bias / W_h slice (shared by all rows) into shared memory
+__device__ __forceinline__ void stage_tile_params(const TcParams& P, float* sp, int et, int ut) {
+  const int h4 = 4 * P.h;
+  const int c = ut * kTcBN + et;
+  const bool ok = c < h4;
+  sp[et]             = ok ? __ldg(P.wc + c) : 0.f;
+  sp[kTcBN + et]     = ok ? __ldg(P.wc + h4 + c) : 0.f;
+  sp[2 * kTcBN + et] = ok ? __ldg(P.bias + c) : 0.f;
+  if (et < kTcUnits) {
+    const int u = ut * kTcUnits + et;
+    sp[3 * kTcBN + et] = (u < P.h) ? __ldg(P.wh + u) : 0.f;
+  }
+}
+
+constexpr int kParamFloats = 3 * kTcBN + kTcUnits;
+
+// ================================================================================================
+// variant A: one CTA per tile (cta_group::1), tile = 128 rows x 256 gate columns
+// ================================================================================================
 template <int NPROD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -171,7 +351,6 @@ gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = P.stages;
   float* sparam = reinterpret_cast<float*>(smem + (size_t)stages * kStageBytes);
-  constexpr int kParamFloats = 3 * kTcBN + kTcUnits;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sparam + 2 * kParamFloats);
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + stages;           // [stages]
@@ -284,90 +463,14 @@ gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const long rt = tile / unit_tiles;
       const int buf = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
-      const int col0 = ut * kTcBN;
-      // stage this tile's W rows / bias / W_h slice (shared by all rows)
       float* sp = sparam + buf * kParamFloats;
-      {
-        const int c = col0 + et;
-        const bool ok = c < h4;
-        sp[et]             = ok ? __ldg(P.wc + c) : 0.f;
-        sp[kTcBN + et]     = ok ? __ldg(P.wc + h4 + c) : 0.f;
-        sp[2 * kTcBN + et] = ok ? __ldg(P.bias + c) : 0.f;
-        if (et < kTcUnits) {
-          const int u = ut * kTcUnits + et;
-          sp[3 * kTcBN + et] = (u < P.h) ? __ldg(P.wh + u) : 0.f;
-        }
-      }
-      const long row = rt * kTcBM + quarter * 32 + lane;
-      const bool row_ok = row < P.rows;
-      const float xr = row_ok ? __ldg(P.xv + row) : 0.f;
-      const float gr = row_ok ? __ldg(P.g + row) : 0.f;
+      stage_tile_params(P, sp, et, ut);
+      EpiRow R;
+      lstm_epilogue_prefetch(P, R, quarter, half, lane, ut, rt * kTcBM);
       asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
-
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1);
       tc_fence_after();
-
-      float hp = 0.f;
-      constexpr int kChunksPerHalf = kTcBN / kTcChunk / 2;   // 4
-#pragma unroll 1
-      for (int cc = 0; cc < kChunksPerHalf; ++cc) {
-        const int chunk = half * kChunksPerHalf + cc;
-        const int unit0 = ut * kTcUnits + chunk * 8;          // first hidden unit of this chunk
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kTcBN + chunk * kTcChunk);
-        tc_ld32(taddr, v);
-        tc_wait_ld();
-        if (row_ok && unit0 < P.h) {
-          const size_t o = (size_t)row * P.h + unit0;
-          const float4 c_lo = *reinterpret_cast<const float4*>(P.C + o);
-          const float4 c_hi = *reinterpret_cast<const float4*>(P.C + o + 4);
-          const float cold[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
-          float cnew[8], hnew[8];
-          const float* w0 = sp + chunk * kTcChunk;
-          const float* w1 = sp + kTcBN + chunk * kTcChunk;
-          const float* bb = sp + 2 * kTcBN + chunk * kTcChunk;
-          const float* wh = sp + 3 * kTcBN + chunk * 8;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float pre[4];
-#pragma unroll
-            for (int gte = 0; gte < 4; ++gte) {
-              const int j = u * 4 + gte;
-              const float iw = fmaf(gr, w1[j], __fmul_rn(xr, w0[j]));
-              pre[gte] = __fadd_rn(__fadd_rn(iw, __fmul_rn(__uint_as_float(v[j]), dequant)), bb[j]);
-            }
-            const float gi = sigmoid_fast(pre[0]);
-            const float gf = sigmoid_fast(pre[1]);
-            const float go = sigmoid_fast(pre[2]);
-            const float gu = tanhf(pre[3]);
-            const float cn = __fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, cold[u]));
-            const float hn = __fmul_rn(go, tanhf(cn));
-            cnew[u] = cn;
-            hnew[u] = hn;
-            hp = fmaf(hn, wh[u], hp);
-          }
-          *reinterpret_cast<float4*>(P.C + o)     = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
-          *reinterpret_cast<float4*>(P.C + o + 4) = make_float4(cnew[4], cnew[5], cnew[6], cnew[7]);
-          // fp16 hi/lo image of H * 2^14 for the next iteration's MMAs
-          __align__(16) __half hh[8];
-          __align__(16) __half hl[8];
-          const float hs = (float)(1 << kHShift);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float s = hnew[u] * hs;
-            hh[u] = __float2half_rn(s);
-            hl[u] = __float2half_rn(s - __half2float(hh[u]));
-          }
-          *reinterpret_cast<uint4*>(P.hout_hi + o) = *reinterpret_cast<const uint4*>(hh);
-          if (NPROD == 3) *reinterpret_cast<uint4*>(P.hout_lo + o) = *reinterpret_cast<const uint4*>(hl);
-          if (P.hout_f32) {
-            *reinterpret_cast<float4*>(P.hout_f32 + o)     = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
-            *reinterpret_cast<float4*>(P.hout_f32 + o + 4) = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
-          }
-        }
-      }
-      if (row_ok) P.head_part[((size_t)ut * 2 + half) * P.rows + row] = hp;
-      // this warp is done reading the accumulator buffer
+      lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, half, ut, dequant);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
@@ -379,6 +482,166 @@ gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ================================================================================================
+// variant B: CTA pair (cta_group::2): tile = 256 rows x 256 gate columns over two SMs.  Each CTA loads its
+// own 128 rows of H and HALF of the U tile; the leader issues M=256 MMAs that read both halves, so the
+// shared-memory traffic per MMA drops from 12 KB to 8 KB per SM and the TMA fill from 48 to 32 KB per
+// K-block -- the single-CTA form is shared-memory-bandwidth bound (ncu: tensor pipe 71 % active).
+// Barrier protocol: `full` lives in the leader and counts the TMA bytes of BOTH CTAs; `empty` and
+// `tmem_full` are signalled in both CTAs by multicast tcgen05.commit; `tmem_empty` lives in the leader and
+// collects the epilogue warps of both CTAs (the peer's arrive remotely through the cluster window).
+// ================================================================================================
+constexpr int kTcPairBBytes = (kTcBN / 2) * kTcBK * 2;   // each CTA holds half of the U tile: 8 KB
+
+template <int NPROD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                     const TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kStageBytes = (NPROD == 3) ? 2 * (kTcABytes + kTcPairBBytes) : (kTcABytes + kTcPairBBytes);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = P.stages;
+  float* sparam = reinterpret_cast<float*>(smem + (size_t)stages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sparam + 2 * kParamFloats);
+  uint64_t* full_bar = bars;                     // [stages]   (leader's copy is the live one)
+  uint64_t* empty_bar = bars + stages;           // [stages]   both CTAs
+  uint64_t* tfull_bar = bars + 2 * stages;       // [2]        both CTAs
+  uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]        leader's copy is the live one
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_b_hi);
+    if (NPROD == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kTcEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int unit_tiles = P.unit_tiles;
+  const int h4 = 4 * P.h;
+  const long pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long tile = pair; tile < P.num_tiles; tile += num_pairs) {
+        const int  ut = (int)(tile % unit_tiles);
+        const long rt = tile / unit_tiles;
+        const int n_cols = min(kTcBN, h4 - ut * kTcBN);
+        const int row0 = (int)(rt * (2 * kTcBM)) + (int)rank * kTcBM;          // this CTA's 128 rows of H
+        const int col0 = ut * kTcBN + (int)rank * (n_cols / 2);               // this CTA's half of the U tile
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb_local = smem_u32(&full_bar[stage]);
+          if (leader) mbar_expect_tx(fb_local, 2 * kStageBytes);              // bytes of both CTAs
+          const uint32_t fb = map_to_cta(fb_local, 0);
+          uint8_t* sbase = smem + (size_t)stage * kStageBytes;
+          const int k0 = kb * kTcBK;
+          tma_load_2d_pair(smem_u32(sbase), &map_a_hi, fb, k0, row0);
+          if (NPROD == 3) {
+            tma_load_2d_pair(smem_u32(sbase + kTcABytes), &map_a_lo, fb, k0, row0);
+            tma_load_2d_pair(smem_u32(sbase + 2 * kTcABytes), &map_b_hi, fb, k0, col0);
+            tma_load_2d_pair(smem_u32(sbase + 2 * kTcABytes + kTcPairBBytes), &map_b_lo, fb, k0, col0);
+          } else {
+            tma_load_2d_pair(smem_u32(sbase + kTcABytes), &map_b_hi, fb, k0, col0);
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      long it = 0;
+      for (long tile = pair; tile < P.num_tiles; tile += num_pairs, ++it) {
+        const int ut = (int)(tile % unit_tiles);
+        const int n_cols = min(kTcBN, h4 - ut * kTcBN);
+        const uint32_t idesc = make_idesc_f16(n_cols, 2 * kTcBM);
+        const int buf = (int)(it & 1);
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1) ^ 1);     // both CTAs' epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcBN);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + (size_t)stage * kStageBytes);
+          const int k_len = min(kTcBK, P.h - kb * kTcBK);
+          const int k_steps = (k_len + kTcUK - 1) / kTcUK;
+          for (int ks = 0; ks < k_steps; ++ks) {
+            const uint32_t koff = (uint32_t)(ks * kTcUK * 2);
+            if (NPROD == 3) {
+              const uint64_t a_hi = make_smem_desc_sw64(sbase + koff);
+              const uint64_t a_lo = make_smem_desc_sw64(sbase + kTcABytes + koff);
+              const uint64_t b_hi = make_smem_desc_sw64(sbase + 2 * kTcABytes + koff);
+              const uint64_t b_lo = make_smem_desc_sw64(sbase + 2 * kTcABytes + kTcPairBBytes + koff);
+              tc_mma_f16_pair(d_tmem, a_lo, b_hi, idesc, acc); acc = 1;
+              tc_mma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1);
+              tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+            } else {
+              const uint64_t a_hi = make_smem_desc_sw64(sbase + koff);
+              const uint64_t b_hi = make_smem_desc_sw64(sbase + kTcABytes + koff);
+              tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, acc); acc = 1;
+            }
+          }
+          tc_commit_pair(smem_u32(&empty_bar[stage]));             // frees the stage in both CTAs
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(smem_u32(&tfull_bar[buf]));                 // accumulators complete in both CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = (ew >= 4) ? 1 : 0;
+    const int et = threadIdx.x - 64;
+    const float dequant = P.scale[1];
+    long it = 0;
+    for (long tile = pair; tile < P.num_tiles; tile += num_pairs, ++it) {
+      const int  ut = (int)(tile % unit_tiles);
+      const long rt = tile / unit_tiles;
+      const int buf = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      float* sp = sparam + buf * kParamFloats;
+      stage_tile_params(P, sp, et, ut);
+      EpiRow R;
+      lstm_epilogue_prefetch(P, R, quarter, half, lane, ut, rt * (2 * kTcBM) + (long)rank * kTcBM);
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
+      mbar_wait(smem_u32(&tfull_bar[buf]), use & 1);
+      tc_fence_after();
+      lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, half, ut, dequant);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -417,18 +680,44 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows_total, int
   return IADMM_OK;
 }
 
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IADMM_TC_CTA_PAIR");      // development switch: 0 = single-CTA tiles
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename KernelT>
+static int set_smem_attr(KernelT kernel, bool* done) {
+  if (!*done) {
+    IADMM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    *done = true;
+  }
+  return IADMM_OK;
+}
+
 int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g, const __half* Hin_hi,
                     const __half* Hin_lo, __half* Hout_hi, __half* Hout_lo, float* H_out_f32, float* C,
                     float* head_part, long rows, int h, int nprod, cudaStream_t st) {
   if (h % 8 != 0) IADMM_FAIL(IADMM_EMODE, "tensor-core gate path needs hidden_dim %% 8 == 0");
-  if (rows > 0x7fffffffL - kTcBM) IADMM_FAIL(IADMM_ESHAPE, "too many rows for one launch");
+  if (rows > 0x7fffffffL - 2 * kTcBM) IADMM_FAIL(IADMM_ESHAPE, "too many rows for one launch");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    IADMM_CUDA(cudaGetDevice(&dev));
+    IADMM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool pair = use_cta_pairs() && num_sms >= 2;
   const char* base = static_cast<const char*>(packed);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
+  const int b_box_rows = pair ? kTcBN / 2 : kTcBN;
   if ((rc = make_map(&ma_hi, Hin_hi, (uint64_t)rows, h, kTcBM))) return rc;
   if ((rc = make_map(&ma_lo, Hin_lo, (uint64_t)rows, h, kTcBM))) return rc;
-  if ((rc = make_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, kTcBN))) return rc;
-  if ((rc = make_map(&mb_lo, base + L.off_ulo, (uint64_t)4 * h, h, kTcBN))) return rc;
+  if ((rc = make_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, b_box_rows))) return rc;
+  if ((rc = make_map(&mb_lo, base + L.off_ulo, (uint64_t)4 * h, h, b_box_rows))) return rc;
 
   TcParams P;
   P.wc = reinterpret_cast<const float*>(base + L.off_wc);
@@ -441,32 +730,35 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.unit_tiles = cdiv(h, kTcUnits);
   P.k_blocks = cdiv(h, kTcBK);
   P.nprod = nprod;
-  P.num_tiles = ((rows + kTcBM - 1) / kTcBM) * P.unit_tiles;
-  const int stage_bytes = (nprod == 3) ? 2 * (kTcABytes + kTcBBytes) : (kTcABytes + kTcBBytes);
-  P.stages = (nprod == 3) ? 4 : 8;
-  const size_t smem = 1024 + (size_t)P.stages * stage_bytes + 2 * (3 * kTcBN + kTcUnits) * sizeof(float) +
+  const int tile_rows = pair ? 2 * kTcBM : kTcBM;
+  P.num_tiles = ((rows + tile_rows - 1) / tile_rows) * P.unit_tiles;
+  const int b_bytes = pair ? kTcPairBBytes : kTcBBytes;
+  const int stage_bytes = (nprod == 3) ? 2 * (kTcABytes + b_bytes) : (kTcABytes + b_bytes);
+  P.stages = (192 * 1024) / stage_bytes;                 // 4 / 8 (single CTA), 6 / 12 (pair)
+  const size_t smem = 1024 + (size_t)P.stages * stage_bytes + 2 * kParamFloats * sizeof(float) +
                       (2 * P.stages + 4) * sizeof(uint64_t) + 16;
 
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    IADMM_CUDA(cudaGetDevice(&dev));
-    IADMM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (pair) {
+    long pairs = P.num_tiles < num_sms / 2 ? P.num_tiles : num_sms / 2;
+    const unsigned grid = (unsigned)(2 * pairs);
+    static bool a3 = false, a1 = false;
+    if (nprod == 3) {
+      if ((rc = set_smem_attr(gates_tc_pair_kernel<3>, &a3))) return rc;
+      gates_tc_pair_kernel<3><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+    } else {
+      if ((rc = set_smem_attr(gates_tc_pair_kernel<1>, &a1))) return rc;
+      gates_tc_pair_kernel<1><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+    }
+    IADMM_LAUNCH_CHECK("gates_tc_pair_kernel");
+    return IADMM_OK;
   }
   const long grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
+  static bool a3 = false, a1 = false;
   if (nprod == 3) {
-    static bool attr3 = false;
-    if (!attr3) {
-      IADMM_CUDA(cudaFuncSetAttribute(gates_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr3 = true;
-    }
+    if ((rc = set_smem_attr(gates_tc_kernel<3>, &a3))) return rc;
     gates_tc_kernel<3><<<(unsigned)grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
   } else {
-    static bool attr1 = false;
-    if (!attr1) {
-      IADMM_CUDA(cudaFuncSetAttribute(gates_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr1 = true;
-    }
+    if ((rc = set_smem_attr(gates_tc_kernel<1>, &a1))) return rc;
     gates_tc_kernel<1><<<(unsigned)grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
   }
   IADMM_LAUNCH_CHECK("gates_tc_kernel");
