@@ -61,11 +61,12 @@ static inline void prof_record(int slot, cudaStream_t st) {
   if (g_prof.on && g_prof.used < g_prof.cap) cudaEventRecord(g_prof.ev[(size_t)g_prof.used * 4 + slot], st);
 }
 
-static int is_tc(int mode) { return mode == IADMM_GATES_TC_3XFP16 || mode == IADMM_GATES_TC_1XFP16; }
+static int is_tc(int mode) { return mode == IADMM_GATES_TC_3XFP16 || mode == IADMM_GATES_TC_1XFP16 || mode == IADMM_GATES_TC_F16F8; }
 
 static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, void* base, SolveWs* ws) {
   if (mode != IADMM_GATES_SIMT_FP32 && !is_tc(mode)) IADMM_FAIL(IADMM_EMODE, "unknown gate mode %d", mode);
   if (is_tc(mode) && (h % 8 != 0)) IADMM_FAIL(IADMM_EMODE, "tensor-core gate modes need hidden_dim %% 8 == 0 (got %d)", h);
+  if (mode == IADMM_GATES_TC_F16F8 && (h % 16 != 0)) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0 (got %d)", h);
   ws->d = make_kkt_dims(B, n, m, num_ineq);
   const size_t rows = (size_t)B * (n + m);
   ws->tiles = is_tc(mode) ? tc_gate_tiles(h) : simt_gate_tiles(h);
@@ -183,14 +184,14 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   const float* b_h = reinterpret_cast<const float*>(wbase + L.off_bh);
   const long rows = (long)B * (n + m);
   const bool tc = is_tc(mode);
-  const int nprod = (mode == IADMM_GATES_TC_3XFP16) ? 3 : 1;
+  const int nprod = (mode == IADMM_GATES_TC_3XFP16) ? 3 : (mode == IADMM_GATES_TC_F16F8 ? 2 : 1);
   const bool want_trace = pri_trace || dual_trace || pri_trace_u || dual_trace_u;
 
   float* hbuf[2] = {H, ws.h_alt};
   int cur = 0;
   if (tc) {
     if (flags & IADMM_F_ZERO_STATE) rc = launch_zero_state(ws.tc.h_hi[0], ws.tc.h_lo[0], rows * h, st);
-    else                            rc = launch_split_state(H, ws.tc.h_hi[0], ws.tc.h_lo[0], rows * h, st);
+    else                            rc = launch_split_state(H, ws.tc.h_hi[0], ws.tc.h_lo[0], rows * h, nprod, st);
     if (rc) return rc;
   }
   for (int k = 0; k < K; ++k) {

@@ -29,6 +29,7 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <cuda_fp8.h>
 #include <cuda.h>   // CUtensorMap (types only; the encode entry point is resolved at run time)
 
 namespace iadmm {
@@ -159,6 +160,15 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc,
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_f8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, rows of 64 bytes, 64B swizzle (as written by TMA):
@@ -170,6 +180,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
   d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset                  bits [32,46)
   d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)      bits [46,48)
   d |= (uint64_t)4 << 61;                            // layout type SWIZZLE_64B             bits [61,64)
+  return d;
+}
+// rows of 128 bytes, 128B swizzle: 8-row groups are 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
+  return d;
+}
+// same for rows of 32 bytes (32 fp8 elements), 32B swizzle: 8-row groups are 256 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                            // layout type SWIZZLE_32B
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n_cols
@@ -216,7 +244,7 @@ struct TcParams {
   const float* xv;        // [rows]
   const float* g;         // [rows]
   __half* hout_hi;        // [rows][h]
-  __half* hout_lo;
+  __half* hout_lo;        // NPROD==2: two e4m3 arrays, [rows*h] residual then [rows*h] coarse copy
   float*  hout_f32;       // optional
   float*  C;              // [rows][h] in place
   float*  head_part;      // [2*unit_tiles][rows]
@@ -308,10 +336,26 @@ __device__ __forceinline__ void lstm_epilogue_tile(const TcParams& P, const EpiR
         const float s0 = hnew[2 * u] * hs, s1 = hnew[2 * u + 1] * hs;
         hh[u] = __floats2half2_rn(s0, s1);
         const float2 back = __half22float2(hh[u]);
-        hl[u] = __floats2half2_rn(s0 - back.x, s1 - back.y);
+        if (NPROD == 3) hl[u] = __floats2half2_rn(s0 - back.x, s1 - back.y);
       }
       *reinterpret_cast<uint4*>(P.hout_hi + o) = *reinterpret_cast<const uint4*>(hh);
       if (NPROD == 3) *reinterpret_cast<uint4*>(P.hout_lo + o) = *reinterpret_cast<const uint4*>(hl);
+      if (NPROD == 2) {
+        // e4m3 images for the two correction products: residual * 2^5 and (H*2^14) * 2^-6
+        uint8_t* q8lo = reinterpret_cast<uint8_t*>(P.hout_lo);
+        uint8_t* q8hi = q8lo + (size_t)P.rows * P.h;
+        __align__(8) __nv_fp8x2_storage_t ql[4];
+        __align__(8) __nv_fp8x2_storage_t qh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float s0 = hnew[2 * u] * hs, s1 = hnew[2 * u + 1] * hs;
+          const float2 back = __half22float2(hh[u]);
+          ql[u] = __nv_cvt_float2_to_fp8x2(make_float2((s0 - back.x) * 32.0f, (s1 - back.y) * 32.0f), __NV_SATFINITE, __NV_E4M3);
+          qh[u] = __nv_cvt_float2_to_fp8x2(make_float2(s0 * 0.015625f, s1 * 0.015625f), __NV_SATFINITE, __NV_E4M3);
+        }
+        *reinterpret_cast<uint2*>(q8lo + o) = *reinterpret_cast<const uint2*>(ql);
+        *reinterpret_cast<uint2*>(q8hi + o) = *reinterpret_cast<const uint2*>(qh);
+      }
       if (P.hout_f32) {
         *reinterpret_cast<float4*>(P.hout_f32 + o)     = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
         *reinterpret_cast<float4*>(P.hout_f32 + o + 4) = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
@@ -494,15 +538,24 @@ gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 // `tmem_full` are signalled in both CTAs by multicast tcgen05.commit; `tmem_empty` lives in the leader and
 // collects the epilogue warps of both CTAs (the peer's arrive remotely through the cluster window).
 // ================================================================================================
-constexpr int kTcPairBBytes = (kTcBN / 2) * kTcBK * 2;   // each CTA holds half of the U tile: 8 KB
+// The pair kernel moves 64 K-elements per stage: fp16 operand rows are full 128-byte lines (128B swizzle), the
+// e4m3 operand rows 64 bytes (64B swizzle); 3 stages of 64 KB.
+constexpr int kPairBK = 64;
+constexpr int kPairABytes = kTcBM * kPairBK * 2;          // 16 KB: this CTA's 128 rows of H (fp16)
+constexpr int kPairBBytes = (kTcBN / 2) * kPairBK * 2;    // 16 KB: this CTA's half of the U tile (fp16)
 
 template <int NPROD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                     const __grid_constant__ CUtensorMap map_a_q8hi, const __grid_constant__ CUtensorMap map_b_q8lo,
                      const TcParams P) {
+  // NPROD: 3 = fp16 hi/lo split (3 MMAs), 1 = single fp16 MMA, 2 = fp16 MMA + two e4m3 correction MMAs.
+  // Stage layout NPROD 3: A_hi16 | A_lo16 | B_hi16 | B_lo16 (16 KB each)
+  //              NPROD 2: A_hi16 16K | A_res8 8K | A_crs8 8K | B_hi16 16K | B_crs8 8K | B_res8 8K   (map_a_lo/map_b_lo
+  //                       carry the e4m3 "residual of H" and "coarse U" operands, map_a_q8hi/map_b_q8lo the other pair)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int kStageBytes = (NPROD == 3) ? 2 * (kTcABytes + kTcPairBBytes) : (kTcABytes + kTcPairBBytes);
+  constexpr int kStageBytes = (NPROD == 1) ? (kPairABytes + kPairBBytes) : 2 * (kPairABytes + kPairBBytes);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = P.stages;
   float* sparam = reinterpret_cast<float*>(smem + (size_t)stages * kStageBytes);
@@ -519,7 +572,8 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_b_hi);
-    if (NPROD == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+    if (NPROD != 1) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+    if (NPROD == 2) { tma_prefetch_desc(&map_a_q8hi); tma_prefetch_desc(&map_b_q8lo); }
     for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -554,14 +608,20 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
           if (leader) mbar_expect_tx(fb_local, 2 * kStageBytes);              // bytes of both CTAs
           const uint32_t fb = map_to_cta(fb_local, 0);
           uint8_t* sbase = smem + (size_t)stage * kStageBytes;
-          const int k0 = kb * kTcBK;
+          const int k0 = kb * kPairBK;
           tma_load_2d_pair(smem_u32(sbase), &map_a_hi, fb, k0, row0);
           if (NPROD == 3) {
-            tma_load_2d_pair(smem_u32(sbase + kTcABytes), &map_a_lo, fb, k0, row0);
-            tma_load_2d_pair(smem_u32(sbase + 2 * kTcABytes), &map_b_hi, fb, k0, col0);
-            tma_load_2d_pair(smem_u32(sbase + 2 * kTcABytes + kTcPairBBytes), &map_b_lo, fb, k0, col0);
+            tma_load_2d_pair(smem_u32(sbase + kPairABytes), &map_a_lo, fb, k0, row0);
+            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes), &map_b_hi, fb, k0, col0);
+            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes + kPairBBytes), &map_b_lo, fb, k0, col0);
+          } else if (NPROD == 2) {
+            tma_load_2d_pair(smem_u32(sbase + kPairABytes), &map_a_lo, fb, k0, row0);                       // H residual (e4m3)
+            tma_load_2d_pair(smem_u32(sbase + kPairABytes + kPairABytes / 2), &map_a_q8hi, fb, k0, row0);     // H coarse   (e4m3)
+            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes), &map_b_hi, fb, k0, col0);                   // U fp16
+            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes + kPairBBytes), &map_b_lo, fb, k0, col0);   // U coarse   (e4m3)
+            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes + kPairBBytes + kPairBBytes / 2), &map_b_q8lo, fb, k0, col0);  // U residual
           } else {
-            tma_load_2d_pair(smem_u32(sbase + kTcABytes), &map_b_hi, fb, k0, col0);
+            tma_load_2d_pair(smem_u32(sbase + kPairABytes), &map_b_hi, fb, k0, col0);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -586,21 +646,35 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + (size_t)stage * kStageBytes);
-          const int k_len = min(kTcBK, P.h - kb * kTcBK);
+          const int k_len = min(kPairBK, P.h - kb * kPairBK);
           const int k_steps = (k_len + kTcUK - 1) / kTcUK;
           for (int ks = 0; ks < k_steps; ++ks) {
-            const uint32_t koff = (uint32_t)(ks * kTcUK * 2);
+            const uint32_t koff = (uint32_t)(ks * kTcUK * 2);      // bytes inside the 128-byte swizzled row
             if (NPROD == 3) {
-              const uint64_t a_hi = make_smem_desc_sw64(sbase + koff);
-              const uint64_t a_lo = make_smem_desc_sw64(sbase + kTcABytes + koff);
-              const uint64_t b_hi = make_smem_desc_sw64(sbase + 2 * kTcABytes + koff);
-              const uint64_t b_lo = make_smem_desc_sw64(sbase + 2 * kTcABytes + kTcPairBBytes + koff);
+              const uint64_t a_hi = make_smem_desc_sw128(sbase + koff);
+              const uint64_t a_lo = make_smem_desc_sw128(sbase + kPairABytes + koff);
+              const uint64_t b_hi = make_smem_desc_sw128(sbase + 2 * kPairABytes + koff);
+              const uint64_t b_lo = make_smem_desc_sw128(sbase + 2 * kPairABytes + kPairBBytes + koff);
               tc_mma_f16_pair(d_tmem, a_lo, b_hi, idesc, acc); acc = 1;
               tc_mma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1);
               tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+            } else if (NPROD == 2) {
+              if ((ks & 1) == 0) {
+                // one e4m3 MMA covers 32 K-elements = two fp16 K-steps (rows of 64 bytes, 64B swizzle)
+                const uint32_t koff8 = (uint32_t)(ks * kTcUK);
+                const uint64_t a_res = make_smem_desc_sw64(sbase + kPairABytes + koff8);
+                const uint64_t a_crs = make_smem_desc_sw64(sbase + kPairABytes + kPairABytes / 2 + koff8);
+                const uint64_t b_crs = make_smem_desc_sw64(sbase + 2 * kPairABytes + kPairBBytes + koff8);
+                const uint64_t b_res = make_smem_desc_sw64(sbase + 2 * kPairABytes + kPairBBytes + kPairBBytes / 2 + koff8);
+                tc_mma_f8_pair(d_tmem, a_res, b_crs, idesc, acc); acc = 1;       // (H - fp16(H)) * U
+                tc_mma_f8_pair(d_tmem, a_crs, b_res, idesc, 1);                  // H * (U - fp16(U))
+              }
+              const uint64_t a_hi = make_smem_desc_sw128(sbase + koff);
+              const uint64_t b_hi = make_smem_desc_sw128(sbase + 2 * kPairABytes + koff);
+              tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
             } else {
-              const uint64_t a_hi = make_smem_desc_sw64(sbase + koff);
-              const uint64_t b_hi = make_smem_desc_sw64(sbase + kTcABytes + koff);
+              const uint64_t a_hi = make_smem_desc_sw128(sbase + koff);
+              const uint64_t b_hi = make_smem_desc_sw128(sbase + kPairABytes + koff);
               tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, acc); acc = 1;
             }
           }
@@ -664,17 +738,22 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D fp16 row-major [rows_total][h] tensor, box = [box_rows][32], 64B swizzle, OOB reads as zero
-static int make_map(CUtensorMap* map, const void* base, uint64_t rows_total, int h, int box_rows) {
+// 2D row-major [rows_total][h] tensor of fp16 (elem_bytes 2, 64B swizzle) or e4m3 bytes (elem_bytes 1, 32B
+// swizzle), box = [box_rows][32 elements], OOB reads as zero
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows_total, int h, int box_rows, int elem_bytes = 2,
+                    int box_k = kTcBK) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) IADMM_FAIL(IADMM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[2] = {(cuuint64_t)h, (cuuint64_t)rows_total};
-  const cuuint64_t strides[1] = {(cuuint64_t)h * sizeof(__half)};
-  const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)h * (cuuint64_t)elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+  const int row_bytes = box_k * elem_bytes;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) IADMM_FAIL(IADMM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu h=%d)", (int)r,
                                     (unsigned long long)rows_total, h);
   return IADMM_OK;
@@ -709,15 +788,31 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
     IADMM_CUDA(cudaGetDevice(&dev));
     IADMM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  if (const char* e = getenv("IADMM_TC_MAX_SMS")) {      // development switch: restrict the persistent grid
+    const int v = atoi(e);
+    if (v >= 2 && v < num_sms) num_sms = v;
+  }
   const bool pair = use_cta_pairs() && num_sms >= 2;
   const char* base = static_cast<const char*>(packed);
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  if (nprod == 2 && !pair) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode runs on CTA pairs only");
+  if (nprod == 2 && h % 16 != 0) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0");
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, ma_q8hi, mb_q8lo;
   int rc;
   const int b_box_rows = pair ? kTcBN / 2 : kTcBN;
-  if ((rc = make_map(&ma_hi, Hin_hi, (uint64_t)rows, h, kTcBM))) return rc;
-  if ((rc = make_map(&ma_lo, Hin_lo, (uint64_t)rows, h, kTcBM))) return rc;
-  if ((rc = make_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, b_box_rows))) return rc;
-  if ((rc = make_map(&mb_lo, base + L.off_ulo, (uint64_t)4 * h, h, b_box_rows))) return rc;
+  const int bk = pair ? kPairBK : kTcBK;
+  if ((rc = make_map(&ma_hi, Hin_hi, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
+  if ((rc = make_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
+  if (nprod == 2) {
+    const uint8_t* q8 = reinterpret_cast<const uint8_t*>(Hin_lo);
+    if ((rc = make_map(&ma_lo, q8, (uint64_t)rows, h, kTcBM, 1, bk))) return rc;                               // H residual
+    if ((rc = make_map(&ma_q8hi, q8 + (size_t)rows * h, (uint64_t)rows, h, kTcBM, 1, bk))) return rc;          // H coarse
+    if ((rc = make_map(&mb_lo, base + L.off_uq8hi, (uint64_t)4 * h, h, b_box_rows, 1, bk))) return rc;         // U coarse
+    if ((rc = make_map(&mb_q8lo, base + L.off_uq8lo, (uint64_t)4 * h, h, b_box_rows, 1, bk))) return rc;       // U residual
+  } else {
+    if ((rc = make_map(&ma_lo, Hin_lo, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
+    if ((rc = make_map(&mb_lo, base + L.off_ulo, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
+    ma_q8hi = ma_lo; mb_q8lo = mb_lo;
+  }
 
   TcParams P;
   P.wc = reinterpret_cast<const float*>(base + L.off_wc);
@@ -728,26 +823,30 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.hout_hi = Hout_hi; P.hout_lo = Hout_lo; P.hout_f32 = H_out_f32; P.C = C; P.head_part = head_part;
   P.rows = rows; P.h = h;
   P.unit_tiles = cdiv(h, kTcUnits);
-  P.k_blocks = cdiv(h, kTcBK);
+  P.k_blocks = cdiv(h, bk);
   P.nprod = nprod;
   const int tile_rows = pair ? 2 * kTcBM : kTcBM;
   P.num_tiles = ((rows + tile_rows - 1) / tile_rows) * P.unit_tiles;
-  const int b_bytes = pair ? kTcPairBBytes : kTcBBytes;
-  const int stage_bytes = (nprod == 3) ? 2 * (kTcABytes + b_bytes) : (kTcABytes + b_bytes);
-  P.stages = (192 * 1024) / stage_bytes;                 // 4 / 8 (single CTA), 6 / 12 (pair)
+  const int a_bytes = pair ? kPairABytes : kTcABytes;
+  const int b_bytes = pair ? kPairBBytes : kTcBBytes;
+  const int stage_bytes = (nprod == 1) ? (a_bytes + b_bytes) : 2 * (a_bytes + b_bytes);
+  P.stages = (192 * 1024) / stage_bytes;                 // 4 / 8 (single CTA, 32-wide K), 3 / 6 (pair, 64-wide K)
   const size_t smem = 1024 + (size_t)P.stages * stage_bytes + 2 * kParamFloats * sizeof(float) +
                       (2 * P.stages + 4) * sizeof(uint64_t) + 16;
 
   if (pair) {
     long pairs = P.num_tiles < num_sms / 2 ? P.num_tiles : num_sms / 2;
     const unsigned grid = (unsigned)(2 * pairs);
-    static bool a3 = false, a1 = false;
+    static bool a3 = false, a2 = false, a1 = false;
     if (nprod == 3) {
       if ((rc = set_smem_attr(gates_tc_pair_kernel<3>, &a3))) return rc;
-      gates_tc_pair_kernel<3><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+      gates_tc_pair_kernel<3><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ma_q8hi, mb_q8lo, P);
+    } else if (nprod == 2) {
+      if ((rc = set_smem_attr(gates_tc_pair_kernel<2>, &a2))) return rc;
+      gates_tc_pair_kernel<2><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ma_q8hi, mb_q8lo, P);
     } else {
       if ((rc = set_smem_attr(gates_tc_pair_kernel<1>, &a1))) return rc;
-      gates_tc_pair_kernel<1><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+      gates_tc_pair_kernel<1><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ma_q8hi, mb_q8lo, P);
     }
     IADMM_LAUNCH_CHECK("gates_tc_pair_kernel");
     return IADMM_OK;

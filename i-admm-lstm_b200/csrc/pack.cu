@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <cuda_fp8.h>
 
 namespace iadmm {
 
@@ -28,6 +29,8 @@ WeightLayout weight_layout(int h, int length) {
   L.off_scale = take(4 * sizeof(float));
   L.off_uhi   = take(4 * H * H * sizeof(__half));
   L.off_ulo   = take(4 * H * H * sizeof(__half));
+  L.off_uq8hi = take(4 * H * H);
+  L.off_uq8lo = take(4 * H * H);
   L.total = off;
   return L;
 }
@@ -80,8 +83,13 @@ __global__ void __launch_bounds__(256) pack_absmax_kernel(PackSrc S, int h, floa
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(scale + 2), __float_as_int(mx));  // mx >= 0
 }
 
+__device__ __forceinline__ uint8_t to_e4m3(float v) {
+  return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+}
+
 __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __restrict__ u32, __half* __restrict__ uhi,
-                                                     __half* __restrict__ ulo, float* __restrict__ scale) {
+                                                     __half* __restrict__ ulo, uint8_t* __restrict__ uq8hi,
+                                                     uint8_t* __restrict__ uq8lo, float* __restrict__ scale) {
   const float mx = scale[2];
   float us = 1.f;
   if (mx > 0.f) us = exp2f((float)(12 - ilogbf(mx)));
@@ -103,6 +111,8 @@ __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __
     const __half lo = __float2half_rn(vs - __half2float(hi));
     uhi[(size_t)c * h + k] = hi;
     ulo[(size_t)c * h + k] = lo;
+    uq8hi[(size_t)c * h + k] = to_e4m3(ldexpf(__half2float(hi), kQ8UHiShift));
+    uq8lo[(size_t)c * h + k] = to_e4m3(ldexpf(vs - __half2float(hi), kQ8ULoShift));
   }
 }
 
@@ -126,7 +136,9 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
   IADMM_LAUNCH_CHECK("pack_absmax_kernel");
   pack_u_kernel<<<blocks, 256, 0, st>>>(S, h, reinterpret_cast<float*>(base + L.off_u32),
                                         reinterpret_cast<__half*>(base + L.off_uhi),
-                                        reinterpret_cast<__half*>(base + L.off_ulo), scale);
+                                        reinterpret_cast<__half*>(base + L.off_ulo),
+                                        reinterpret_cast<uint8_t*>(base + L.off_uq8hi),
+                                        reinterpret_cast<uint8_t*>(base + L.off_uq8lo), scale);
   IADMM_LAUNCH_CHECK("pack_u_kernel");
   return IADMM_OK;
 }
@@ -134,20 +146,30 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
 // ------------------------------------------------------------------------------------------------
 // fp32 <-> fp16 hi/lo images of the hidden state (tensor-core path)
 // ------------------------------------------------------------------------------------------------
+template <bool Q8>
 __global__ void __launch_bounds__(256) split_state_kernel(const float* __restrict__ H, __half* __restrict__ hi,
                                                           __half* __restrict__ lo, size_t count) {
   const float s = (float)(1 << kHShift);
+  uint8_t* q8lo = reinterpret_cast<uint8_t*>(lo);
+  uint8_t* q8hi = q8lo + count;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     const float v = H[i] * s;
     const __half a = __float2half_rn(v);
     hi[i] = a;
-    lo[i] = __float2half_rn(v - __half2float(a));
+    if (Q8) {
+      q8lo[i] = to_e4m3(ldexpf(v - __half2float(a), kQ8HLoShift));
+      q8hi[i] = to_e4m3(ldexpf(v, kQ8HHiShift));
+    } else {
+      lo[i] = __float2half_rn(v - __half2float(a));
+    }
   }
 }
 
-int launch_split_state(const float* H, __half* hi, __half* lo, long count, cudaStream_t st) {
+int launch_split_state(const float* H, __half* hi, __half* lo, long count, int nprod, cudaStream_t st) {
   const long blocks = (count + 255) / 256;
-  split_state_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(H, hi, lo, (size_t)count);
+  const unsigned grid = (unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks);
+  if (nprod == 2) split_state_kernel<true><<<grid, 256, 0, st>>>(H, hi, lo, (size_t)count);
+  else            split_state_kernel<false><<<grid, 256, 0, st>>>(H, hi, lo, (size_t)count);
   IADMM_LAUNCH_CHECK("split_state_kernel");
   return IADMM_OK;
 }

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libiadmm_b200.so")
 GATES_SIMT_FP32 = 0
 GATES_TC_3XFP16 = 1
 GATES_TC_1XFP16 = 2
-GATE_MODES = {"simt_fp32": GATES_SIMT_FP32, "tc_3xfp16": GATES_TC_3XFP16, "tc_1xfp16": GATES_TC_1XFP16}
+GATES_TC_F16F8 = 3
+GATE_MODES = {"simt_fp32": GATES_SIMT_FP32, "tc_3xfp16": GATES_TC_3XFP16, "tc_1xfp16": GATES_TC_1XFP16, "tc_f16f8": GATES_TC_F16F8}
 
 F_ZERO_STATE = 1
 F_SKIP_FINAL_RESID = 2

@@ -34,7 +34,7 @@ class SolveResult:
 
 
 class LSTM(nn.Module):
-    def __init__(self, num_constr, input_dim, hidden_dim, length, device, gate_mode="tc_3xfp16"):
+    def __init__(self, num_constr, input_dim, hidden_dim, length, device, gate_mode="tc_f16f8"):
         super(LSTM, self).__init__()
         if input_dim != 2:
             raise ValueError("the I-ADMM-LSTM cell takes [xv, grad] (input_dim=2, models/lstm.py:72)")
@@ -75,6 +75,8 @@ class LSTM(nn.Module):
         mode = self.gate_mode
         if isinstance(mode, str):
             mode = _lib.GATE_MODES[mode]
+        if mode == _lib.GATES_TC_F16F8 and self.hidden_dim % 16 != 0:
+            mode = _lib.GATES_TC_3XFP16    # fp8 operand rows must be 16-byte multiples
         if mode != _lib.GATES_SIMT_FP32 and self.hidden_dim % 8 != 0:
             mode = _lib.GATES_SIMT_FP32    # the tcgen05 tiles need 16-byte rows of fp16
         return mode

@@ -47,7 +47,10 @@ enum {
   IADMM_GATES_SIMT_FP32   = 0,  /* fp32 FMA on CUDA cores: bit-stable validation path                   */
   IADMM_GATES_TC_3XFP16   = 1,  /* tcgen05, fp16 hi/lo split of both operands, 3 MMAs, fp32 accumulate: */
                                 /* ~22-bit operands, the default (parity <= 1e-4 after K=100)           */
-  IADMM_GATES_TC_1XFP16   = 2   /* tcgen05, single fp16 MMA (TF32-class operands): opt-in fast mode     */
+  IADMM_GATES_TC_1XFP16   = 2,  /* tcgen05, single fp16 MMA (TF32-class operands): opt-in fast mode     */
+  IADMM_GATES_TC_F16F8    = 3   /* tcgen05, fp16 main product + two fp8 (e4m3) correction products for  */
+                                /* the operand rounding residuals: ~16-bit operands at 2/3 of the cost  */
+                                /* of the 3-way split (needs hidden_dim % 16 == 0)                      */
 };
 
 /* Flags of iadmm_solve. */

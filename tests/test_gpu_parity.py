@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 NORTH_STAR_TOL = 1e-4
 
-MODES = ["simt_fp32", "tc_3xfp16", "tc_1xfp16"]
+MODES = ["simt_fp32", "tc_3xfp16", "tc_f16f8", "tc_1xfp16"]
 # per-mode tolerance for K<=100 trajectories at random-init-sized weights
-MODE_TOL = {"simt_fp32": 2e-5, "tc_3xfp16": 5e-5, "tc_1xfp16": 2e-3}
+MODE_TOL = {"simt_fp32": 2e-5, "tc_3xfp16": 5e-5, "tc_f16f8": 5e-5, "tc_1xfp16": 2e-3}
 
 
 def make_model(prm, h, K, mode):
@@ -43,7 +43,7 @@ def test_single_step_vs_reference(name, mode):
     torch.cuda.synchronize()
     for k in keep:                                   # pure-functional like the reference: inputs untouched
         assert torch.equal(keep[k], st[k]), k
-    tol = {"simt_fp32": 5e-6, "tc_3xfp16": 2e-5, "tc_1xfp16": 2e-3}[mode]
+    tol = {"simt_fp32": 5e-6, "tc_3xfp16": 2e-5, "tc_f16f8": 2e-5, "tc_1xfp16": 2e-3}[mode]
     for k, v in zip(("x", "y", "z", "xv", "H", "C"), out[:6]):
         assert v.shape == g["out_" + k].shape
         assert rel_err(v, g["out_" + k]) < tol, (k, rel_err(v, g["out_" + k]))
@@ -193,7 +193,7 @@ def test_instance_sharding_is_bit_exact(mode):
     assert torch.equal(full.x, again.x) and torch.equal(full.H, again.H) and torch.equal(full.dual, again.dual)
 
 
-@pytest.mark.parametrize("mode", ["simt_fp32", "tc_3xfp16"])
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_3xfp16", "tc_f16f8"])
 def test_config2_shape_vs_oracle(mode):
     """BASELINE config-2 dimensions (n=1000, 500+500, h=800, --scaling) at a batch/K the CPU oracle
     finishes in seconds: Ruiz + K=4 iterations + residual traces."""

@@ -16,7 +16,7 @@ def run(B, n, mi, me, h, K, scale=1.0, seed=3):
           torch.randn((B, n + m, 1), generator=g), torch.tanh(torch.randn((B, n + m, h), generator=g)), torch.randn((B, n + m, h), generator=g)]
     ref = orc.solve(prm, K, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6, h, state=[s.clone() for s in st], form="block")
     out = {}
-    for mode in ("simt_fp32", "tc_3xfp16", "tc_1xfp16"):
+    for mode in os.environ.get("MODES", "simt_fp32,tc_3xfp16,tc_f16f8,tc_1xfp16").split(","):
         model = ia.LSTM(None, 2, h, max(K, 4), "cuda:0", gate_mode=mode)
         with torch.no_grad():
             for k, v in prm.items(): getattr(model, k).copy_(v.cuda())
@@ -25,6 +25,29 @@ def run(B, n, mi, me, h, K, scale=1.0, seed=3):
         errs = {k: rel_err(getattr(r, k), getattr(ref, k)) for k in ("x", "y", "z", "xv", "H", "C")}
         print(f"B={B} n={n} m={m} h={h} K={K} wscale={scale} {mode:10s}", {k: f"{v:.1e}" for k, v in errs.items()}, flush=True)
 
+if os.environ.get("LONG"):
+    # K=100 trajectories at config-2 dimensions: every tensor-core mode against the fp32 CUDA-core path
+    def long_run(B, n, mi, me, h, K, scale, seed):
+        qp = {k: v.cuda() for k, v in orc.qp_instances(B, n, mi, me, seed).items()}
+        prm = orc.lstm_parameters(h, K, seed, scale=scale)
+        sc = ia.Scaling(n, mi + me, 10, "cuda:0")
+        Q, p, A0, zl, zu = sc.scale_data(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"])
+        res = {}
+        for mode in ("simt_fp32", "tc_3xfp16", "tc_f16f8", "tc_1xfp16"):
+            model = ia.LSTM(None, 2, h, K, "cuda:0", gate_mode=mode)
+            with torch.no_grad():
+                for k, v in prm.items(): getattr(model, k).copy_(v.cuda())
+                res[mode] = model.solve(K, mi, me, Q, p, A0, zl, zu, 6e-6, scaling=sc)
+            torch.cuda.synchronize()
+            if mode != "simt_fp32":
+                errs = {k: rel_err(getattr(res[mode], k), getattr(res["simt_fp32"], k)) for k in ("x", "y", "z", "pri", "dual", "pri_unscaled", "dual_unscaled")}
+                print(f"K={K} B={B} n={n} h={h} wscale={scale} {mode:10s} vs simt_fp32", {k: f"{v:.1e}" for k, v in errs.items()}, flush=True)
+    long_run(4, 1000, 500, 500, 800, 100, 1.0, 3)
+    long_run(4, 1000, 500, 500, 800, 100, 3.0, 4)
+    long_run(8, 100, 50, 50, 64, 100, 1.0, 5)
+    long_run(8, 100, 50, 50, 64, 100, 10.0, 6)
+    long_run(4, 1000, 500, 500, 208, 100, 1.0, 7)
+    sys.exit(0)
 run(2, 12, 5, 7, 8, 1)
 run(2, 12, 5, 7, 64, 1)
 run(3, 100, 50, 50, 64, 1)
