@@ -187,7 +187,7 @@ int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, con
 int  simt_gate_tiles(int h);
 int  launch_gates_simt(const void* packed, const WeightLayout& L, const float* xv, const float* g,
                        const float* H_in, float* H_out, float* C, float* head_part, long rows, int h,
-                       cudaStream_t st);
+                       cudaStream_t st, float* gates_out = nullptr);
 
 // tensor-core path (gate_tc.cu)
 struct TcState {               // fp16 hi/lo images of H * 2^14, ping-pong.  In F16F8 mode the `lo` buffer holds two

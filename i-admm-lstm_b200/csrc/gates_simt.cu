@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(kSgThreads)
 gates_simt_kernel(const float* __restrict__ u32, const float* __restrict__ wc, const float* __restrict__ bias,
                   const float* __restrict__ wh, const float* __restrict__ xv, const float* __restrict__ gvec,
                   const float* __restrict__ H_in, float* __restrict__ H_out, float* __restrict__ C,
-                  float* __restrict__ head_part, long rows, int h, int tiles_u) {
+                  float* __restrict__ head_part, float* __restrict__ gates_out, long rows, int h, int tiles_u) {
   __shared__ float As[kSgBK][kSgBM + 4];
   __shared__ float Bs[kSgBK][kSgBN];
 
@@ -109,6 +109,9 @@ gates_simt_kernel(const float* __restrict__ u32, const float* __restrict__ wc, c
           const float go = sigmoid_ref(pre[2]);
           const float gu = tanhf(pre[3]);
           const size_t o = (size_t)row * h + unit;
+          if (gates_out) {   // training: keep the gate activations for the backward pass ([rows][4h], column 4j+g)
+            *reinterpret_cast<float4*>(gates_out + (size_t)row * h4 + 4 * (size_t)unit) = make_float4(gi, gf, go, gu);
+          }
           const float cn = __fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, C[o]));
           const float hn = __fmul_rn(go, tanhf(cn));
           C[o] = cn;
@@ -127,7 +130,7 @@ gates_simt_kernel(const float* __restrict__ u32, const float* __restrict__ wc, c
 }
 
 int launch_gates_simt(const void* packed, const WeightLayout& L, const float* xv, const float* g, const float* H_in,
-                      float* H_out, float* C, float* head_part, long rows, int h, cudaStream_t st) {
+                      float* H_out, float* C, float* head_part, long rows, int h, cudaStream_t st, float* gates_out) {
   const char* base = static_cast<const char*>(packed);
   const int tiles_u = simt_gate_tiles(h);
   const long row_tiles = (rows + kSgBM - 1) / kSgBM;
@@ -136,7 +139,7 @@ int launch_gates_simt(const void* packed, const WeightLayout& L, const float* xv
   gates_simt_kernel<<<(unsigned)grid, kSgThreads, 0, st>>>(
       reinterpret_cast<const float*>(base + L.off_u32), reinterpret_cast<const float*>(base + L.off_wc),
       reinterpret_cast<const float*>(base + L.off_bias), reinterpret_cast<const float*>(base + L.off_wh), xv, g, H_in,
-      H_out, C, head_part, rows, h, tiles_u);
+      H_out, C, head_part, gates_out, rows, h, tiles_u);
   IADMM_LAUNCH_CHECK("gates_simt_kernel");
   return IADMM_OK;
 }

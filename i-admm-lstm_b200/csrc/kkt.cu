@@ -72,7 +72,8 @@ __device__ __forceinline__ float4 load_cols4(const float* __restrict__ rowp, int
 template <bool VEC>
 __device__ __forceinline__ float4 load_vec4(const float* __restrict__ v, int col, int n) {
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (VEC) {
+  // the per-instance vectors start at b*(n+m) floats, which is 16-byte aligned only when (n+m) % 4 == 0
+  if (VEC && (reinterpret_cast<uintptr_t>(v) & 15u) == 0) {
     if (col < n) r = __ldg(reinterpret_cast<const float4*>(v + col));
     return r;
   }

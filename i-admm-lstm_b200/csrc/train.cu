@@ -1,0 +1,699 @@
+// Training path: one differentiable I-ADMM-LSTM iteration (forward that saves activations + hand-written
+// backward) and the backward of primal_dual_loss.
+//
+// Reference: the autograd tape PyTorch builds through models/lstm.py:47-96 and utils.py:68-71 inside the
+// truncated-BPTT loop main.py:336-358.  Here the backward of one iteration is derived by hand
+// (notation: a bar is an adjoint, ' marks the iteration's outputs):
+//   tail     y' = y + rho (z~ - z'),  z' = clip(z~ + y/rho),  x' = alpha x~' + (1-alpha) x,  z~ = z + (v' - y)/rho
+//   step     xv' = xv - (H' W_h + b_h)
+//   cell     H' = O tanh(C'), C' = I U~ + F C, gates = act([xv, g] W + H U + b)
+//   KKT      g = K^T w,  w = K xv - rhs(x, y, z)      (K symmetric in structure: the adjoint passes ARE the
+//            forward passes: w_bar = K g_bar, xv_bar += K^T w_bar, rhs_bar = -w_bar)
+// so the two streaming KKT kernels of the forward are reused unchanged, and the only new heavy work is
+// two plain fp32 GEMMs (H_bar = D U^T, U_bar = H^T D) plus column sums for the small parameters.
+// This is the fp32 CUDA-core path (correctness first: gradients match torch.autograd through the float64 restatement of the reference
+// to ~1e-5); tensor-core backward kernels are future work.
+#include "common.cuh"
+
+namespace iadmm {
+
+int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, const float* x, const float* y,
+                           const KktScratch& s, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// flat gradient buffer layout = the state_dict order of models/lstm.py:21-41
+// ------------------------------------------------------------------------------------------------
+struct GradLayout {
+  size_t W[4], U[4], b[4], W_h, b_h, rho, alpha, total;
+};
+GradLayout grad_layout(int h, int length) {
+  GradLayout G;
+  size_t o = 0;
+  for (int g = 0; g < 4; ++g) {
+    G.W[g] = o; o += 2 * (size_t)h;
+    G.U[g] = o; o += (size_t)h * h;
+    G.b[g] = o; o += h;
+  }
+  G.W_h = o; o += h;
+  G.b_h = o; o += 1;
+  G.rho = o; o += length;
+  G.alpha = o; o += length;
+  G.total = o;
+  return G;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic fp32 GEMM  C[M,N] = op(A) op(B),  A(m,k) = TA ? A[k*lda+m] : A[m*lda+k],  B(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
+// 128x128x16 tiles, 8x8 per thread.  Plain GEMM (no fusion): used only by the backward pass.
+// ------------------------------------------------------------------------------------------------
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                    float* __restrict__ C, long M, long N, long K, long lda, long ldb,
+                                                    long ldc) {
+  __shared__ float As[16][128 + 4];
+  __shared__ float Bs[16][128 + 4];
+  const long m0 = (long)blockIdx.y * 128, n0 = (long)blockIdx.x * 128;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (long k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int idx = tid + e * 256;
+      int mm, kk;
+      if (TA) { mm = idx % 128; kk = idx / 128; } else { kk = idx % 16; mm = idx / 16; }
+      const long m = m0 + mm, k = k0 + kk;
+      float v = 0.f;
+      if (m < M && k < K) v = TA ? A[k * lda + m] : A[m * lda + k];
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int idx = tid + e * 256;
+      int nn, kk;
+      if (TB) { kk = idx % 16; nn = idx / 16; } else { nn = idx % 128; kk = idx / 128; }
+      const long n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if (n < N && k < K) v = TB ? Bm[n * ldb + k] : Bm[k * ldb + n];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long n = n0 + tx * 8 + j;
+      if (n < N) C[m * ldc + n] = acc[i][j];
+    }
+  }
+}
+
+template <bool TA, bool TB>
+static int launch_sgemm(const float* A, const float* Bm, float* C, long M, long N, long K, long lda, long ldb, long ldc,
+                        cudaStream_t st) {
+  const dim3 grid((unsigned)((N + 127) / 128), (unsigned)((M + 127) / 128));
+  sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, Bm, C, M, N, K, lda, ldb, ldc);
+  IADMM_LAUNCH_CHECK("sgemm_kernel");
+  return IADMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weighted column sums  out[w][c] = sum_r weight_w[r] * M[r,c]   (weight NULL = ones), two deterministic stages
+// ------------------------------------------------------------------------------------------------
+constexpr int kCsRows = 256;   // rows per partial
+
+template <int NW>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ Mx, long rows, int cols,
+                                                             const float* __restrict__ w0, const float* __restrict__ w1,
+                                                             const float* __restrict__ w2, float wscale,
+                                                             float* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const long r0 = (long)blockIdx.y * kCsRows;
+  if (c >= cols) return;
+  const long r1 = (r0 + kCsRows < rows) ? r0 + kCsRows : rows;
+  float acc[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) acc[w] = 0.f;
+  for (long r = r0; r < r1; ++r) {
+    const float v = Mx[r * cols + c];
+    const float* ws[3] = {w0, w1, w2};
+#pragma unroll
+    for (int w = 0; w < NW; ++w) acc[w] = fmaf(v, ws[w] ? ws[w][r] * wscale : 1.0f, acc[w]);
+  }
+#pragma unroll
+  for (int w = 0; w < NW; ++w) part[((size_t)blockIdx.y * NW + w) * cols + c] = acc[w];
+}
+
+// out[w*out_stride + map(c)] += sum over partials; map un-interleaves gate columns when `deinterleave`
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int nparts, int nw, int cols,
+                                                           float* __restrict__ out0, float* __restrict__ out1,
+                                                           float* __restrict__ out2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float* outs[3] = {out0, out1, out2};
+  for (int w = 0; w < nw; ++w) {
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[((size_t)p * nw + w) * cols + c];
+    outs[w][c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the O(N) tail (models/lstm.py:82-94)
+// acc[0] += sum rho_bar over inequality rows, acc[1] += over equality rows, acc[2] += alpha_bar
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tail_bwd_kernel(const KktDims d, const Sched* __restrict__ sched,
+                                                       const float* __restrict__ zl, const float* __restrict__ zu,
+                                                       const float* __restrict__ x, const float* __restrict__ y,
+                                                       const float* __restrict__ z, const float* __restrict__ xv_o,
+                                                       const float* __restrict__ gx_o, const float* __restrict__ gy_o,
+                                                       const float* __restrict__ gz_o, const float* __restrict__ gxv_o,
+                                                       float* __restrict__ Xbar, float* __restrict__ gx,
+                                                       float* __restrict__ gy, float* __restrict__ gz,
+                                                       double* __restrict__ acc) {
+  __shared__ double sh[3][8];
+  const size_t n = d.n, m = d.m, N = n + m;
+  const size_t rows = (size_t)d.B * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double a_ineq = 0.0, a_eq = 0.0, a_alpha = 0.0;
+  if (idx < rows) {
+    const size_t b = idx / N;
+    const int r = (int)(idx - b * N);
+    const float gxv = gxv_o ? gxv_o[idx] : 0.f;
+    if (r < d.n) {
+      const size_t j = b * n + r;
+      const float g = gx_o ? gx_o[j] : 0.f;
+      Xbar[idx] = gxv + sched->alpha * g;
+      gx[j] = sched->one_minus_alpha * g;
+      a_alpha = (double)g * (double)(xv_o[idx] - x[j]);
+    } else {
+      const int i = r - d.n;
+      const size_t k = b * m + i;
+      const bool eq = i >= d.num_ineq;
+      const float rho = eq ? sched->rho_eq : sched->rho_ineq;
+      const float inv = eq ? sched->inv_rho_eq : sched->inv_rho_ineq;
+      const float yo = y[k], zo = z[k], vn = xv_o[idx];
+      const float gyo = gy_o ? gy_o[k] : 0.f, gzo = gz_o ? gz_o[k] : 0.f;
+      const float zmid = zo + inv * (vn - yo);
+      const float u = zmid + inv * yo;
+      const float zuu = zu[k], zll = zl[k];
+      const float mn = fminf(u, zuu);
+      const float zc = fmaxf(mn, zll);
+      // torch.min / torch.max split the gradient evenly on exact ties
+      const float gmin = (u < zuu) ? 1.f : ((u == zuu) ? 0.5f : 0.f);
+      const float gmax = (mn > zll) ? 1.f : ((mn == zll) ? 0.5f : 0.f);
+      double rb = (double)gyo * (double)(zmid - zc);               // y' = y + rho (z~ - z')
+      float zt_bar = rho * gyo;
+      const float zp_bar = gzo - rho * gyo;
+      const float ub = zp_bar * gmin * gmax;                        // z' = clip(u)
+      zt_bar += ub;                                                 // u = z~ + y / rho
+      float yb = gyo + ub * inv;
+      rb += (double)ub * (double)(-yo * inv * inv);
+      yb -= zt_bar * inv;                                           // z~ = z + (v' - y) / rho
+      rb += (double)zt_bar * (double)(-(vn - yo) * inv * inv);
+      Xbar[idx] = gxv + zt_bar * inv;
+      gy[k] = yb;
+      gz[k] = zt_bar;
+      if (eq) a_eq = rb; else a_ineq = rb;
+    }
+  }
+  double vals[3] = {a_ineq, a_eq, a_alpha};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double v = vals[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    if (lane == 0) sh[q][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    if (t != 0.0) atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the cell non-linearities (models/lstm.py:74-80): D = pre-activation adjoints [rows,4h]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ C_in,
+                                                       const float* __restrict__ wh, const float* __restrict__ Xbar,
+                                                       const float* __restrict__ gH_o, const float* __restrict__ gC_o,
+                                                       float* __restrict__ D, float* __restrict__ gC, long rows, int h) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * h) return;
+  const size_t r = idx / h;
+  const int j = (int)(idx - r * h);
+  const float4 g4 = *reinterpret_cast<const float4*>(gates + r * 4 * (size_t)h + 4 * (size_t)j);
+  const float gi = g4.x, gf = g4.y, go = g4.z, gu = g4.w;
+  const float c_in = C_in[idx];
+  const float cn = gi * gu + gf * c_in;
+  const float tc = tanhf(cn);
+  const float hbar = (gH_o ? gH_o[idx] : 0.f) - Xbar[r] * wh[j];      // s_bar = -Xbar (xv' = xv - s)
+  const float obar = hbar * tc;
+  const float cbar = (gC_o ? gC_o[idx] : 0.f) + hbar * go * (1.f - tc * tc);
+  float4 dd;
+  dd.x = cbar * gu * gi * (1.f - gi);
+  dd.y = cbar * c_in * gf * (1.f - gf);
+  dd.z = obar * go * (1.f - go);
+  dd.w = cbar * gi * (1.f - gu * gu);
+  *reinterpret_cast<float4*>(D + r * 4 * (size_t)h + 4 * (size_t)j) = dd;
+  gC[idx] = cbar * gf;
+}
+
+// per-row dots of D with the two W rows:  out0[r] = D_r . W[0,:],  out1[r] = D_r . W[1,:]   (one warp per row)
+__global__ void __launch_bounds__(256) rowdot2_kernel(const float* __restrict__ D, const float* __restrict__ wc, long rows,
+                                                      int h4, float* __restrict__ out0, float* __restrict__ out1) {
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float a = 0.f, b = 0.f;
+  for (int c = lane; c < h4; c += 32) {
+    const float v = D[r * h4 + c];
+    a = fmaf(v, wc[c], a);
+    b = fmaf(v, wc[h4 + c], b);
+  }
+  a = warp_sum(a); b = warp_sum(b);
+  if (lane == 0) { out0[r] = a; out1[r] = b; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// last vector stage of the step backward: assemble the state adjoints and the rho adjoint of the KKT part
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) step_bwd_final_kernel(const KktDims d, const Sched* __restrict__ sched, float sigma,
+                                                             const float* __restrict__ xv, const float* __restrict__ y,
+                                                             const float* __restrict__ w_save, const float* __restrict__ gbar,
+                                                             const float* __restrict__ wbar, const float* __restrict__ ktw,
+                                                             const float* __restrict__ Xbar, const float* __restrict__ xvbar_cell,
+                                                             float* __restrict__ gxv, float* __restrict__ gx,
+                                                             float* __restrict__ gy, float* __restrict__ gz,
+                                                             double* __restrict__ acc) {
+  __shared__ double sh[2][8];
+  const size_t n = d.n, m = d.m, N = n + m;
+  const size_t rows = (size_t)d.B * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double a_ineq = 0.0, a_eq = 0.0;
+  if (idx < rows) {
+    const size_t b = idx / N;
+    const int r = (int)(idx - b * N);
+    gxv[idx] = Xbar[idx] + xvbar_cell[idx] + ktw[idx];
+    if (r < d.n) {
+      gx[b * n + r] += -sigma * wbar[idx];                          // rhs_1 = sigma x - p
+    } else {
+      const int i = r - d.n;
+      const size_t k = b * m + i;
+      const bool eq = i >= d.num_ineq;
+      const float inv = eq ? sched->inv_rho_eq : sched->inv_rho_ineq;
+      const float wb2 = wbar[idx];
+      gz[k] += -wb2;                                                // rhs_2 = z - y / rho
+      gy[k] += wb2 * inv;
+      const double rb = (double)gbar[idx] * (double)(w_save[idx] * inv * inv)        // g_2 = A0 w_1 - w_2 / rho
+                      + (double)wb2 * (double)((xv[idx] - y[k]) * inv * inv);        // w_2 = A0 x~ - (v - y) / rho - z
+      if (eq) a_eq = rb; else a_ineq = rb;
+    }
+  }
+  double vals[2] = {a_ineq, a_eq};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    double v = vals[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    if (lane == 0) sh[q][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    if (t != 0.0) atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
+// scatter the interleaved parameter adjoints into the flat state_dict-ordered gradient buffer (+=)
+__global__ void __launch_bounds__(256) scatter_grads_kernel(int h, int t, const float* __restrict__ u32bar,
+                                                            const float* __restrict__ w0bar, const float* __restrict__ w1bar,
+                                                            const float* __restrict__ bbar, const float* __restrict__ whbar,
+                                                            const float* __restrict__ sbar_sum, const double* __restrict__ acc,
+                                                            const Sched* __restrict__ sched, GradLayout G,
+                                                            float* __restrict__ flat) {
+  const size_t total = (size_t)h * 4 * h;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < total) {
+    const int k = (int)(idx / (4 * (size_t)h));
+    const int c = (int)(idx - (size_t)k * 4 * h);
+    const int j = c >> 2, g = c & 3;
+    flat[G.U[g] + (size_t)k * h + j] += u32bar[idx];
+  }
+  if (idx < (size_t)4 * h) {
+    const int j = (int)idx >> 2, g = (int)idx & 3;
+    flat[G.W[g] + j] += w0bar[idx];
+    flat[G.W[g] + h + j] += w1bar[idx];
+    flat[G.b[g] + j] += bbar[idx];
+  }
+  if (idx < (size_t)h) flat[G.W_h + idx] += whbar[idx];
+  if (idx == 0) {
+    flat[G.b_h] += sbar_sum[0];
+    const float rho = sched->rho_ineq;                       // rho_t = sigmoid(r_t); equality rows carry 1e3 rho_t
+    const double rho_bar = acc[0] + 1000.0 * acc[1];
+    flat[G.rho + t] += (float)(rho_bar * (double)rho * (1.0 - (double)rho));
+    const double s = 0.5 * (double)sched->alpha;              // alpha_t = 2 sigmoid(a_t)
+    flat[G.alpha + t] += (float)(acc[2] * 2.0 * s * (1.0 - s));
+  }
+}
+
+__global__ void negate_sum_kernel(const float* __restrict__ Xbar, long rows, float* __restrict__ out) {
+  // b_h adjoint: sum_r s_bar_r = -sum_r Xbar_r   (single block, deterministic)
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (long r = threadIdx.x; r < rows; r += blockDim.x) a -= (double)Xbar[r];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    out[0] = (float)t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace of the training entry points
+// ------------------------------------------------------------------------------------------------
+struct TrainWs {
+  KktDims d;
+  KktScratch s;
+  float *head_part, *zeros, *Xbar, *xvbar_cell, *gbar, *D, *u32bar, *cs_part, *w0bar, *w1bar, *bbar, *whbar, *sbar_sum;
+  Sched* zero_sched;
+  double* acc;
+  int tiles, cs_parts;
+  size_t bytes;
+};
+
+static void plan_train(int B, int n, int m, int num_ineq, int h, void* base, TrainWs* W) {
+  W->d = make_kkt_dims(B, n, m, num_ineq);
+  const size_t rows = (size_t)B * (n + m);
+  W->tiles = simt_gate_tiles(h);
+  W->cs_parts = (int)((rows + kCsRows - 1) / kCsRows);
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? p + o : nullptr; };
+  float* kkt = reinterpret_cast<float*>(take(kkt_scratch_floats(W->d) * sizeof(float)));
+  if (base) kkt_scratch_carve(W->d, kkt, &W->s);
+  W->head_part = reinterpret_cast<float*>(take((size_t)W->tiles * rows * sizeof(float)));
+  W->zeros = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  W->zero_sched = reinterpret_cast<Sched*>(take(sizeof(Sched)));
+  W->acc = reinterpret_cast<double*>(take(4 * sizeof(double)));
+  W->Xbar = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  W->xvbar_cell = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  W->gbar = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  W->D = reinterpret_cast<float*>(take(rows * 4 * (size_t)h * sizeof(float)));
+  W->u32bar = reinterpret_cast<float*>(take((size_t)h * 4 * h * sizeof(float)));
+  W->cs_part = reinterpret_cast<float*>(take((size_t)W->cs_parts * 3 * 4 * h * sizeof(float)));
+  W->w0bar = reinterpret_cast<float*>(take((size_t)4 * h * sizeof(float)));
+  W->w1bar = reinterpret_cast<float*>(take((size_t)4 * h * sizeof(float)));
+  W->bbar = reinterpret_cast<float*>(take((size_t)4 * h * sizeof(float)));
+  W->whbar = reinterpret_cast<float*>(take((size_t)h * sizeof(float)));
+  W->sbar_sum = reinterpret_cast<float*>(take(4 * sizeof(float)));
+  W->bytes = off;
+}
+
+static int check_sm100() {
+  int dev = 0, major = 0;
+  IADMM_CUDA(cudaGetDevice(&dev));
+  IADMM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) IADMM_FAIL(IADMM_EARCH, "device %d has compute capability %d.x; libiadmm_b200 needs sm_100 (B200)", dev, major);
+  return IADMM_OK;
+}
+
+}  // namespace iadmm
+
+using namespace iadmm;
+
+extern "C" {
+
+int iadmm_param_count(int h, int length, size_t* count) {
+  if (h <= 0 || length <= 0 || !count) IADMM_FAIL(IADMM_ESHAPE, "param_count: h=%d length=%d", h, length);
+  *count = grad_layout(h, length).total;
+  return IADMM_OK;
+}
+
+int iadmm_train_workspace_bytes(int B, int n, int m, int h, size_t* bytes) {
+  if (B <= 0 || n <= 0 || m < 0 || h <= 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "train_workspace_bytes: B=%d n=%d m=%d h=%d", B, n, m, h);
+  TrainWs W;
+  plan_train(B, n, m, 0, h, nullptr, &W);
+  *bytes = W.bytes;
+  return IADMM_OK;
+}
+
+int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
+                   const float* zu, const float* x, const float* y, const float* z, const float* xv, const float* H,
+                   const float* C, float* x_o, float* y_o, float* z_o, float* xv_o, float* H_o, float* C_o,
+                   float* g_save, float* w_save, float* gates_save, int B, int n, int num_ineq, int num_eq, int h,
+                   int length, int t, float sigma, void* workspace, size_t workspace_bytes, void* stream) {
+  const int m = num_ineq + num_eq;
+  if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || t < 0 || t >= length)
+    IADMM_FAIL(IADMM_ESHAPE, "step_fwd: B=%d n=%d ineq=%d eq=%d h=%d t=%d length=%d", B, n, num_ineq, num_eq, h, t, length);
+  if (B > 65535) IADMM_FAIL(IADMM_ESHAPE, "step_fwd: batch %d > 65535", B);
+  if (!packed_weights || !Q || !p || !x || !xv || !H || !C || !x_o || !xv_o || !H_o || !C_o || !g_save || !w_save ||
+      !gates_save || !workspace)
+    IADMM_FAIL(IADMM_EALIGN, "step_fwd: NULL pointer");
+  if (h % 4 != 0) IADMM_FAIL(IADMM_ESHAPE, "step_fwd: hidden_dim %% 4 != 0 not supported by the training path");
+  int rc = check_sm100();
+  if (rc) return rc;
+  TrainWs W;
+  plan_train(B, n, m, num_ineq, h, workspace, &W);
+  if (W.bytes > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "step_fwd: workspace too small: %zu < %zu", workspace_bytes, W.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const WeightLayout L = weight_layout(h, length);
+  const char* wbase = static_cast<const char*>(packed_weights);
+  const Sched* sk = reinterpret_cast<const Sched*>(wbase + L.off_sched) + t;
+  const float* b_h = reinterpret_cast<const float*>(wbase + L.off_bh);
+  const size_t N = (size_t)n + m, rows = (size_t)B * N;
+  const size_t fb = sizeof(float);
+  IADMM_CUDA(cudaMemcpyAsync(x_o, x, (size_t)B * n * fb, cudaMemcpyDeviceToDevice, st));
+  if (m > 0) {
+    IADMM_CUDA(cudaMemcpyAsync(y_o, y, (size_t)B * m * fb, cudaMemcpyDeviceToDevice, st));
+    IADMM_CUDA(cudaMemcpyAsync(z_o, z, (size_t)B * m * fb, cudaMemcpyDeviceToDevice, st));
+  }
+  IADMM_CUDA(cudaMemcpyAsync(xv_o, xv, rows * fb, cudaMemcpyDeviceToDevice, st));
+  IADMM_CUDA(cudaMemcpyAsync(C_o, C, rows * h * fb, cudaMemcpyDeviceToDevice, st));
+  if ((rc = launch_kkt_pass1(W.d, Q, A0, xv, x, y, W.s, st))) return rc;
+  if ((rc = launch_kkt_combine1(W.d, p, xv, x, y, z, sk, sigma, W.s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                nullptr, -1, 0, st))) return rc;
+  IADMM_CUDA(cudaMemcpyAsync(w_save, W.s.w, rows * fb, cudaMemcpyDeviceToDevice, st));
+  if ((rc = launch_kkt_pass2(W.d, Q, A0, W.s, st))) return rc;
+  if ((rc = launch_kkt_combine2(W.d, sk, sigma, W.s, st))) return rc;
+  IADMM_CUDA(cudaMemcpyAsync(g_save, W.s.g, rows * fb, cudaMemcpyDeviceToDevice, st));
+  if ((rc = launch_gates_simt(packed_weights, L, xv, W.s.g, H, H_o, C_o, W.head_part, (long)rows, h, st, gates_save))) return rc;
+  return launch_tail(W.d, W.head_part, W.tiles, b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
+}
+
+int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
+                   const float* zu, const float* x, const float* y, const float* z, const float* xv, const float* H,
+                   const float* C, const float* xv_o, const float* H_o, const float* g_save, const float* w_save,
+                   const float* gates_save, const float* gx_o, const float* gy_o, const float* gz_o, const float* gxv_o,
+                   const float* gH_o, const float* gC_o, float* gx, float* gy, float* gz, float* gxv, float* gH, float* gC,
+                   float* grad_flat, int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  (void)p;
+  const int m = num_ineq + num_eq;
+  if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || t < 0 || t >= length)
+    IADMM_FAIL(IADMM_ESHAPE, "step_bwd: B=%d n=%d ineq=%d eq=%d h=%d t=%d length=%d", B, n, num_ineq, num_eq, h, t, length);
+  if (!packed_weights || !Q || !x || !xv || !H || !C || !xv_o || !H_o || !g_save || !w_save || !gates_save || !gx || !gxv ||
+      !gH || !gC || !grad_flat || !workspace)
+    IADMM_FAIL(IADMM_EALIGN, "step_bwd: NULL pointer");
+  if (m > 0 && (!gy || !gz || !y || !z || !A0 || !zl || !zu)) IADMM_FAIL(IADMM_EALIGN, "step_bwd: NULL constraint pointer");
+  if (h % 4 != 0) IADMM_FAIL(IADMM_ESHAPE, "step_bwd: hidden_dim %% 4 != 0 not supported by the training path");
+  int rc = check_sm100();
+  if (rc) return rc;
+  TrainWs W;
+  plan_train(B, n, m, num_ineq, h, workspace, &W);
+  if (W.bytes > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "step_bwd: workspace too small: %zu < %zu", workspace_bytes, W.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const WeightLayout L = weight_layout(h, length);
+  const GradLayout G = grad_layout(h, length);
+  const char* wbase = static_cast<const char*>(packed_weights);
+  const Sched* sk = reinterpret_cast<const Sched*>(wbase + L.off_sched) + t;
+  const float* u32 = reinterpret_cast<const float*>(wbase + L.off_u32);
+  const float* wc = reinterpret_cast<const float*>(wbase + L.off_wc);
+  const float* wh = reinterpret_cast<const float*>(wbase + L.off_wh);
+  const size_t N = (size_t)n + m, rows = (size_t)B * N;
+  const int h4 = 4 * h;
+  const unsigned row_blocks = (unsigned)((rows + 255) / 256);
+
+  IADMM_CUDA(cudaMemsetAsync(W.zeros, 0, rows * sizeof(float), st));
+  IADMM_CUDA(cudaMemsetAsync(W.zero_sched, 0, sizeof(Sched), st));
+  IADMM_CUDA(cudaMemsetAsync(W.acc, 0, 4 * sizeof(double), st));
+
+  // 1. tail
+  tail_bwd_kernel<<<row_blocks, 256, 0, st>>>(W.d, sk, zl, zu, x, y, z, xv_o, gx_o, gy_o, gz_o, gxv_o, W.Xbar, gx, gy, gz, W.acc);
+  IADMM_LAUNCH_CHECK("tail_bwd_kernel");
+  // 2. cell non-linearities -> D, gC
+  cell_bwd_kernel<<<(unsigned)((rows * h + 255) / 256), 256, 0, st>>>(gates_save, C, wh, W.Xbar, gH_o, gC_o, W.D, gC, (long)rows, h);
+  IADMM_LAUNCH_CHECK("cell_bwd_kernel");
+  // 3. small parameter adjoints: W_h (weights s_bar = -Xbar over H'), b_h, and b, W rows over D
+  {
+    const dim3 g1((unsigned)cdiv(h, 256), (unsigned)W.cs_parts);
+    colsum_partial_kernel<1><<<g1, 256, 0, st>>>(H_o, (long)rows, h, W.Xbar, nullptr, nullptr, -1.0f, W.cs_part);
+    IADMM_LAUNCH_CHECK("colsum_partial_kernel<1>");
+    colsum_final_kernel<<<cdiv(h, 256), 256, 0, st>>>(W.cs_part, W.cs_parts, 1, h, W.whbar, nullptr, nullptr);
+    IADMM_LAUNCH_CHECK("colsum_final_kernel");
+    negate_sum_kernel<<<1, 1024, 0, st>>>(W.Xbar, (long)rows, W.sbar_sum);
+    IADMM_LAUNCH_CHECK("negate_sum_kernel");
+    const dim3 g3((unsigned)cdiv(h4, 256), (unsigned)W.cs_parts);
+    colsum_partial_kernel<3><<<g3, 256, 0, st>>>(W.D, (long)rows, h4, nullptr, xv, g_save, 1.0f, W.cs_part);
+    IADMM_LAUNCH_CHECK("colsum_partial_kernel<3>");
+    colsum_final_kernel<<<cdiv(h4, 256), 256, 0, st>>>(W.cs_part, W.cs_parts, 3, h4, W.bbar, W.w0bar, W.w1bar);
+    IADMM_LAUNCH_CHECK("colsum_final_kernel");
+  }
+  // 4. input adjoints of the cell: xv (direct) and g
+  rowdot2_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(W.D, wc, (long)rows, h4, W.xvbar_cell, W.gbar);
+  IADMM_LAUNCH_CHECK("rowdot2_kernel");
+  // 5. the two GEMMs: H_bar = D U^T ; U_bar = H^T D
+  if ((rc = launch_sgemm<false, true>(W.D, u32, gH, (long)rows, h, h4, h4, h4, h, st))) return rc;
+  if ((rc = launch_sgemm<true, false>(H, W.D, W.u32bar, h, h4, (long)rows, h, h4, h4, st))) return rc;
+  // 6. KKT adjoint: w_bar = K g_bar (pass 1 with zero rhs), then K^T w_bar (pass 2)
+  if ((rc = launch_kkt_pass1(W.d, Q, A0, W.gbar, W.zeros, W.zeros, W.s, st))) return rc;
+  if ((rc = launch_kkt_combine1(W.d, W.zeros, W.gbar, W.zeros, W.zeros, W.zeros, sk, sigma, W.s, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, nullptr, nullptr, -1, 0, st))) return rc;
+  if ((rc = launch_kkt_pass2(W.d, Q, A0, W.s, st))) return rc;
+  if ((rc = launch_kkt_combine2(W.d, sk, sigma, W.s, st))) return rc;
+  // 7. assemble
+  step_bwd_final_kernel<<<row_blocks, 256, 0, st>>>(W.d, sk, sigma, xv, y, w_save, W.gbar, W.s.w, W.s.g, W.Xbar, W.xvbar_cell,
+                                                    gxv, gx, gy, gz, W.acc);
+  IADMM_LAUNCH_CHECK("step_bwd_final_kernel");
+  // 8. parameters
+  scatter_grads_kernel<<<(unsigned)(((size_t)h * h4 + 255) / 256), 256, 0, st>>>(h, t, W.u32bar, W.w0bar, W.w1bar, W.bbar,
+                                                                                W.whbar, W.sbar_sum, W.acc, sk, G, grad_flat);
+  IADMM_LAUNCH_CHECK("scatter_grads_kernel");
+  return IADMM_OK;
+}
+
+// primal_dual_loss (utils.py:68-71) keeping the residual vectors for the backward
+int iadmm_residuals_fwd(const float* x, const float* y, const float* z, const float* Q, const float* p, const float* A0,
+                        float* pri, float* dual, float* rp_save, float* rd_save, int B, int n, int m, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+}  // extern "C"
+
+namespace iadmm {
+
+// r_p = A0 x - z, r_d = Q x + p + A0^T y from the pass-1 products
+__global__ void __launch_bounds__(256) residual_vectors_kernel(const KktDims d, const float* __restrict__ p,
+                                                               const float* __restrict__ z, const KktScratch s,
+                                                               float* __restrict__ rp, float* __restrict__ rd) {
+  const size_t n = d.n, m = d.m, N = n + m;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)d.B * N) return;
+  const size_t b = idx / N;
+  const int r = (int)(idx - b * N);
+  if (r < d.n) {
+    float aty = 0.f;
+    const float* part = s.part_a + b * d.chunks_a * 2 * n;
+    for (int c = 0; c < d.chunks_a; ++c) aty += part[((size_t)c * 2 + 1) * n + r];
+    rd[b * n + r] = __fadd_rn(__fadd_rn(s.qx[b * n + r], p[b * n + r]), aty);
+  } else {
+    const int i = r - d.n;
+    rp[b * m + i] = __fsub_rn(s.ax[b * m + i], z[b * m + i]);
+  }
+}
+
+// a = gdual / dual * r_d (as w_1), b = gpri / pri * r_p (as w_2); gz = -b
+__global__ void __launch_bounds__(256) residual_bwd_seed_kernel(const KktDims d, const float* __restrict__ pri,
+                                                                const float* __restrict__ dual, const float* __restrict__ rp,
+                                                                const float* __restrict__ rd, const float* __restrict__ gpri,
+                                                                const float* __restrict__ gdual, float* __restrict__ w,
+                                                                float* __restrict__ gz) {
+  const size_t n = d.n, m = d.m, N = n + m;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)d.B * N) return;
+  const size_t b = idx / N;
+  const int r = (int)(idx - b * N);
+  if (r < d.n) {
+    const float dn = dual[b];
+    const float gd = gdual ? gdual[b] : 0.f;
+    w[idx] = (dn > 0.f) ? gd / dn * rd[b * n + r] : 0.f;       // torch: d||v||/dv = v/||v|| (0 at v = 0)
+  } else {
+    const int i = r - d.n;
+    const float pn = pri[b];
+    const float gp = gpri ? gpri[b] : 0.f;
+    const float v = (pn > 0.f) ? gp / pn * rp[b * m + i] : 0.f;
+    w[idx] = v;
+    gz[b * m + i] = -v;
+  }
+}
+
+__global__ void __launch_bounds__(256) residual_bwd_split_kernel(const KktDims d, const float* __restrict__ g,
+                                                                 float* __restrict__ gx, float* __restrict__ gy) {
+  const size_t n = d.n, m = d.m, N = n + m;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)d.B * N) return;
+  const size_t b = idx / N;
+  const int r = (int)(idx - b * N);
+  if (r < d.n) gx[b * n + r] = g[idx];
+  else         gy[b * m + (r - d.n)] = g[idx];
+}
+
+}  // namespace iadmm
+
+extern "C" {
+
+int iadmm_residuals_train_workspace_bytes(int B, int n, int m, size_t* bytes) {
+  if (B <= 0 || n <= 0 || m < 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "residuals_train_workspace_bytes: B=%d n=%d m=%d", B, n, m);
+  *bytes = kkt_scratch_floats(make_kkt_dims(B, n, m, 0)) * sizeof(float) + 1024;
+  return IADMM_OK;
+}
+
+int iadmm_residuals_fwd(const float* x, const float* y, const float* z, const float* Q, const float* p, const float* A0,
+                        float* pri, float* dual, float* rp_save, float* rd_save, int B, int n, int m, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n <= 0 || m < 0 || B > 65535) IADMM_FAIL(IADMM_ESHAPE, "residuals_fwd: B=%d n=%d m=%d", B, n, m);
+  if (!x || !Q || !p || !pri || !dual || !rd_save || !workspace) IADMM_FAIL(IADMM_EALIGN, "residuals_fwd: NULL pointer");
+  if (m > 0 && (!y || !z || !A0 || !rp_save)) IADMM_FAIL(IADMM_EALIGN, "residuals_fwd: NULL constraint pointer");
+  int rc = check_sm100();
+  if (rc) return rc;
+  const KktDims d = make_kkt_dims(B, n, m, 0);
+  if (kkt_scratch_floats(d) * sizeof(float) > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "residuals_fwd: workspace too small");
+  KktScratch s;
+  kkt_scratch_carve(d, static_cast<float*>(workspace), &s);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = launch_kkt_pass1_plain(d, Q, A0, x, y, s, st))) return rc;
+  if ((rc = launch_kkt_combine1(d, p, nullptr, x, y, z, nullptr, 0.f, s, pri, dual, nullptr, nullptr, nullptr, nullptr,
+                                nullptr, 0, 1, st))) return rc;
+  const size_t rows = (size_t)B * (n + m);
+  residual_vectors_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, p, z, s, rp_save, rd_save);
+  IADMM_LAUNCH_CHECK("residual_vectors_kernel");
+  return IADMM_OK;
+}
+
+int iadmm_residuals_bwd(const float* Q, const float* A0, const float* pri, const float* dual, const float* rp_save,
+                        const float* rd_save, const float* gpri, const float* gdual, float* gx, float* gy, float* gz, int B,
+                        int n, int m, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n <= 0 || m < 0 || B > 65535) IADMM_FAIL(IADMM_ESHAPE, "residuals_bwd: B=%d n=%d m=%d", B, n, m);
+  if (!Q || !pri || !dual || !rd_save || !gx || !workspace) IADMM_FAIL(IADMM_EALIGN, "residuals_bwd: NULL pointer");
+  if (m > 0 && (!A0 || !rp_save || !gy || !gz)) IADMM_FAIL(IADMM_EALIGN, "residuals_bwd: NULL constraint pointer");
+  int rc = check_sm100();
+  if (rc) return rc;
+  const KktDims d = make_kkt_dims(B, n, m, 0);
+  const size_t need = kkt_scratch_floats(d) * sizeof(float) + 1024;
+  if (need > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "residuals_bwd: workspace too small");
+  KktScratch s;
+  kkt_scratch_carve(d, static_cast<float*>(workspace), &s);
+  Sched* zero_sched = reinterpret_cast<Sched*>(static_cast<char*>(workspace) + align_up(kkt_scratch_floats(d) * sizeof(float), 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  IADMM_CUDA(cudaMemsetAsync(zero_sched, 0, sizeof(Sched), st));
+  const size_t rows = (size_t)B * (n + m);
+  const unsigned blocks = (unsigned)((rows + 255) / 256);
+  residual_bwd_seed_kernel<<<blocks, 256, 0, st>>>(d, pri, dual, rp_save, rd_save, gpri, gdual, s.w, gz);
+  IADMM_LAUNCH_CHECK("residual_bwd_seed_kernel");
+  // [gx; gy] = [Q^T a + A0^T b ; A0 a]  = K^T [a; b] with sigma = 0 and 1/rho = 0
+  if ((rc = launch_kkt_pass2(d, Q, A0, s, st))) return rc;
+  if ((rc = launch_kkt_combine2(d, zero_sched, 0.f, s, st))) return rc;
+  residual_bwd_split_kernel<<<blocks, 256, 0, st>>>(d, s.g, gx, gy);
+  IADMM_LAUNCH_CHECK("residual_bwd_split_kernel");
+  return IADMM_OK;
+}
+
+}  // extern "C"

@@ -155,10 +155,17 @@ class LSTM(nn.Module):
     def forward(self, t, num_ineq, num_eq, x, y, z, xv, sigma, H_t, C_t, **kwargs):
         """One iteration; returns (x, y, z, xv, H_t, C_t, A_tild, b_tild, rho_vec) like models/lstm.py:96.
         `lb`/`ub` are accepted and ignored, as in the reference (lstm.py:89-90 is commented out)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("libiadmm_b200: forward() is the inference path; wrap it in torch.no_grad() "
-                                      "(truncated-BPTT training kernels are not part of this build)")
         Q, p, A0, zl, zu = (kwargs[k] for k in ("Q", "p", "A0", "zl", "zu"))
+        if torch.is_grad_enabled() and (any(prm.requires_grad for prm in self.parameters())
+                                        or any(v.requires_grad for v in (x, y, z, xv, H_t, C_t))):
+            # training (main.py:336-358): one autograd node per iteration, fp32 forward + hand-written backward
+            if not (0 <= int(t) < self.length):
+                raise IndexError(f"index {t} is out of bounds for dimension 0 with size {self.length}")
+            from .autograd import StepFunction, PARAM_ORDER as _ORDER
+            _lib.require_cuda(Q, p, A0, zl, zu, x, y, z, xv, H_t, C_t)
+            outs = StepFunction.apply(self, int(t), int(num_ineq), int(num_eq), float(sigma), Q, p, A0, zl, zu,
+                                      x, y, z, xv, H_t, C_t, *[getattr(self, k) for k in _ORDER])
+            return (*outs, None, None, None)
         if not (0 <= int(t) < self.length):
             raise IndexError(f"index {t} is out of bounds for dimension 0 with size {self.length}")
         L = _lib.lib()

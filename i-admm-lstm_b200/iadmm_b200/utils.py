@@ -15,6 +15,11 @@ def primal_dual_loss(x, y, z, Q, p, A0):
     """Returns (||A0 x - z||, ||Q x + p + A0^T y||, sum), each [B,1,1] like the reference."""
     L = _lib.lib()
     _lib.require_cuda(x, y, z, Q, p, A0)
+    if torch.is_grad_enabled() and any(v.requires_grad for v in (x, y, z)):
+        from .autograd import ResidualFunction        # training loss (main.py:346): differentiable node
+        pri, dual = ResidualFunction.apply(x, y, z, Q, p, A0)
+        pri, dual = pri.reshape(-1, 1, 1), dual.reshape(-1, 1, 1)
+        return pri, dual, pri + dual
     dev = Q.device
     x, y, z, Q, p, A0 = (_lib.f32(t, dev) for t in (x, y, z, Q, p, A0))
     B, n = Q.shape[0], Q.shape[1]

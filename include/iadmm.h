@@ -139,6 +139,50 @@ int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, 
                     int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
                     void* stream);
 
+/* ---- training: truncated BPTT through the unroll -------------------------------------------------------
+ * Replaces: the autograd tape PyTorch records through LSTM.forward (models/lstm.py:47-96) and
+ * primal_dual_loss (utils.py:68-71) in the training loop main.py:336-358.  One differentiable iteration =
+ * iadmm_step_fwd (out of place, saves g = K^T(K xv - rhs), w = K xv - rhs and the gate activations) +
+ * iadmm_step_bwd (hand-written adjoint; reuses the two streaming KKT passes, two fp32 GEMMs for the gate
+ * products).  fp32 CUDA-core arithmetic throughout.  Adam (main.py:191) stays in PyTorch; data-parallel
+ * training all-reduces the flat gradient buffer over NCCL (iadmm_b200/dist.py).
+ *
+ * grad_flat: [iadmm_param_count] floats in state_dict order (W_i,U_i,b_i, W_f,.., W_u,U_u,b_u, W_h, b_h, rho,
+ * alpha); iadmm_step_bwd ADDS this iteration's parameter adjoints to it.  Incoming adjoints g*_o may be
+ * NULL (= zero); outgoing adjoints gx..gC are overwritten.  gates_save: [B*(n+m), 4h].
+ */
+int iadmm_param_count(int h, int length, size_t* count);
+int iadmm_train_workspace_bytes(int B, int n, int m, int h, size_t* bytes);
+int iadmm_step_fwd(const void* packed_weights,
+                   const float* Q, const float* p, const float* A0, const float* zl, const float* zu,
+                   const float* x, const float* y, const float* z, const float* xv, const float* H, const float* C,
+                   float* x_o, float* y_o, float* z_o, float* xv_o, float* H_o, float* C_o,
+                   float* g_save, float* w_save, float* gates_save,
+                   int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int iadmm_step_bwd(const void* packed_weights,
+                   const float* Q, const float* p, const float* A0, const float* zl, const float* zu,
+                   const float* x, const float* y, const float* z, const float* xv, const float* H, const float* C,
+                   const float* xv_o, const float* H_o,
+                   const float* g_save, const float* w_save, const float* gates_save,
+                   const float* gx_o, const float* gy_o, const float* gz_o, const float* gxv_o,
+                   const float* gH_o, const float* gC_o,
+                   float* gx, float* gy, float* gz, float* gxv, float* gH, float* gC,
+                   float* grad_flat,
+                   int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* primal_dual_loss keeping r_p = A0 x - z [B,m] and r_d = Q x + p + A0^T y [B,n], and its adjoint
+ * (gpri/gdual [B], NULL = zero). */
+int iadmm_residuals_train_workspace_bytes(int B, int n, int m, size_t* bytes);
+int iadmm_residuals_fwd(const float* x, const float* y, const float* z,
+                        const float* Q, const float* p, const float* A0,
+                        float* pri, float* dual, float* rp_save, float* rd_save,
+                        int B, int n, int m, void* workspace, size_t workspace_bytes, void* stream);
+int iadmm_residuals_bwd(const float* Q, const float* A0, const float* pri, const float* dual,
+                        const float* rp_save, const float* rd_save, const float* gpri, const float* gdual,
+                        float* gx, float* gy, float* gz,
+                        int B, int n, int m, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------
  * The reference times its solve with time.time() around model() (main.py:881-890, no device sync).
  * Between iadmm_profile_begin and iadmm_profile_end every iadmm_solve call records CUDA events on its

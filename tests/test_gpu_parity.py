@@ -221,6 +221,22 @@ def test_config2_shape_vs_oracle(mode):
         assert v < 2e-5, (k, v)
 
 
+def test_aligned_n_with_odd_constraint_count():
+    """n % 4 == 0 takes the 128-bit matrix loads while the stacked vectors [x~; v] of instance b start at
+    b*(n+m) floats, unaligned when (n+m) % 4 != 0: the vector loads must not assume alignment."""
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, K = 3, 24, 5, 5, 16, 4
+    qp = orc.qp_instances(B, n, mi, me, seed=55)
+    prm = orc.lstm_parameters(h, K, seed=55, scale=4.0)
+    ref = orc.solve(prm, K, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6, h, form="block")
+    for mode in ("simt_fp32", "tc_f16f8"):
+        model = make_model(prm, h, K, mode)
+        with torch.no_grad():
+            r = model.solve(K, mi, me, *(qp[k].to(DEV) for k in ("Q", "p", "A0", "zl", "zu")), 6e-6)
+        for k in ("x", "y", "z", "xv", "pri", "dual"):
+            assert rel_err(getattr(r, k), getattr(ref, k)) < 1e-5, (mode, k)
+
+
 def test_inf_bounds_and_odd_sizes():
     """Ragged sizes (n, m not multiples of 4; h not a multiple of 8 falls back to the fp32 cell),
     inequality-only rows with -inf lower bounds, one-sided +inf upper bounds."""
