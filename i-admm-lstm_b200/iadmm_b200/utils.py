@@ -38,21 +38,30 @@ def primal_dual_loss(x, y, z, Q, p, A0):
     return pri, dual, pri + dual
 
 
+def _colsum(t):
+    return t.sum(dim=1, keepdim=True)
+
+
 def obj_fn(x, Q, p):
-    return 0.5 * torch.bmm(x.permute(0, 2, 1), torch.bmm(Q, x)) + torch.bmm(p.permute(0, 2, 1), x)
+    """0.5 x^T Q x + p^T x per instance, [B,1,1] (utils.py:53-54)."""
+    return 0.5 * _colsum(x * torch.bmm(Q, x)) + _colsum(p * x)
 
 
 def ineq_dist(x, G, c):
-    return torch.clamp(torch.bmm(G, x) - c, 0)
+    """Violation of G x <= c, [B,mi,1] (utils.py:56-57)."""
+    return torch.relu(torch.bmm(G, x) - c)
 
 
 def eq_dist(x, A, b):
-    return torch.abs(b - torch.bmm(A, x))
+    """Violation of A x = b, [B,me,1] (utils.py:59-60)."""
+    return (torch.bmm(A, x) - b).abs()
 
 
 def lb_dist(x, lb):
-    return torch.clamp(lb - x, 0)
+    """Violation of x >= lb (utils.py:62-63)."""
+    return torch.relu(lb - x)
 
 
 def ub_dist(x, ub):
-    return torch.clamp(x - ub, 0)
+    """Violation of x <= ub (utils.py:65-66)."""
+    return torch.relu(x - ub)
