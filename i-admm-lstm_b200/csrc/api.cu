@@ -80,9 +80,10 @@ static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, vo
   memset(&ws->tc, 0, sizeof(ws->tc));
   if (is_tc(mode)) {
     const size_t hb = rows * (size_t)h * sizeof(__half);
+    const size_t lb = tc_lo_bytes((long)rows, h);
     for (int i = 0; i < 2; ++i) {
       ws->tc.h_hi[i] = reinterpret_cast<__half*>(take(hb));
-      ws->tc.h_lo[i] = reinterpret_cast<__half*>(take(hb));
+      ws->tc.h_lo[i] = reinterpret_cast<__half*>(take(lb));
     }
   } else {
     ws->h_alt = reinterpret_cast<float*>(take(rows * (size_t)h * sizeof(float)));
@@ -190,9 +191,11 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   float* hbuf[2] = {H, ws.h_alt};
   int cur = 0;
   if (tc) {
-    if (flags & IADMM_F_ZERO_STATE) rc = launch_zero_state(ws.tc.h_hi[0], ws.tc.h_lo[0], rows * h, st);
-    else                            rc = launch_split_state(H, ws.tc.h_hi[0], ws.tc.h_lo[0], rows * h, nprod, st);
+    if (flags & IADMM_F_ZERO_STATE) rc = launch_zero_state(ws.tc.h_hi[0], ws.tc.h_lo[0], rows, h, nprod, st);
+    else                            rc = launch_split_state(H, ws.tc.h_hi[0], ws.tc.h_lo[0], rows, h, nprod, st);
     if (rc) return rc;
+    // the other ping-pong buffer: padding bytes of the packed e4m3 rows must be finite (never multiplied, but loaded)
+    if (nprod == 2 && K > 1) IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[1], 0, tc_lo_bytes(rows, h), st));
   }
   for (int k = 0; k < K; ++k) {
     const Sched* sk = sched + (t0 + k);

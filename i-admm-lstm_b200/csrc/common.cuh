@@ -62,8 +62,8 @@ struct WeightLayout {
                       //           dequant = 1/(u_scale*2^14), |U|max, unused
   size_t off_uhi;     // fp16 [4h][h]   row 4*j+g, K-major (k = input unit): tcgen05 B operand, hi part
   size_t off_ulo;     // fp16 [4h][h]   lo part
-  size_t off_uq8hi;   // e4m3 [4h][h]   fp16(U*2^s) * 2^-5          (partner of the H residual, F16F8 mode)
-  size_t off_uq8lo;   // e4m3 [4h][h]   (U*2^s - fp16(U*2^s)) * 2^6 (U residual, F16F8 mode)
+  size_t off_uq8;     // e4m3 [4h][q8_pitch(h)]: per 64-wide K block 64 B of residual (U*2^s - fp16(U*2^s)) * 2^6 followed by
+                      //                64 B of the coarse copy fp16(U*2^s) * 2^-5   (F16F8 mode; one 128-byte TMA row)
   size_t total;
 };
 WeightLayout weight_layout(int h, int length);
@@ -190,10 +190,12 @@ int  launch_gates_simt(const void* packed, const WeightLayout& L, const float* x
                        cudaStream_t st, float* gates_out = nullptr);
 
 // tensor-core path (gate_tc.cu)
-struct TcState {               // fp16 hi/lo images of H * 2^14, ping-pong.  In F16F8 mode the `lo` buffer holds two
-  __half* h_hi[2];             // e4m3 arrays instead: [rows*h] residual*2^5 followed by [rows*h] (H*2^14)*2^-6
-  __half* h_lo[2];
+struct TcState {               // fp16 hi/lo images of H * 2^14, ping-pong.  In F16F8 mode the `lo` buffer holds the packed
+  __half* h_hi[2];             // e4m3 image instead: [rows][q8_pitch(h)] bytes, per 64-wide K block 64 B of residual*2^5
+  __half* h_lo[2];             // followed by 64 B of the coarse copy (H*2^14)*2^-6 (one 128-byte TMA row per block)
 };
+// bytes per row of a packed e4m3 operand pair
+static inline size_t q8_pitch(int h) { return (size_t)((h + 63) / 64) * 128; }
 // F16F8 scalings (powers of two, exact): residual of H*2^14 is < 4 -> *2^5 < 128; H*2^14*2^-6 < 256;
 // fp16(U*2^s) < 2^13 -> *2^-5 < 256; residual of U*2^s is < 2 -> *2^6 < 128  (e4m3 max = 448)
 constexpr int kQ8HLoShift = 5, kQ8HHiShift = -6, kQ8UHiShift = -5, kQ8ULoShift = 6;
@@ -203,8 +205,9 @@ int  launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv,
                      const __half* Hin_hi, const __half* Hin_lo, __half* Hout_hi, __half* Hout_lo,
                      float* H_out_f32 /* may be NULL */, float* C, float* head_part, long rows, int h,
                      int nprod, cudaStream_t st);
-int  launch_split_state(const float* H, __half* hi, __half* lo, long count, int nprod, cudaStream_t st);
-int  launch_zero_state(__half* hi, __half* lo, long count, cudaStream_t st);
+int  launch_split_state(const float* H, __half* hi, __half* lo, long rows, int h, int nprod, cudaStream_t st);
+int  launch_zero_state(__half* hi, __half* lo, long rows, int h, int nprod, cudaStream_t st);
+size_t tc_lo_bytes(long rows, int h);   // size of one `lo` buffer (fits both the fp16 and the packed e4m3 form)
 
 // O(N) tail: xv -= head ; x,z,y updates (models/lstm.py:82-94)
 int launch_tail(const KktDims& d, const float* head_part, int tiles, const float* b_h, const Sched* sched_t,

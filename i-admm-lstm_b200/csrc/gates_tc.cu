@@ -146,10 +146,22 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar_local) {   // arrives on the barrier at this offset in BOTH CTAs
+// arrives on the barrier at this CTA-relative offset in every CTA of `cta_mask` once the issued MMAs retire
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar_local, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_local),
-               "h"((uint16_t)3)
+               "h"(cta_mask)
                : "memory");
+}
+// TMA load delivered to the same CTA-relative smem offset in every CTA of `cta_mask`; the completion bytes are
+// credited, per destination CTA, to the mbarrier at `bar_local`'s offset in the LEADER of that CTA's pair
+// (peer bit 24 of the rank-encoded shared address cleared)
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar_local, int c0, int c1,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar_local & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -251,7 +263,25 @@ struct TcParams {
   long rows;
   int  h, unit_tiles, k_blocks, stages, nprod;
   long num_tiles;
+  size_t q8_pitch;        // bytes per row of the packed e4m3 image (NPROD 2)
 };
+
+// 256-bit global accesses (sm_100): one request per 32-byte sector instead of two
+__device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v8u(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 
 // The fused LSTM-cell epilogue of one tile, executed by the 8 epilogue warps of a CTA (thread = one
 // accumulator lane = one coordinate row; a warp pair splits the tile's 8 column chunks of 8 hidden units).
@@ -262,7 +292,7 @@ struct EpiRow {
   long row;
   bool row_ok;
   float xr, gr;
-  float4 c_lo[kChunksPerHalf], c_hi[kChunksPerHalf];
+  float c[kChunksPerHalf][8];
 };
 
 __device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRow& R, int quarter, int half, int lane, int ut,
@@ -275,13 +305,41 @@ __device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRow
   for (int cc = 0; cc < kChunksPerHalf; ++cc) {
     const int unit0 = ut * kTcUnits + (half * kChunksPerHalf + cc) * 8;
     if (R.row_ok && unit0 < P.h) {
-      const float* cp = P.C + (size_t)R.row * P.h + unit0;
-      R.c_lo[cc] = *reinterpret_cast<const float4*>(cp);
-      R.c_hi[cc] = *reinterpret_cast<const float4*>(cp + 4);
+      ld_global_v8(P.C + (size_t)R.row * P.h + unit0, R.c[cc]);
     } else {
-      R.c_lo[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-      R.c_hi[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) R.c[cc][u] = 0.f;
     }
+  }
+}
+
+// fp16 / e4m3 images of 8 hidden values for the next iteration's MMAs:
+//   hi  = fp16(H*2^14)                                   (4 x half2)
+//   lo  = fp16(H*2^14 - hi)                              (NPROD 3)
+//   res = e4m3((H*2^14 - hi) * 2^5), crs = e4m3(H*2^14 * 2^-6)   (NPROD 2; 2 words each)
+template <int NPROD>
+__device__ __forceinline__ void split_hidden8(const float (&hnew)[8], uint32_t (&hi)[4], uint32_t (&lo)[4], uint32_t (&res)[2],
+                                              uint32_t (&crs)[2]) {
+  const float hs = (float)(1 << kHShift);
+  __nv_fp8x2_storage_t r2[4], c2[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float s0 = hnew[2 * u] * hs, s1 = hnew[2 * u + 1] * hs;
+    const __half2 hh = __floats2half2_rn(s0, s1);
+    hi[u] = *reinterpret_cast<const uint32_t*>(&hh);
+    const float2 back = __half22float2(hh);
+    if (NPROD == 3) {
+      const __half2 hl = __floats2half2_rn(s0 - back.x, s1 - back.y);
+      lo[u] = *reinterpret_cast<const uint32_t*>(&hl);
+    }
+    if (NPROD == 2) {
+      r2[u] = __nv_cvt_float2_to_fp8x2(make_float2((s0 - back.x) * 32.0f, (s1 - back.y) * 32.0f), __NV_SATFINITE, __NV_E4M3);
+      c2[u] = __nv_cvt_float2_to_fp8x2(make_float2(s0 * 0.015625f, s1 * 0.015625f), __NV_SATFINITE, __NV_E4M3);
+    }
+  }
+  if (NPROD == 2) {
+    res[0] = (uint32_t)r2[0] | ((uint32_t)r2[1] << 16); res[1] = (uint32_t)r2[2] | ((uint32_t)r2[3] << 16);
+    crs[0] = (uint32_t)c2[0] | ((uint32_t)c2[1] << 16); crs[1] = (uint32_t)c2[2] | ((uint32_t)c2[3] << 16);
   }
 }
 
@@ -289,6 +347,10 @@ template <int NPROD>
 __device__ __forceinline__ void lstm_epilogue_tile(const TcParams& P, const EpiRow& R, const float* sp, uint32_t tmem_base, int buf,
                                                    int quarter, int half, int ut, float dequant) {
   float hp = 0.f;
+  // with h % 16 == 0 two consecutive 8-unit chunks are written together: 32-byte stores of the fp16 image
+  // (one sector, one request) and 16-byte stores of the e4m3 images
+  const bool wide = (P.h % 16) == 0;
+  uint32_t hi_st[4], lo_st[4], res_st[2], crs_st[2];
 #pragma unroll
   for (int cc = 0; cc < kChunksPerHalf; ++cc) {
     const int chunk = half * kChunksPerHalf + cc;
@@ -299,8 +361,6 @@ __device__ __forceinline__ void lstm_epilogue_tile(const TcParams& P, const EpiR
     tc_wait_ld();
     if (R.row_ok && unit0 < P.h) {
       const size_t o = (size_t)R.row * P.h + unit0;
-      const float cold[8] = {R.c_lo[cc].x, R.c_lo[cc].y, R.c_lo[cc].z, R.c_lo[cc].w,
-                             R.c_hi[cc].x, R.c_hi[cc].y, R.c_hi[cc].z, R.c_hi[cc].w};
       float cnew[8], hnew[8];
       const float4* w0 = reinterpret_cast<const float4*>(sp + chunk * kTcChunk);
       const float4* w1 = reinterpret_cast<const float4*>(sp + kTcBN + chunk * kTcChunk);
@@ -320,45 +380,43 @@ __device__ __forceinline__ void lstm_epilogue_tile(const TcParams& P, const EpiR
         const float gf = sigmoid_fast(pf);
         const float go = sigmoid_fast(po);
         const float gu = tanh_fast(pu);
-        const float cn = __fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, cold[u]));     // lstm.py:78
+        const float cn = __fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, R.c[cc][u]));  // lstm.py:78
         const float hn = __fmul_rn(go, tanh_fast(cn));                              // lstm.py:79
         cnew[u] = cn;
         hnew[u] = hn;
         hp = fmaf(hn, whv[u], hp);                                                  // lstm.py:80 (partial)
       }
-      *reinterpret_cast<float4*>(P.C + o)     = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
-      *reinterpret_cast<float4*>(P.C + o + 4) = make_float4(cnew[4], cnew[5], cnew[6], cnew[7]);
-      // fp16 hi/lo image of H * 2^14 for the next iteration's MMAs
-      const float hs = (float)(1 << kHShift);
-      __half2 hh[4], hl[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float s0 = hnew[2 * u] * hs, s1 = hnew[2 * u + 1] * hs;
-        hh[u] = __floats2half2_rn(s0, s1);
-        const float2 back = __half22float2(hh[u]);
-        if (NPROD == 3) hl[u] = __floats2half2_rn(s0 - back.x, s1 - back.y);
-      }
-      *reinterpret_cast<uint4*>(P.hout_hi + o) = *reinterpret_cast<const uint4*>(hh);
-      if (NPROD == 3) *reinterpret_cast<uint4*>(P.hout_lo + o) = *reinterpret_cast<const uint4*>(hl);
-      if (NPROD == 2) {
-        // e4m3 images for the two correction products: residual * 2^5 and (H*2^14) * 2^-6
-        uint8_t* q8lo = reinterpret_cast<uint8_t*>(P.hout_lo);
-        uint8_t* q8hi = q8lo + (size_t)P.rows * P.h;
-        __align__(8) __nv_fp8x2_storage_t ql[4];
-        __align__(8) __nv_fp8x2_storage_t qh[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float s0 = hnew[2 * u] * hs, s1 = hnew[2 * u + 1] * hs;
-          const float2 back = __half22float2(hh[u]);
-          ql[u] = __nv_cvt_float2_to_fp8x2(make_float2((s0 - back.x) * 32.0f, (s1 - back.y) * 32.0f), __NV_SATFINITE, __NV_E4M3);
-          qh[u] = __nv_cvt_float2_to_fp8x2(make_float2(s0 * 0.015625f, s1 * 0.015625f), __NV_SATFINITE, __NV_E4M3);
+      st_global_v8(P.C + o, cnew);
+      if (P.hout_f32) st_global_v8(P.hout_f32 + o, hnew);
+      uint32_t hi[4], lo[4], res[2], crs[2];
+      split_hidden8<NPROD>(hnew, hi, lo, res, crs);
+      uint8_t* q8row = reinterpret_cast<uint8_t*>(P.hout_lo) + (size_t)R.row * P.q8_pitch;
+      if (!wide) {
+        *reinterpret_cast<uint4*>(P.hout_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (NPROD == 3) *reinterpret_cast<uint4*>(P.hout_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (NPROD == 2) {
+          uint8_t* q = q8row + (size_t)(unit0 >> 6) * 128 + (unit0 & 63);
+          *reinterpret_cast<uint2*>(q)      = make_uint2(res[0], res[1]);
+          *reinterpret_cast<uint2*>(q + 64) = make_uint2(crs[0], crs[1]);
         }
-        *reinterpret_cast<uint2*>(q8lo + o) = *reinterpret_cast<const uint2*>(ql);
-        *reinterpret_cast<uint2*>(q8hi + o) = *reinterpret_cast<const uint2*>(qh);
-      }
-      if (P.hout_f32) {
-        *reinterpret_cast<float4*>(P.hout_f32 + o)     = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
-        *reinterpret_cast<float4*>(P.hout_f32 + o + 4) = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
+      } else if ((cc & 1) == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { hi_st[u] = hi[u]; lo_st[u] = lo[u]; }
+        res_st[0] = res[0]; res_st[1] = res[1]; crs_st[0] = crs[0]; crs_st[1] = crs[1];
+      } else {
+        const size_t o2 = o - 8;                           // first unit of the chunk pair (multiple of 16)
+        const uint32_t w8[8] = {hi_st[0], hi_st[1], hi_st[2], hi_st[3], hi[0], hi[1], hi[2], hi[3]};
+        st_global_v8u(P.hout_hi + o2, w8);
+        if (NPROD == 3) {
+          const uint32_t l8[8] = {lo_st[0], lo_st[1], lo_st[2], lo_st[3], lo[0], lo[1], lo[2], lo[3]};
+          st_global_v8u(P.hout_lo + o2, l8);
+        }
+        if (NPROD == 2) {
+          const int u2 = unit0 - 8;
+          uint8_t* q = q8row + (size_t)(u2 >> 6) * 128 + (u2 & 63);
+          *reinterpret_cast<uint4*>(q)      = make_uint4(res_st[0], res_st[1], res[0], res[1]);
+          *reinterpret_cast<uint4*>(q + 64) = make_uint4(crs_st[0], crs_st[1], crs[0], crs[1]);
+        }
       }
     }
   }
@@ -543,17 +601,19 @@ gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 constexpr int kPairBK = 64;
 constexpr int kPairABytes = kTcBM * kPairBK * 2;          // 16 KB: this CTA's 128 rows of H (fp16)
 constexpr int kPairBBytes = (kTcBN / 2) * kPairBK * 2;    // 16 KB: this CTA's half of the U tile (fp16)
+constexpr int kPairBBoxRows = 64;                         // U tiles are fetched in 64-row TMA boxes
 
-template <int NPROD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+// CL = cluster size: 2 = one CTA pair; 4 = two pairs working on the SAME unit tile for two different row tiles,
+// which lets each 64-row piece of the U tile be fetched from L2 once and multicast to both pairs (the kernel is
+// L2->SM fill bound, profiles/README.md): U-tile L2 reads halve, at the price of 132 instead of 148 usable SMs.
+template <int NPROD, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kTcThreads, 1)
 gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                     const __grid_constant__ CUtensorMap map_a_q8hi, const __grid_constant__ CUtensorMap map_b_q8lo,
                      const TcParams P) {
   // NPROD: 3 = fp16 hi/lo split (3 MMAs), 1 = single fp16 MMA, 2 = fp16 MMA + two e4m3 correction MMAs.
-  // Stage layout NPROD 3: A_hi16 | A_lo16 | B_hi16 | B_lo16 (16 KB each)
-  //              NPROD 2: A_hi16 16K | A_res8 8K | A_crs8 8K | B_hi16 16K | B_crs8 8K | B_res8 8K   (map_a_lo/map_b_lo
-  //                       carry the e4m3 "residual of H" and "coarse U" operands, map_a_q8hi/map_b_q8lo the other pair)
+  // Stage layout: A_hi16 | A_lo | B_hi16 | B_lo, 16 KB each, every row 128 bytes (128B swizzle).  NPROD 3: lo = fp16
+  // residual.  NPROD 2: lo = packed e4m3 image, bytes [0,64) of a row = residual, [64,128) = coarse copy.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kStageBytes = (NPROD == 1) ? (kPairABytes + kPairBBytes) : 2 * (kPairABytes + kPairBBytes);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -568,13 +628,19 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
+  const bool leader = (rank & 1u) == 0;
+  const uint32_t leader_rank = rank & ~1u;                 // leader of this CTA's pair
+  const uint32_t pair_in_cluster = rank >> 1;
+  constexpr int kPairsPerCluster = CL / 2;
+  const uint16_t all_mask = (uint16_t)((1u << CL) - 1u);
+  const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_b_hi);
     if (NPROD != 1) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
-    if (NPROD == 2) { tma_prefetch_desc(&map_a_q8hi); tma_prefetch_desc(&map_b_q8lo); }
-    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    // a stage is refilled only after the MMAs of EVERY pair of the cluster have consumed it (multicast writes
+    // land in the sibling pair's shared memory too)
+    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), kPairsPerCluster); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -590,38 +656,53 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 
   const int unit_tiles = P.unit_tiles;
   const int h4 = 4 * P.h;
-  const long pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  // work unit of a cluster = (unit tile, kPairsPerCluster consecutive 256-row tiles); `pair`/`num_pairs` count clusters
+  const long pair = blockIdx.x / CL, num_pairs = gridDim.x / CL;
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
+    // ===================== TMA producer (every CTA) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      constexpr uint32_t kATotal = (NPROD == 1) ? kPairABytes : 2 * kPairABytes;          // bytes of H operands per CTA and stage
+      constexpr uint32_t kBBoxTotal = ((NPROD == 1) ? 1 : 2) * kPairBBoxRows * kPairBK * 2; // bytes of one 64-row box of every U operand
       for (long tile = pair; tile < P.num_tiles; tile += num_pairs) {
         const int  ut = (int)(tile % unit_tiles);
         const long rt = tile / unit_tiles;
         const int n_cols = min(kTcBN, h4 - ut * kTcBN);
-        const int row0 = (int)(rt * (2 * kTcBM)) + (int)rank * kTcBM;          // this CTA's 128 rows of H
-        const int col0 = ut * kTcBN + (int)rank * (n_cols / 2);               // this CTA's half of the U tile
+        const int row0 = (int)((rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM)) + (int)(rank & 1u) * kTcBM;   // this CTA's 128 rows of H
+        const int col0 = ut * kTcBN + (int)(rank & 1u) * (n_cols / 2);        // first row of this CTA's half of the U tile
+        // U boxes are 64 rows.  Full tiles in a 4-CTA cluster: each CTA fetches ONE 64-row piece of its half and
+        // multicasts it to the CTA with the same role in the sibling pair.  Otherwise the CTA loads its half itself.
+        const bool mcast = (CL == 4) && (n_cols == kTcBN);
+        const int  b_boxes = mcast ? 2 : (n_cols / 2 + kPairBBoxRows - 1) / kPairBBoxRows;   // boxes landing in this CTA
+        const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank ^ 2u)));
         for (int kb = 0; kb < P.k_blocks; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
-          if (leader) mbar_expect_tx(fb_local, 2 * kStageBytes);              // bytes of both CTAs
-          const uint32_t fb = map_to_cta(fb_local, 0);
+          if (leader) mbar_expect_tx(fb_local, 2u * (kATotal + (uint32_t)b_boxes * kBBoxTotal));   // both CTAs of the pair
+          const uint32_t fb = map_to_cta(fb_local, leader_rank);
           uint8_t* sbase = smem + (size_t)stage * kStageBytes;
           const int k0 = kb * kPairBK;
-          tma_load_2d_pair(smem_u32(sbase), &map_a_hi, fb, k0, row0);
-          if (NPROD == 3) {
-            tma_load_2d_pair(smem_u32(sbase + kPairABytes), &map_a_lo, fb, k0, row0);
-            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes), &map_b_hi, fb, k0, col0);
-            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes + kPairBBytes), &map_b_lo, fb, k0, col0);
-          } else if (NPROD == 2) {
-            tma_load_2d_pair(smem_u32(sbase + kPairABytes), &map_a_lo, fb, k0, row0);                       // H residual (e4m3)
-            tma_load_2d_pair(smem_u32(sbase + kPairABytes + kPairABytes / 2), &map_a_q8hi, fb, k0, row0);     // H coarse   (e4m3)
-            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes), &map_b_hi, fb, k0, col0);                   // U fp16
-            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes + kPairBBytes), &map_b_lo, fb, k0, col0);   // U coarse   (e4m3)
-            tma_load_2d_pair(smem_u32(sbase + 2 * kPairABytes + kPairBBytes + kPairBBytes / 2), &map_b_q8lo, fb, k0, col0);  // U residual
+          auto load_u = [&](const CUtensorMap* map, uint32_t region, int kc) {
+            constexpr uint32_t kBoxBytes = kPairBBoxRows * 128;
+            if (mcast) {
+              const uint32_t q = pair_in_cluster;
+              tma_load_2d_pair_mc(region + q * kBoxBytes, map, fb_local, kc, col0 + (int)q * kPairBBoxRows, mc_mask);
+            } else {
+              for (int bx = 0; bx < b_boxes; ++bx)
+                tma_load_2d_pair(region + (uint32_t)bx * kBoxBytes, map, fb, kc, col0 + bx * kPairBBoxRows);
+            }
+          };
+          const uint32_t sb = smem_u32(sbase);
+          tma_load_2d_pair(sb, &map_a_hi, fb, k0, row0);
+          if (NPROD != 1) {
+            // the packed e4m3 tensors are addressed in bytes: K block kb starts at byte kb*128 of a row
+            const int k0_lo = (NPROD == 2) ? kb * 128 : k0;
+            tma_load_2d_pair(sb + kPairABytes, &map_a_lo, fb, k0_lo, row0);
+            load_u(&map_b_hi, sb + 2 * kPairABytes, k0);
+            load_u(&map_b_lo, sb + 2 * kPairABytes + kPairBBytes, k0_lo);
           } else {
-            tma_load_2d_pair(smem_u32(sbase + kPairABytes), &map_b_hi, fb, k0, col0);
+            load_u(&map_b_hi, sb + kPairABytes, k0);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -660,12 +741,13 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
               tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
             } else if (NPROD == 2) {
               if ((ks & 1) == 0) {
-                // one e4m3 MMA covers 32 K-elements = two fp16 K-steps (rows of 64 bytes, 64B swizzle)
+                // one e4m3 MMA covers 32 K-elements = two fp16 K-steps; residual in bytes [0,64) of the row, coarse in [64,128)
                 const uint32_t koff8 = (uint32_t)(ks * kTcUK);
-                const uint64_t a_res = make_smem_desc_sw64(sbase + kPairABytes + koff8);
-                const uint64_t a_crs = make_smem_desc_sw64(sbase + kPairABytes + kPairABytes / 2 + koff8);
-                const uint64_t b_crs = make_smem_desc_sw64(sbase + 2 * kPairABytes + kPairBBytes + koff8);
-                const uint64_t b_res = make_smem_desc_sw64(sbase + 2 * kPairABytes + kPairBBytes + kPairBBytes / 2 + koff8);
+                const uint32_t a8 = sbase + kPairABytes, b8 = sbase + 2 * kPairABytes + kPairBBytes;
+                const uint64_t a_res = make_smem_desc_sw128(a8 + koff8);
+                const uint64_t a_crs = make_smem_desc_sw128(a8 + 64 + koff8);
+                const uint64_t b_res = make_smem_desc_sw128(b8 + koff8);
+                const uint64_t b_crs = make_smem_desc_sw128(b8 + 64 + koff8);
                 tc_mma_f8_pair(d_tmem, a_res, b_crs, idesc, acc); acc = 1;       // (H - fp16(H)) * U
                 tc_mma_f8_pair(d_tmem, a_crs, b_res, idesc, 1);                  // H * (U - fp16(U))
               }
@@ -678,10 +760,10 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
               tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, acc); acc = 1;
             }
           }
-          tc_commit_pair(smem_u32(&empty_bar[stage]));             // frees the stage in both CTAs
+          tc_commit_pair(smem_u32(&empty_bar[stage]), all_mask);   // one of the kPairsPerCluster arrivals, in every CTA
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(smem_u32(&tfull_bar[buf]));                 // accumulators complete in both CTAs
+        tc_commit_pair(smem_u32(&tfull_bar[buf]), pair_mask);      // accumulators complete in both CTAs of this pair
       }
     }
   } else {
@@ -700,14 +782,15 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       float* sp = sparam + buf * kParamFloats;
       stage_tile_params(P, sp, et, ut);
       EpiRow R;
-      lstm_epilogue_prefetch(P, R, quarter, half, lane, ut, rt * (2 * kTcBM) + (long)rank * kTcBM);
+      lstm_epilogue_prefetch(P, R, quarter, half, lane, ut,
+                             (rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM) + (long)(rank & 1u) * kTcBM);
       asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1);
       tc_fence_after();
       lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, half, ut, dequant);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), 0));
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), leader_rank));
     }
   }
 
@@ -759,6 +842,17 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows_total, int
   return IADMM_OK;
 }
 
+static bool use_quads() {
+  static int v = -1;
+  if (v < 0) {
+    // 4-CTA multicast clusters are bit-identical to plain pairs but measured 3-4 % slower on B200 (the kernel is
+    // bound by the per-SM request port, not by L2 reads, and only 132 SMs host 4-CTA clusters): opt-in only.
+    const char* e = getenv("IADMM_TC_QUAD");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool use_cta_pairs() {
   static int v = -1;
   if (v < 0) {
@@ -796,22 +890,20 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   const char* base = static_cast<const char*>(packed);
   if (nprod == 2 && !pair) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode runs on CTA pairs only");
   if (nprod == 2 && h % 16 != 0) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0");
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, ma_q8hi, mb_q8lo;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  const int b_box_rows = pair ? kTcBN / 2 : kTcBN;
+  const int b_box_rows = pair ? kPairBBoxRows : kTcBN;
   const int bk = pair ? kPairBK : kTcBK;
   if ((rc = make_map(&ma_hi, Hin_hi, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
   if ((rc = make_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
   if (nprod == 2) {
-    const uint8_t* q8 = reinterpret_cast<const uint8_t*>(Hin_lo);
-    if ((rc = make_map(&ma_lo, q8, (uint64_t)rows, h, kTcBM, 1, bk))) return rc;                               // H residual
-    if ((rc = make_map(&ma_q8hi, q8 + (size_t)rows * h, (uint64_t)rows, h, kTcBM, 1, bk))) return rc;          // H coarse
-    if ((rc = make_map(&mb_lo, base + L.off_uq8hi, (uint64_t)4 * h, h, b_box_rows, 1, bk))) return rc;         // U coarse
-    if ((rc = make_map(&mb_q8lo, base + L.off_uq8lo, (uint64_t)4 * h, h, b_box_rows, 1, bk))) return rc;       // U residual
+    // packed e4m3 images: byte tensors [rows][q8_pitch], one 128-byte box row per 64-wide K block
+    const int pitch = (int)q8_pitch(h);
+    if ((rc = make_map(&ma_lo, Hin_lo, (uint64_t)rows, pitch, kTcBM, 1, 128))) return rc;
+    if ((rc = make_map(&mb_lo, base + L.off_uq8, (uint64_t)4 * h, pitch, b_box_rows, 1, 128))) return rc;
   } else {
     if ((rc = make_map(&ma_lo, Hin_lo, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
     if ((rc = make_map(&mb_lo, base + L.off_ulo, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
-    ma_q8hi = ma_lo; mb_q8lo = mb_lo;
   }
 
   TcParams P;
@@ -821,11 +913,19 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.scale = reinterpret_cast<const float*>(base + L.off_scale);
   P.xv = xv; P.g = g;
   P.hout_hi = Hout_hi; P.hout_lo = Hout_lo; P.hout_f32 = H_out_f32; P.C = C; P.head_part = head_part;
-  P.rows = rows; P.h = h;
+  P.rows = rows; P.h = h; P.q8_pitch = q8_pitch(h);
   P.unit_tiles = cdiv(h, kTcUnits);
   P.k_blocks = cdiv(h, bk);
   P.nprod = nprod;
-  const int tile_rows = pair ? 2 * kTcBM : kTcBM;
+  // cluster size: 4 (two pairs sharing each U tile through TMA multicast) when there is enough work, else 2
+  static int max_quads = -1;
+  int cl = 1;
+  if (pair) {
+    cl = 2;
+    const long row_tiles = (rows + 2 * kTcBM - 1) / (2 * kTcBM);
+    if (use_quads() && row_tiles >= 2 && num_sms >= 4) cl = 4;
+  }
+  const int tile_rows = (pair ? 2 * kTcBM : kTcBM) * (cl == 4 ? 2 : 1);
   P.num_tiles = ((rows + tile_rows - 1) / tile_rows) * P.unit_tiles;
   const int a_bytes = pair ? kPairABytes : kTcABytes;
   const int b_bytes = pair ? kPairBBytes : kTcBBytes;
@@ -835,19 +935,39 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
                       (2 * P.stages + 4) * sizeof(uint64_t) + 16;
 
   if (pair) {
-    long pairs = P.num_tiles < num_sms / 2 ? P.num_tiles : num_sms / 2;
-    const unsigned grid = (unsigned)(2 * pairs);
-    static bool a3 = false, a2 = false, a1 = false;
-    if (nprod == 3) {
-      if ((rc = set_smem_attr(gates_tc_pair_kernel<3>, &a3))) return rc;
-      gates_tc_pair_kernel<3><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ma_q8hi, mb_q8lo, P);
-    } else if (nprod == 2) {
-      if ((rc = set_smem_attr(gates_tc_pair_kernel<2>, &a2))) return rc;
-      gates_tc_pair_kernel<2><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ma_q8hi, mb_q8lo, P);
+    auto launch = [&](auto kernel, bool* attr_done, int cluster) -> int {
+      int rc2;
+      if ((rc2 = set_smem_attr(kernel, attr_done))) return rc2;
+      long clusters = num_sms / cluster;
+      if (cluster == 4) {
+        if (max_quads < 0) {      // co-resident 4-CTA clusters (GPC granularity: 33 on a 148-SM B200)
+          cudaLaunchConfig_t cfg{};
+          cfg.gridDim = dim3((unsigned)(num_sms / 4 * 4)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          int n = 0;
+          if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) n = num_sms / 4 - 4;
+          max_quads = n;
+        }
+        clusters = max_quads < num_sms / 4 ? max_quads : num_sms / 4;
+      }
+      if (P.num_tiles < clusters) clusters = P.num_tiles;
+      kernel<<<(unsigned)(cluster * clusters), kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+      return IADMM_OK;
+    };
+    static bool a34 = false, a24 = false, a14 = false, a32 = false, a22 = false, a12 = false;
+    if (cl == 4) {
+      if (nprod == 3)      rc = launch(gates_tc_pair_kernel<3, 4>, &a34, 4);
+      else if (nprod == 2) rc = launch(gates_tc_pair_kernel<2, 4>, &a24, 4);
+      else                 rc = launch(gates_tc_pair_kernel<1, 4>, &a14, 4);
     } else {
-      if ((rc = set_smem_attr(gates_tc_pair_kernel<1>, &a1))) return rc;
-      gates_tc_pair_kernel<1><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ma_q8hi, mb_q8lo, P);
+      if (nprod == 3)      rc = launch(gates_tc_pair_kernel<3, 2>, &a32, 2);
+      else if (nprod == 2) rc = launch(gates_tc_pair_kernel<2, 2>, &a22, 2);
+      else                 rc = launch(gates_tc_pair_kernel<1, 2>, &a12, 2);
     }
+    if (rc) return rc;
     IADMM_LAUNCH_CHECK("gates_tc_pair_kernel");
     return IADMM_OK;
   }

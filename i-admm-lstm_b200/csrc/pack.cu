@@ -29,8 +29,7 @@ WeightLayout weight_layout(int h, int length) {
   L.off_scale = take(4 * sizeof(float));
   L.off_uhi   = take(4 * H * H * sizeof(__half));
   L.off_ulo   = take(4 * H * H * sizeof(__half));
-  L.off_uq8hi = take(4 * H * H);
-  L.off_uq8lo = take(4 * H * H);
+  L.off_uq8   = take(4 * H * q8_pitch(h));
   L.total = off;
   return L;
 }
@@ -83,13 +82,15 @@ __global__ void __launch_bounds__(256) pack_absmax_kernel(PackSrc S, int h, floa
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(scale + 2), __float_as_int(mx));  // mx >= 0
 }
 
+__device__ __forceinline__ size_t q8_pitch_dev(int h) { return (size_t)((h + 63) / 64) * 128; }
+
 __device__ __forceinline__ uint8_t to_e4m3(float v) {
   return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
 }
 
 __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __restrict__ u32, __half* __restrict__ uhi,
-                                                     __half* __restrict__ ulo, uint8_t* __restrict__ uq8hi,
-                                                     uint8_t* __restrict__ uq8lo, float* __restrict__ scale) {
+                                                     __half* __restrict__ ulo, uint8_t* __restrict__ uq8,
+                                                     float* __restrict__ scale) {
   const float mx = scale[2];
   float us = 1.f;
   if (mx > 0.f) us = exp2f((float)(12 - ilogbf(mx)));
@@ -111,8 +112,9 @@ __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __
     const __half lo = __float2half_rn(vs - __half2float(hi));
     uhi[(size_t)c * h + k] = hi;
     ulo[(size_t)c * h + k] = lo;
-    uq8hi[(size_t)c * h + k] = to_e4m3(ldexpf(__half2float(hi), kQ8UHiShift));
-    uq8lo[(size_t)c * h + k] = to_e4m3(ldexpf(vs - __half2float(hi), kQ8ULoShift));
+    uint8_t* q = uq8 + (size_t)c * q8_pitch_dev(h) + (size_t)(k >> 6) * 128 + (k & 63);
+    q[0]  = to_e4m3(ldexpf(vs - __half2float(hi), kQ8ULoShift));      // residual
+    q[64] = to_e4m3(ldexpf(__half2float(hi), kQ8UHiShift));           // coarse copy
   }
 }
 
@@ -137,8 +139,7 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
   pack_u_kernel<<<blocks, 256, 0, st>>>(S, h, reinterpret_cast<float*>(base + L.off_u32),
                                         reinterpret_cast<__half*>(base + L.off_uhi),
                                         reinterpret_cast<__half*>(base + L.off_ulo),
-                                        reinterpret_cast<uint8_t*>(base + L.off_uq8hi),
-                                        reinterpret_cast<uint8_t*>(base + L.off_uq8lo), scale);
+                                        reinterpret_cast<uint8_t*>(base + L.off_uq8), scale);
   IADMM_LAUNCH_CHECK("pack_u_kernel");
   return IADMM_OK;
 }
@@ -148,35 +149,48 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
 // ------------------------------------------------------------------------------------------------
 template <bool Q8>
 __global__ void __launch_bounds__(256) split_state_kernel(const float* __restrict__ H, __half* __restrict__ hi,
-                                                          __half* __restrict__ lo, size_t count) {
+                                                          __half* __restrict__ lo, size_t count, int h) {
   const float s = (float)(1 << kHShift);
-  uint8_t* q8lo = reinterpret_cast<uint8_t*>(lo);
-  uint8_t* q8hi = q8lo + count;
+  uint8_t* q8 = reinterpret_cast<uint8_t*>(lo);
+  const size_t pitch = q8_pitch_dev(h);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     const float v = H[i] * s;
     const __half a = __float2half_rn(v);
     hi[i] = a;
     if (Q8) {
-      q8lo[i] = to_e4m3(ldexpf(v - __half2float(a), kQ8HLoShift));
-      q8hi[i] = to_e4m3(ldexpf(v, kQ8HHiShift));
+      const size_t r = i / h;
+      const int k = (int)(i - r * h);
+      uint8_t* q = q8 + r * pitch + (size_t)(k >> 6) * 128 + (k & 63);
+      q[0]  = to_e4m3(ldexpf(v - __half2float(a), kQ8HLoShift));
+      q[64] = to_e4m3(ldexpf(v, kQ8HHiShift));
     } else {
       lo[i] = __float2half_rn(v - __half2float(a));
     }
   }
 }
 
-int launch_split_state(const float* H, __half* hi, __half* lo, long count, int nprod, cudaStream_t st) {
-  const long blocks = (count + 255) / 256;
+size_t tc_lo_bytes(long rows, int h) {
+  const size_t a = (size_t)rows * h * sizeof(__half), b = (size_t)rows * q8_pitch(h);
+  return a > b ? a : b;
+}
+
+int launch_split_state(const float* H, __half* hi, __half* lo, long rows, int h, int nprod, cudaStream_t st) {
+  const size_t count = (size_t)rows * h;
+  const size_t blocks = (count + 255) / 256;
   const unsigned grid = (unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks);
-  if (nprod == 2) split_state_kernel<true><<<grid, 256, 0, st>>>(H, hi, lo, (size_t)count);
-  else            split_state_kernel<false><<<grid, 256, 0, st>>>(H, hi, lo, (size_t)count);
+  if (nprod == 2) {
+    IADMM_CUDA(cudaMemsetAsync(lo, 0, (size_t)rows * q8_pitch(h), st));      // padding of the last K block
+    split_state_kernel<true><<<grid, 256, 0, st>>>(H, hi, lo, count, h);
+  } else {
+    split_state_kernel<false><<<grid, 256, 0, st>>>(H, hi, lo, count, h);
+  }
   IADMM_LAUNCH_CHECK("split_state_kernel");
   return IADMM_OK;
 }
 
-int launch_zero_state(__half* hi, __half* lo, long count, cudaStream_t st) {
-  IADMM_CUDA(cudaMemsetAsync(hi, 0, (size_t)count * sizeof(__half), st));
-  IADMM_CUDA(cudaMemsetAsync(lo, 0, (size_t)count * sizeof(__half), st));
+int launch_zero_state(__half* hi, __half* lo, long rows, int h, int nprod, cudaStream_t st) {
+  IADMM_CUDA(cudaMemsetAsync(hi, 0, (size_t)rows * h * sizeof(__half), st));
+  IADMM_CUDA(cudaMemsetAsync(lo, 0, nprod == 2 ? (size_t)rows * q8_pitch(h) : (size_t)rows * h * sizeof(__half), st));
   return IADMM_OK;
 }
 
