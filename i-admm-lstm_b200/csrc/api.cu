@@ -157,7 +157,7 @@ int iadmm_solve_workspace_bytes(int B, int n, int m, int h, int mode, size_t* by
 int iadmm_solve(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
                 const float* zu, const float* sd, const float* se, const float* sc, float* x, float* y, float* z,
                 float* xv, float* H, float* C, float* pri_trace, float* dual_trace, float* pri_trace_u,
-                float* dual_trace_u, int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
+                float* dual_trace_u, float* metric_trace, int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
                 float sigma, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream) {
   const int m = num_ineq + num_eq;
   if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || K < 0 || t0 < 0)
@@ -186,7 +186,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   const long rows = (long)B * (n + m);
   const bool tc = is_tc(mode);
   const int nprod = (mode == IADMM_GATES_TC_3XFP16) ? 3 : (mode == IADMM_GATES_TC_F16F8 ? 2 : 1);
-  const bool want_trace = pri_trace || dual_trace || pri_trace_u || dual_trace_u;
+  const bool want_trace = pri_trace || dual_trace || pri_trace_u || dual_trace_u || metric_trace;
 
   float* hbuf[2] = {H, ws.h_alt};
   int cur = 0;
@@ -202,7 +202,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
     prof_record(0, st);
     if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, sk, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
-                                  dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st))) return rc;
+                                  dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st, metric_trace, zu))) return rc;
     if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st))) return rc;
     prof_record(1, st);
@@ -224,7 +224,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   if (want_trace && !(flags & IADMM_F_SKIP_FINAL_RESID)) {
     if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, nullptr, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
-                                  dual_trace_u, sd, se, sc, K - 1, 1, st))) return rc;
+                                  dual_trace_u, sd, se, sc, K - 1, 1, st, metric_trace, zu))) return rc;
   }
   return IADMM_OK;
 }

@@ -176,7 +176,7 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
                         const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
                         float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
                         const float* sd, const float* se, const float* sc, int trace_row, int residual_only,
-                        cudaStream_t st);
+                        cudaStream_t st, float* metric_trace = nullptr, const float* zu = nullptr);
 // pass 2: column partials of Q^T w1, A0^T w2 and rows A0 w1
 int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st);
 // combine 2: g = K^T w

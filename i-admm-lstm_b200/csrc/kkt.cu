@@ -322,6 +322,8 @@ struct Combine1Args {
   float sigma;
   KktScratch s;
   float *pri, *dual, *pri_u, *dual_u;   // trace rows (already offset to the row), may be NULL
+  float *metrics;                       // [5][B] row block: objective, ineq max/mean, eq max/mean; may be NULL
+  const float *zu;                      // upper bounds (c for inequality rows, b for equality rows)
   const float *sd, *se, *sc;            // Ruiz diagonals, may be NULL
   int residual_only;
 };
@@ -338,19 +340,37 @@ __device__ __forceinline__ double block_sum_double(double v, double* sh) {
   return t;
 }
 
+__device__ __forceinline__ double block_max_double(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFullMask, v, o));
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = sh[0];
+  for (int w = 1; w < kCombThreads / 32; ++w) t = fmax(t, sh[w]);
+  return t;
+}
+
 __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combine1Args A) {
   __shared__ double sh[kCombThreads / 32];
   const KktDims& d = A.d;
   const int b = blockIdx.x;
   const size_t n = d.n, m = d.m, N = n + m;
   const float* part = A.s.part_a + (size_t)b * d.chunks_a * 2 * n;
-  const bool want_res = (A.pri != nullptr) || (A.dual != nullptr) || (A.pri_u != nullptr) || (A.dual_u != nullptr);
-  const bool unscaled = (A.sd != nullptr) && ((A.pri_u != nullptr) || (A.dual_u != nullptr));
+  const bool want_met = A.metrics != nullptr;
+  const bool want_res = (A.pri != nullptr) || (A.dual != nullptr) || (A.pri_u != nullptr) || (A.dual_u != nullptr) || want_met;
+  const bool unscaled = (A.sd != nullptr) && ((A.pri_u != nullptr) || (A.dual_u != nullptr) || want_met);
   float inv_ineq = 0.f, inv_eq = 0.f;
   if (!A.residual_only) { inv_ineq = A.sched->inv_rho_ineq; inv_eq = A.sched->inv_rho_eq; }
   const float cscale = unscaled ? A.sc[b] : 1.f;
 
   double dual2 = 0.0, dual2u = 0.0, pri2 = 0.0, pri2u = 0.0;
+  // main.py:949-968 metrics of the iterate (x,y,z): objective 0.5 x^T Q x + p^T x and the constraint violations
+  // relu(G x - c), |b - A x|; on the original data they follow from the scaled products through the Ruiz
+  // diagonals: x_u^T Q_0 x_u = x^T Q x / c, p_0^T x_u = p^T x / c, (A0_0 x_u)_i = (A0 x)_i / e_i
+  double obj = 0.0, isum = 0.0, esum = 0.0;
+  float imax = 0.f, emax = 0.f;
   for (int j = threadIdx.x; j < d.n; j += kCombThreads) {
     float atv = 0.f, aty = 0.f;
     for (int c = 0; c < d.chunks_a; ++c) {
@@ -363,6 +383,10 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
       const float kxv = __fadd_rn(__fadd_rn(A.s.qxt[b * n + j], __fmul_rn(A.sigma, xt)), atv);
       const float rhs = __fsub_rn(__fmul_rn(A.sigma, A.x[b * n + j]), pj);
       A.s.w[b * N + j] = __fsub_rn(kxv, rhs);
+    }
+    if (want_met) {
+      const float xj = A.x[b * n + j];
+      obj += (double)xj * (0.5 * (double)A.s.qx[b * n + j] + (double)pj);
     }
     if (want_res) {
       const float r = __fadd_rn(__fadd_rn(A.s.qx[b * n + j], pj), aty);
@@ -382,6 +406,12 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
       const float rhs = __fsub_rn(zi, __fmul_rn(inv, A.y[b * m + i]));
       A.s.w[b * N + n + i] = __fsub_rn(kxv, rhs);
     }
+    if (want_met) {
+      const float einv = unscaled ? 1.0f / A.se[b * m + i] : 1.0f;
+      const float dv = (A.s.ax[b * m + i] - A.zu[b * m + i]) * einv;
+      if (i < d.num_ineq) { const float v = fmaxf(dv, 0.f); imax = fmaxf(imax, v); isum += (double)v; }
+      else                { const float v = fabsf(dv);      emax = fmaxf(emax, v); esum += (double)v; }
+    }
     if (want_res) {
       const float r = __fsub_rn(A.s.ax[b * m + i], zi);
       pri2 += (double)r * (double)r;
@@ -395,11 +425,24 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
     pri2  = block_sum_double(pri2, sh);
     dual2 = block_sum_double(dual2, sh);
     if (unscaled) { pri2u = block_sum_double(pri2u, sh); dual2u = block_sum_double(dual2u, sh); }
+    if (want_met) {
+      obj = block_sum_double(obj, sh); isum = block_sum_double(isum, sh); esum = block_sum_double(esum, sh);
+      imax = (float)block_max_double((double)imax, sh); emax = (float)block_max_double((double)emax, sh);
+    }
     if (threadIdx.x == 0) {
       if (A.pri)  A.pri[b]  = (float)sqrt(pri2);
       if (A.dual) A.dual[b] = (float)sqrt(dual2);
       if (unscaled && A.pri_u)  A.pri_u[b]  = (float)sqrt(pri2u);
       if (unscaled && A.dual_u) A.dual_u[b] = (float)sqrt(dual2u);
+      if (want_met) {
+        const size_t B = d.B;
+        const int me = d.m - d.num_ineq;
+        A.metrics[0 * B + b] = (float)(unscaled ? obj / (double)cscale : obj);
+        A.metrics[1 * B + b] = imax;
+        A.metrics[2 * B + b] = d.num_ineq > 0 ? (float)(isum / d.num_ineq) : 0.f;
+        A.metrics[3 * B + b] = emax;
+        A.metrics[4 * B + b] = me > 0 ? (float)(esum / me) : 0.f;
+      }
     }
   }
 }
@@ -408,7 +451,7 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
                         const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
                         float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
                         const float* sd, const float* se, const float* sc, int trace_row, int residual_only,
-                        cudaStream_t st) {
+                        cudaStream_t st, float* metric_trace, const float* zu) {
   Combine1Args A;
   A.d = d; A.p = p; A.x = x; A.y = y; A.z = z;
   A.xt = xv; A.v = xv ? xv + d.n : nullptr; A.xt_stride = A.v_stride = d.n + d.m;
@@ -418,6 +461,8 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
   A.dual   = (trace_row >= 0 && dual_trace)   ? dual_trace + off   : nullptr;
   A.pri_u  = (trace_row >= 0 && pri_trace_u)  ? pri_trace_u + off  : nullptr;
   A.dual_u = (trace_row >= 0 && dual_trace_u) ? dual_trace_u + off : nullptr;
+  A.metrics = (trace_row >= 0 && metric_trace && zu) ? metric_trace + (size_t)trace_row * 5 * d.B : nullptr;
+  A.zu = zu;
   A.sd = sd; A.se = se; A.sc = sc;
   A.residual_only = residual_only;
   kkt_combine1_kernel<<<d.B, kCombThreads, 0, st>>>(A);

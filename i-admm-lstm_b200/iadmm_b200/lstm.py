@@ -31,6 +31,18 @@ class SolveResult:
     dual: Optional[torch.Tensor] = None
     pri_unscaled: Optional[torch.Tensor] = None  # [K,B] on the original data (needs `scaling`)
     dual_unscaled: Optional[torch.Tensor] = None
+    metrics: Optional[torch.Tensor] = None       # [K,5,B]: objective, ineq max/mean, eq max/mean (main.py:949-968)
+
+    @property
+    def objective(self): return None if self.metrics is None else self.metrics[:, 0]
+    @property
+    def ineq_violation_max(self): return None if self.metrics is None else self.metrics[:, 1]
+    @property
+    def ineq_violation_mean(self): return None if self.metrics is None else self.metrics[:, 2]
+    @property
+    def eq_violation_max(self): return None if self.metrics is None else self.metrics[:, 3]
+    @property
+    def eq_violation_mean(self): return None if self.metrics is None else self.metrics[:, 4]
 
 
 class LSTM(nn.Module):
@@ -134,9 +146,10 @@ class LSTM(nn.Module):
         mode = self._mode()
         packed = self.packed_weights()
         ws = self._workspace(B, n, m, mode, dev)
-        pri = dual = pri_u = dual_u = None
+        pri = dual = pri_u = dual_u = met = None
         if traces and K > 0:
             pri = torch.empty((K, B), device=dev); dual = torch.empty((K, B), device=dev)
+            met = torch.empty((K, 5, B), device=dev)
             if scaling is not None:
                 pri_u = torch.empty((K, B), device=dev); dual_u = torch.empty((K, B), device=dev)
         sd = se = sc = None
@@ -146,10 +159,10 @@ class LSTM(nn.Module):
             _lib.check(L.iadmm_solve(_lib.ptr(packed), _lib.ptr(Q), _lib.ptr(p), _lib.ptr(A0), _lib.ptr(zl), _lib.ptr(zu),
                                      _lib.ptr(sd), _lib.ptr(se), _lib.ptr(sc),
                                      _lib.ptr(x), _lib.ptr(y), _lib.ptr(z), _lib.ptr(xv), _lib.ptr(H), _lib.ptr(C),
-                                     _lib.ptr(pri), _lib.ptr(dual), _lib.ptr(pri_u), _lib.ptr(dual_u),
+                                     _lib.ptr(pri), _lib.ptr(dual), _lib.ptr(pri_u), _lib.ptr(dual_u), _lib.ptr(met),
                                      B, n, int(num_ineq), int(num_eq), h, self.length, int(t0), int(K),
                                      float(sigma), mode, flags, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
-        return SolveResult(x, y, z, xv, H, C, pri, dual, pri_u, dual_u)
+        return SolveResult(x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met)
 
     # -- the reference's per-iteration interface -------------------------------------------------
     def forward(self, t, num_ineq, num_eq, x, y, z, xv, sigma, H_t, C_t, **kwargs):

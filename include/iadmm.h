@@ -108,6 +108,11 @@ int iadmm_ruiz(const float* Q, const float* p, const float* A0, const float* zl,
  *   pri_trace/dual_trace     residuals on the data passed in                       (main.py:346)
  *   pri_trace_u/dual_trace_u residuals of the un-scaled iterates on the original data, computed from
  *                            the diagonals d,e,c of iadmm_ruiz (main.py:922-955); need d,e,c != NULL.
+ *   metric_trace             [K,5,B]: objective 0.5 x^T Q x + p^T x (utils.py:53), max and mean of relu(G x - c)
+ *                            over the inequality rows (utils.py:56) and of |b - A x| over the equality rows
+ *                            (utils.py:59), i.e. the per-instance quantities main.py:949-968 prints; evaluated on
+ *                            the original data when d,e,c are given (with the un-scaled iterate), else on the
+ *                            data passed in.
  * mode: IADMM_GATES_*; flags: IADMM_F_*.
  */
 int iadmm_solve_workspace_bytes(int B, int n, int m, int h, int mode, size_t* bytes);
@@ -116,6 +121,7 @@ int iadmm_solve(const void* packed_weights,
                 const float* d, const float* e, const float* c,
                 float* x, float* y, float* z, float* xv, float* H, float* C,
                 float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
+                float* metric_trace,
                 int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
                 float sigma, int mode, int flags,
                 void* workspace, size_t workspace_bytes, void* stream);

@@ -22,7 +22,7 @@ sys.path.insert(0, "/root/reference")
 
 from models.lstm import LSTM            # noqa: E402  (reference)
 from methods.scaling import Scaling     # noqa: E402  (reference)
-from utils import primal_dual_loss, obj_fn   # noqa: E402  (reference)
+from utils import primal_dual_loss, obj_fn, ineq_dist, eq_dist   # noqa: E402  (reference)
 
 from oracle.iadmm_oracle import qp_instances, lstm_parameters   # noqa: E402  (input generators only)
 
@@ -110,6 +110,9 @@ def case_solve(name, B, n, mi, me, h, K, seed, scaling, wscale=1.0, store_inputs
         z = torch.zeros((B, m, 1), dtype=dt); xv = torch.zeros((B, n + m, 1), dtype=dt)
         H = torch.zeros((B, n + m, h), dtype=dt); C = torch.zeros((B, n + m, h), dtype=dt)
         pri, dual, pri_u, dual_u, obj_u, ls = [], [], [], [], [], []
+        vio = []     # [K, 4, B]: ineq max, ineq mean, eq max, eq mean on the original data (main.py:959-968)
+        G0, c0 = qp["G"].to(dt), qp["c"].to(dt)
+        Aeq0, b0 = qp["A"].to(dt), qp["b"].to(dt)
         with torch.no_grad():
             for t in range(K):
                 x, y, z, xv, H, C, Kmat, rhs, rho_vec = model(t, mi, me, x, y, z, xv, SIGMA, H, C, Q=Q, p=p, A0=A0,
@@ -122,12 +125,16 @@ def case_solve(name, B, n, mi, me, h, K, seed, scaling, wscale=1.0, store_inputs
                     pr, du, _ = primal_dual_loss(xu, yu, zu_, Q0, p0, A00)
                     pri_u.append(pr.reshape(B).numpy()); dual_u.append(du.reshape(B).numpy())
                     obj_u.append(obj_fn(xu, Q=Q0, p=p0).reshape(B).numpy())
+                    iv, ev = ineq_dist(xu, G=G0, c=c0), eq_dist(xu, A=Aeq0, b=b0)
+                    vio.append(np.stack([iv.max(dim=1).values.reshape(B).numpy(), iv.mean(dim=1).reshape(B).numpy(),
+                                         ev.max(dim=1).values.reshape(B).numpy(), ev.mean(dim=1).reshape(B).numpy()]))
         blob.update({f"{tag}_x": x.numpy(), f"{tag}_y": y.numpy(), f"{tag}_z": z.numpy(), f"{tag}_xv": xv.numpy(),
                      f"{tag}_pri": np.stack(pri), f"{tag}_dual": np.stack(dual), f"{tag}_ls": np.stack(ls)})
         if tag == "f32":
             blob.update(f32_H=H.numpy().astype(np.float32), f32_C=C.numpy().astype(np.float32))
         if scaling:
-            blob.update({f"{tag}_pri_u": np.stack(pri_u), f"{tag}_dual_u": np.stack(dual_u), f"{tag}_obj_u": np.stack(obj_u)})
+            blob.update({f"{tag}_pri_u": np.stack(pri_u), f"{tag}_dual_u": np.stack(dual_u), f"{tag}_obj_u": np.stack(obj_u),
+                         f"{tag}_vio_u": np.stack(vio)})
     torch.set_default_dtype(torch.float32)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
     print("wrote", name)

@@ -146,6 +146,11 @@ def test_solve_vs_reference(name, mode):
     if scaled:
         errs["pri_u"] = rel_err(r.pri_unscaled, g["f32_pri_u"])
         errs["dual_u"] = rel_err(r.dual_unscaled, g["f32_dual_u"])
+        # per-iteration objective and violations of the un-scaled iterate on the original data (main.py:949-968)
+        errs["obj_u"] = rel_err(r.objective, g["f32_obj_u"])
+        vio = t(g["f32_vio_u"])
+        errs["ineq_max"] = rel_err(r.ineq_violation_max, vio[:, 0]); errs["ineq_mean"] = rel_err(r.ineq_violation_mean, vio[:, 1])
+        errs["eq_max"] = rel_err(r.eq_violation_max, vio[:, 2]); errs["eq_mean"] = rel_err(r.eq_violation_mean, vio[:, 3])
     print(name, mode, {k: f"{v:.1e}" for k, v in errs.items()})
     for k, v in errs.items():
         assert v < tol, (k, v)
