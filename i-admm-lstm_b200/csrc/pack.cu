@@ -136,6 +136,8 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
   const int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
   pack_absmax_kernel<<<blocks, 256, 0, st>>>(S, h, scale);
   IADMM_LAUNCH_CHECK("pack_absmax_kernel");
+  // padding bytes of the packed e4m3 rows (last K block when h % 64 != 0) are read by the K=32 MMAs: keep them zero
+  IADMM_CUDA(cudaMemsetAsync(base + L.off_uq8, 0, (size_t)4 * h * q8_pitch(h), st));
   pack_u_kernel<<<blocks, 256, 0, st>>>(S, h, reinterpret_cast<float*>(base + L.off_u32),
                                         reinterpret_cast<__half*>(base + L.off_uhi),
                                         reinterpret_cast<__half*>(base + L.off_ulo),

@@ -3,13 +3,15 @@
 Public surface = the reference's own call boundary for this path:
     LSTM            (models/lstm.py)        + LSTM.solve for K fused iterations
     Scaling         (methods/scaling.py)
+    LU              (models/lu.py; library-backed Stage II, outside the accelerated path)
     primal_dual_loss, obj_fn, ineq_dist, eq_dist, lb_dist, ub_dist   (utils.py)
 All compute goes through the C ABI of libiadmm_b200.so (include/iadmm.h); there is no fallback.
 """
 from ._lib import IadmmError, LIB_PATH, GATE_MODES, lib
 from .lstm import LSTM, SolveResult
 from .scaling import Scaling
+from .lu import LU
 from .utils import primal_dual_loss, obj_fn, ineq_dist, eq_dist, lb_dist, ub_dist
 
-__all__ = ["LSTM", "SolveResult", "Scaling", "primal_dual_loss", "obj_fn", "ineq_dist", "eq_dist",
+__all__ = ["LSTM", "SolveResult", "Scaling", "LU", "primal_dual_loss", "obj_fn", "ineq_dist", "eq_dist",
            "lb_dist", "ub_dist", "IadmmError", "LIB_PATH", "GATE_MODES", "lib"]

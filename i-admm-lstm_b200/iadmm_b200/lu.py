@@ -1,0 +1,43 @@
+"""Drop-in for the reference's `models/lu.py` (class `LU`, the optional Stage-II "feasibility restoration").
+
+Stage II is OUTSIDE the accelerated path: it is exact OSQP-style ADMM, one dense LU of
+the KKT matrix and a triangular solve per iteration.  This module keeps `main.py --feas_rest` working on a B200
+next to the drop-in `LSTM`/`Scaling`: the factorisation and the solves are plain library calls
+(`torch.linalg.lu_factor` / `lu_solve`, i.e. cuSOLVER/cuBLAS -- no hand-written kernel yet), the K matrix
+comes from `LSTM.forward`'s return tuple (`iadmm_build_kkt`).
+"""
+import torch
+import torch.nn as nn
+
+
+class LU(nn.Module):
+    def __init__(self, device):
+        super(LU, self).__init__()
+        self.device = device
+
+    def name(self):
+        return 'torch_solver'
+
+    def forward(self, rho_vec, x, y, z, xv, sigma, A_tild, lu, piv, **kwargs):
+        """Same contract as models/lu.py:13-47: returns (x, y, z, xv, A_tild, b_tild, lu, piv)."""
+        p, zl, zu = kwargs['p'], kwargs['zl'], kwargs['zu']
+        inv_rho = 1 / rho_vec
+        relax = 1.6                                         # models/lu.py:24
+        b_tild = torch.cat((sigma * x - p, z - inv_rho * y), dim=1)
+        if lu is None and piv is None:
+            if A_tild is None:                              # assemble K as models/lu.py:28-29 does
+                Q, A0 = kwargs['Q'], kwargs['A0']
+                n, m = Q.shape[1], A0.shape[1]
+                top = torch.cat((Q + sigma * torch.eye(n, device=Q.device), A0.transpose(1, 2)), dim=2)
+                bot = torch.cat((A0, torch.diag_embed(-inv_rho.squeeze(-1))), dim=2)
+                A_tild = torch.cat((top, bot), dim=1)
+            lu, piv = torch.linalg.lu_factor(A_tild)
+        xv = torch.linalg.lu_solve(lu, piv, b_tild)
+        n = x.shape[1]
+        x_tild, v = xv[:, :n, :], xv[:, n:, :]
+        z_tild = z + inv_rho * (v - y)
+        x = relax * x_tild + (1 - relax) * x
+        z_rel = relax * z_tild + (1 - relax) * z
+        z = torch.max(torch.min(z_rel + inv_rho * y, zu), zl)
+        y = y + rho_vec * (z_rel - z)
+        return x, y, z, xv, A_tild, b_tild, lu, piv

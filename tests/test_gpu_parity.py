@@ -306,6 +306,32 @@ def test_aligned_n_with_odd_constraint_count():
             assert rel_err(getattr(r, k), getattr(ref, k)) < 1e-5, (mode, k)
 
 
+def test_unconstrained_and_single_instance():
+    """Degenerate sizes: no constraint rows at all (m = 0, the reference's Scaling has a special branch for it,
+    methods/scaling.py:58-61) and a batch of one."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, h, K = 1, 20, 16, 4
+    g = torch.Generator().manual_seed(57)
+    Q = torch.diag_embed(torch.rand((B, n), generator=g)) + 0.01 * torch.ones((B, n, n))
+    p = torch.rand((B, n, 1), generator=g)
+    A0 = torch.zeros((B, 0, n)); zl = torch.zeros((B, 0, 1)); zu = torch.zeros((B, 0, 1))
+    prm = orc.lstm_parameters(h, K, seed=57, scale=5.0)
+    Qs, ps, As, zls, zus, so = orc.ruiz_equilibrate(Q, p, A0, zl, zu, 10)
+    ref = orc.solve(prm, K, 0, 0, Qs, ps, As, zls, zus, 6e-6, h, form="block")
+    sc = ia.Scaling(n, 0, 10, DEV)
+    Qd, pd, Ad, zld, zud = sc.scale_data(*(v.to(DEV) for v in (Q, p, A0, zl, zu)))
+    assert rel_err(Qd, Qs) < 1e-6 and rel_err(pd, ps) < 1e-6 and rel_err(sc.c, so.c) < 1e-6
+    for mode in ("simt_fp32", "tc_f16f8"):
+        model = make_model(prm, h, K, mode)
+        with torch.no_grad():
+            r = model.solve(K, 0, 0, Qd, pd, Ad, zld, zud, 6e-6)
+        assert r.y.shape == (B, 0, 1) and r.z.shape == (B, 0, 1)
+        for k in ("x", "xv", "H", "C", "dual"):
+            assert rel_err(getattr(r, k), getattr(ref, k)) < 1e-5, (mode, k)
+        assert float(r.pri.abs().max()) == 0.0
+
+
 def test_inf_bounds_and_odd_sizes():
     """Ragged sizes (n, m not multiples of 4; h not a multiple of 8 falls back to the fp32 cell),
     inequality-only rows with -inf lower bounds, one-sided +inf upper bounds."""
@@ -323,3 +349,32 @@ def test_inf_bounds_and_odd_sizes():
     for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual"):
         assert rel_err(getattr(r, k), getattr(ref, k)) < 1e-5, k
     assert torch.isfinite(r.z).all()
+
+
+def test_stage2_lu_dropin_runs_after_the_learned_solve():
+    """main.py:1035-1115 (--feas_rest): Stage II consumes rho_vec / A_tild of the last LSTM.forward call and the final
+    iterates.  The drop-in LU (library-backed) reproduces the oracle's exact ADMM and reduces the residuals."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, K = 3, 40, 12, 14, 16, 5
+    qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=97).items()}
+    prm = orc.lstm_parameters(h, K, seed=97)
+    model = make_model(prm, h, K, "tc_f16f8")
+    m = mi + me
+    st = [torch.zeros((B, n, 1), device=DEV), torch.zeros((B, m, 1), device=DEV), torch.zeros((B, m, 1), device=DEV),
+          torch.zeros((B, n + m, 1), device=DEV), torch.zeros((B, n + m, h), device=DEV), torch.zeros((B, n + m, h), device=DEV)]
+    kw = dict(Q=qp["Q"], p=qp["p"], A0=qp["A0"], lb=None, ub=None, zl=qp["zl"], zu=qp["zu"])
+    with torch.no_grad():
+        for tt in range(K):
+            x, y, z, xv, H, C, A_tild, b_tild, rho_vec = model(tt, mi, me, *st[:4], 6e-6, st[4], st[5], **kw)
+            st = [x, y, z, xv, H, C]
+        stage2 = ia.LU(DEV)
+        lu = piv = None
+        xr, yr, zr = (v.cpu().double() for v in (x, y, z))
+        for _ in range(30):
+            x, y, z, xv, A_tild, b_tild, lu, piv = stage2(rho_vec, x, y, z, xv, 6e-6, A_tild, lu, piv, **kw)
+        ref = orc.exact_admm(*(qp[k].cpu().double() for k in ("Q", "p", "A0", "zl", "zu")), rho_vec.cpu().double(), 6e-6, 30,
+                             state=(xr, yr, zr))
+        pri, dual, _ = ia.primal_dual_loss(x, y, z, qp["Q"], qp["p"], qp["A0"])
+    assert rel_err(x, ref[0]) < 1e-3 and rel_err(z, ref[2]) < 1e-3
+    assert float(pri.max()) < 1e-2
