@@ -461,7 +461,7 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
   A.dual   = (trace_row >= 0 && dual_trace)   ? dual_trace + off   : nullptr;
   A.pri_u  = (trace_row >= 0 && pri_trace_u)  ? pri_trace_u + off  : nullptr;
   A.dual_u = (trace_row >= 0 && dual_trace_u) ? dual_trace_u + off : nullptr;
-  A.metrics = (trace_row >= 0 && metric_trace && zu) ? metric_trace + (size_t)trace_row * 5 * d.B : nullptr;
+  A.metrics = (trace_row >= 0 && metric_trace && (zu || d.m == 0)) ? metric_trace + (size_t)trace_row * 5 * d.B : nullptr;
   A.zu = zu;
   A.sd = sd; A.se = se; A.sc = sc;
   A.residual_only = residual_only;

@@ -378,3 +378,53 @@ def test_stage2_lu_dropin_runs_after_the_learned_solve():
         pri, dual, _ = ia.primal_dual_loss(x, y, z, qp["Q"], qp["p"], qp["A0"])
     assert rel_err(x, ref[0]) < 1e-3 and rel_err(z, ref[2]) < 1e-3
     assert float(pri.max()) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(3, 37, 9, 11, 16), (2, 132, 40, 29, 48), (2, 200, 50, 50, 208), (1, 20, 0, 0, 16)])
+def test_poisoned_workspaces_change_nothing(shape, monkeypatch):
+    """Every workspace and the packed-weight buffer are handed to the library filled with 0xFF bytes (NaN as fp32,
+    fp16 and e4m3): results must be bit-identical to a clean run, i.e. no kernel reads a byte it (or an earlier
+    kernel of the same call) did not write.  (compute-sanitizer is closed on this pool.)"""
+    import iadmm_b200 as ia
+    from iadmm_b200 import _lib
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h = shape
+    K = 4
+    if mi + me > 0:
+        qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=33).items()}
+    else:
+        qp = dict(Q=torch.eye(n, device=DEV).repeat(B, 1, 1) * 0.7, p=torch.rand((B, n, 1), device=DEV),
+                  A0=torch.zeros((B, 0, n), device=DEV), zl=torch.zeros((B, 0, 1), device=DEV), zu=torch.zeros((B, 0, 1), device=DEV))
+    prm = orc.lstm_parameters(h, K, seed=33, scale=3.0)
+
+    def run(mode):
+        model = make_model(prm, h, K, mode)
+        sc = ia.Scaling(n, mi + me, 10, DEV)
+        Q, p, A0, zl, zu = sc.scale_data(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"])
+        with torch.no_grad():
+            r = model.solve(K, mi, me, Q, p, A0, zl, zu, 6e-6, scaling=sc)
+            pr = ia.primal_dual_loss(r.x, r.y, r.z, Q, p, A0)
+        torch.cuda.synchronize()
+        return [Q, p, A0, zl, zu, sc.d, sc.e, sc.c_vec, r.x, r.y, r.z, r.xv, r.H, r.C, r.pri, r.dual, r.pri_unscaled,
+                r.dual_unscaled, r.metrics, pr[0], pr[1]]
+
+    def poisoned(nbytes, device):
+        return torch.full((max(int(nbytes), 16),), 0xFF, dtype=torch.uint8, device=device)
+
+    real_empty = torch.empty
+
+    def poisoned_empty(*a, **kw):             # also the packed-weight buffer (allocated as uint8 with torch.empty)
+        out = real_empty(*a, **kw)
+        if out.dtype == torch.uint8 and out.is_cuda:
+            out.fill_(0xFF)
+        return out
+
+    for mode in ("simt_fp32", "tc_3xfp16", "tc_f16f8"):
+        clean = run(mode)
+        with monkeypatch.context() as mp:
+            mp.setattr(_lib, "workspace", poisoned)
+            mp.setattr(torch, "empty", poisoned_empty)
+            dirty = run(mode)
+        for i, (a, b) in enumerate(zip(clean, dirty)):
+            assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)), (mode, i)
+            assert not torch.isnan(b).any(), (mode, i)
