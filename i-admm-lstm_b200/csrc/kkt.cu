@@ -29,11 +29,12 @@ constexpr int kChunkCols  = kSlabCols * kKktWarps;  // 1024
 KktDims make_kkt_dims(int B, int n, int m, int num_ineq) {
   KktDims d;
   d.B = B; d.n = n; d.m = m; d.num_ineq = num_ineq;
-  // Aim for >= ~6 waves of 148 SMs x 3 resident CTAs; keep chunks >= 32 rows so the column-partial
-  // traffic (4n bytes per chunk and product) stays a few percent of the 4nR bytes streamed.
-  int R = 128;
-  const long target = 148L * 3 * 6;
-  while (R > 32 && (long)B * (cdiv(n, R) + cdiv(m, R)) < target) R /= 2;
+  // Rows per CTA depend on the problem size only, never on the batch: the grouping of the column partial sums
+  // (and with it every rounding) is then identical however a batch is sharded over calls or GPUs, so
+  // "concatenation of shards == whole batch" holds bit for bit.  64 rows keep the column-partial traffic
+  // (4n bytes per chunk and product) at ~3 % of the 4nR bytes streamed and give B*(n+m)/64 CTAs.
+  (void)B;
+  const int R = ((n > m ? n : m) >= 64) ? 64 : 32;
   d.rows_per_chunk = R;
   d.chunks_q = cdiv(n, R);
   d.chunks_a = cdiv(m, R);

@@ -198,6 +198,29 @@ def test_instance_sharding_is_bit_exact(mode):
     assert torch.equal(full.x, again.x) and torch.equal(full.H, again.H) and torch.equal(full.dual, again.dual)
 
 
+def test_sharding_bit_exact_at_config2_size():
+    """Same property at n=1000 with very different shard sizes (40 instances vs 1 + 39): the kernels' work
+    decomposition must not depend on the batch size."""
+    from bench import device_qp_batch
+    import iadmm_b200 as ia
+    B, n, mi, me, h, K = 40, 1000, 500, 500, 64, 3
+    torch.manual_seed(5)
+    model = ia.LSTM(None, 2, h, K, DEV)
+    Q, p, A0, zl, zu = device_qp_batch(B, n, mi, me, 3, DEV)
+    sc = ia.Scaling(n, mi + me, 10, DEV)
+    data = sc.scale_data(Q, p, A0, zl, zu)
+    with torch.no_grad():
+        full = model.solve(K, mi, me, *data, 6e-6)
+        parts = []
+        for s in (slice(0, 1), slice(1, B)):
+            sc2 = ia.Scaling(n, mi + me, 10, DEV)
+            d2 = sc2.scale_data(*(t_[s].contiguous() for t_ in (Q, p, A0, zl, zu)))
+            parts.append(model.solve(K, mi, me, *d2, 6e-6))
+    for k in ("x", "y", "z", "xv"):
+        assert torch.equal(getattr(full, k), torch.cat([getattr(q, k) for q in parts], 0)), k
+    assert torch.equal(full.pri, torch.cat([q.pri for q in parts], 1))
+
+
 @pytest.mark.parametrize("mode", ["simt_fp32", "tc_3xfp16", "tc_f16f8"])
 def test_config2_shape_vs_oracle(mode):
     """BASELINE config-2 dimensions (n=1000, 500+500, h=800, --scaling) at a batch/K the CPU oracle
