@@ -451,3 +451,41 @@ def test_poisoned_workspaces_change_nothing(shape, monkeypatch):
         for i, (a, b) in enumerate(zip(clean, dirty)):
             assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)), (mode, i)
             assert not torch.isnan(b).any(), (mode, i)
+
+
+def test_main_py_test_loop_with_dropins():
+    """The reference's test-mode loop (main.py:818-988), restated with the drop-in modules in place of
+    models.lstm.LSTM / methods.scaling.Scaling / utils.*: scale_data, zero state, K calls of model(t, ...), the dense
+    D / Einv / cinv*E attributes for un-scaling, obj_fn / primal_dual_loss / ls-residual on the original data.
+    Outputs are compared with the traces the REFERENCE produced on the same inputs (golden fixture)."""
+    import iadmm_b200 as ia
+    g = load_golden("solve_small_scaled")
+    B, n, mi, me, h, K, _ = (int(v) for v in g["meta"])
+    qp = golden_qp(g, device=DEV)
+    model = make_model(golden_params(g), h, K, "tc_f16f8")      # h=8 -> falls back to the fp32 cell (h % 8 == 0 but < 16)
+    sigma = float(g["sigma"])
+    num_constr = mi + me
+    scaling = ia.Scaling(n, num_constr, 10, DEV)
+    Q_pre, p_pre, A0_pre = qp["Q"], qp["p"], qp["A0"]
+    Q, p, A0, zl, zu = scaling.scale_data(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"])
+    x = torch.zeros((B, n, 1), device=DEV); y = torch.zeros((B, num_constr, 1), device=DEV)
+    z = torch.zeros((B, num_constr, 1), device=DEV); xv = torch.zeros((B, n + num_constr, 1), device=DEV)
+    H = torch.zeros((B, n + num_constr, h), device=DEV); C = torch.zeros((B, n + num_constr, h), device=DEV)
+    objs, pris, duals, lss = [], [], [], []
+    with torch.no_grad():
+        for t_ in range(K):
+            x, y, z, xv, H, C, A_tild, b_tild, rho_vec = model(t_, mi, me, x, y, z, xv, sigma, H, C, Q=Q, p=p, A0=A0,
+                                                               lb=None, ub=None, zl=zl, zu=zu)
+            x_u = torch.bmm(scaling.D, x)                       # main.py:922
+            z_u = torch.bmm(scaling.Einv, z)                    # main.py:923
+            y_u = torch.bmm(scaling.cinv * scaling.E, y)        # main.py:940
+            objs.append(ia.obj_fn(x_u, Q=Q_pre, p=p_pre).reshape(B))
+            lss.append(torch.linalg.vector_norm(torch.bmm(A_tild, xv) - b_tild, dim=(1, 2)))     # main.py:952
+            pr, du, _ = ia.primal_dual_loss(x_u, y_u, z_u, Q_pre, p_pre, A0_pre)                 # main.py:955
+            pris.append(pr.reshape(B)); duals.append(du.reshape(B))
+    assert rho_vec.shape == (B, num_constr, 1) and A_tild.shape == (B, n + num_constr, n + num_constr)
+    for name, ours, ref in (("obj", objs, "f32_obj_u"), ("pri", pris, "f32_pri_u"), ("dual", duals, "f32_dual_u"), ("ls", lss, "f32_ls")):
+        e = rel_err(torch.stack(ours), g[ref])
+        assert e < 2e-5, (name, e)
+    for k, v in (("x", x), ("y", y), ("z", z), ("xv", xv)):
+        assert rel_err(v, g["f32_" + k]) < 2e-5, k
