@@ -57,21 +57,9 @@ def parse_args():
 # synthetic inputs: generate_data.py:67-76 restated on the device (main.py:718 doubles Q on load)
 # ---------------------------------------------------------------------------------------------------
 def device_qp_batch(B, n, mi, me, seed, dev):
-    g = torch.Generator(device=dev).manual_seed(seed)
-    Q = torch.diag_embed(torch.rand((B, n), device=dev, generator=g))            # 2 * (0.5 * diag(U[0,1)))
-    p = torch.rand((B, n, 1), device=dev, generator=g)
-    A = torch.randn((B, me, n), device=dev, generator=g)
-    b = 2 * torch.rand((B, me, 1), device=dev, generator=g) - 1
-    G = torch.randn((B, mi, n), device=dev, generator=g)
-    c = torch.empty((B, mi, 1), device=dev)
-    for lo in range(0, B, 32):     # c = sum_j |G A^+|, A^+ = A^T (A A^T)^-1 for full row rank A
-        Ab, Gb = A[lo:lo + 32].double(), G[lo:lo + 32].double()
-        GAp = torch.linalg.solve(Ab @ Ab.mT, (Gb @ Ab.mT).mT).mT
-        c[lo:lo + 32] = GAp.abs().sum(dim=2, keepdim=True).float()
-    A0 = torch.cat((G, A), dim=1).contiguous()
-    zl = torch.cat((torch.full_like(c, float("-inf")), b), dim=1).contiguous()
-    zu = torch.cat((c, b), dim=1).contiguous()
-    return Q, p, A0, zl, zu
+    from iadmm_b200.data import generate_qp_batch
+    d = generate_qp_batch(B, n, mi, me, seed, dev)
+    return d["Q"], d["p"], d["A0"], d["zl"], d["zu"]
 
 
 # ---------------------------------------------------------------------------------------------------

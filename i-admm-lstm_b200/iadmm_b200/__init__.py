@@ -11,7 +11,8 @@ from ._lib import IadmmError, LIB_PATH, GATE_MODES, lib
 from .lstm import LSTM, SolveResult
 from .scaling import Scaling
 from .lu import LU
+from . import data
 from .utils import primal_dual_loss, obj_fn, ineq_dist, eq_dist, lb_dist, ub_dist
 
 __all__ = ["LSTM", "SolveResult", "Scaling", "LU", "primal_dual_loss", "obj_fn", "ineq_dist", "eq_dist",
-           "lb_dist", "ub_dist", "IadmmError", "LIB_PATH", "GATE_MODES", "lib"]
+           "lb_dist", "ub_dist", "data", "IadmmError", "LIB_PATH", "GATE_MODES", "lib"]
