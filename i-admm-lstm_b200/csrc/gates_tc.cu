@@ -136,8 +136,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// Relaxed: the barrier only orders the (already completed, tcgen05.wait::ld) TMEM reads of the epilogue against the
+// next MMAs into that accumulator; no global-memory data is published through it, so no MEMBAR is needed
+// (the .release form cost 8 % of the kernel's stall samples in fences).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
