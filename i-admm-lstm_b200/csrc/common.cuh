@@ -204,7 +204,7 @@ size_t tc_state_bytes(long rows, int h);
 int  launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g,
                      const __half* Hin_hi, const __half* Hin_lo, __half* Hout_hi, __half* Hout_lo,
                      float* H_out_f32 /* may be NULL */, float* C, float* head_part, long rows, int h,
-                     int nprod, cudaStream_t st);
+                     int nprod, cudaStream_t st, float* gates_out = nullptr);
 int  launch_split_state(const float* H, __half* hi, __half* lo, long rows, int h, int nprod, cudaStream_t st);
 int  launch_zero_state(__half* hi, __half* lo, long rows, int h, int nprod, cudaStream_t st);
 size_t tc_lo_bytes(long rows, int h);   // size of one `lo` buffer (fits both the fp16 and the packed e4m3 form)

@@ -261,6 +261,7 @@ struct TcParams {
   __half* hout_hi;        // [rows][h]
   __half* hout_lo;        // NPROD==2: two e4m3 arrays, [rows*h] residual then [rows*h] coarse copy
   float*  hout_f32;       // optional
+  float*  gates_out;      // optional (training): gate activations [rows][4h], column 4j+g
   float*  C;              // [rows][h] in place
   float*  head_part;      // [2*unit_tiles][rows]
   long rows;
@@ -388,6 +389,8 @@ __device__ __forceinline__ void lstm_epilogue_tile(const TcParams& P, const EpiR
         cnew[u] = cn;
         hnew[u] = hn;
         hp = fmaf(hn, whv[u], hp);                                                  // lstm.py:80 (partial)
+        if (P.gates_out)      // training forward: keep the activations for the hand-written backward
+          *reinterpret_cast<float4*>(P.gates_out + (size_t)R.row * 4 * P.h + 4 * (size_t)(unit0 + u)) = make_float4(gi, gf, go, gu);
       }
       st_global_v8(P.C + o, cnew);
       if (P.hout_f32) st_global_v8(P.hout_f32 + o, hnew);
@@ -876,7 +879,7 @@ static int set_smem_attr(KernelT kernel, bool* done) {
 
 int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g, const __half* Hin_hi,
                     const __half* Hin_lo, __half* Hout_hi, __half* Hout_lo, float* H_out_f32, float* C,
-                    float* head_part, long rows, int h, int nprod, cudaStream_t st) {
+                    float* head_part, long rows, int h, int nprod, cudaStream_t st, float* gates_out) {
   if (h % 8 != 0) IADMM_FAIL(IADMM_EMODE, "tensor-core gate path needs hidden_dim %% 8 == 0");
   if (rows > 0x7fffffffL - 2 * kTcBM) IADMM_FAIL(IADMM_ESHAPE, "too many rows for one launch");
   static int num_sms = 0;
@@ -916,6 +919,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.scale = reinterpret_cast<const float*>(base + L.off_scale);
   P.xv = xv; P.g = g;
   P.hout_hi = Hout_hi; P.hout_lo = Hout_lo; P.hout_f32 = H_out_f32; P.C = C; P.head_part = head_part;
+  P.gates_out = gates_out;
   P.rows = rows; P.h = h; P.q8_pitch = q8_pitch(h);
   P.unit_tiles = cdiv(h, kTcUnits);
   P.k_blocks = cdiv(h, bk);

@@ -385,6 +385,7 @@ struct TrainWs {
   KktDims d;
   KktScratch s;
   float *head_part, *zeros, *Xbar, *xvbar_cell, *gbar, *D, *u32bar, *cs_part, *w0bar, *w1bar, *bbar, *whbar, *sbar_sum;
+  __half *h_hi, *h_lo, *h_hi_out, *h_lo_out;      // tensor-core forward: fp16 / e4m3 images of H (in) and scratch (out)
   Sched* zero_sched;
   double* acc;
   int tiles, cs_parts;
@@ -395,13 +396,22 @@ static void plan_train(int B, int n, int m, int num_ineq, int h, void* base, Tra
   W->d = make_kkt_dims(B, n, m, num_ineq);
   const size_t rows = (size_t)B * (n + m);
   W->tiles = simt_gate_tiles(h);
+  const int tc_tiles = (h % 8 == 0) ? tc_gate_tiles(h) : 0;
+  const int max_tiles = W->tiles > tc_tiles ? W->tiles : tc_tiles;
   W->cs_parts = (int)((rows + kCsRows - 1) / kCsRows);
   char* p = static_cast<char*>(base);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? p + o : nullptr; };
   float* kkt = reinterpret_cast<float*>(take(kkt_scratch_floats(W->d) * sizeof(float)));
   if (base) kkt_scratch_carve(W->d, kkt, &W->s);
-  W->head_part = reinterpret_cast<float*>(take((size_t)W->tiles * rows * sizeof(float)));
+  W->head_part = reinterpret_cast<float*>(take((size_t)max_tiles * rows * sizeof(float)));
+  W->h_hi = W->h_lo = W->h_hi_out = W->h_lo_out = nullptr;
+  if (h % 8 == 0) {
+    W->h_hi = reinterpret_cast<__half*>(take(rows * (size_t)h * sizeof(__half)));
+    W->h_lo = reinterpret_cast<__half*>(take(tc_lo_bytes((long)rows, h)));
+    W->h_hi_out = reinterpret_cast<__half*>(take(rows * (size_t)h * sizeof(__half)));
+    W->h_lo_out = reinterpret_cast<__half*>(take(tc_lo_bytes((long)rows, h)));
+  }
   W->zeros = reinterpret_cast<float*>(take(rows * sizeof(float)));
   W->zero_sched = reinterpret_cast<Sched*>(take(sizeof(Sched)));
   W->acc = reinterpret_cast<double*>(take(4 * sizeof(double)));
@@ -451,7 +461,7 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
                    const float* zu, const float* x, const float* y, const float* z, const float* xv, const float* H,
                    const float* C, float* x_o, float* y_o, float* z_o, float* xv_o, float* H_o, float* C_o,
                    float* g_save, float* w_save, float* gates_save, int B, int n, int num_ineq, int num_eq, int h,
-                   int length, int t, float sigma, void* workspace, size_t workspace_bytes, void* stream) {
+                   int length, int t, float sigma, int mode, void* workspace, size_t workspace_bytes, void* stream) {
   const int m = num_ineq + num_eq;
   if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || t < 0 || t >= length)
     IADMM_FAIL(IADMM_ESHAPE, "step_fwd: B=%d n=%d ineq=%d eq=%d h=%d t=%d length=%d", B, n, num_ineq, num_eq, h, t, length);
@@ -486,8 +496,23 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
   if ((rc = launch_kkt_pass2(W.d, Q, A0, W.s, st))) return rc;
   if ((rc = launch_kkt_combine2(W.d, sk, sigma, W.s, st))) return rc;
   IADMM_CUDA(cudaMemcpyAsync(g_save, W.s.g, rows * fb, cudaMemcpyDeviceToDevice, st));
-  if ((rc = launch_gates_simt(packed_weights, L, xv, W.s.g, H, H_o, C_o, W.head_part, (long)rows, h, st, gates_save))) return rc;
-  return launch_tail(W.d, W.head_part, W.tiles, b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
+  // gate contraction of the forward: fp32 CUDA cores, or the tensor-core kernel (same arithmetic as the solve) with
+  // the state converted at the boundary; both keep the gate activations for the backward
+  int nprod = 0;
+  if (mode == IADMM_GATES_TC_3XFP16 && h % 8 == 0) nprod = 3;
+  else if (mode == IADMM_GATES_TC_F16F8 && h % 16 == 0) nprod = 2;
+  else if (mode == IADMM_GATES_TC_F16F8 && h % 8 == 0) nprod = 3;
+  else if (mode == IADMM_GATES_TC_1XFP16 && h % 8 == 0) nprod = 1;
+  else if (mode != IADMM_GATES_SIMT_FP32 && h % 8 == 0) IADMM_FAIL(IADMM_EMODE, "step_fwd: unknown gate mode %d", mode);
+  if (nprod == 0) {
+    if ((rc = launch_gates_simt(packed_weights, L, xv, W.s.g, H, H_o, C_o, W.head_part, (long)rows, h, st, gates_save))) return rc;
+    return launch_tail(W.d, W.head_part, W.tiles, b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
+  }
+  if ((rc = launch_split_state(H, W.h_hi, W.h_lo, (long)rows, h, nprod, st))) return rc;
+  if (nprod == 2) IADMM_CUDA(cudaMemsetAsync(W.h_lo_out, 0, tc_lo_bytes((long)rows, h), st));
+  if ((rc = launch_gates_tc(packed_weights, L, xv, W.s.g, W.h_hi, W.h_lo, W.h_hi_out, W.h_lo_out, H_o, C_o, W.head_part,
+                            (long)rows, h, nprod, st, gates_save))) return rc;
+  return launch_tail(W.d, W.head_part, tc_gate_tiles(h), b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
 }
 
 int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,

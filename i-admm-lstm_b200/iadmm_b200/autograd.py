@@ -52,7 +52,7 @@ class StepFunction(torch.autograd.Function):
             _lib.check(L.iadmm_step_fwd(_lib.ptr(packed), _lib.ptr(Q), _lib.ptr(p), _lib.ptr(A0), _lib.ptr(zl), _lib.ptr(zu),
                                         _lib.ptr(x), _lib.ptr(y), _lib.ptr(z), _lib.ptr(xv), _lib.ptr(H), _lib.ptr(C),
                                         *[_lib.ptr(o) for o in outs], _lib.ptr(g_save), _lib.ptr(w_save), _lib.ptr(gates),
-                                        B, n, int(num_ineq), int(num_eq), h, model.length, int(t), float(sigma),
+                                        B, n, int(num_ineq), int(num_eq), h, model.length, int(t), float(sigma), model._mode(),
                                         _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         ctx.model, ctx.meta = model, (int(t), int(num_ineq), int(num_eq), float(sigma), B, n, m, h)
         ctx.save_for_backward(Q, p, A0, zl, zu, x, y, z, xv, H, C, outs[3], outs[4], g_save, w_save, gates)

@@ -150,7 +150,8 @@ int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, 
  * primal_dual_loss (utils.py:68-71) in the training loop main.py:336-358.  One differentiable iteration =
  * iadmm_step_fwd (out of place, saves g = K^T(K xv - rhs), w = K xv - rhs and the gate activations) +
  * iadmm_step_bwd (hand-written adjoint; reuses the two streaming KKT passes, two fp32 GEMMs for the gate
- * products).  fp32 CUDA-core arithmetic throughout.  Adam (main.py:191) stays in PyTorch; data-parallel
+ * products).  The forward gate contraction runs in `mode` (IADMM_GATES_*, tensor cores by default like the solve);
+ * the backward is fp32 CUDA-core arithmetic.  Adam (main.py:191) stays in PyTorch; data-parallel
  * training all-reduces the flat gradient buffer over NCCL (iadmm_b200/dist.py).
  *
  * grad_flat: [iadmm_param_count] floats in state_dict order (W_i,U_i,b_i, W_f,.., W_u,U_u,b_u, W_h, b_h, rho,
@@ -164,7 +165,7 @@ int iadmm_step_fwd(const void* packed_weights,
                    const float* x, const float* y, const float* z, const float* xv, const float* H, const float* C,
                    float* x_o, float* y_o, float* z_o, float* xv_o, float* H_o, float* C_o,
                    float* g_save, float* w_save, float* gates_save,
-                   int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
+                   int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma, int mode,
                    void* workspace, size_t workspace_bytes, void* stream);
 int iadmm_step_bwd(const void* packed_weights,
                    const float* Q, const float* p, const float* A0, const float* zl, const float* zu,

@@ -31,9 +31,9 @@ def oracle_window(prm, qp, mi, me, h, TL, outer_T, state=None, dtype=torch.float
     return float(loss), {k: v.grad for k, v in p64.items()}, [s.detach() for s in (x, y, z, xv, H, C)]
 
 
-def our_window(prm, qp, mi, me, h, TL, outer_T, state=None):
+def our_window(prm, qp, mi, me, h, TL, outer_T, state=None, mode="simt_fp32"):
     import iadmm_b200 as ia
-    model = ia.LSTM(None, 2, h, outer_T, DEV, gate_mode="simt_fp32")
+    model = ia.LSTM(None, 2, h, outer_T, DEV, gate_mode=mode)
     with torch.no_grad():
         for k, v in prm.items():
             getattr(model, k).copy_(v.to(DEV))
@@ -57,9 +57,10 @@ def our_window(prm, qp, mi, me, h, TL, outer_T, state=None):
     return float(loss), {k: getattr(model, k).grad for k in prm}, [s.detach() for s in (x, y, z, xv, H, C)], model
 
 
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16f8"])
 @pytest.mark.parametrize("shape", [(2, 12, 5, 7, 8, 4, 1.0), (3, 40, 12, 16, 32, 5, 3.0), (2, 100, 50, 50, 64, 6, 1.0),
                                    (2, 24, 10, 0, 16, 4, 2.0)])
-def test_window_gradients_match_autograd(shape):
+def test_window_gradients_match_autograd(shape, mode):
     from oracle import iadmm_oracle as orc
     B, n, mi, me, h, TL, wscale = shape
     outer_T = TL + 2
@@ -68,12 +69,12 @@ def test_window_gradients_match_autograd(shape):
         qp["zl"][:] = -0.7                     # two-sided inequality rows exercise both clip branches
     prm = orc.lstm_parameters(h, outer_T, seed=61, scale=wscale)
     ref_loss, ref_g, ref_state = oracle_window(prm, qp, mi, me, h, TL, outer_T)
-    loss, g, state, _ = our_window(prm, qp, mi, me, h, TL, outer_T)
+    loss, g, state, _ = our_window(prm, qp, mi, me, h, TL, outer_T, mode=mode)
     assert abs(loss - ref_loss) <= 2e-5 * abs(ref_loss)
     errs = {k: rel_err(g[k], ref_g[k]) for k in ref_g if float(ref_g[k].abs().max()) > 0}
-    print(shape, {k: f"{v:.1e}" for k, v in errs.items()})
+    print(shape, mode, {k: f"{v:.1e}" for k, v in errs.items()})
     for k, v in errs.items():
-        assert v < 2e-4, (k, v)
+        assert v < (2e-4 if mode == "simt_fp32" else 5e-4), (k, v)
     # rows >= TL of the schedule never receive gradient (main.py:338 restarts t at 0)
     assert float(g["rho"][TL:].abs().max()) == 0.0 and float(g["alpha"][TL:].abs().max()) == 0.0
     # fp32 state vs the fp64 run; y = y + rho (z~ - z) cancels catastrophically on equality rows, so its fp32

@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=2); ap.add_argument("--tl", type=int, default=100)
 ap.add_argument("--windows", type=int, default=3); ap.add_argument("--n", type=int, default=1000)
 ap.add_argument("--hidden", type=int, default=800); ap.add_argument("--lr", type=float, default=5e-5)
+ap.add_argument("--gate-mode", default="tc_f16f8")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr_ = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr_); dev = torch.device("cuda", lr_)
@@ -24,7 +25,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 n, mi, me, h, TL, B = a.n, a.n // 2, a.n // 2, a.hidden, a.tl, a.batch
 torch.manual_seed(17)
-model = ia.LSTM(None, 2, h, TL, dev, gate_mode="simt_fp32")
+model = ia.LSTM(None, 2, h, TL, dev, gate_mode=a.gate_mode)
 opt = torch.optim.Adam(model.parameters(), lr=a.lr, weight_decay=0.0)          # main.py:191
 Q, p, A0, zl, zu = device_qp_batch(B, n, mi, me, 17 + rank, dev)
 sc = ia.Scaling(n, mi + me, 10, dev)
