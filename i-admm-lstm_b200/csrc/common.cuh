@@ -62,6 +62,8 @@ struct WeightLayout {
                       //           dequant = 1/(u_scale*2^14), |U|max, unused
   size_t off_uhi;     // fp16 [4h][h]   row 4*j+g, K-major (k = input unit): tcgen05 B operand, hi part
   size_t off_ulo;     // fp16 [4h][h]   lo part
+  size_t off_u32hi;   // fp16 [h][4h]   hi part of U*2^s in the fp32 image's layout (K-major for H_bar = D U^T)
+  size_t off_u32lo;   // fp16 [h][4h]   lo part
   size_t off_uq8;     // e4m3 [4h][q8_pitch(h)]: per 64-wide K block 64 B of residual (U*2^s - fp16(U*2^s)) * 2^6 followed by
                       //                64 B of the coarse copy fp16(U*2^s) * 2^-5   (F16F8 mode; one 128-byte TMA row)
   size_t total;

@@ -29,6 +29,8 @@ WeightLayout weight_layout(int h, int length) {
   L.off_scale = take(4 * sizeof(float));
   L.off_uhi   = take(4 * H * H * sizeof(__half));
   L.off_ulo   = take(4 * H * H * sizeof(__half));
+  L.off_u32hi = take(4 * H * H * sizeof(__half));
+  L.off_u32lo = take(4 * H * H * sizeof(__half));
   L.off_uq8   = take(4 * H * q8_pitch(h));
   L.total = off;
   return L;
@@ -89,7 +91,8 @@ __device__ __forceinline__ uint8_t to_e4m3(float v) {
 }
 
 __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __restrict__ u32, __half* __restrict__ uhi,
-                                                     __half* __restrict__ ulo, uint8_t* __restrict__ uq8,
+                                                     __half* __restrict__ ulo, __half* __restrict__ u32hi,
+                                                     __half* __restrict__ u32lo, uint8_t* __restrict__ uq8,
                                                      float* __restrict__ scale) {
   const float mx = scale[2];
   float us = 1.f;
@@ -112,6 +115,8 @@ __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __
     const __half lo = __float2half_rn(vs - __half2float(hi));
     uhi[(size_t)c * h + k] = hi;
     ulo[(size_t)c * h + k] = lo;
+    u32hi[i] = hi;
+    u32lo[i] = lo;
     uint8_t* q = uq8 + (size_t)c * q8_pitch_dev(h) + (size_t)(k >> 6) * 128 + (k & 63);
     q[0]  = to_e4m3(ldexpf(vs - __half2float(hi), kQ8ULoShift));      // residual
     q[64] = to_e4m3(ldexpf(__half2float(hi), kQ8UHiShift));           // coarse copy
@@ -141,6 +146,8 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
   pack_u_kernel<<<blocks, 256, 0, st>>>(S, h, reinterpret_cast<float*>(base + L.off_u32),
                                         reinterpret_cast<__half*>(base + L.off_uhi),
                                         reinterpret_cast<__half*>(base + L.off_ulo),
+                                        reinterpret_cast<__half*>(base + L.off_u32hi),
+                                        reinterpret_cast<__half*>(base + L.off_u32lo),
                                         reinterpret_cast<uint8_t*>(base + L.off_uq8), scale);
   IADMM_LAUNCH_CHECK("pack_u_kernel");
   return IADMM_OK;

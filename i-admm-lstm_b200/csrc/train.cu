@@ -15,10 +15,28 @@
 // to ~1e-5); tensor-core backward kernels are future work.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace iadmm {
 
 int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, const float* x, const float* y,
                            const KktScratch& s, cudaStream_t st);
+// gemm_tc.cu
+int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi, const __half* B_lo, float* C,
+                      const float* scale, long M, long N, long K, long lda, long ldb, long ldc, cudaStream_t st);
+int launch_absmax(const float* X, size_t count, float* out, cudaStream_t st);
+int launch_gemm_scales(const float* absmax, const float* other, float* scales, cudaStream_t st);
+int launch_split_rows(const float* X, size_t count, const float* scale, __half* hi, __half* lo, cudaStream_t st);
+int launch_split_transpose(const float* X, long R, long Cc, long Rp, const float* scale, __half* hi, __half* lo, cudaStream_t st);
+
+static bool use_tc_backward() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IADMM_TRAIN_SIMT_GEMM");     // development switch: 1 = fp32 CUDA-core GEMMs in the backward
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // ------------------------------------------------------------------------------------------------
 // flat gradient buffer layout = the state_dict order of models/lstm.py:21-41
@@ -386,6 +404,9 @@ struct TrainWs {
   KktScratch s;
   float *head_part, *zeros, *Xbar, *xvbar_cell, *gbar, *D, *u32bar, *cs_part, *w0bar, *w1bar, *bbar, *whbar, *sbar_sum;
   __half *h_hi, *h_lo, *h_hi_out, *h_lo_out;      // tensor-core forward: fp16 / e4m3 images of H (in) and scratch (out)
+  __half *d_hi, *d_lo, *dt_hi, *dt_lo, *ht_hi, *ht_lo;   // tensor-core backward GEMM operands (D, D^T, H^T as fp16 hi/lo)
+  float *gscal;                                   // [8]: absmax(D), then the scales of gemm_scales_kernel at [4..6]
+  long rows_p;                                    // row count padded to 8 (pitch of the transposed operands)
   Sched* zero_sched;
   double* acc;
   int tiles, cs_parts;
@@ -411,6 +432,17 @@ static void plan_train(int B, int n, int m, int num_ineq, int h, void* base, Tra
     W->h_lo = reinterpret_cast<__half*>(take(tc_lo_bytes((long)rows, h)));
     W->h_hi_out = reinterpret_cast<__half*>(take(rows * (size_t)h * sizeof(__half)));
     W->h_lo_out = reinterpret_cast<__half*>(take(tc_lo_bytes((long)rows, h)));
+  }
+  W->rows_p = (long)((rows + 7) / 8 * 8);
+  W->d_hi = W->d_lo = W->dt_hi = W->dt_lo = W->ht_hi = W->ht_lo = nullptr;
+  W->gscal = reinterpret_cast<float*>(take(8 * sizeof(float)));
+  if (h % 16 == 0) {
+    W->d_hi = reinterpret_cast<__half*>(take(rows * 4 * (size_t)h * sizeof(__half)));
+    W->d_lo = reinterpret_cast<__half*>(take(rows * 4 * (size_t)h * sizeof(__half)));
+    W->dt_hi = reinterpret_cast<__half*>(take((size_t)W->rows_p * 4 * h * sizeof(__half)));
+    W->dt_lo = reinterpret_cast<__half*>(take((size_t)W->rows_p * 4 * h * sizeof(__half)));
+    W->ht_hi = reinterpret_cast<__half*>(take((size_t)W->rows_p * h * sizeof(__half)));
+    W->ht_lo = reinterpret_cast<__half*>(take((size_t)W->rows_p * h * sizeof(__half)));
   }
   W->zeros = reinterpret_cast<float*>(take(rows * sizeof(float)));
   W->zero_sched = reinterpret_cast<Sched*>(take(sizeof(Sched)));
@@ -577,8 +609,29 @@ int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, c
   rowdot2_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(W.D, wc, (long)rows, h4, W.xvbar_cell, W.gbar);
   IADMM_LAUNCH_CHECK("rowdot2_kernel");
   // 5. the two GEMMs: H_bar = D U^T ; U_bar = H^T D
-  if ((rc = launch_sgemm<false, true>(W.D, u32, gH, (long)rows, h, h4, h4, h4, h, st))) return rc;
-  if ((rc = launch_sgemm<true, false>(H, W.D, W.u32bar, h, h4, (long)rows, h, h4, h4, st))) return rc;
+  if (use_tc_backward() && h % 16 == 0 && rows / 32 < 65535) {
+    // tensor cores, fp16 hi/lo split of D * s_D (s_D from max|D|), U * s_U, H * 2^14: fp32-class products
+    const float* wscale = reinterpret_cast<const float*>(wbase + L.off_scale);            // [0] = s_U
+    const __half* u32hi = reinterpret_cast<const __half*>(wbase + L.off_u32hi);
+    const __half* u32lo = reinterpret_cast<const __half*>(wbase + L.off_u32lo);
+    if ((rc = launch_absmax(W.D, rows * (size_t)h4, W.gscal, st))) return rc;
+    if ((rc = launch_gemm_scales(W.gscal, wscale, W.gscal + 4, st))) return rc;          // [4] s_D, [5] 1/(s_D s_U), [6] 1/(s_D 2^14)
+    if ((rc = launch_split_rows(W.D, rows * (size_t)h4, W.gscal + 4, W.d_hi, W.d_lo, st))) return rc;
+    if (W.rows_p != (long)rows) {        // zero the pitch padding of the transposed operands
+      IADMM_CUDA(cudaMemsetAsync(W.dt_hi, 0, (size_t)W.rows_p * h4 * sizeof(__half), st));
+      IADMM_CUDA(cudaMemsetAsync(W.dt_lo, 0, (size_t)W.rows_p * h4 * sizeof(__half), st));
+      IADMM_CUDA(cudaMemsetAsync(W.ht_hi, 0, (size_t)W.rows_p * h * sizeof(__half), st));
+      IADMM_CUDA(cudaMemsetAsync(W.ht_lo, 0, (size_t)W.rows_p * h * sizeof(__half), st));
+    }
+    if ((rc = launch_split_transpose(W.D, (long)rows, h4, W.rows_p, W.gscal + 4, W.dt_hi, W.dt_lo, st))) return rc;
+    if ((rc = launch_split_transpose(H, (long)rows, h, W.rows_p, nullptr, W.ht_hi, W.ht_lo, st))) return rc;
+    if ((rc = launch_tc_gemm_nt(W.d_hi, W.d_lo, u32hi, u32lo, gH, W.gscal + 5, (long)rows, h, h4, h4, h4, h, st))) return rc;
+    if ((rc = launch_tc_gemm_nt(W.ht_hi, W.ht_lo, W.dt_hi, W.dt_lo, W.u32bar, W.gscal + 6, h, h4, (long)rows, W.rows_p, W.rows_p,
+                                h4, st))) return rc;
+  } else {
+    if ((rc = launch_sgemm<false, true>(W.D, u32, gH, (long)rows, h, h4, h4, h4, h, st))) return rc;
+    if ((rc = launch_sgemm<true, false>(H, W.D, W.u32bar, h, h4, (long)rows, h, h4, h4, st))) return rc;
+  }
   // 6. KKT adjoint: w_bar = K g_bar (pass 1 with zero rhs), then K^T w_bar (pass 2)
   if ((rc = launch_kkt_pass1(W.d, Q, A0, W.gbar, W.zeros, W.zeros, W.s, st))) return rc;
   if ((rc = launch_kkt_combine1(W.d, W.zeros, W.gbar, W.zeros, W.zeros, W.zeros, sk, sigma, W.s, nullptr, nullptr, nullptr,
