@@ -489,3 +489,61 @@ def test_main_py_test_loop_with_dropins():
         assert e < 2e-5, (name, e)
     for k, v in (("x", x), ("y", y), ("z", z), ("xv", xv)):
         assert rel_err(v, g["f32_" + k]) < 2e-5, k
+
+
+def test_schedule_offset_continuation():
+    """iterations t0..t0+K-1 of the learned rho/alpha schedule: solve(3) followed by solve(4, t0=3) from the carried
+    state equals solve(7) (fp32 cell: bit for bit; tensor-core modes keep H in fp16/e4m3 images between iterations, so
+    the fp32 round trip at the call boundary shows up at the 1e-6 level)."""
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, K = 3, 48, 12, 20, 32, 7
+    qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=101).items()}
+    prm = orc.lstm_parameters(h, K, seed=101, scale=3.0)
+    for mode, tol in (("simt_fp32", 0.0), ("tc_f16f8", 5e-6)):
+        model = make_model(prm, h, K, mode)
+        args = (qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6)
+        with torch.no_grad():
+            whole = model.solve(K, mi, me, *args)
+            a = model.solve(3, mi, me, *args)
+            b = model.solve(4, mi, me, *args, state=(a.x, a.y, a.z, a.xv, a.H, a.C), t0=3)
+        for k in ("x", "y", "z", "xv", "H", "C"):
+            assert rel_err(getattr(b, k), getattr(whole, k)) <= tol, (mode, k)
+        assert rel_err(torch.cat((a.pri, b.pri)), whole.pri) <= max(tol, 1e-7)
+
+
+def test_error_behaviour():
+    """Error codes of the C ABI surface as exceptions with the library's message; nothing is silently clamped."""
+    import ctypes
+    import iadmm_b200 as ia
+    from iadmm_b200 import _lib
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, K = 2, 16, 4, 4, 16, 3
+    qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=103).items()}
+    model = make_model(orc.lstm_parameters(h, K, seed=103), h, K, "tc_f16f8")
+    args = (qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6)
+    with torch.no_grad():
+        with pytest.raises(ia.IadmmError, match="schedule length"):          # like the reference's IndexError (lstm.py:60)
+            model.solve(K + 1, mi, me, *args)
+        with pytest.raises(ia.IadmmError, match="schedule length"):
+            model.solve(2, mi, me, *args, t0=2)
+        with pytest.raises(ValueError):                                        # A0 does not match num_ineq + num_eq
+            model.solve(K, mi + 1, me, *args)
+        with pytest.raises(ia.IadmmError, match="contiguous"):
+            _lib.ptr(qp["A0"].transpose(1, 2))
+        r = model.solve(0, mi, me, *args)                                      # K = 0 is a no-op
+        assert float(r.x.abs().max()) == 0.0
+    L = _lib.lib()
+    nbytes = ctypes.c_size_t()
+    _lib.check(L.iadmm_solve_workspace_bytes(B, n, mi + me, h, 3, ctypes.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=DEV)
+    st = [torch.zeros(s, device=DEV) for s in ((B, n), (B, mi + me), (B, mi + me), (B, n + mi + me), (B, n + mi + me, h), (B, n + mi + me, h))]
+    base = [_lib.ptr(model.packed_weights())] + [_lib.ptr(qp[k]) for k in ("Q", "p", "A0", "zl", "zu")] + [None, None, None] + \
+           [_lib.ptr(s) for s in st] + [None] * 5
+    tail = [B, n, mi, me, h, K, 0, K, 6e-6, 3, 0]
+    assert L.iadmm_solve(*base, *tail, _lib.ptr(ws), 1024, _lib.stream_ptr()) == -5                      # IADMM_EWORK
+    assert b"workspace too small" in L.iadmm_last_error()
+    assert L.iadmm_solve(*base, *tail[:9], 77, 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()) == -6     # IADMM_EMODE
+    bad = list(base); bad[1] = None
+    assert L.iadmm_solve(*bad, *tail, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()) == -2                 # IADMM_EALIGN (NULL Q)
+    assert L.iadmm_solve(*base, *tail, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()) == 0
+    torch.cuda.synchronize()
