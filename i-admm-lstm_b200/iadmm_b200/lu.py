@@ -2,12 +2,40 @@
 
 Stage II is OUTSIDE the accelerated path: it is exact OSQP-style ADMM, one dense LU of
 the KKT matrix and a triangular solve per iteration.  This module keeps `main.py --feas_rest` working on a B200
-next to the drop-in `LSTM`/`Scaling`: the factorisation and the solves are plain library calls
-(`torch.linalg.lu_factor` / `lu_solve`, i.e. cuSOLVER/cuBLAS -- no hand-written kernel yet), the K matrix
-comes from `LSTM.forward`'s return tuple (`iadmm_build_kkt`).
+next to the drop-in `LSTM`/`Scaling`.  The factorisation (`iadmm_lu_factor`, csrc/lu.cu: register-resident
+16-column panels, partial pivoting with LAPACK's first-maximum rule) and the per-iteration triangular solves
+(`iadmm_lu_solve`) are the library's own kernels; the K matrix comes from `LSTM.forward`'s return tuple
+(`iadmm_build_kkt`).  `lu`/`piv` in the return tuple are opaque to the caller exactly as in the reference
+(main.py only hands them back): `lu` is the packed L\\U factor [B,N,N], `piv` an int32 tensor [2,B,N] holding
+the interchange sequence and the row permutation derived from it.
 """
 import torch
 import torch.nn as nn
+
+from . import _lib
+
+
+def lu_factor(K):
+    """Batched LU of K [B,N,N] (fp32, CUDA).  Returns (lu, piv, info): see include/iadmm.h."""
+    _lib.require_cuda(K)
+    B, N = K.shape[0], K.shape[1]
+    lu = K.detach().to(torch.float32).contiguous().clone()
+    piv = torch.empty(2, B, N, dtype=torch.int32, device=K.device)
+    info = torch.empty(B, dtype=torch.int32, device=K.device)
+    with torch.cuda.device(K.device):
+        _lib.check(_lib.lib().iadmm_lu_factor(_lib.ptr(lu), _lib.ptr(piv[0]), _lib.ptr(piv[1]), _lib.ptr(info), B, N,
+                                              _lib.stream_ptr()))
+    return lu, piv, info
+
+
+def lu_solve(lu, piv, rhs):
+    """Solves K x = rhs with the factors of `lu_factor`; rhs [B,N] or [B,N,1]; returns x with rhs's shape."""
+    _lib.require_cuda(lu)
+    B, N = lu.shape[0], lu.shape[1]
+    x = rhs.detach().to(torch.float32).reshape(B, N).contiguous().clone()
+    with torch.cuda.device(lu.device):
+        _lib.check(_lib.lib().iadmm_lu_solve(_lib.ptr(lu), _lib.ptr(piv[1]), _lib.ptr(x), B, N, _lib.stream_ptr()))
+    return x.reshape(rhs.shape)
 
 
 class LU(nn.Module):
@@ -31,8 +59,8 @@ class LU(nn.Module):
                 top = torch.cat((Q + sigma * torch.eye(n, device=Q.device), A0.transpose(1, 2)), dim=2)
                 bot = torch.cat((A0, torch.diag_embed(-inv_rho.squeeze(-1))), dim=2)
                 A_tild = torch.cat((top, bot), dim=1)
-            lu, piv = torch.linalg.lu_factor(A_tild)
-        xv = torch.linalg.lu_solve(lu, piv, b_tild)
+            lu, piv, _ = lu_factor(A_tild)
+        xv = lu_solve(lu, piv, b_tild)
         n = x.shape[1]
         x_tild, v = xv[:, :n, :], xv[:, n:, :]
         z_tild = z + inv_rho * (v - y)

@@ -145,6 +145,17 @@ int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, 
                     int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
                     void* stream);
 
+/* ---- Stage II (feasibility restoration): batched dense LU --------------------------------------------
+ * Replaces: `torch.lu(A_tild, pivot=True)` (models/lu.py:30) -- LAPACK getrf semantics, partial pivoting,
+ * first maximum.  Kmat [B,N,N] row-major is overwritten by L (unit, below the diagonal) and U; piv [B,N] is
+ * the 0-based interchange sequence, perm [B,N] the resulting row permutation (row i of P*K = row perm[i] of
+ * K), info [B] (may be NULL) is 0 or 1 + the index of the first exactly-zero pivot.  N <= 4096. */
+int iadmm_lu_factor(float* Kmat, int* piv, int* perm, int* info, int B, int N, void* stream);
+
+/* Replaces: `torch.lu_solve(b_tild, lu, piv)` (models/lu.py:35), once per Stage-II iteration.
+ * rhs [B,N] is overwritten by the solution. */
+int iadmm_lu_solve(const float* LU, const int* perm, float* rhs, int B, int N, void* stream);
+
 /* ---- training: truncated BPTT through the unroll -------------------------------------------------------
  * Replaces: the autograd tape PyTorch records through LSTM.forward (models/lstm.py:47-96) and
  * primal_dual_loss (utils.py:68-71) in the training loop main.py:336-358.  One differentiable iteration =
