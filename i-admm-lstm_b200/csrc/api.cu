@@ -188,6 +188,11 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   const int nprod = (mode == IADMM_GATES_TC_3XFP16) ? 3 : (mode == IADMM_GATES_TC_F16F8 ? 2 : 1);
   const bool want_trace = pri_trace || dual_trace || pri_trace_u || dual_trace_u || metric_trace;
 
+  // small instances: one persistent CTA per instance keeps the whole iteration on chip (resident.cu)
+  if (tc && resident_eligible(n, m, h, nprod, flags))
+    return launch_solve_resident(packed_weights, L, Q, p, A0, zl, zu, sd, se, sc, x, y, z, xv, H, C, pri_trace, dual_trace,
+                                 pri_trace_u, dual_trace_u, metric_trace, B, n, m, num_ineq, t0, K, sigma, nprod, flags, st);
+
   float* hbuf[2] = {H, ws.h_alt};
   int cur = 0;
   if (tc) {

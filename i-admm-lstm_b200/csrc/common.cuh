@@ -212,6 +212,13 @@ int  launch_zero_state(__half* hi, __half* lo, long rows, int h, int nprod, cuda
 size_t tc_lo_bytes(long rows, int h);   // size of one `lo` buffer (fits both the fp16 and the packed e4m3 form)
 
 // O(N) tail: xv -= head ; x,z,y updates (models/lstm.py:82-94)
+// on-chip-resident solve for small instances (resident.cu)
+bool resident_eligible(int n, int m, int h, int nprod, int flags);
+int launch_solve_resident(const void* packed, const WeightLayout& L, const float* Q, const float* p, const float* A0,
+                          const float* zl, const float* zu, const float* sd, const float* se, const float* sc, float* x, float* y,
+                          float* z, float* xv, float* H, float* C, float* pri, float* dual, float* pri_u, float* dual_u,
+                          float* metrics, int B, int n, int m, int num_ineq, int t0, int K, float sigma, int nprod, int flags,
+                          cudaStream_t st);
 int launch_tail(const KktDims& d, const float* head_part, int tiles, const float* b_h, const Sched* sched_t,
                 const float* zl, const float* zu, float* x, float* y, float* z, float* xv, cudaStream_t st);
 

@@ -27,9 +27,9 @@
 // read from HBM once per iteration.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "gate_math.cuh"
 
 #include <stdlib.h>
-#include <cuda_fp8.h>
 
 namespace iadmm {
 
@@ -44,33 +44,6 @@ constexpr int kTcChunk = 32;                     // TMEM columns per epilogue st
 
 int tc_gate_tiles(int h) { return 2 * cdiv(h, kTcUnits); }   // two head partials per unit tile
 size_t tc_state_bytes(long rows, int h) { return (size_t)rows * h * sizeof(__half) * 4; }
-
-// Transcendentals of the epilogue: MUFU ex2/rcp based, relative error ~2e-7 (measured against fp64 on the
-// host for the polynomial; the gate-GEMM split error and fp32 summation order are larger).
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float sigmoid_fast(float x) {            // 1 / (1 + 2^(-x log2 e))
-  return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f));
-}
-// tanh: odd minimax polynomial x + x^3 q(x^2) for |x| < 0.55 (rel err 1e-7 in fp32), 1 - 2/(e^{2x}+1) beyond;
-// both evaluated, selected without a branch.
-__device__ __forceinline__ float tanh_fast(float x) {
-  const float t = x * x;
-  float q = fmaf(t, 0.016433170300270403f, -0.052669384762106176f);
-  q = fmaf(q, t, 0.133206865150314f);
-  q = fmaf(q, t, -0.33332945121698027f);
-  const float small = fmaf(x * t, q, x);
-  const float big = fmaf(-2.0f, rcp_approx(ex2_approx(x * 2.8853900817779268f) + 1.0f), 1.0f);
-  return (fabsf(x) < 0.55f) ? small : big;
-}
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
@@ -93,23 +66,6 @@ struct TcParams {
   long num_tiles;
   size_t q8_pitch;        // bytes per row of the packed e4m3 image (NPROD 2)
 };
-
-// 256-bit global accesses (sm_100): one request per 32-byte sector instead of two
-__device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void st_global_v8u(void* p, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
-               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
 
 // The fused LSTM-cell epilogue of one tile, executed by the 8 epilogue warps of a CTA (thread = one
 // accumulator lane = one coordinate row; a warp pair splits the tile's 8 column chunks of 8 hidden units).
@@ -138,36 +94,6 @@ __device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRow
 #pragma unroll
       for (int u = 0; u < 8; ++u) R.c[cc][u] = 0.f;
     }
-  }
-}
-
-// fp16 / e4m3 images of 8 hidden values for the next iteration's MMAs:
-//   hi  = fp16(H*2^14)                                   (4 x half2)
-//   lo  = fp16(H*2^14 - hi)                              (NPROD 3)
-//   res = e4m3((H*2^14 - hi) * 2^5), crs = e4m3(H*2^14 * 2^-6)   (NPROD 2; 2 words each)
-template <int NPROD>
-__device__ __forceinline__ void split_hidden8(const float (&hnew)[8], uint32_t (&hi)[4], uint32_t (&lo)[4], uint32_t (&res)[2],
-                                              uint32_t (&crs)[2]) {
-  const float hs = (float)(1 << kHShift);
-  __nv_fp8x2_storage_t r2[4], c2[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const float s0 = hnew[2 * u] * hs, s1 = hnew[2 * u + 1] * hs;
-    const __half2 hh = __floats2half2_rn(s0, s1);
-    hi[u] = *reinterpret_cast<const uint32_t*>(&hh);
-    const float2 back = __half22float2(hh);
-    if (NPROD == 3) {
-      const __half2 hl = __floats2half2_rn(s0 - back.x, s1 - back.y);
-      lo[u] = *reinterpret_cast<const uint32_t*>(&hl);
-    }
-    if (NPROD == 2) {
-      r2[u] = __nv_cvt_float2_to_fp8x2(make_float2((s0 - back.x) * 32.0f, (s1 - back.y) * 32.0f), __NV_SATFINITE, __NV_E4M3);
-      c2[u] = __nv_cvt_float2_to_fp8x2(make_float2(s0 * 0.015625f, s1 * 0.015625f), __NV_SATFINITE, __NV_E4M3);
-    }
-  }
-  if (NPROD == 2) {
-    res[0] = (uint32_t)r2[0] | ((uint32_t)r2[1] << 16); res[1] = (uint32_t)r2[2] | ((uint32_t)r2[3] << 16);
-    crs[0] = (uint32_t)c2[0] | ((uint32_t)c2[1] << 16); crs[1] = (uint32_t)c2[2] | ((uint32_t)c2[3] << 16);
   }
 }
 

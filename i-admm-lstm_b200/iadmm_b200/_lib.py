@@ -20,6 +20,7 @@ GATE_MODES = {"simt_fp32": GATES_SIMT_FP32, "tc_3xfp16": GATES_TC_3XFP16, "tc_1x
 
 F_ZERO_STATE = 1
 F_SKIP_FINAL_RESID = 2
+F_STREAMING = 4
 
 # every symbol include/iadmm.h declares, with its argument types
 _P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t

@@ -121,9 +121,10 @@ class LSTM(nn.Module):
 
     # -- K fused iterations -------------------------------------------------------------------
     def solve(self, K, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state=None, t0=0, scaling=None,
-              traces=True, inplace=False):
+              traces=True, inplace=False, streaming=False):
         """K iterations of `forward` (t = t0..t0+K-1) plus the residuals of utils.py:68-71 after each,
-        in one library call.  `state=(x,y,z,xv,H,C)` or None for the zero state of main.py:837-843.
+        in one library call.  Small instances (n+m <= 256, hidden_dim 64, tensor-core modes) run on the
+        on-chip-resident kernel (one persistent CTA per instance); `streaming=True` forces the HBM-streaming path.  `state=(x,y,z,xv,H,C)` or None for the zero state of main.py:837-843.
         `scaling` is the `Scaling` object that produced (Q,p,A0,zl,zu): with it the residuals of the
         un-scaled iterates on the original data (main.py:922-955) are traced too."""
         L = _lib.lib()
@@ -135,7 +136,7 @@ class LSTM(nn.Module):
         h = self.hidden_dim
         if A0.shape != (B, m, n):
             raise ValueError(f"A0 has shape {tuple(A0.shape)}, expected {(B, m, n)}")
-        flags = 0
+        flags = _lib.F_STREAMING if streaming else 0
         if state is None:
             x = torch.zeros((B, n, 1), device=dev); y = torch.zeros((B, m, 1), device=dev)
             z = torch.zeros((B, m, 1), device=dev); xv = torch.zeros((B, n + m, 1), device=dev)

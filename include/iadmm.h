@@ -56,7 +56,8 @@ enum {
 /* Flags of iadmm_solve. */
 enum {
   IADMM_F_ZERO_STATE = 1,       /* H (and the other state) is known to be all-zero on entry (main.py:837-843) */
-  IADMM_F_SKIP_FINAL_RESID = 2  /* do not run the trailing residual pass (traces row K-1 left untouched)      */
+  IADMM_F_SKIP_FINAL_RESID = 2, /* do not run the trailing residual pass (traces row K-1 left untouched)      */
+  IADMM_F_STREAMING = 4         /* force the streaming (HBM) variant even where the on-chip-resident one applies  */
 };
 
 int         iadmm_abi_version(void);
