@@ -24,7 +24,9 @@
 
 namespace iadmm {
 
-constexpr int kResThreads = 256;
+constexpr int kResThreads = 512;                  // 16 warps: 4 per TMEM lane quarter, each owning 2 of a tile's 8 column chunks
+constexpr int kResGroups = kResThreads / 128;     // column groups of the epilogue
+constexpr int kResChunks = 8 / kResGroups;        // 8-unit chunks per thread and tile
 constexpr int kResH = 64;                  // hidden units (one 64-wide K block, N = 256 gate columns)
 constexpr int kResMaxN = 256;              // n + m: two 128-row accumulator tiles fill the 512 TMEM columns
 constexpr int kResTileBytes = 128 * 128;   // one 128-row operand tile, 128-byte rows
@@ -67,9 +69,9 @@ struct ResSmem {
   float *w0, *w1, *bias, *wh;                       // gate-column parameters (interleaved 4*unit + gate)
   float *x, *y, *z, *xt, *v, *p, *zl, *zu;          // iterates (xv = [xt; v]) and instance vectors
   float *w1v, *w2v, *g, *t0, *t1, *qx, *ax, *aty;   // KKT temporaries (w = [w1v; w2v])
-  float *cp;                                        // [512] column partials
-  float *head;                                      // [2][256] head partials of the two column halves
-  double* red;                                      // [8][9] block-reduction scratch
+  float *cp;                                        // [parts][2][cw] column partials (KKT phases)
+  float *head;                                      // [groups][256] head partials (cell phase; aliases cp)
+  double* red;                                      // [warps][9] block-reduction scratch
   uint64_t* bar;
   uint32_t* tmem_slot;
   float* mat;                                       // stacked [Q; A0], (n+m) rows of `ld` floats, when cached
@@ -86,7 +88,7 @@ __host__ __device__ inline size_t res_vec_floats(int n, int m) {
 }
 __host__ __device__ inline size_t res_fixed_bytes(int n, int m) {
   return 1024 /*alignment slack*/ + kResOperandBytes + (3 * 256 + 64) * sizeof(float) + res_vec_floats(n, m) * sizeof(float) +
-         512 * sizeof(float) + 512 * sizeof(float) + 8 * 9 * sizeof(double) + 64;
+         2 * kResThreads * sizeof(float) + (kResThreads / 32) * 9 * sizeof(double) + 64;
 }
 
 // `base` is the 1024-byte aligned start of the dynamic shared memory (pointer arithmetic only, so that the compiler
@@ -94,13 +96,13 @@ __host__ __device__ inline size_t res_fixed_bytes(int n, int m) {
 __device__ __forceinline__ void res_carve(uint8_t* base, int n, int m, ResSmem& S) {
   S.a_hi = base; S.a_lo = base + 2 * kResTileBytes; S.b_hi = base + 4 * kResTileBytes; S.b_lo = base + 6 * kResTileBytes;
   double* dp = reinterpret_cast<double*>(base + kResOperandBytes);
-  S.red = dp; dp += 8 * 9;
+  S.red = dp; dp += (kResThreads / 32) * 9;
   S.bar = reinterpret_cast<uint64_t*>(dp); dp += 2;
   S.tmem_slot = reinterpret_cast<uint32_t*>(dp); dp += 2;
   float* fp = reinterpret_cast<float*>(dp);
   const int N = n + m;
   S.w0 = fp; fp += 256; S.w1 = fp; fp += 256; S.bias = fp; fp += 256; S.wh = fp; fp += 64;
-  S.cp = fp; fp += 512; S.head = fp; fp += 512;
+  S.cp = fp; S.head = fp; fp += 2 * kResThreads;
   S.x = fp; fp += r4(n); S.y = fp; fp += r4(m); S.z = fp; fp += r4(m); S.xt = fp; fp += r4(n); S.v = fp; fp += r4(m);
   S.p = fp; fp += r4(n); S.zl = fp; fp += r4(m); S.zu = fp; fp += r4(m);
   S.w1v = fp; fp += r4(n); S.w2v = fp; fp += r4(m); S.g = fp; fp += r4(N); S.t0 = fp; fp += r4(N); S.t1 = fp; fp += r4(N);
@@ -132,14 +134,27 @@ __device__ __forceinline__ void res_row_dot_thread(const float* row, int n, cons
   }
   d0 = a0; d1 = a1;
 }
-// column sums over rows [0, rows) of a matrix block: thread (part, c) takes rows part, part+parts, ...
+// column sums over rows [0, rows) of a matrix block: thread (part, c) takes a contiguous group of rows (multiple of 4,
+// so the vector entries are broadcast float4 reads)
 template <bool TWO>
 __device__ __forceinline__ void res_col_sum_thread(const float* Mc, int ld, int rows, int part, int parts, const float* u0,
                                                    const float* u1, float& s0, float& s1) {
   float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-  for (int r = part; r < rows; r += parts) {
-    const float a = Mc[(size_t)r * ld];
+  const int per = r4((rows + parts - 1) / parts);
+  int r = part * per;
+  const int r_end = min(rows, r + per);
+  const float* pm = Mc + (size_t)r * ld;
+  for (; r + 4 <= r_end; r += 4, pm += 4 * ld) {
+    const float m0 = pm[0], m1 = pm[ld], m2 = pm[2 * ld], m3 = pm[3 * ld];
+    const float4 p = *reinterpret_cast<const float4*>(u0 + r);
+    a0 = fmaf(m0, p.x, a0); a0 = fmaf(m1, p.y, a0); a0 = fmaf(m2, p.z, a0); a0 = fmaf(m3, p.w, a0);
+    if (TWO) {
+      const float4 q = *reinterpret_cast<const float4*>(u1 + r);
+      a1 = fmaf(m0, q.x, a1); a1 = fmaf(m1, q.y, a1); a1 = fmaf(m2, q.z, a1); a1 = fmaf(m3, q.w, a1);
+    }
+  }
+  for (; r < r_end; ++r, pm += ld) {
+    const float a = pm[0];
     a0 = fmaf(a, u0[r], a0);
     if (TWO) a1 = fmaf(a, u1[r], a1);
   }
@@ -238,7 +253,7 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
   const int n = A.n, m = A.m, N = n + m;
   res_carve(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u), n, m, S);
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, half = warp >> 2;
+  const int quarter = warp & 3, grp = warp >> 2;
   const int ntiles = (N + 127) >> 7;
   const bool want_trace = A.pri || A.dual || A.pri_u || A.dual_u || A.metrics;
   const int ld = res_ld(n);
@@ -290,13 +305,13 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
   __syncthreads();          // zero-filled A tiles visible before the state is written into them
 
   // ---------------- state: C into registers, H into the operand tiles ----------------
-  float creg[2][4][8];
+  float creg[2][kResChunks][8];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int row = t * 128 + quarter * 32 + lane;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int unit0 = half * 32 + cc * 8;
+    for (int cc = 0; cc < kResChunks; ++cc) {
+      const int unit0 = (grp * kResChunks + cc) * 8;
       if (row < N) {
         const size_t o = ((size_t)b * N + row) * kResH + unit0;
         ld_global_v8(A.C + o, creg[t][cc]);
@@ -319,7 +334,7 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
   const float dequant = A.scale[1];
   const float b_h = A.bh[0];
   const uint32_t idesc = make_idesc_f16(256);
-  const int cw = (n <= 32) ? 32 : (n <= 64) ? 64 : (n <= 128) ? 128 : 256;
+  const int cw = (n <= 32) ? 32 : (n <= 64) ? 64 : (n <= 128) ? 128 : 256;      // column-sum group width
   const int parts = kResThreads / cw, part = tid / cw, col = tid % cw;
 
   for (int k = 0; k < A.K; ++k) {
@@ -425,8 +440,8 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
         const float xr = row_ok ? (row < n ? S.xt[row] : S.v[row - n]) : 0.f, gr = row_ok ? S.g[row] : 0.f;
         float hp = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int chunk = half * 4 + cc;
+        for (int cc = 0; cc < kResChunks; ++cc) {
+          const int chunk = grp * kResChunks + cc;
           const int unit0 = chunk * 8;
           uint32_t acc[32];
           tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 256 + chunk * 32), acc);
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
             if (last) st_global_v8(A.H + ((size_t)b * N + row) * kResH + unit0, hnew);
           }
         }
-        if (row_ok) S.head[half * 256 + row] = hp;
+        if (row_ok) S.head[grp * 256 + row] = hp;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // new H images -> visible to the next MMAs
@@ -465,8 +480,8 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
     // ---- tail (models/lstm.py:80-94), every product and sum rounded as the reference rounds it ----
     if (tid < N) {
       float head = 0.f;
-      head += S.head[tid];
-      head += S.head[256 + tid];
+#pragma unroll
+      for (int q = 0; q < kResGroups; ++q) head += S.head[q * 256 + tid];
       head = __fadd_rn(head, b_h);
       if (tid < n) {
         const float xvn = __fsub_rn(S.xt[tid], head);
@@ -522,8 +537,8 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
     const int row = t * 128 + quarter * 32 + lane;
     if (row < N) {
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-        st_global_v8(A.C + ((size_t)b * N + row) * kResH + half * 32 + cc * 8, creg[t][cc]);
+      for (int cc = 0; cc < kResChunks; ++cc)
+        st_global_v8(A.C + ((size_t)b * N + row) * kResH + (grp * kResChunks + cc) * 8, creg[t][cc]);
     }
   }
   tc_fence_before();
