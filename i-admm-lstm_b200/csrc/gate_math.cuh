@@ -36,6 +36,31 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return (fabsf(x) < 0.55f) ? small : big;
 }
 
+// exp-only tanh, 1 - 2 / (e^{2x} + 1): 5 instructions, ABSOLUTE error <= 3e-7 (the relative error grows as x -> 0,
+// where the cancellation sits).  Used by the on-chip-resident kernel, which is instruction-issue bound in its
+// epilogue; the streaming kernels keep the branch-free polynomial/exp pair above.
+__device__ __forceinline__ float tanh_exp(float x) {
+  return fmaf(-2.0f, rcp_approx(ex2_approx(x * 2.8853900817779268f) + 1.0f), 1.0f);
+}
+
+// The four gate activations of one hidden unit with ONE reciprocal: sigmoid(p) = 1/(1+e^-p), tanh(p) = 1 - 2/(1+e^2p);
+// 1/a, 1/b, 1/c, 1/d follow from r = 1/(abcd) by multiplications.  The special-function unit (16 lanes/clk/SM) is
+// the bottleneck of the resident kernel's epilogue: this form needs 4 ex2 + 1 rcp instead of 4 + 4.  Exponent
+// arguments are clamped at 30 so the product stays below 2^121 (sigmoid(-20.8) = 9e-10 is returned for anything
+// smaller: an absolute error below 1e-9).  Relative error ~5 ulp.
+__device__ __forceinline__ void gates4_shared_rcp(float pi, float pf, float po, float pu, float& gi, float& gf, float& go, float& gu) {
+  const float kL = 1.4426950408889634f;
+  const float a = 1.0f + ex2_approx(fminf(pi * -kL, 30.0f));
+  const float b = 1.0f + ex2_approx(fminf(pf * -kL, 30.0f));
+  const float c = 1.0f + ex2_approx(fminf(po * -kL, 30.0f));
+  const float d = 1.0f + ex2_approx(fminf(pu * (2.0f * kL), 30.0f));
+  const float ab = a * b, cd = c * d;
+  const float r = rcp_approx(ab * cd);
+  const float rab = r * cd, rcd = r * ab;
+  gi = rab * b; gf = rab * a; go = rcd * d;
+  gu = fmaf(-2.0f, rcd * c, 1.0f);
+}
+
 // 256-bit global accesses (sm_100): one request per 32-byte sector instead of two
 __device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
   asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -71,7 +71,6 @@ struct ResSmem {
   float *w1v, *w2v, *g, *t0, *t1, *qx, *ax, *aty;   // KKT temporaries (w = [w1v; w2v])
   float *cp;                                        // [parts][2][cw] column partials (KKT phases)
   float *head;                                      // [groups][256] head partials (cell phase; aliases cp)
-  double* red;                                      // [warps][9] block-reduction scratch
   uint64_t* bar;
   uint32_t* tmem_slot;
   float* mat;                                       // stacked [Q; A0], (n+m) rows of `ld` floats, when cached
@@ -88,7 +87,7 @@ __host__ __device__ inline size_t res_vec_floats(int n, int m) {
 }
 __host__ __device__ inline size_t res_fixed_bytes(int n, int m) {
   return 1024 /*alignment slack*/ + kResOperandBytes + (3 * 256 + 64) * sizeof(float) + res_vec_floats(n, m) * sizeof(float) +
-         2 * kResThreads * sizeof(float) + (kResThreads / 32) * 9 * sizeof(double) + 64;
+         2 * kResThreads * sizeof(float) + 64;
 }
 
 // `base` is the 1024-byte aligned start of the dynamic shared memory (pointer arithmetic only, so that the compiler
@@ -96,7 +95,6 @@ __host__ __device__ inline size_t res_fixed_bytes(int n, int m) {
 __device__ __forceinline__ void res_carve(uint8_t* base, int n, int m, ResSmem& S) {
   S.a_hi = base; S.a_lo = base + 2 * kResTileBytes; S.b_hi = base + 4 * kResTileBytes; S.b_lo = base + 6 * kResTileBytes;
   double* dp = reinterpret_cast<double*>(base + kResOperandBytes);
-  S.red = dp; dp += (kResThreads / 32) * 9;
   S.bar = reinterpret_cast<uint64_t*>(dp); dp += 2;
   S.tmem_slot = reinterpret_cast<uint32_t*>(dp); dp += 2;
   float* fp = reinterpret_cast<float*>(dp);
@@ -183,67 +181,71 @@ __device__ __forceinline__ float res_col_total(const float* cp, int cw, int whic
 }
 
 // residual norms / metrics of the iterate (x, y, z) from qx = Q x, ax = A0 x, aty = A0^T y (all in shared memory);
-// same quantities, accumulation type and output layout as kkt_combine1_kernel
-__device__ __forceinline__ void res_trace_row(const ResArgs& A, const ResSmem& S, int b, int row, int tid) {
+// same quantities, accumulation type (double) and output layout as kkt_combine1_kernel.  Five warps take one
+// quantity group each and write their trace entries themselves: no block-wide reduction, no barrier.
+__device__ __forceinline__ double warp_sum_double(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ void res_trace_row(const ResArgs& A, const ResSmem& S, int b, int row, int warp, int lane) {
+  if (warp > 4) return;
   const int n = A.n, m = A.m;
   const bool want_met = A.metrics != nullptr;
   const bool unscaled = (A.sd != nullptr) && (A.pri_u || A.dual_u || want_met);
   const float cscale = unscaled ? A.sc[b] : 1.f;
-  double v[7] = {0, 0, 0, 0, 0, 0, 0};      // pri2 dual2 pri2u dual2u obj isum esum
-  float imax = 0.f, emax = 0.f;
-  for (int j = tid; j < n; j += kResThreads) {
-    const float r = __fadd_rn(__fadd_rn(S.qx[j], S.p[j]), S.aty[j]);
-    v[1] += (double)r * (double)r;
-    if (unscaled) { const float ru = r / (cscale * A.sd[(size_t)b * n + j]); v[3] += (double)ru * (double)ru; }
-    if (want_met) v[4] += (double)S.x[j] * (0.5 * (double)S.qx[j] + (double)S.p[j]);
-  }
-  for (int i = tid; i < m; i += kResThreads) {
-    const float r = __fsub_rn(S.ax[i], S.z[i]);
-    v[0] += (double)r * (double)r;
-    const float se = unscaled ? A.se[(size_t)b * m + i] : 1.f;
-    if (unscaled) { const float ru = r / se; v[2] += (double)ru * (double)ru; }
-    if (want_met) {
-      const float einv = unscaled ? 1.0f / se : 1.0f;
+  const size_t B = A.B, o = (size_t)row * B + b;
+  float* mt = want_met ? A.metrics + (size_t)row * 5 * B : nullptr;
+  if (warp == 0) {                                   // dual residual || Q x + p + A0^T y ||
+    double s = 0.0, su = 0.0;
+    for (int j = lane; j < n; j += 32) {
+      const float r = __fadd_rn(__fadd_rn(S.qx[j], S.p[j]), S.aty[j]);
+      s += (double)r * (double)r;
+      if (unscaled) { const float ru = r / (cscale * A.sd[(size_t)b * n + j]); su += (double)ru * (double)ru; }
+    }
+    s = warp_sum_double(s);
+    if (unscaled) su = warp_sum_double(su);
+    if (lane == 0) {
+      if (A.dual) A.dual[o] = (float)sqrt(s);
+      if (unscaled && A.dual_u) A.dual_u[o] = (float)sqrt(su);
+    }
+  } else if (warp == 1) {                            // primal residual || A0 x - z ||
+    double s = 0.0, su = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const float r = __fsub_rn(S.ax[i], S.z[i]);
+      s += (double)r * (double)r;
+      if (unscaled) { const float ru = r / A.se[(size_t)b * m + i]; su += (double)ru * (double)ru; }
+    }
+    s = warp_sum_double(s);
+    if (unscaled) su = warp_sum_double(su);
+    if (lane == 0) {
+      if (A.pri) A.pri[o] = (float)sqrt(s);
+      if (unscaled && A.pri_u) A.pri_u[o] = (float)sqrt(su);
+    }
+  } else if (!want_met) {
+    return;
+  } else if (warp == 2) {                            // objective 0.5 x^T Q x + p^T x (main.py:950)
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) s += (double)S.x[j] * (0.5 * (double)S.qx[j] + (double)S.p[j]);
+    s = warp_sum_double(s);
+    if (lane == 0) mt[0 * B + b] = (float)(unscaled ? s / (double)cscale : s);
+  } else {                                           // warp 3: inequality rows, warp 4: equality rows (main.py:957-968)
+    const bool ineq = (warp == 3);
+    const int i0 = ineq ? 0 : A.num_ineq, i1 = ineq ? A.num_ineq : m;
+    double s = 0.0; float mx = 0.f;
+    for (int i = i0 + lane; i < i1; i += 32) {
+      const float einv = unscaled ? 1.0f / A.se[(size_t)b * m + i] : 1.0f;
       const float dv = (S.ax[i] - S.zu[i]) * einv;
-      if (i < A.num_ineq) { const float q = fmaxf(dv, 0.f); imax = fmaxf(imax, q); v[5] += (double)q; }
-      else                { const float q = fabsf(dv);      emax = fmaxf(emax, q); v[6] += (double)q; }
+      const float q = ineq ? fmaxf(dv, 0.f) : fabsf(dv);
+      mx = fmaxf(mx, q); s += (double)q;
+    }
+    s = warp_sum_double(s); mx = warp_max(mx);
+    if (lane == 0) {
+      const int cnt = i1 - i0;
+      mt[(ineq ? 1 : 3) * B + b] = mx;
+      mt[(ineq ? 2 : 4) * B + b] = cnt > 0 ? (float)(s / cnt) : 0.f;
     }
   }
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int q = 0; q < 7; ++q)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(kFullMask, v[q], o);
-  imax = warp_max(imax); emax = warp_max(emax);
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < 7; ++q) S.red[warp * 9 + q] = v[q];
-    S.red[warp * 9 + 7] = (double)imax; S.red[warp * 9 + 8] = (double)emax;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double t[9];
-    for (int q = 0; q < 9; ++q) t[q] = S.red[q];
-    for (int w = 1; w < kResThreads / 32; ++w) {
-      for (int q = 0; q < 7; ++q) t[q] += S.red[w * 9 + q];
-      t[7] = fmax(t[7], S.red[w * 9 + 7]); t[8] = fmax(t[8], S.red[w * 9 + 8]);
-    }
-    const size_t B = A.B, o = (size_t)row * B + b;
-    if (A.pri)  A.pri[o]  = (float)sqrt(t[0]);
-    if (A.dual) A.dual[o] = (float)sqrt(t[1]);
-    if (unscaled && A.pri_u)  A.pri_u[o]  = (float)sqrt(t[2]);
-    if (unscaled && A.dual_u) A.dual_u[o] = (float)sqrt(t[3]);
-    if (want_met) {
-      float* mt = A.metrics + (size_t)row * 5 * B;
-      const int me = m - A.num_ineq;
-      mt[0 * B + b] = (float)(unscaled ? t[4] / (double)cscale : t[4]);
-      mt[1 * B + b] = (float)t[7];
-      mt[2 * B + b] = A.num_ineq > 0 ? (float)(t[5] / A.num_ineq) : 0.f;
-      mt[3 * B + b] = (float)t[8];
-      mt[4 * B + b] = me > 0 ? (float)(t[6] / me) : 0.f;
-    }
-  }
-  __syncthreads();
 }
 
 template <int NPROD, bool CACHED>
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
       S.ax[i] = S.t1[tid];
     }
     __syncthreads();
-    if (k > 0 && want_trace) res_trace_row(A, S, b, k - 1, tid);     // residuals of the iterate entering this iteration
+    if (k > 0 && want_trace) res_trace_row(A, S, b, k - 1, warp, lane);   // residuals of the iterate entering this iteration
 
     // ---- KKT pass 2: g = K^T w: Q^T w1 and A0^T w2 (column sums), A0 w1 (row dots) ----
     {
@@ -458,9 +460,10 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
               const float pf = fmaf(__uint_as_float(acc[u * 4 + 1]), dequant, fmaf(gr, a1.y, fmaf(xr, a0.y, ab.y)));
               const float po = fmaf(__uint_as_float(acc[u * 4 + 2]), dequant, fmaf(gr, a1.z, fmaf(xr, a0.z, ab.z)));
               const float pu = fmaf(__uint_as_float(acc[u * 4 + 3]), dequant, fmaf(gr, a1.w, fmaf(xr, a0.w, ab.w)));
-              const float gi = sigmoid_fast(pi), gf = sigmoid_fast(pf), go = sigmoid_fast(po), gu = tanh_fast(pu);
+              float gi, gf, go, gu;
+              gates4_shared_rcp(pi, pf, po, pu, gi, gf, go, gu);
               const float cn = __fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, creg[t][cc][u]));
-              const float hn = __fmul_rn(go, tanh_fast(cn));
+              const float hn = __fmul_rn(go, tanh_exp(cn));
               creg[t][cc][u] = cn;
               hnew[u] = hn;
               hp = fmaf(hn, S.wh[unit0 + u], hp);
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
     if (tid < n) { S.qx[tid] = S.t1[tid]; S.aty[tid] = (m > 0) ? res_col_total(S.cp, cw, 0, tid) : 0.f; }
     else if (tid < N) S.ax[tid - n] = S.t1[tid];
     __syncthreads();
-    res_trace_row(A, S, b, A.K - 1, tid);
+    res_trace_row(A, S, b, A.K - 1, warp, lane);
   }
   for (int i = tid; i < n; i += kResThreads) { A.x[(size_t)b * n + i] = S.x[i]; A.xv[(size_t)b * N + i] = S.xt[i]; }
   for (int i = tid; i < m; i += kResThreads) {
