@@ -20,29 +20,31 @@ def timeit(fn, reps=10):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-for mode in ("tc_f16f8", "simt_fp32"):
+for mode, streaming in (("tc_f16f8", False), ("tc_f16f8", True), ("simt_fp32", True)):
     model = ia.LSTM(None, 2, h, K, dev, gate_mode=mode)
     with torch.no_grad():
         for k, v in prm.items(): getattr(model, k).copy_(v.to(dev))
         args = (K, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6)
-        ms = timeit(lambda: model.solve(*args))
+        kw = dict(streaming=streaming)
+        ms = timeit(lambda: model.solve(*args, **kw))
         m = mi + me
         st = [torch.zeros((B, n, 1), device=dev), torch.zeros((B, m, 1), device=dev), torch.zeros((B, m, 1), device=dev),
               torch.zeros((B, n + m, 1), device=dev), torch.zeros((B, n + m, h), device=dev), torch.zeros((B, n + m, h), device=dev)]
         work = [s.clone() for s in st]
         side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            model.solve(*args, state=work, inplace=True)
+            model.solve(*args, state=work, inplace=True, **kw)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         for w, s in zip(work, st): w.copy_(s)
         with torch.cuda.graph(g):
-            res = model.solve(*args, state=work, inplace=True)
+            res = model.solve(*args, state=work, inplace=True, **kw)
         def replay():
             for w, s in zip(work, st): w.copy_(s)
             g.replay()
         ms_g = timeit(replay)
-    out[mode] = {"eager_ms": ms, "eager_solves_per_s": B / ms * 1e3, "graph_ms": ms_g, "graph_solves_per_s": B / ms_g * 1e3}
+    name = mode + ("_streaming" if streaming and mode != "simt_fp32" else "_resident" if not streaming else "")
+    out[name] = {"eager_ms": ms, "eager_solves_per_s": B / ms * 1e3, "graph_ms": ms_g, "graph_solves_per_s": B / ms_g * 1e3}
 torch.set_num_threads(os.cpu_count())
 with torch.no_grad():
     orc.solve(prm, 3, mi, me, qp_cpu["Q"], qp_cpu["p"], qp_cpu["A0"], qp_cpu["zl"], qp_cpu["zu"], 6e-6, h)
