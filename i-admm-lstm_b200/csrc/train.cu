@@ -775,3 +775,189 @@ int iadmm_residuals_bwd(const float* Q, const float* A0, const float* pri, const
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// One whole truncated-BPTT window in a single call (main.py:336-358): TL x (iteration + primal_dual_loss) forward,
+// loss = loss_scale * sum_t mean_b (pri_t + dual_t), then the backward sweep -- the same kernels as the per-iteration
+// entry points above, launched back to back from C.  The per-iteration autograd path is launch/Python bound at
+// small batch (config 3, batch 2: 61 ms of 93 ms per window are host overhead); here the host only enqueues.
+// ------------------------------------------------------------------------------------------------
+namespace iadmm {
+
+struct WindowWs {
+  void* step_ws; size_t step_bytes;
+  void* res_ws;  size_t res_bytes;
+  float *x, *y, *z, *xv, *H, *C;                 // [TL+1] states each
+  float *g_save, *w_save, *gates, *pri, *dual, *rp, *rd;   // [TL] each
+  float *adj[2][6];                              // ping-pong adjoints gx gy gz gxv gH gC
+  float *rgx, *rgy, *rgz, *seed;
+  size_t bytes;
+};
+
+static void plan_window(int B, int n, int m, int h, int TL, void* base, WindowWs* W) {
+  const size_t N = (size_t)n + m, rows = (size_t)B * N, fb = sizeof(float);
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? p + o : nullptr; };
+  TrainWs T;
+  plan_train(B, n, m, 0, h, nullptr, &T);
+  W->step_bytes = T.bytes; W->step_ws = take(T.bytes);
+  W->res_bytes = kkt_scratch_floats(make_kkt_dims(B, n, m, 0)) * fb + 1024; W->res_ws = take(W->res_bytes);
+  const size_t S = (size_t)TL + 1;
+  W->x = reinterpret_cast<float*>(take(S * B * n * fb));
+  W->y = reinterpret_cast<float*>(take(S * B * (m > 0 ? m : 1) * fb));
+  W->z = reinterpret_cast<float*>(take(S * B * (m > 0 ? m : 1) * fb));
+  W->xv = reinterpret_cast<float*>(take(S * rows * fb));
+  W->H = reinterpret_cast<float*>(take(S * rows * h * fb));
+  W->C = reinterpret_cast<float*>(take(S * rows * h * fb));
+  W->g_save = reinterpret_cast<float*>(take((size_t)TL * rows * fb));
+  W->w_save = reinterpret_cast<float*>(take((size_t)TL * rows * fb));
+  W->gates = reinterpret_cast<float*>(take((size_t)TL * rows * 4 * h * fb));
+  W->pri = reinterpret_cast<float*>(take((size_t)TL * B * fb));
+  W->dual = reinterpret_cast<float*>(take((size_t)TL * B * fb));
+  W->rp = reinterpret_cast<float*>(take((size_t)TL * B * (m > 0 ? m : 1) * fb));
+  W->rd = reinterpret_cast<float*>(take((size_t)TL * B * n * fb));
+  for (int s = 0; s < 2; ++s) {
+    W->adj[s][0] = reinterpret_cast<float*>(take((size_t)B * n * fb));
+    W->adj[s][1] = reinterpret_cast<float*>(take((size_t)B * (m > 0 ? m : 1) * fb));
+    W->adj[s][2] = reinterpret_cast<float*>(take((size_t)B * (m > 0 ? m : 1) * fb));
+    W->adj[s][3] = reinterpret_cast<float*>(take(rows * fb));
+    W->adj[s][4] = reinterpret_cast<float*>(take(rows * h * fb));
+    W->adj[s][5] = reinterpret_cast<float*>(take(rows * h * fb));
+  }
+  W->rgx = reinterpret_cast<float*>(take((size_t)B * n * fb));
+  W->rgy = reinterpret_cast<float*>(take((size_t)B * (m > 0 ? m : 1) * fb));
+  W->rgz = reinterpret_cast<float*>(take((size_t)B * (m > 0 ? m : 1) * fb));
+  W->seed = reinterpret_cast<float*>(take((size_t)B * fb));
+  W->bytes = off;
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ a, size_t count, float v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) a[i] = v;
+}
+// a += b (three small vectors at once)
+__global__ void __launch_bounds__(256) add3_kernel(float* __restrict__ a0, const float* __restrict__ b0, size_t c0,
+                                                   float* __restrict__ a1, const float* __restrict__ b1, size_t c1,
+                                                   float* __restrict__ a2, const float* __restrict__ b2, size_t c2) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c0) a0[i] = __fadd_rn(a0[i], b0[i]);
+  if (i < c1) a1[i] = __fadd_rn(a1[i], b1[i]);
+  if (i < c2) a2[i] = __fadd_rn(a2[i], b2[i]);
+}
+// loss = scale * sum_t ( (1/B) sum_b (pri + dual) ), summed per step in the reference's order (main.py:346-347)
+__global__ void __launch_bounds__(256) window_loss_kernel(const float* __restrict__ pri, const float* __restrict__ dual, int TL, int B,
+                                                          float scale, float* __restrict__ out) {
+  __shared__ double sh[8];
+  double total = 0.0;
+  for (int t = 0; t < TL; ++t) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < B; b += 256) s += (double)__fadd_rn(pri[(size_t)t * B + b], dual[(size_t)t * B + b]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += sh[w];
+      total += v / B * (double)scale;
+    }
+  }
+  if (threadIdx.x == 0) out[0] = (float)total;
+}
+
+}  // namespace iadmm
+
+extern "C" {
+
+int iadmm_window_workspace_bytes(int B, int n, int m, int h, int TL, size_t* bytes) {
+  if (B <= 0 || n <= 0 || m < 0 || h <= 0 || TL <= 0 || !bytes)
+    IADMM_FAIL(IADMM_ESHAPE, "window_workspace_bytes: B=%d n=%d m=%d h=%d TL=%d", B, n, m, h, TL);
+  WindowWs W;
+  plan_window(B, n, m, h, TL, nullptr, &W);
+  *bytes = W.bytes;
+  return IADMM_OK;
+}
+
+int iadmm_train_window(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
+                       const float* zu, float* x, float* y, float* z, float* xv, float* H, float* C, float* grad_flat,
+                       float* loss_out, int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int TL, float sigma,
+                       float loss_scale, int mode, void* workspace, size_t workspace_bytes, void* stream) {
+  const int m = num_ineq + num_eq;
+  if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || TL <= 0 || t0 < 0 || t0 + TL > length)
+    IADMM_FAIL(IADMM_ESHAPE, "train_window: B=%d n=%d ineq=%d eq=%d h=%d t0=%d TL=%d length=%d", B, n, num_ineq, num_eq, h, t0, TL, length);
+  if (!packed_weights || !Q || !p || !x || !xv || !H || !C || !grad_flat || !loss_out || !workspace)
+    IADMM_FAIL(IADMM_EALIGN, "train_window: NULL pointer");
+  if (m > 0 && (!A0 || !zl || !zu || !y || !z)) IADMM_FAIL(IADMM_EALIGN, "train_window: NULL constraint pointer");
+  WindowWs W;
+  plan_window(B, n, m, h, TL, workspace, &W);
+  if (W.bytes > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "train_window: workspace too small: %zu < %zu", workspace_bytes, W.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)n + m, rows = (size_t)B * N, fb = sizeof(float);
+  const size_t sx = (size_t)B * n, sy = (size_t)B * m, sxv = rows, sH = rows * h, sG = rows * 4 * h;
+  int rc;
+  // state 0 = the caller's state
+  IADMM_CUDA(cudaMemcpyAsync(W.x, x, sx * fb, cudaMemcpyDeviceToDevice, st));
+  if (m > 0) {
+    IADMM_CUDA(cudaMemcpyAsync(W.y, y, sy * fb, cudaMemcpyDeviceToDevice, st));
+    IADMM_CUDA(cudaMemcpyAsync(W.z, z, sy * fb, cudaMemcpyDeviceToDevice, st));
+  }
+  IADMM_CUDA(cudaMemcpyAsync(W.xv, xv, sxv * fb, cudaMemcpyDeviceToDevice, st));
+  IADMM_CUDA(cudaMemcpyAsync(W.H, H, sH * fb, cudaMemcpyDeviceToDevice, st));
+  IADMM_CUDA(cudaMemcpyAsync(W.C, C, sH * fb, cudaMemcpyDeviceToDevice, st));
+  // ---- forward sweep ----
+  for (int t = 0; t < TL; ++t) {
+    const size_t a = (size_t)t, b = (size_t)t + 1;
+    if ((rc = iadmm_step_fwd(packed_weights, Q, p, A0, zl, zu, W.x + a * sx, W.y + a * sy, W.z + a * sy, W.xv + a * sxv, W.H + a * sH,
+                             W.C + a * sH, W.x + b * sx, W.y + b * sy, W.z + b * sy, W.xv + b * sxv, W.H + b * sH, W.C + b * sH,
+                             W.g_save + a * sxv, W.w_save + a * sxv, W.gates + a * sG, B, n, num_ineq, num_eq, h, length, t0 + t,
+                             sigma, mode, W.step_ws, W.step_bytes, stream))) return rc;
+    if ((rc = iadmm_residuals_fwd(W.x + b * sx, W.y + b * sy, W.z + b * sy, Q, p, A0, W.pri + a * B, W.dual + a * B, W.rp + a * sy,
+                                  W.rd + a * sx, B, n, m, W.res_ws, W.res_bytes, stream))) return rc;
+  }
+  window_loss_kernel<<<1, 256, 0, st>>>(W.pri, W.dual, TL, B, loss_scale, loss_out);
+  IADMM_LAUNCH_CHECK("window_loss_kernel");
+  // ---- backward sweep ----
+  fill_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(W.seed, (size_t)B, loss_scale / (float)B);
+  IADMM_LAUNCH_CHECK("fill_kernel");
+  const GradLayout G = grad_layout(h, length);
+  IADMM_CUDA(cudaMemsetAsync(grad_flat, 0, G.total * fb, st));
+  int cur = 0;
+  for (int t = TL - 1; t >= 0; --t) {
+    const size_t a = (size_t)t, b = (size_t)t + 1;
+    float** gin = W.adj[cur];           // adjoint of state t+1 coming from the future (unset at t = TL-1)
+    float** gout = W.adj[cur ^ 1];
+    const bool last = (t == TL - 1);
+    // adjoint of the loss term of this iteration w.r.t. (x, y, z)_{t+1}
+    float* rgx = last ? gin[0] : W.rgx;
+    float* rgy = last ? gin[1] : W.rgy;
+    float* rgz = last ? gin[2] : W.rgz;
+    if ((rc = iadmm_residuals_bwd(Q, A0, W.pri + a * B, W.dual + a * B, W.rp + a * sy, W.rd + a * sx, W.seed, W.seed, rgx, rgy, rgz, B,
+                                  n, m, W.res_ws, W.res_bytes, stream))) return rc;
+    if (!last) {
+      const size_t mx = sx > sy ? sx : sy;
+      add3_kernel<<<(unsigned)((mx + 255) / 256), 256, 0, st>>>(gin[0], W.rgx, sx, gin[1], W.rgy, sy, gin[2], W.rgz, sy);
+      IADMM_LAUNCH_CHECK("add3_kernel");
+    }
+    if ((rc = iadmm_step_bwd(packed_weights, Q, p, A0, zl, zu, W.x + a * sx, W.y + a * sy, W.z + a * sy, W.xv + a * sxv, W.H + a * sH,
+                             W.C + a * sH, W.xv + b * sxv, W.H + b * sH, W.g_save + a * sxv, W.w_save + a * sxv, W.gates + a * sG,
+                             gin[0], m > 0 ? gin[1] : nullptr, m > 0 ? gin[2] : nullptr, last ? nullptr : gin[3],
+                             last ? nullptr : gin[4], last ? nullptr : gin[5], gout[0], gout[1], gout[2], gout[3], gout[4], gout[5],
+                             grad_flat, B, n, num_ineq, num_eq, h, length, t0 + t, sigma, W.step_ws, W.step_bytes, stream))) return rc;
+    cur ^= 1;
+  }
+  // ---- the state leaving the window ----
+  const size_t e = (size_t)TL;
+  IADMM_CUDA(cudaMemcpyAsync(x, W.x + e * sx, sx * fb, cudaMemcpyDeviceToDevice, st));
+  if (m > 0) {
+    IADMM_CUDA(cudaMemcpyAsync(y, W.y + e * sy, sy * fb, cudaMemcpyDeviceToDevice, st));
+    IADMM_CUDA(cudaMemcpyAsync(z, W.z + e * sy, sy * fb, cudaMemcpyDeviceToDevice, st));
+  }
+  IADMM_CUDA(cudaMemcpyAsync(xv, W.xv + e * sxv, sxv * fb, cudaMemcpyDeviceToDevice, st));
+  IADMM_CUDA(cudaMemcpyAsync(H, W.H + e * sH, sH * fb, cudaMemcpyDeviceToDevice, st));
+  IADMM_CUDA(cudaMemcpyAsync(C, W.C + e * sH, sH * fb, cudaMemcpyDeviceToDevice, st));
+  return IADMM_OK;
+}
+
+}  // extern "C"

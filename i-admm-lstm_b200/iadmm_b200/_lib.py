@@ -43,6 +43,8 @@ SIGNATURES = {
     "iadmm_train_workspace_bytes": ([_I, _I, _I, _I, POINTER(_Z)], c_int),
     "iadmm_step_fwd": ([_P] * 21 + [_I] * 7 + [_F, _I, _P, _Z, _P], c_int),
     "iadmm_step_bwd": ([_P] * 30 + [_I] * 7 + [_F, _P, _Z, _P], c_int),
+    "iadmm_window_workspace_bytes": ([_I] * 5 + [POINTER(_Z)], c_int),
+    "iadmm_train_window": ([_P] * 14 + [_I] * 8 + [_F, _F, _I, _P, _Z, _P], c_int),
     "iadmm_residuals_train_workspace_bytes": ([_I, _I, _I, POINTER(_Z)], c_int),
     "iadmm_residuals_fwd": ([_P] * 10 + [_I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_residuals_bwd": ([_P] * 11 + [_I, _I, _I, _P, _Z, _P], c_int),

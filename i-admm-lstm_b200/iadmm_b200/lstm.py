@@ -165,6 +165,48 @@ class LSTM(nn.Module):
                                      float(sigma), mode, flags, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         return SolveResult(x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met)
 
+    # -- one truncated-BPTT window, forward + backward, in one library call ------------------------
+    def train_window(self, TL, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state, t0=0, loss_scale=None, inplace=False):
+        """The body of main.py:336-358 for one window: TL iterations (t = t0..t0+TL-1), the loss
+        `sum_t primal_dual_loss(...).mean() * loss_scale` (default 1/TL; main.py uses 1/outer_T) and its gradient
+        w.r.t. every parameter, ADDED to `.grad` like `loss.backward()` does.  Returns (loss, state') with
+        state' = (x, y, z, xv, H, C) after the window, detached.  Equivalent to running `forward` +
+        `primal_dual_loss` under autograd, without a host round trip per iteration."""
+        from .autograd import PARAM_ORDER
+        L = _lib.lib()
+        _lib.require_cuda(Q, p, A0, zl, zu, *[prm for prm in self.parameters()])
+        dev = Q.device
+        Q, p, A0, zl, zu = (_lib.f32(t, dev) for t in (Q, p, A0, zl, zu))
+        B, n = Q.shape[0], Q.shape[1]
+        m = num_ineq + num_eq
+        h = self.hidden_dim
+        x, y, z, xv, H, C = (_lib.f32(t.detach(), dev) if inplace else _lib.f32(t.detach(), dev).clone() for t in state)
+        count, nbytes = c_size_t(), c_size_t()
+        _lib.check(L.iadmm_param_count(h, self.length, byref(count)))
+        _lib.check(L.iadmm_window_workspace_bytes(B, n, m, h, int(TL), byref(nbytes)))
+        ws = getattr(self, "_window_ws", None)
+        if ws is None or ws.numel() < nbytes.value or ws.device != dev:
+            self._window_ws = None
+            ws = self._window_ws = _lib.workspace(nbytes.value, dev)
+        flat = torch.empty((count.value,), device=dev)
+        loss = torch.empty((1,), device=dev)
+        scale = 1.0 / TL if loss_scale is None else float(loss_scale)
+        packed = self.packed_weights()
+        with torch.cuda.device(dev):
+            _lib.check(L.iadmm_train_window(_lib.ptr(packed), _lib.ptr(Q), _lib.ptr(p), _lib.ptr(A0), _lib.ptr(zl), _lib.ptr(zu),
+                                            _lib.ptr(x), _lib.ptr(y), _lib.ptr(z), _lib.ptr(xv), _lib.ptr(H), _lib.ptr(C),
+                                            _lib.ptr(flat), _lib.ptr(loss), B, n, int(num_ineq), int(num_eq), h, self.length,
+                                            int(t0), int(TL), float(sigma), scale, self._mode(), _lib.ptr(ws), ws.numel(),
+                                            _lib.stream_ptr()))
+        off = 0
+        for name in PARAM_ORDER:
+            prm = getattr(self, name)
+            k = prm.numel()
+            g = flat[off:off + k].view(prm.shape)
+            prm.grad = g.clone() if prm.grad is None else prm.grad + g
+            off += k
+        return loss[0], (x, y, z, xv, H, C)
+
     # -- the reference's per-iteration interface -------------------------------------------------
     def forward(self, t, num_ineq, num_eq, x, y, z, xv, sigma, H_t, C_t, **kwargs):
         """One iteration; returns (x, y, z, xv, H_t, C_t, A_tild, b_tild, rho_vec) like models/lstm.py:96.

@@ -202,6 +202,20 @@ int iadmm_residuals_bwd(const float* Q, const float* A0, const float* pri, const
                         float* gx, float* gy, float* gz,
                         int B, int n, int m, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One whole truncated-BPTT window (main.py:336-358) in a single call: for t = t0 .. t0+TL-1 the iteration
+ * (iadmm_step_fwd) and primal_dual_loss on its output, loss = loss_scale * sum_t mean_b(pri_t + dual_t)
+ * (loss_scale = 1/outer_T in main.py:347), then the backward sweep through the window.  x..C are updated in place to
+ * the state after the window (the reference detaches it there, main.py:353-358); grad_flat [iadmm_param_count] is
+ * OVERWRITTEN with d loss / d parameters (state_dict order, see above); loss_out [1].  Same kernels and results as
+ * the per-iteration entry points, without the host round trips between them. */
+int iadmm_window_workspace_bytes(int B, int n, int m, int h, int TL, size_t* bytes);
+int iadmm_train_window(const void* packed_weights,
+                       const float* Q, const float* p, const float* A0, const float* zl, const float* zu,
+                       float* x, float* y, float* z, float* xv, float* H, float* C,
+                       float* grad_flat, float* loss_out,
+                       int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int TL, float sigma,
+                       float loss_scale, int mode, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------
  * The reference times its solve with time.time() around model() (main.py:881-890, no device sync).
  * Between iadmm_profile_begin and iadmm_profile_end every iadmm_solve call records CUDA events on its

@@ -133,3 +133,61 @@ def test_residual_gradients():
     w = wts.float().to(DEV)
     (gp * w + 2.0 * gd * (1 - w)).sum().backward()
     assert rel_err(xg.grad, xr.grad) < 1e-5 and rel_err(yg.grad, yr.grad) < 1e-5 and rel_err(zg.grad, zr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16f8"])
+@pytest.mark.parametrize("shape", [(3, 24, 7, 9, 16, 6), (2, 37, 9, 11, 48, 5), (2, 20, 0, 0, 16, 4)])
+def test_fused_window_equals_per_iteration_autograd(shape, mode):
+    """iadmm_train_window (one call per window) against the per-iteration autograd path it replaces: same kernels in
+    the same order, so loss, end state and every parameter gradient agree to rounding of the loss seed."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, TL = shape
+    outer_T = 2 * TL
+    if mi + me:
+        qp = orc.qp_instances(B, n, mi, me, seed=71)
+    else:
+        g = torch.Generator().manual_seed(71)
+        M = torch.randn(B, n, n, generator=g)
+        qp = dict(Q=M @ M.transpose(1, 2) / n + 0.1 * torch.eye(n), p=torch.randn(B, n, 1, generator=g),
+                  A0=torch.zeros(B, 0, n), zl=torch.zeros(B, 0, 1), zu=torch.zeros(B, 0, 1))
+    prm = orc.lstm_parameters(h, outer_T, seed=71)
+    loss_a, grads_a, state_a, model = our_window(prm, qp, mi, me, h, TL, outer_T, mode=mode)
+    # second window from the state the first one left, both ways
+    loss_a2, grads_a2, state_a2, _ = our_window(prm, qp, mi, me, h, TL, outer_T, state=state_a, mode=mode)
+    m = mi + me
+    Q, p, A0, zl, zu = (qp[k].to(DEV) for k in ("Q", "p", "A0", "zl", "zu"))
+    st = [torch.zeros((B, n, 1), device=DEV), torch.zeros((B, m, 1), device=DEV), torch.zeros((B, m, 1), device=DEV),
+          torch.zeros((B, n + m, 1), device=DEV), torch.zeros((B, n + m, h), device=DEV), torch.zeros((B, n + m, h), device=DEV)]
+    model.zero_grad()
+    loss_f, st1 = model.train_window(TL, mi, me, Q, p, A0, zl, zu, 6e-6, st, t0=0, loss_scale=1.0 / outer_T)
+    grads_f = {k: getattr(model, k).grad.clone() for k in prm}
+    model.zero_grad()
+    loss_f2, st2 = model.train_window(TL, mi, me, Q, p, A0, zl, zu, 6e-6, st1, t0=0, loss_scale=1.0 / outer_T)
+    grads_f2 = {k: getattr(model, k).grad.clone() for k in prm}
+    assert abs(float(loss_f) - loss_a) <= 1e-6 * abs(loss_a) and abs(float(loss_f2) - loss_a2) <= 1e-6 * abs(loss_a2)
+    for a, f in zip(state_a + state_a2, list(st1) + list(st2)):
+        assert torch.equal(a.reshape(-1), f.reshape(-1))
+    for ga, gf in ((grads_a, grads_f), (grads_a2, grads_f2)):
+        for k in prm:
+            if k in ("rho", "alpha"):
+                assert torch.allclose(ga[k], gf[k], rtol=1e-4, atol=1e-7 * float(ga[k].abs().max() + 1e-30)), k
+            else:
+                assert rel_err(gf[k], ga[k]) < 1e-5, (k, rel_err(gf[k], ga[k]))
+
+
+def test_fused_window_accumulates_into_existing_grads():
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, TL = 2, 20, 5, 6, 16, 3
+    qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=3).items()}
+    model = ia.LSTM(None, 2, h, TL, DEV)
+    m = mi + me
+    st = [torch.zeros((B, n, 1), device=DEV), torch.zeros((B, m, 1), device=DEV), torch.zeros((B, m, 1), device=DEV),
+          torch.zeros((B, n + m, 1), device=DEV), torch.zeros((B, n + m, h), device=DEV), torch.zeros((B, n + m, h), device=DEV)]
+    args = (TL, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6, st)
+    model.train_window(*args)
+    g1 = model.U_i.grad.clone()
+    model.train_window(*args)
+    assert torch.allclose(model.U_i.grad, 2 * g1, rtol=1e-6, atol=0)
+    assert all(torch.count_nonzero(s) == 0 for s in st)          # the caller's state is not modified unless inplace=True

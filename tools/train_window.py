@@ -17,7 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=2); ap.add_argument("--tl", type=int, default=100)
 ap.add_argument("--windows", type=int, default=3); ap.add_argument("--n", type=int, default=1000)
 ap.add_argument("--hidden", type=int, default=800); ap.add_argument("--lr", type=float, default=5e-5)
-ap.add_argument("--gate-mode", default="tc_f16f8")
+ap.add_argument("--gate-mode", default="tc_f16f8"); ap.add_argument("--fused", type=int, default=1)
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr_ = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr_); dev = torch.device("cuda", lr_)
@@ -35,22 +35,27 @@ x = torch.zeros((B, n, 1), device=dev); y = torch.zeros((B, m, 1), device=dev); 
 xv = torch.zeros((B, n + m, 1), device=dev); H = torch.zeros((B, n + m, h), device=dev); C = torch.zeros((B, n + m, h), device=dev)
 times, losses = [], []
 for wdw in range(a.windows):
+    if os.environ.get("PROFILE_WINDOW") == str(wdw): torch.cuda.profiler.start()
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     t0 = time.perf_counter()
-    loss = 0.0
-    for t in range(TL):
-        x, y, z, xv, H, C, _, _, _ = model(t, mi, me, x, y, z, xv, 6e-6, H, C, Q=Q, p=p, A0=A0, lb=None, ub=None, zl=zl, zu=zu)
-        pr, du, tot = ia.primal_dual_loss(x, y, z, Q, p, A0)
-        loss = loss + tot.mean() / TL
     opt.zero_grad()
-    loss.backward()
+    if a.fused:                                      # one library call per window (iadmm_train_window)
+        loss, (x, y, z, xv, H, C) = model.train_window(TL, mi, me, Q, p, A0, zl, zu, 6e-6, (x, y, z, xv, H, C), loss_scale=1.0 / TL)
+    else:                                            # the reference's loop, one autograd node per iteration
+        loss = 0.0
+        for t in range(TL):
+            x, y, z, xv, H, C, _, _, _ = model(t, mi, me, x, y, z, xv, 6e-6, H, C, Q=Q, p=p, A0=A0, lb=None, ub=None, zl=zl, zu=zu)
+            pr, du, tot = ia.primal_dual_loss(x, y, z, Q, p, A0)
+            loss = loss + tot.mean() / TL
+        loss.backward()
     if world > 1:
         allreduce_gradients(model)                   # ONE all-reduce of the flat gradient buffer per window
     opt.step()
     x, y, z, xv, H, C = (v.detach() for v in (x, y, z, xv, H, C))
     torch.cuda.synchronize()
     times.append(time.perf_counter() - t0); losses.append(float(loss))
+    if os.environ.get("PROFILE_WINDOW") == str(wdw): torch.cuda.profiler.stop()
 chk = torch.stack([prm.detach().double().sum() for prm in model.parameters()]).sum()
 if world > 1:
     lo, hi = chk.clone(), chk.clone()
@@ -59,7 +64,8 @@ if world > 1:
 else:
     same = True
 if rank == 0:
-    print(json.dumps({"workload": f"TBPTT window: n={n}, {mi}+{me}, h={h}, TL={TL}, batch {B}/GPU, fwd+bwd+allreduce+Adam",
+    print(json.dumps({"workload": f"TBPTT window: n={n}, {mi}+{me}, h={h}, TL={TL}, batch {B}/GPU, fwd+bwd+allreduce+Adam, " +
+                                  ("one fused call per window" if a.fused else "per-iteration autograd"),
                       "n_gpus": world, "s_per_window": times, "instances_per_s": world * B / min(times[1:] or times),
                       "loss": losses, "weights_identical_across_ranks": same,
                       "mem_GB": torch.cuda.max_memory_allocated() / 1e9}))
