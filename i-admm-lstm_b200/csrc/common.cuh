@@ -153,8 +153,11 @@ struct KktDims {
   int B, n, m, num_ineq;
   int rows_per_chunk;          // R: rows of Q / A0 one CTA streams (multiple of 8)
   int chunks_q, chunks_a;      // ceil(n/R), ceil(m/R)
+  int sum_q, sum_a;            // column partials the combine kernels add up (1 once folded into chunk 0, else = chunks)
 };
 KktDims make_kkt_dims(int B, int n, int m, int num_ineq);
+int kkt_sum_chunks(int chunks);   // partials left to add after launch_kkt_combine1/2 (1 when they were folded)
+KktDims make_kkt_dims_train(int B, int n, int m, int num_ineq);   // batch-aware chunking for the training entry points
 
 struct KktScratch {            // all [B, ...] fp32, carved from the solve workspace
   float* qxt;   // [B,n]   Q  x~          (pass 1)

@@ -270,6 +270,65 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
   }
 }
 
+// One read of X fp32 [R][Cc] -> fp16 hi/lo of X * scale both row-major [R][Cc] (hi/lo, may be NULL) and transposed
+// [Cc][Rp] (thi/tlo; Rp even, padding columns pre-zeroed).  64 x 64 tiles: every global access is a full 128-byte
+// (fp16 pairs) or 256-byte (fp32 pairs) warp request.
+__global__ void __launch_bounds__(256) split_both_kernel(const float* __restrict__ X, long R, long Cc, long Rp,
+                                                         const float* __restrict__ scale, __half* __restrict__ hi,
+                                                         __half* __restrict__ lo, __half* __restrict__ thi,
+                                                         __half* __restrict__ tlo) {
+  __shared__ float tile[64][65];
+  const float s = scale ? scale[0] : (float)(1 << kHShift);
+  const long r0 = (long)blockIdx.y * 64, c0 = (long)blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool cvec = (Cc % 2 == 0);
+  for (int j = warp; j < 64; j += 8) {
+    const long r = r0 + j, c = c0 + 2 * lane;
+    float v0 = 0.f, v1 = 0.f;
+    if (r < R) {
+      if (cvec && c + 1 < Cc) { const float2 t = *reinterpret_cast<const float2*>(X + r * Cc + c); v0 = t.x * s; v1 = t.y * s; }
+      else { if (c < Cc) v0 = X[r * Cc + c] * s; if (c + 1 < Cc) v1 = X[r * Cc + c + 1] * s; }
+    }
+    tile[j][2 * lane] = v0; tile[j][2 * lane + 1] = v1;
+    if (hi && r < R) {
+      const __half2 a = __floats2half2_rn(v0, v1);
+      const float2 back = __half22float2(a);
+      const __half2 l = __floats2half2_rn(v0 - back.x, v1 - back.y);
+      if (cvec && c + 1 < Cc) {
+        *reinterpret_cast<__half2*>(hi + r * Cc + c) = a;
+        *reinterpret_cast<__half2*>(lo + r * Cc + c) = l;
+      } else {
+        if (c < Cc) { hi[r * Cc + c] = __low2half(a); lo[r * Cc + c] = __low2half(l); }
+        if (c + 1 < Cc) { hi[r * Cc + c + 1] = __high2half(a); lo[r * Cc + c + 1] = __high2half(l); }
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = warp; j < 64; j += 8) {
+    const long c = c0 + j, r = r0 + 2 * lane;
+    if (c < Cc && r < R) {
+      const float v0 = tile[2 * lane][j], v1 = (r + 1 < R) ? tile[2 * lane + 1][j] : 0.f;
+      const __half2 a = __floats2half2_rn(v0, v1);
+      const float2 back = __half22float2(a);
+      const __half2 l = __floats2half2_rn(v0 - back.x, v1 - back.y);
+      if (r + 1 < Rp) {                      // Rp is even: the pair never crosses the pitch
+        *reinterpret_cast<__half2*>(thi + c * Rp + r) = a;
+        *reinterpret_cast<__half2*>(tlo + c * Rp + r) = l;
+      } else {
+        thi[c * Rp + r] = __low2half(a); tlo[c * Rp + r] = __low2half(l);
+      }
+    }
+  }
+}
+
+int launch_split_both(const float* X, long R, long Cc, long Rp, const float* scale, __half* hi, __half* lo, __half* thi, __half* tlo,
+                      cudaStream_t st) {
+  const dim3 grid((unsigned)((Cc + 63) / 64), (unsigned)((R + 63) / 64));
+  split_both_kernel<<<grid, 256, 0, st>>>(X, R, Cc, Rp, scale, hi, lo, thi, tlo);
+  IADMM_LAUNCH_CHECK("split_both_kernel");
+  return IADMM_OK;
+}
+
 int launch_absmax(const float* X, size_t count, float* out, cudaStream_t st) {
   IADMM_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   const size_t blocks = (count + 255) / 256;

@@ -26,19 +26,33 @@ constexpr int kRowUnroll  = 8;
 constexpr int kSlabCols   = 128;                    // columns per warp per column chunk
 constexpr int kChunkCols  = kSlabCols * kKktWarps;  // 1024
 
-KktDims make_kkt_dims(int B, int n, int m, int num_ineq) {
+static KktDims kkt_dims_with_rows(int B, int n, int m, int num_ineq, int R) {
   KktDims d;
   d.B = B; d.n = n; d.m = m; d.num_ineq = num_ineq;
+  d.rows_per_chunk = R;
+  d.chunks_q = cdiv(n, R);
+  d.chunks_a = cdiv(m, R);
+  d.sum_q = d.chunks_q; d.sum_a = d.chunks_a;
+  return d;
+}
+
+KktDims make_kkt_dims(int B, int n, int m, int num_ineq) {
   // Rows per CTA depend on the problem size only, never on the batch: the grouping of the column partial sums
   // (and with it every rounding) is then identical however a batch is sharded over calls or GPUs, so
   // "concatenation of shards == whole batch" holds bit for bit.  64 rows keep the column-partial traffic
   // (4n bytes per chunk and product) at ~3 % of the 4nR bytes streamed and give B*(n+m)/64 CTAs.
-  (void)B;
-  const int R = ((n > m ? n : m) >= 64) ? 64 : 32;
-  d.rows_per_chunk = R;
-  d.chunks_q = cdiv(n, R);
-  d.chunks_a = cdiv(m, R);
-  return d;
+  return kkt_dims_with_rows(B, n, m, num_ineq, ((n > m ? n : m) >= 64) ? 64 : 32);
+}
+
+KktDims make_kkt_dims_train(int B, int n, int m, int num_ineq) {
+  // Training runs at a few instances per GPU (BASELINE config 3: batch 2): 64-row chunks would give B*(n+m)/64 = 62
+  // CTAs for 148 SMs.  The training entry points therefore shrink the chunk until one wave (148 SMs x 4 CTAs) is
+  // filled -- at the price of more column-partial traffic, and of results that depend on the batch size in the last
+  // bits (gradients are averaged over ranks anyway).
+  const int base = make_kkt_dims(B, n, m, num_ineq).rows_per_chunk;
+  int R = base;
+  while (R > 8 && (long)(cdiv(n, R) + cdiv(m, R)) * B < 592) R >>= 1;
+  return kkt_dims_with_rows(B, n, m, num_ineq, R);
 }
 
 size_t kkt_scratch_floats(const KktDims& d) {
@@ -374,7 +388,7 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
   float imax = 0.f, emax = 0.f;
   for (int j = threadIdx.x; j < d.n; j += kCombThreads) {
     float atv = 0.f, aty = 0.f;
-    for (int c = 0; c < d.chunks_a; ++c) {
+    for (int c = 0; c < d.sum_a; ++c) {
       atv += part[((size_t)c * 2 + 0) * n + j];
       aty += part[((size_t)c * 2 + 1) * n + j];
     }
@@ -448,6 +462,29 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
   }
 }
 
+// With many small chunks (training at a few instances per GPU) the per-column loops over the chunk partials in the
+// combine kernels become a serial chain in too few CTAs.  fold_partials sums them with 4 x 64 threads per 64 columns
+// into chunk 0 (fixed order: four interleaved groups, then ((g0+g1)+g2)+g3) and the combine kernels read one partial.
+constexpr int kFoldThreshold = 32;
+__global__ void __launch_bounds__(256) fold_partials_kernel(float* __restrict__ part, int chunks, int slots, int n) {
+  __shared__ float sh[4][64];
+  const int t = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + t;
+  float* base = part + ((size_t)blockIdx.z * chunks * slots + blockIdx.y) * n;
+  float s = 0.f;
+  if (j < n)
+    for (int c = g; c < chunks; c += 4) s += base[(size_t)c * slots * n + j];
+  sh[g][t] = s;
+  __syncthreads();
+  if (g == 0 && j < n) base[j] = ((sh[0][t] + sh[1][t]) + sh[2][t]) + sh[3][t];
+}
+static int fold_partials(float* part, int B, int chunks, int slots, int nfold, int n, cudaStream_t st) {
+  fold_partials_kernel<<<dim3(cdiv(n, 64), nfold, B), 256, 0, st>>>(part, chunks, slots, n);
+  IADMM_LAUNCH_CHECK("fold_partials_kernel");
+  return IADMM_OK;
+}
+int kkt_sum_chunks(int chunks) { return chunks >= kFoldThreshold ? 1 : chunks; }
+
 int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const float* x, const float* y,
                         const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
                         float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
@@ -466,6 +503,11 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
   A.zu = zu;
   A.sd = sd; A.se = se; A.sc = sc;
   A.residual_only = residual_only;
+  if (d.m > 0 && d.chunks_a >= kFoldThreshold) {
+    int rc = fold_partials(s.part_a, d.B, d.chunks_a, 2, 2, d.n, st);
+    if (rc) return rc;
+    A.d.sum_a = 1;
+  }
   kkt_combine1_kernel<<<d.B, kCombThreads, 0, st>>>(A);
   IADMM_LAUNCH_CHECK("kkt_combine1_kernel");
   return IADMM_OK;
@@ -484,9 +526,9 @@ __global__ void __launch_bounds__(256) kkt_combine2_kernel(const KktDims d, cons
   if (r < d.n) {
     float qtw = 0.f, atw = 0.f;
     const float* pq = s.part_q + b * d.chunks_q * n + r;
-    for (int c = 0; c < d.chunks_q; ++c) qtw += pq[(size_t)c * n];
+    for (int c = 0; c < d.sum_q; ++c) qtw += pq[(size_t)c * n];
     const float* pa = s.part_a + b * d.chunks_a * 2 * n + r;
-    for (int c = 0; c < d.chunks_a; ++c) atw += pa[(size_t)c * 2 * n];
+    for (int c = 0; c < d.sum_a; ++c) atw += pa[(size_t)c * 2 * n];
     const float w1 = s.w[b * N + r];
     s.g[idx] = __fadd_rn(__fadd_rn(qtw, __fmul_rn(sigma, w1)), atw);
   } else {
@@ -498,7 +540,14 @@ __global__ void __launch_bounds__(256) kkt_combine2_kernel(const KktDims d, cons
 
 int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, const KktScratch& s, cudaStream_t st) {
   const size_t total = (size_t)d.B * (d.n + d.m);
-  kkt_combine2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, sched_t, sigma, s);
+  KktDims d2 = d;
+  int rc;
+  if (d.chunks_q >= kFoldThreshold) { if ((rc = fold_partials(s.part_q, d.B, d.chunks_q, 1, 1, d.n, st))) return rc; d2.sum_q = 1; }
+  if (d.m > 0 && d.chunks_a >= kFoldThreshold) {     // slot 0 only is live after pass 2
+    if ((rc = fold_partials(s.part_a, d.B, d.chunks_a, 2, 1, d.n, st))) return rc;
+    d2.sum_a = 1;
+  }
+  kkt_combine2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d2, sched_t, sigma, s);
   IADMM_LAUNCH_CHECK("kkt_combine2_kernel");
   return IADMM_OK;
 }

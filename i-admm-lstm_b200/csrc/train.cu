@@ -28,6 +28,8 @@ int launch_absmax(const float* X, size_t count, float* out, cudaStream_t st);
 int launch_gemm_scales(const float* absmax, const float* other, float* scales, cudaStream_t st);
 int launch_split_rows(const float* X, size_t count, const float* scale, __half* hi, __half* lo, cudaStream_t st);
 int launch_split_transpose(const float* X, long R, long Cc, long Rp, const float* scale, __half* hi, __half* lo, cudaStream_t st);
+int launch_split_both(const float* X, long R, long Cc, long Rp, const float* scale, __half* hi, __half* lo, __half* thi, __half* tlo,
+                      cudaStream_t st);
 
 static bool use_tc_backward() {
   static int v = -1;
@@ -138,20 +140,27 @@ static int launch_sgemm(const float* A, const float* Bm, float* C, long M, long 
 // ------------------------------------------------------------------------------------------------
 // weighted column sums  out[w][c] = sum_r weight_w[r] * M[r,c]   (weight NULL = ones), two deterministic stages
 // ------------------------------------------------------------------------------------------------
-constexpr int kCsRows = 256;   // rows per partial
+// rows per partial: 256 at large row counts (bounded partial buffer), down to 32 so that a few thousand rows still
+// fill the GPU; a function of the row count only
+static int cs_rows_per_part(size_t rows) {
+  size_t r = rows / 1024;
+  r = (r + 7) / 8 * 8;
+  return (int)(r < 32 ? 32 : (r > 256 ? 256 : r));
+}
 
 template <int NW>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ Mx, long rows, int cols,
                                                              const float* __restrict__ w0, const float* __restrict__ w1,
                                                              const float* __restrict__ w2, float wscale,
-                                                             float* __restrict__ part) {
+                                                             float* __restrict__ part, int rows_per_part) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const long r0 = (long)blockIdx.y * kCsRows;
+  const long r0 = (long)blockIdx.y * rows_per_part;
   if (c >= cols) return;
-  const long r1 = (r0 + kCsRows < rows) ? r0 + kCsRows : rows;
+  const long r1 = (r0 + rows_per_part < rows) ? r0 + rows_per_part : rows;
   float acc[NW];
 #pragma unroll
   for (int w = 0; w < NW; ++w) acc[w] = 0.f;
+#pragma unroll 8
   for (long r = r0; r < r1; ++r) {
     const float v = Mx[r * cols + c];
     const float* ws[3] = {w0, w1, w2};
@@ -162,17 +171,23 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   for (int w = 0; w < NW; ++w) part[((size_t)blockIdx.y * NW + w) * cols + c] = acc[w];
 }
 
-// out[w*out_stride + map(c)] += sum over partials; map un-interleaves gate columns when `deinterleave`
+// out_w[c] = sum over partials (fixed order: four interleaved groups of partials, then ((g0+g1)+g2)+g3).
+// block = 64 columns x 4 groups
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int nparts, int nw, int cols,
                                                            float* __restrict__ out0, float* __restrict__ out1,
                                                            float* __restrict__ out2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ float sh[4][64];
+  const int t = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + t;
   float* outs[3] = {out0, out1, out2};
   for (int w = 0; w < nw; ++w) {
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[((size_t)p * nw + w) * cols + c];
-    outs[w][c] = s;
+    if (c < cols)
+      for (int p = g; p < nparts; p += 4) s += part[((size_t)p * nw + w) * cols + c];
+    sh[g][t] = s;
+    __syncthreads();
+    if (g == 0 && c < cols) outs[w][c] = ((sh[0][t] + sh[1][t]) + sh[2][t]) + sh[3][t];
+    __syncthreads();
   }
 }
 
@@ -255,45 +270,50 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const KktDims d, const Sc
 // ------------------------------------------------------------------------------------------------
 // backward of the cell non-linearities (models/lstm.py:74-80): D = pre-activation adjoints [rows,4h]
 // ------------------------------------------------------------------------------------------------
+// One warp per coordinate row.  Besides D and gC the same sweep produces what used to be two more passes over D:
+// the per-row dots with the two W rows (the cell's direct xv adjoint and the adjoint of g) and max|D| (the scale of
+// the fp16 split of the tensor-core backward GEMMs; atomicMax on the bits of a non-negative float).
 __global__ void __launch_bounds__(256) cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ C_in,
                                                        const float* __restrict__ wh, const float* __restrict__ Xbar,
                                                        const float* __restrict__ gH_o, const float* __restrict__ gC_o,
-                                                       float* __restrict__ D, float* __restrict__ gC, long rows, int h) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)rows * h) return;
-  const size_t r = idx / h;
-  const int j = (int)(idx - r * h);
-  const float4 g4 = *reinterpret_cast<const float4*>(gates + r * 4 * (size_t)h + 4 * (size_t)j);
-  const float gi = g4.x, gf = g4.y, go = g4.z, gu = g4.w;
-  const float c_in = C_in[idx];
-  const float cn = gi * gu + gf * c_in;
-  const float tc = tanhf(cn);
-  const float hbar = (gH_o ? gH_o[idx] : 0.f) - Xbar[r] * wh[j];      // s_bar = -Xbar (xv' = xv - s)
-  const float obar = hbar * tc;
-  const float cbar = (gC_o ? gC_o[idx] : 0.f) + hbar * go * (1.f - tc * tc);
-  float4 dd;
-  dd.x = cbar * gu * gi * (1.f - gi);
-  dd.y = cbar * c_in * gf * (1.f - gf);
-  dd.z = obar * go * (1.f - go);
-  dd.w = cbar * gi * (1.f - gu * gu);
-  *reinterpret_cast<float4*>(D + r * 4 * (size_t)h + 4 * (size_t)j) = dd;
-  gC[idx] = cbar * gf;
-}
-
-// per-row dots of D with the two W rows:  out0[r] = D_r . W[0,:],  out1[r] = D_r . W[1,:]   (one warp per row)
-__global__ void __launch_bounds__(256) rowdot2_kernel(const float* __restrict__ D, const float* __restrict__ wc, long rows,
-                                                      int h4, float* __restrict__ out0, float* __restrict__ out1) {
+                                                       const float* __restrict__ wc, float* __restrict__ D,
+                                                       float* __restrict__ gC, float* __restrict__ out0,
+                                                       float* __restrict__ out1, float* __restrict__ absmax, long rows, int h) {
   const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
-  float a = 0.f, b = 0.f;
-  for (int c = lane; c < h4; c += 32) {
-    const float v = D[r * h4 + c];
-    a = fmaf(v, wc[c], a);
-    b = fmaf(v, wc[h4 + c], b);
+  const float xb = Xbar[r];
+  const size_t h4 = 4 * (size_t)h;
+  float a = 0.f, b = 0.f, mx = 0.f;
+  for (int j = lane; j < h; j += 32) {
+    const size_t idx = (size_t)r * h + j;
+    const float4 g4 = *reinterpret_cast<const float4*>(gates + r * h4 + 4 * (size_t)j);
+    const float gi = g4.x, gf = g4.y, go = g4.z, gu = g4.w;
+    const float c_in = C_in[idx];
+    const float cn = gi * gu + gf * c_in;
+    const float tc = tanhf(cn);
+    const float hbar = (gH_o ? gH_o[idx] : 0.f) - xb * wh[j];            // s_bar = -Xbar (xv' = xv - s)
+    const float obar = hbar * tc;
+    const float cbar = (gC_o ? gC_o[idx] : 0.f) + hbar * go * (1.f - tc * tc);
+    float4 dd;
+    dd.x = cbar * gu * gi * (1.f - gi);
+    dd.y = cbar * c_in * gf * (1.f - gf);
+    dd.z = obar * go * (1.f - go);
+    dd.w = cbar * gi * (1.f - gu * gu);
+    *reinterpret_cast<float4*>(D + r * h4 + 4 * (size_t)j) = dd;
+    gC[idx] = cbar * gf;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + 4 * (size_t)j));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + h4 + 4 * (size_t)j));
+    a = fmaf(dd.x, w0.x, a); a = fmaf(dd.y, w0.y, a); a = fmaf(dd.z, w0.z, a); a = fmaf(dd.w, w0.w, a);
+    b = fmaf(dd.x, w1.x, b); b = fmaf(dd.y, w1.y, b); b = fmaf(dd.z, w1.z, b); b = fmaf(dd.w, w1.w, b);
+    const float m4 = fmaxf(fmaxf(fabsf(dd.x), fabsf(dd.y)), fmaxf(fabsf(dd.z), fabsf(dd.w)));
+    if (isfinite(m4)) mx = fmaxf(mx, m4);
   }
-  a = warp_sum(a); b = warp_sum(b);
-  if (lane == 0) { out0[r] = a; out1[r] = b; }
+  a = warp_sum(a); b = warp_sum(b); mx = warp_max(mx);
+  if (lane == 0) {
+    out0[r] = a; out1[r] = b;
+    atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(mx));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -409,17 +429,18 @@ struct TrainWs {
   long rows_p;                                    // row count padded to 8 (pitch of the transposed operands)
   Sched* zero_sched;
   double* acc;
-  int tiles, cs_parts;
+  int tiles, cs_parts, cs_rows;
   size_t bytes;
 };
 
 static void plan_train(int B, int n, int m, int num_ineq, int h, void* base, TrainWs* W) {
-  W->d = make_kkt_dims(B, n, m, num_ineq);
+  W->d = make_kkt_dims_train(B, n, m, num_ineq);
   const size_t rows = (size_t)B * (n + m);
   W->tiles = simt_gate_tiles(h);
   const int tc_tiles = (h % 8 == 0) ? tc_gate_tiles(h) : 0;
   const int max_tiles = W->tiles > tc_tiles ? W->tiles : tc_tiles;
-  W->cs_parts = (int)((rows + kCsRows - 1) / kCsRows);
+  W->cs_rows = cs_rows_per_part(rows);
+  W->cs_parts = (int)((rows + W->cs_rows - 1) / W->cs_rows);
   char* p = static_cast<char*>(base);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? p + o : nullptr; };
@@ -588,43 +609,41 @@ int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, c
   tail_bwd_kernel<<<row_blocks, 256, 0, st>>>(W.d, sk, zl, zu, x, y, z, xv_o, gx_o, gy_o, gz_o, gxv_o, W.Xbar, gx, gy, gz, W.acc);
   IADMM_LAUNCH_CHECK("tail_bwd_kernel");
   // 2. cell non-linearities -> D, gC
-  cell_bwd_kernel<<<(unsigned)((rows * h + 255) / 256), 256, 0, st>>>(gates_save, C, wh, W.Xbar, gH_o, gC_o, W.D, gC, (long)rows, h);
+  IADMM_CUDA(cudaMemsetAsync(W.gscal, 0, sizeof(float), st));
+  cell_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(gates_save, C, wh, W.Xbar, gH_o, gC_o, wc, W.D, gC, W.xvbar_cell, W.gbar,
+                                                               W.gscal, (long)rows, h);
   IADMM_LAUNCH_CHECK("cell_bwd_kernel");
   // 3. small parameter adjoints: W_h (weights s_bar = -Xbar over H'), b_h, and b, W rows over D
   {
     const dim3 g1((unsigned)cdiv(h, 256), (unsigned)W.cs_parts);
-    colsum_partial_kernel<1><<<g1, 256, 0, st>>>(H_o, (long)rows, h, W.Xbar, nullptr, nullptr, -1.0f, W.cs_part);
+    colsum_partial_kernel<1><<<g1, 256, 0, st>>>(H_o, (long)rows, h, W.Xbar, nullptr, nullptr, -1.0f, W.cs_part, W.cs_rows);
     IADMM_LAUNCH_CHECK("colsum_partial_kernel<1>");
-    colsum_final_kernel<<<cdiv(h, 256), 256, 0, st>>>(W.cs_part, W.cs_parts, 1, h, W.whbar, nullptr, nullptr);
+    colsum_final_kernel<<<cdiv(h, 64), 256, 0, st>>>(W.cs_part, W.cs_parts, 1, h, W.whbar, nullptr, nullptr);
     IADMM_LAUNCH_CHECK("colsum_final_kernel");
     negate_sum_kernel<<<1, 1024, 0, st>>>(W.Xbar, (long)rows, W.sbar_sum);
     IADMM_LAUNCH_CHECK("negate_sum_kernel");
     const dim3 g3((unsigned)cdiv(h4, 256), (unsigned)W.cs_parts);
-    colsum_partial_kernel<3><<<g3, 256, 0, st>>>(W.D, (long)rows, h4, nullptr, xv, g_save, 1.0f, W.cs_part);
+    colsum_partial_kernel<3><<<g3, 256, 0, st>>>(W.D, (long)rows, h4, nullptr, xv, g_save, 1.0f, W.cs_part, W.cs_rows);
     IADMM_LAUNCH_CHECK("colsum_partial_kernel<3>");
-    colsum_final_kernel<<<cdiv(h4, 256), 256, 0, st>>>(W.cs_part, W.cs_parts, 3, h4, W.bbar, W.w0bar, W.w1bar);
+    colsum_final_kernel<<<cdiv(h4, 64), 256, 0, st>>>(W.cs_part, W.cs_parts, 3, h4, W.bbar, W.w0bar, W.w1bar);
     IADMM_LAUNCH_CHECK("colsum_final_kernel");
   }
-  // 4. input adjoints of the cell: xv (direct) and g
-  rowdot2_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(W.D, wc, (long)rows, h4, W.xvbar_cell, W.gbar);
-  IADMM_LAUNCH_CHECK("rowdot2_kernel");
+  // 4. (input adjoints of the cell, xv direct and g: produced by cell_bwd_kernel)
   // 5. the two GEMMs: H_bar = D U^T ; U_bar = H^T D
   if (use_tc_backward() && h % 16 == 0 && rows / 32 < 65535) {
     // tensor cores, fp16 hi/lo split of D * s_D (s_D from max|D|), U * s_U, H * 2^14: fp32-class products
     const float* wscale = reinterpret_cast<const float*>(wbase + L.off_scale);            // [0] = s_U
     const __half* u32hi = reinterpret_cast<const __half*>(wbase + L.off_u32hi);
     const __half* u32lo = reinterpret_cast<const __half*>(wbase + L.off_u32lo);
-    if ((rc = launch_absmax(W.D, rows * (size_t)h4, W.gscal, st))) return rc;
     if ((rc = launch_gemm_scales(W.gscal, wscale, W.gscal + 4, st))) return rc;          // [4] s_D, [5] 1/(s_D s_U), [6] 1/(s_D 2^14)
-    if ((rc = launch_split_rows(W.D, rows * (size_t)h4, W.gscal + 4, W.d_hi, W.d_lo, st))) return rc;
     if (W.rows_p != (long)rows) {        // zero the pitch padding of the transposed operands
       IADMM_CUDA(cudaMemsetAsync(W.dt_hi, 0, (size_t)W.rows_p * h4 * sizeof(__half), st));
       IADMM_CUDA(cudaMemsetAsync(W.dt_lo, 0, (size_t)W.rows_p * h4 * sizeof(__half), st));
       IADMM_CUDA(cudaMemsetAsync(W.ht_hi, 0, (size_t)W.rows_p * h * sizeof(__half), st));
       IADMM_CUDA(cudaMemsetAsync(W.ht_lo, 0, (size_t)W.rows_p * h * sizeof(__half), st));
     }
-    if ((rc = launch_split_transpose(W.D, (long)rows, h4, W.rows_p, W.gscal + 4, W.dt_hi, W.dt_lo, st))) return rc;
-    if ((rc = launch_split_transpose(H, (long)rows, h, W.rows_p, nullptr, W.ht_hi, W.ht_lo, st))) return rc;
+    if ((rc = launch_split_both(W.D, (long)rows, h4, W.rows_p, W.gscal + 4, W.d_hi, W.d_lo, W.dt_hi, W.dt_lo, st))) return rc;
+    if ((rc = launch_split_both(H, (long)rows, h, W.rows_p, nullptr, nullptr, nullptr, W.ht_hi, W.ht_lo, st))) return rc;
     if ((rc = launch_tc_gemm_nt(W.d_hi, W.d_lo, u32hi, u32lo, gH, W.gscal + 5, (long)rows, h, h4, h4, h4, h, st))) return rc;
     if ((rc = launch_tc_gemm_nt(W.ht_hi, W.ht_lo, W.dt_hi, W.dt_lo, W.u32bar, W.gscal + 6, h, h4, (long)rows, W.rows_p, W.rows_p,
                                 h4, st))) return rc;
@@ -670,7 +689,7 @@ __global__ void __launch_bounds__(256) residual_vectors_kernel(const KktDims d, 
   if (r < d.n) {
     float aty = 0.f;
     const float* part = s.part_a + b * d.chunks_a * 2 * n;
-    for (int c = 0; c < d.chunks_a; ++c) aty += part[((size_t)c * 2 + 1) * n + r];
+    for (int c = 0; c < d.sum_a; ++c) aty += part[((size_t)c * 2 + 1) * n + r];
     rd[b * n + r] = __fadd_rn(__fadd_rn(s.qx[b * n + r], p[b * n + r]), aty);
   } else {
     const int i = r - d.n;
@@ -720,7 +739,7 @@ extern "C" {
 
 int iadmm_residuals_train_workspace_bytes(int B, int n, int m, size_t* bytes) {
   if (B <= 0 || n <= 0 || m < 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "residuals_train_workspace_bytes: B=%d n=%d m=%d", B, n, m);
-  *bytes = kkt_scratch_floats(make_kkt_dims(B, n, m, 0)) * sizeof(float) + 1024;
+  *bytes = kkt_scratch_floats(make_kkt_dims_train(B, n, m, 0)) * sizeof(float) + 1024;
   return IADMM_OK;
 }
 
@@ -732,7 +751,7 @@ int iadmm_residuals_fwd(const float* x, const float* y, const float* z, const fl
   if (m > 0 && (!y || !z || !A0 || !rp_save)) IADMM_FAIL(IADMM_EALIGN, "residuals_fwd: NULL constraint pointer");
   int rc = check_sm100();
   if (rc) return rc;
-  const KktDims d = make_kkt_dims(B, n, m, 0);
+  const KktDims d = make_kkt_dims_train(B, n, m, 0);
   if (kkt_scratch_floats(d) * sizeof(float) > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "residuals_fwd: workspace too small");
   KktScratch s;
   kkt_scratch_carve(d, static_cast<float*>(workspace), &s);
@@ -741,7 +760,9 @@ int iadmm_residuals_fwd(const float* x, const float* y, const float* z, const fl
   if ((rc = launch_kkt_combine1(d, p, nullptr, x, y, z, nullptr, 0.f, s, pri, dual, nullptr, nullptr, nullptr, nullptr,
                                 nullptr, 0, 1, st))) return rc;
   const size_t rows = (size_t)B * (n + m);
-  residual_vectors_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, p, z, s, rp_save, rd_save);
+  KktDims dv = d;
+  dv.sum_a = kkt_sum_chunks(d.chunks_a);           // launch_kkt_combine1 folded the partials into chunk 0
+  residual_vectors_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(dv, p, z, s, rp_save, rd_save);
   IADMM_LAUNCH_CHECK("residual_vectors_kernel");
   return IADMM_OK;
 }
@@ -754,7 +775,7 @@ int iadmm_residuals_bwd(const float* Q, const float* A0, const float* pri, const
   if (m > 0 && (!A0 || !rp_save || !gy || !gz)) IADMM_FAIL(IADMM_EALIGN, "residuals_bwd: NULL constraint pointer");
   int rc = check_sm100();
   if (rc) return rc;
-  const KktDims d = make_kkt_dims(B, n, m, 0);
+  const KktDims d = make_kkt_dims_train(B, n, m, 0);
   const size_t need = kkt_scratch_floats(d) * sizeof(float) + 1024;
   if (need > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "residuals_bwd: workspace too small");
   KktScratch s;
@@ -802,7 +823,7 @@ static void plan_window(int B, int n, int m, int h, int TL, void* base, WindowWs
   TrainWs T;
   plan_train(B, n, m, 0, h, nullptr, &T);
   W->step_bytes = T.bytes; W->step_ws = take(T.bytes);
-  W->res_bytes = kkt_scratch_floats(make_kkt_dims(B, n, m, 0)) * fb + 1024; W->res_ws = take(W->res_bytes);
+  W->res_bytes = kkt_scratch_floats(make_kkt_dims_train(B, n, m, 0)) * fb + 1024; W->res_ws = take(W->res_bytes);
   const size_t S = (size_t)TL + 1;
   W->x = reinterpret_cast<float*>(take(S * B * n * fb));
   W->y = reinterpret_cast<float*>(take(S * B * (m > 0 ? m : 1) * fb));
