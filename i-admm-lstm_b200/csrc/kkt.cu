@@ -472,8 +472,10 @@ __global__ void __launch_bounds__(256) fold_partials_kernel(float* __restrict__ 
   const int j = blockIdx.x * 64 + t;
   float* base = part + ((size_t)blockIdx.z * chunks * slots + blockIdx.y) * n;
   float s = 0.f;
-  if (j < n)
+  if (j < n) {
+#pragma unroll 8
     for (int c = g; c < chunks; c += 4) s += base[(size_t)c * slots * n + j];
+  }
   sh[g][t] = s;
   __syncthreads();
   if (g == 0 && j < n) base[j] = ((sh[0][t] + sh[1][t]) + sh[2][t]) + sh[3][t];

@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
   float* outs[3] = {out0, out1, out2};
   for (int w = 0; w < nw; ++w) {
     float s = 0.f;
-    if (c < cols)
+    if (c < cols) {
+#pragma unroll 8
       for (int p = g; p < nparts; p += 4) s += part[((size_t)p * nw + w) * cols + c];
+    }
     sh[g][t] = s;
     __syncthreads();
     if (g == 0 && c < cols) outs[w][c] = ((sh[0][t] + sh[1][t]) + sh[2][t]) + sh[3][t];
