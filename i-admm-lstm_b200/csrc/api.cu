@@ -207,7 +207,8 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
     prof_record(0, st);
     if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, sk, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
-                                  dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st, metric_trace, zu))) return rc;
+                                  dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st, metric_trace, zu,
+                                  k > 0 ? sk - 1 : nullptr))) return rc;
     if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st))) return rc;
     prof_record(1, st);
@@ -220,7 +221,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
     if (rc) return rc;
     prof_record(2, st);
     cur ^= 1;
-    if ((rc = launch_tail(ws.d, ws.head_part, ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st))) return rc;
+    if ((rc = launch_tail(ws.d, ws.head_part, ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st, metric_trace ? &ws.s : nullptr))) return rc;
     prof_record(3, st);
     if (g_prof.on && g_prof.used < g_prof.cap) ++g_prof.used;
   }
@@ -229,7 +230,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   if (want_trace && !(flags & IADMM_F_SKIP_FINAL_RESID)) {
     if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, nullptr, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
-                                  dual_trace_u, sd, se, sc, K - 1, 1, st, metric_trace, zu))) return rc;
+                                  dual_trace_u, sd, se, sc, K - 1, 1, st, metric_trace, zu, sched + (t0 + K - 1)))) return rc;
   }
   return IADMM_OK;
 }

@@ -169,7 +169,9 @@ struct KktScratch {            // all [B, ...] fp32, carved from the solve works
   float* part_q;  // [B, chunks_q, n]     column partials of Q^T w1     (pass 2)
   float* w;     // [B, n+m]  K xv - rhs
   float* g;     // [B, n+m]  K^T w
+  float *x_old, *y_old, *z_old;   // [B,n], [B,m], [B,m]: the iterate BEFORE the last tail update (linear-system residual trace)
 };
+constexpr int kMetricRows = 6;   // rows of one metric_trace block: objective, ineq max/mean, eq max/mean, ||K xv - rhs||
 size_t kkt_scratch_floats(const KktDims& d);
 void   kkt_scratch_carve(const KktDims& d, float* base, KktScratch* s);
 
@@ -181,7 +183,8 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
                         const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
                         float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
                         const float* sd, const float* se, const float* sc, int trace_row, int residual_only,
-                        cudaStream_t st, float* metric_trace = nullptr, const float* zu = nullptr);
+                        cudaStream_t st, float* metric_trace = nullptr, const float* zu = nullptr,
+                        const Sched* sched_prev = nullptr);
 // pass 2: column partials of Q^T w1, A0^T w2 and rows A0 w1
 int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st);
 // combine 2: g = K^T w
@@ -223,6 +226,7 @@ int launch_solve_resident(const void* packed, const WeightLayout& L, const float
                           float* metrics, int B, int n, int m, int num_ineq, int t0, int K, float sigma, int nprod, int flags,
                           cudaStream_t st);
 int launch_tail(const KktDims& d, const float* head_part, int tiles, const float* b_h, const Sched* sched_t,
-                const float* zl, const float* zu, float* x, float* y, float* z, float* xv, cudaStream_t st);
+                const float* zl, const float* zu, float* x, float* y, float* z, float* xv, cudaStream_t st,
+                const KktScratch* keep_old = nullptr);
 
 }  // namespace iadmm

@@ -57,7 +57,7 @@ KktDims make_kkt_dims_train(int B, int n, int m, int num_ineq) {
 
 size_t kkt_scratch_floats(const KktDims& d) {
   const size_t B = d.B, n = d.n, m = d.m;
-  return 2 * B * n + 3 * B * m + B * (size_t)d.chunks_a * 2 * n + B * (size_t)d.chunks_q * n + 2 * B * (n + m) + 64;
+  return 3 * B * n + 5 * B * m + B * (size_t)d.chunks_a * 2 * n + B * (size_t)d.chunks_q * n + 2 * B * (n + m) + 64;
 }
 
 void kkt_scratch_carve(const KktDims& d, float* base, KktScratch* s) {
@@ -69,6 +69,7 @@ void kkt_scratch_carve(const KktDims& d, float* base, KktScratch* s) {
   s->part_q = take(B * d.chunks_q * n);
   s->w = take(B * (n + m));
   s->g = take(B * (n + m));
+  s->x_old = take(B * n); s->y_old = take(B * m); s->z_old = take(B * m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -339,6 +340,7 @@ struct Combine1Args {
   float *pri, *dual, *pri_u, *dual_u;   // trace rows (already offset to the row), may be NULL
   float *metrics;                       // [5][B] row block: objective, ineq max/mean, eq max/mean; may be NULL
   const float *zu;                      // upper bounds (c for inequality rows, b for equality rows)
+  const Sched* sched_prev;              // schedule row of the iteration that produced (x,y,z): linear-system residual; may be NULL
   const float *sd, *se, *sc;            // Ruiz diagonals, may be NULL
   int residual_only;
 };
@@ -386,6 +388,12 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
   // diagonals: x_u^T Q_0 x_u = x^T Q x / c, p_0^T x_u = p^T x / c, (A0_0 x_u)_i = (A0 x)_i / e_i
   double obj = 0.0, isum = 0.0, esum = 0.0;
   float imax = 0.f, emax = 0.f;
+  // main.py:952: || K xv - rhs || with the K and rhs of the iteration that produced this iterate, i.e. built from the
+  // iterate BEFORE its tail update (x_old, y_old, z_old) and that iteration's penalties, and the xv it produced
+  const bool want_ls = want_met && A.sched_prev != nullptr && A.xt != nullptr;
+  double ls2 = 0.0;
+  float pinv_ineq = 0.f, pinv_eq = 0.f;
+  if (want_ls) { pinv_ineq = A.sched_prev->inv_rho_ineq; pinv_eq = A.sched_prev->inv_rho_eq; }
   for (int j = threadIdx.x; j < d.n; j += kCombThreads) {
     float atv = 0.f, aty = 0.f;
     for (int c = 0; c < d.sum_a; ++c) {
@@ -402,6 +410,12 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
     if (want_met) {
       const float xj = A.x[b * n + j];
       obj += (double)xj * (0.5 * (double)A.s.qx[b * n + j] + (double)pj);
+    }
+    if (want_ls) {
+      const float xt  = A.xt[(size_t)b * A.xt_stride + j];
+      const float kxv = __fadd_rn(__fadd_rn(A.s.qxt[b * n + j], __fmul_rn(A.sigma, xt)), atv);
+      const float r = __fsub_rn(kxv, __fsub_rn(__fmul_rn(A.sigma, A.s.x_old[b * n + j]), pj));
+      ls2 += (double)r * (double)r;
     }
     if (want_res) {
       const float r = __fadd_rn(__fadd_rn(A.s.qx[b * n + j], pj), aty);
@@ -427,6 +441,13 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
       if (i < d.num_ineq) { const float v = fmaxf(dv, 0.f); imax = fmaxf(imax, v); isum += (double)v; }
       else                { const float v = fabsf(dv);      emax = fmaxf(emax, v); esum += (double)v; }
     }
+    if (want_ls) {
+      const float inv = (i < d.num_ineq) ? pinv_ineq : pinv_eq;
+      const float vi  = A.v[(size_t)b * A.v_stride + i];
+      const float kxv = __fsub_rn(A.s.axt[b * m + i], __fmul_rn(inv, vi));
+      const float r = __fsub_rn(kxv, __fsub_rn(A.s.z_old[b * m + i], __fmul_rn(inv, A.s.y_old[b * m + i])));
+      ls2 += (double)r * (double)r;
+    }
     if (want_res) {
       const float r = __fsub_rn(A.s.ax[b * m + i], zi);
       pri2 += (double)r * (double)r;
@@ -443,6 +464,7 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
     if (want_met) {
       obj = block_sum_double(obj, sh); isum = block_sum_double(isum, sh); esum = block_sum_double(esum, sh);
       imax = (float)block_max_double((double)imax, sh); emax = (float)block_max_double((double)emax, sh);
+      ls2 = block_sum_double(ls2, sh);
     }
     if (threadIdx.x == 0) {
       if (A.pri)  A.pri[b]  = (float)sqrt(pri2);
@@ -457,6 +479,7 @@ __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combin
         A.metrics[2 * B + b] = d.num_ineq > 0 ? (float)(isum / d.num_ineq) : 0.f;
         A.metrics[3 * B + b] = emax;
         A.metrics[4 * B + b] = me > 0 ? (float)(esum / me) : 0.f;
+        A.metrics[5 * B + b] = want_ls ? (float)sqrt(ls2) : 0.f;
       }
     }
   }
@@ -491,7 +514,7 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
                         const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
                         float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
                         const float* sd, const float* se, const float* sc, int trace_row, int residual_only,
-                        cudaStream_t st, float* metric_trace, const float* zu) {
+                        cudaStream_t st, float* metric_trace, const float* zu, const Sched* sched_prev) {
   Combine1Args A;
   A.d = d; A.p = p; A.x = x; A.y = y; A.z = z;
   A.xt = xv; A.v = xv ? xv + d.n : nullptr; A.xt_stride = A.v_stride = d.n + d.m;
@@ -501,8 +524,8 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
   A.dual   = (trace_row >= 0 && dual_trace)   ? dual_trace + off   : nullptr;
   A.pri_u  = (trace_row >= 0 && pri_trace_u)  ? pri_trace_u + off  : nullptr;
   A.dual_u = (trace_row >= 0 && dual_trace_u) ? dual_trace_u + off : nullptr;
-  A.metrics = (trace_row >= 0 && metric_trace && (zu || d.m == 0)) ? metric_trace + (size_t)trace_row * 5 * d.B : nullptr;
-  A.zu = zu;
+  A.metrics = (trace_row >= 0 && metric_trace && (zu || d.m == 0)) ? metric_trace + (size_t)trace_row * kMetricRows * d.B : nullptr;
+  A.zu = zu; A.sched_prev = sched_prev;
   A.sd = sd; A.se = se; A.sc = sc;
   A.residual_only = residual_only;
   if (d.m > 0 && d.chunks_a >= kFoldThreshold) {
@@ -564,7 +587,8 @@ __global__ void __launch_bounds__(256) tail_kernel(const KktDims d, const float*
                                                    const float* __restrict__ b_h, const Sched* __restrict__ sched,
                                                    const float* __restrict__ zl, const float* __restrict__ zu,
                                                    float* __restrict__ x, float* __restrict__ y, float* __restrict__ z,
-                                                   float* __restrict__ xv) {
+                                                   float* __restrict__ xv, float* __restrict__ x_old,
+                                                   float* __restrict__ y_old, float* __restrict__ z_old) {
   const size_t n = d.n, m = d.m, N = n + m;
   const size_t rows = (size_t)d.B * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,7 +603,9 @@ __global__ void __launch_bounds__(256) tail_kernel(const KktDims d, const float*
   if (r < d.n) {
     const float a = sched->alpha, oma = sched->one_minus_alpha;
     const size_t j = b * n + r;
-    x[j] = __fadd_rn(__fmul_rn(a, xvn), __fmul_rn(oma, x[j]));
+    const float xo = x[j];
+    if (x_old) x_old[j] = xo;
+    x[j] = __fadd_rn(__fmul_rn(a, xvn), __fmul_rn(oma, xo));
   } else {
     const int    i   = r - d.n;
     const size_t k   = b * m + i;
@@ -587,6 +613,7 @@ __global__ void __launch_bounds__(256) tail_kernel(const KktDims d, const float*
     const float  rho = eq ? sched->rho_eq : sched->rho_ineq;
     const float  inv = eq ? sched->inv_rho_eq : sched->inv_rho_ineq;
     const float  yo = y[k], zo = z[k];
+    if (y_old) { y_old[k] = yo; z_old[k] = zo; }
     const float  zmid = __fadd_rn(zo, __fmul_rn(inv, __fsub_rn(xvn, yo)));
     const float  zc   = fmaxf(fminf(__fadd_rn(zmid, __fmul_rn(inv, yo)), zu[k]), zl[k]);
     z[k] = zc;
@@ -595,9 +622,13 @@ __global__ void __launch_bounds__(256) tail_kernel(const KktDims d, const float*
 }
 
 int launch_tail(const KktDims& d, const float* head_part, int tiles, const float* b_h, const Sched* sched_t,
-                const float* zl, const float* zu, float* x, float* y, float* z, float* xv, cudaStream_t st) {
+                const float* zl, const float* zu, float* x, float* y, float* z, float* xv, cudaStream_t st,
+                const KktScratch* keep_old) {
   const size_t rows = (size_t)d.B * (d.n + d.m);
-  tail_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, head_part, tiles, b_h, sched_t, zl, zu, x, y, z, xv);
+  tail_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, head_part, tiles, b_h, sched_t, zl, zu, x, y, z, xv,
+                                                              keep_old ? keep_old->x_old : nullptr,
+                                                              keep_old ? keep_old->y_old : nullptr,
+                                                              keep_old ? keep_old->z_old : nullptr);
   IADMM_LAUNCH_CHECK("tail_kernel");
   return IADMM_OK;
 }

@@ -69,6 +69,7 @@ struct ResSmem {
   float *w0, *w1, *bias, *wh;                       // gate-column parameters (interleaved 4*unit + gate)
   float *x, *y, *z, *xt, *v, *p, *zl, *zu;          // iterates (xv = [xt; v]) and instance vectors
   float *w1v, *w2v, *g, *t0, *t1, *qx, *ax, *aty;   // KKT temporaries (w = [w1v; w2v])
+  float *xo, *yo, *zo;                              // the iterate before the last tail update (linear-system residual)
   float *cp;                                        // [parts][2][cw] column partials (KKT phases)
   float *head;                                      // [groups][256] head partials (cell phase; aliases cp)
   uint64_t* bar;
@@ -81,9 +82,9 @@ __host__ __device__ inline int r4(int v) { return (v + 3) & ~3; }
 __host__ __device__ inline int res_ld(int n) { return n | 1; }
 __host__ __device__ inline size_t res_vec_floats(int n, int m) {
   const int N = n + m;
-  // x y z xt v p zl zu | w1v w2v g t0 t1 qx ax aty   (each rounded up to a multiple of 4 floats)
+  // x y z xt v p zl zu | w1v w2v g t0 t1 qx ax aty | xo yo zo   (each rounded up to a multiple of 4 floats)
   return (size_t)r4(n) + r4(m) + r4(m) + r4(n) + r4(m) + r4(n) + r4(m) + r4(m) + r4(n) + r4(m) + r4(N) + r4(N) + r4(N) + r4(n) +
-         r4(m) + r4(n);
+         r4(m) + r4(n) + r4(n) + r4(m) + r4(m);
 }
 __host__ __device__ inline size_t res_fixed_bytes(int n, int m) {
   return 1024 /*alignment slack*/ + kResOperandBytes + (3 * 256 + 64) * sizeof(float) + res_vec_floats(n, m) * sizeof(float) +
@@ -105,6 +106,7 @@ __device__ __forceinline__ void res_carve(uint8_t* base, int n, int m, ResSmem& 
   S.p = fp; fp += r4(n); S.zl = fp; fp += r4(m); S.zu = fp; fp += r4(m);
   S.w1v = fp; fp += r4(n); S.w2v = fp; fp += r4(m); S.g = fp; fp += r4(N); S.t0 = fp; fp += r4(N); S.t1 = fp; fp += r4(N);
   S.qx = fp; fp += r4(n); S.ax = fp; fp += r4(m); S.aty = fp; fp += r4(n);
+  S.xo = fp; fp += r4(n); S.yo = fp; fp += r4(m); S.zo = fp; fp += r4(m);
   S.mat = fp;
 }
 
@@ -189,13 +191,13 @@ __device__ __forceinline__ double warp_sum_double(double v) {
   return v;
 }
 __device__ __forceinline__ void res_trace_row(const ResArgs& A, const ResSmem& S, int b, int row, int warp, int lane) {
-  if (warp > 4) return;
+  if (warp > 5) return;
   const int n = A.n, m = A.m;
   const bool want_met = A.metrics != nullptr;
   const bool unscaled = (A.sd != nullptr) && (A.pri_u || A.dual_u || want_met);
   const float cscale = unscaled ? A.sc[b] : 1.f;
   const size_t B = A.B, o = (size_t)row * B + b;
-  float* mt = want_met ? A.metrics + (size_t)row * 5 * B : nullptr;
+  float* mt = want_met ? A.metrics + (size_t)row * kMetricRows * B : nullptr;
   if (warp == 0) {                                   // dual residual || Q x + p + A0^T y ||
     double s = 0.0, su = 0.0;
     for (int j = lane; j < n; j += 32) {
@@ -224,6 +226,11 @@ __device__ __forceinline__ void res_trace_row(const ResArgs& A, const ResSmem& S
     }
   } else if (!want_met) {
     return;
+  } else if (warp == 5) {                            // || K xv - rhs || (main.py:952); elements staged in S.g by the caller
+    double s = 0.0;
+    for (int i = lane; i < n + m; i += 32) s += (double)S.g[i] * (double)S.g[i];
+    s = warp_sum_double(s);
+    if (lane == 0) mt[5 * B + b] = (float)sqrt(s);
   } else if (warp == 2) {                            // objective 0.5 x^T Q x + p^T x (main.py:950)
     double s = 0.0;
     for (int j = lane; j < n; j += 32) s += (double)S.x[j] * (0.5 * (double)S.qx[j] + (double)S.p[j]);
@@ -391,6 +398,7 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
       S.w1v[tid] = __fsub_rn(kxv, rhs);
       S.qx[tid] = S.t1[tid];
       S.aty[tid] = aty;
+      if (k > 0 && A.metrics) S.g[tid] = __fsub_rn(kxv, __fsub_rn(__fmul_rn(A.sigma, S.xo[tid]), S.p[tid]));
     } else if (tid < N) {
       const int i = tid - n;
       const float inv = (i < A.num_ineq) ? sk.inv_rho_ineq : sk.inv_rho_eq;
@@ -398,6 +406,10 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
       const float rhs = __fsub_rn(S.z[i], __fmul_rn(inv, S.y[i]));
       S.w2v[i] = __fsub_rn(kxv, rhs);
       S.ax[i] = S.t1[tid];
+      if (k > 0 && A.metrics) {                      // previous iteration's penalties and pre-update iterate
+        const float pinv = (i < A.num_ineq) ? A.sched[k - 1].inv_rho_ineq : A.sched[k - 1].inv_rho_eq;
+        S.g[tid] = __fsub_rn(__fsub_rn(S.t0[tid], __fmul_rn(pinv, S.v[i])), __fsub_rn(S.zo[i], __fmul_rn(pinv, S.yo[i])));
+      }
     }
     __syncthreads();
     if (k > 0 && want_trace) res_trace_row(A, S, b, k - 1, warp, lane);   // residuals of the iterate entering this iteration
@@ -489,7 +501,9 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
       if (tid < n) {
         const float xvn = __fsub_rn(S.xt[tid], head);
         S.xt[tid] = xvn;
-        S.x[tid] = __fadd_rn(__fmul_rn(sk.alpha, xvn), __fmul_rn(sk.one_minus_alpha, S.x[tid]));
+        const float xold = S.x[tid];
+        S.xo[tid] = xold;
+        S.x[tid] = __fadd_rn(__fmul_rn(sk.alpha, xvn), __fmul_rn(sk.one_minus_alpha, xold));
       } else {
         const int i = tid - n;
         const float xvn = __fsub_rn(S.v[i], head);
@@ -497,6 +511,7 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
         const bool eq = i >= A.num_ineq;
         const float rho = eq ? sk.rho_eq : sk.rho_ineq, inv = eq ? sk.inv_rho_eq : sk.inv_rho_ineq;
         const float yo = S.y[i], zo = S.z[i];
+        S.yo[i] = yo; S.zo[i] = zo;
         const float zmid = __fadd_rn(zo, __fmul_rn(inv, __fsub_rn(xvn, yo)));
         const float zc = fmaxf(fminf(__fadd_rn(zmid, __fmul_rn(inv, yo)), S.zu[i]), S.zl[i]);
         S.z[i] = zc;
@@ -508,26 +523,35 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
 
   // ---------------- trailing residual row, state write-back ----------------
   if (want_trace && A.K > 0 && !(A.flags & IADMM_F_SKIP_FINAL_RESID)) {
-    float dummy;
     if (CACHED) {
-      if (tid < N) res_row_dot_thread<false>(Ms + (size_t)tid * ld, n, S.x, nullptr, S.t1[tid], dummy);
+      if (tid < N) res_row_dot_thread<true>(Ms + (size_t)tid * ld, n, S.xt, S.x, S.t0[tid], S.t1[tid]);
       if (m > 0) {
-        float s0;
-        res_col_sum_thread<false>(Msa + col, ld, (col < n) ? m : 0, part, parts, S.y, nullptr, s0, dummy);
-        S.cp[(part * 2 + 0) * cw + col] = s0;
+        float s0, s1;
+        res_col_sum_thread<true>(Msa + col, ld, (col < n) ? m : 0, part, parts, S.v, S.y, s0, s1);
+        S.cp[(part * 2 + 0) * cw + col] = s0; S.cp[(part * 2 + 1) * cw + col] = s1;
       }
     } else {
-      res_row_dots_warp(Qg, n, n, S.x, nullptr, S.t1, nullptr, warp, lane);
+      res_row_dots_warp(Qg, n, n, S.xt, S.x, S.t0, S.t1, warp, lane);
       if (m > 0) {
-        res_row_dots_warp(Ag, n, m, S.x, nullptr, S.t1 + n, nullptr, warp, lane);
-        float s0;
-        res_col_sum_thread<false>(Ag + col, n, (col < n) ? m : 0, part, parts, S.y, nullptr, s0, dummy);
-        S.cp[(part * 2 + 0) * cw + col] = s0;
+        res_row_dots_warp(Ag, n, m, S.xt, S.x, S.t0 + n, S.t1 + n, warp, lane);
+        float s0, s1;
+        res_col_sum_thread<true>(Ag + col, n, (col < n) ? m : 0, part, parts, S.v, S.y, s0, s1);
+        S.cp[(part * 2 + 0) * cw + col] = s0; S.cp[(part * 2 + 1) * cw + col] = s1;
       }
     }
     __syncthreads();
-    if (tid < n) { S.qx[tid] = S.t1[tid]; S.aty[tid] = (m > 0) ? res_col_total(S.cp, cw, 0, tid) : 0.f; }
-    else if (tid < N) S.ax[tid - n] = S.t1[tid];
+    const Sched sl = A.sched[A.K - 1];
+    if (tid < n) {
+      const float atv = (m > 0) ? res_col_total(S.cp, cw, 0, tid) : 0.f;
+      S.qx[tid] = S.t1[tid]; S.aty[tid] = (m > 0) ? res_col_total(S.cp, cw, 1, tid) : 0.f;
+      const float kxv = __fadd_rn(__fadd_rn(S.t0[tid], __fmul_rn(A.sigma, S.xt[tid])), atv);
+      S.g[tid] = __fsub_rn(kxv, __fsub_rn(__fmul_rn(A.sigma, S.xo[tid]), S.p[tid]));
+    } else if (tid < N) {
+      const int i = tid - n;
+      S.ax[i] = S.t1[tid];
+      const float pinv = (i < A.num_ineq) ? sl.inv_rho_ineq : sl.inv_rho_eq;
+      S.g[tid] = __fsub_rn(__fsub_rn(S.t0[tid], __fmul_rn(pinv, S.v[i])), __fsub_rn(S.zo[i], __fmul_rn(pinv, S.yo[i])));
+    }
     __syncthreads();
     res_trace_row(A, S, b, A.K - 1, warp, lane);
   }

@@ -31,7 +31,7 @@ class SolveResult:
     dual: Optional[torch.Tensor] = None
     pri_unscaled: Optional[torch.Tensor] = None  # [K,B] on the original data (needs `scaling`)
     dual_unscaled: Optional[torch.Tensor] = None
-    metrics: Optional[torch.Tensor] = None       # [K,5,B]: objective, ineq max/mean, eq max/mean (main.py:949-968)
+    metrics: Optional[torch.Tensor] = None       # [K,6,B]: objective, ineq max/mean, eq max/mean, ||K xv - rhs|| (main.py:949-968)
 
     @property
     def objective(self): return None if self.metrics is None else self.metrics[:, 0]
@@ -43,6 +43,8 @@ class SolveResult:
     def eq_violation_max(self): return None if self.metrics is None else self.metrics[:, 3]
     @property
     def eq_violation_mean(self): return None if self.metrics is None else self.metrics[:, 4]
+    @property
+    def ls_residual(self): return None if self.metrics is None else self.metrics[:, 5]     # main.py:952
 
 
 class LSTM(nn.Module):
@@ -150,7 +152,7 @@ class LSTM(nn.Module):
         pri = dual = pri_u = dual_u = met = None
         if traces and K > 0:
             pri = torch.empty((K, B), device=dev); dual = torch.empty((K, B), device=dev)
-            met = torch.empty((K, 5, B), device=dev)
+            met = torch.empty((K, 6, B), device=dev)
             if scaling is not None:
                 pri_u = torch.empty((K, B), device=dev); dual_u = torch.empty((K, B), device=dev)
         sd = se = sc = None

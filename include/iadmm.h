@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define IADMM_ABI_VERSION 1
+#define IADMM_ABI_VERSION 2
 
 enum {
   IADMM_OK      = 0,
@@ -109,11 +109,12 @@ int iadmm_ruiz(const float* Q, const float* p, const float* A0, const float* zl,
  *   pri_trace/dual_trace     residuals on the data passed in                       (main.py:346)
  *   pri_trace_u/dual_trace_u residuals of the un-scaled iterates on the original data, computed from
  *                            the diagonals d,e,c of iadmm_ruiz (main.py:922-955); need d,e,c != NULL.
- *   metric_trace             [K,5,B]: objective 0.5 x^T Q x + p^T x (utils.py:53), max and mean of relu(G x - c)
+ *   metric_trace             [K,6,B]: objective 0.5 x^T Q x + p^T x (utils.py:53), max and mean of relu(G x - c)
  *                            over the inequality rows (utils.py:56) and of |b - A x| over the equality rows
  *                            (utils.py:59), i.e. the per-instance quantities main.py:949-968 prints; evaluated on
  *                            the original data when d,e,c are given (with the un-scaled iterate), else on the
- *                            data passed in.
+ *                            data passed in.  Row 5: the linear-system residual ||A_tild xv - b_tild|| of
+ *                            main.py:952 (K and rhs of the iteration that produced xv, on the data passed in).
  * mode: IADMM_GATES_*; flags: IADMM_F_*.
  */
 int iadmm_solve_workspace_bytes(int B, int n, int m, int h, int mode, size_t* bytes);

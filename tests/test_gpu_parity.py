@@ -143,6 +143,7 @@ def test_solve_vs_reference(name, mode):
     if mode != "tc_1xfp16":
         assert tol <= NORTH_STAR_TOL * 2
     errs = {k: rel_err(getattr(r, k), g["f32_" + k]) for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual")}
+    errs["ls"] = rel_err(r.ls_residual, g["f32_ls"])           # ||K xv - rhs|| of main.py:952, fused into the solve
     if scaled:
         errs["pri_u"] = rel_err(r.pri_unscaled, g["f32_pri_u"])
         errs["dual_u"] = rel_err(r.dual_unscaled, g["f32_dual_u"])
