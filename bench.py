@@ -331,14 +331,16 @@ def run_ours(args):
                        "parallelism": "instances sharded over %d GPU(s), no collective" % n_gpus,
                        "results_finite": finite},
             "gpu_launches": steps * launches_per_step,
-            "roofline": {"kernel": "gates_tc_kernel" if args.gate_mode != "simt_fp32" else "gates_simt_kernel",
+            "roofline": {"kernel": "gates_tc_pair_kernel" if args.gate_mode != "simt_fp32" else "gates_simt_kernel",
                          "bound": "tensor", "achieved": gate_tflops, "peak": tf_sus, "unit": "TFLOP/s",
                          "frac": gate_tflops / tf_sus, "traffic": ncu_traffic("gates", B, args.gate_mode),
                          "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,
                          "flops_per_launch": gate_flops, "ms_per_launch": gate_avg_ms,
                          "share_of_step": gate_ms.value / ms,
-                         "note": "logical fp32 flops 8*rows*h^2; the 3xfp16 split issues 3x that on the tensor pipe "
-                                 "(issued rate %.1f TFLOP/s)" % (gate_tflops * {"tc_3xfp16": 3, "tc_f16f8": 2}.get(args.gate_mode, 1))},
+                         "note": "logical fp32 flops 8*rows*h^2; the operand split issues %dx that in fp16-equivalent MMA work "
+                                 "(tc_3xfp16: 3 fp16 products, tc_f16f8: 1 fp16 + 2 e4m3 at twice the rate; issued rate %.1f TFLOP/s)"
+                                 % ({"tc_3xfp16": 3, "tc_f16f8": 2}.get(args.gate_mode, 1),
+                                    gate_tflops * {"tc_3xfp16": 3, "tc_f16f8": 2}.get(args.gate_mode, 1))},
             "roofline_kkt": {"kernel": "kkt_pass1+combine1+pass2+combine2", "bound": "hbm", "achieved": kkt_gbs,
                              "peak": hbm_gbs, "unit": "GB/s", "frac": kkt_gbs / hbm_gbs,
                              "traffic": ncu_traffic("kkt", B, args.gate_mode),
