@@ -4,6 +4,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace iadmm {
@@ -45,6 +46,8 @@ struct SolveWs {
   float* head_part;       // [tiles][rows]
   float* h_alt;           // SIMT: second fp32 H buffer [rows,h]
   TcState tc;             // TC: fp16 hi/lo ping-pong
+  float* c_il;            // F16F8: row-interleaved cell state [h/8][rows_p][8] (see gates_tc.cu)
+  long rows_p;
   int tiles;
   size_t bytes;
 };
@@ -76,15 +79,20 @@ static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, vo
   float* kkt = reinterpret_cast<float*>(take(kkt_scratch_floats(ws->d) * sizeof(float)));
   if (base) kkt_scratch_carve(ws->d, kkt, &ws->s);
   ws->head_part = reinterpret_cast<float*>(take((size_t)ws->tiles * rows * sizeof(float)));
-  ws->h_alt = nullptr;
+  ws->h_alt = nullptr; ws->c_il = nullptr; ws->rows_p = (long)rows;
   memset(&ws->tc, 0, sizeof(ws->tc));
   if (is_tc(mode)) {
-    const size_t hb = rows * (size_t)h * sizeof(__half);
-    const size_t lb = tc_lo_bytes((long)rows, h);
+    // the F16F8 solve keeps its state row-interleaved: rows padded to a multiple of 128
+    const bool il = (mode == IADMM_GATES_TC_F16F8);
+    ws->rows_p = il ? il_rows((long)rows) : (long)rows;
+    const size_t rp = (size_t)ws->rows_p;
+    const size_t hb = rp * (size_t)h * sizeof(__half);
+    const size_t lb = il ? (tc_lo_bytes((long)rows, h) > hb ? tc_lo_bytes((long)rows, h) : hb) : tc_lo_bytes((long)rows, h);
     for (int i = 0; i < 2; ++i) {
       ws->tc.h_hi[i] = reinterpret_cast<__half*>(take(hb));
       ws->tc.h_lo[i] = reinterpret_cast<__half*>(take(lb));
     }
+    ws->c_il = il ? reinterpret_cast<float*>(take(rp * (size_t)h * sizeof(float))) : nullptr;
   } else {
     ws->h_alt = reinterpret_cast<float*>(take(rows * (size_t)h * sizeof(float)));
   }
@@ -195,7 +203,24 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
 
   float* hbuf[2] = {H, ws.h_alt};
   int cur = 0;
-  if (tc) {
+  // Row-interleaved state for the fused F16F8 solve (K >= 2; a single step would only pay the layout conversion):
+  // the epilogue of the gate kernel then touches whole 128-byte lines instead of one 32-byte sector per row.
+  static int il_env = -1;
+  if (il_env < 0) { const char* e = getenv("IADMM_TC_INTERLEAVED"); il_env = (e && e[0] == '0') ? 0 : 1; }   // development switch
+  const bool il = tc && nprod == 2 && K >= 2 && il_env == 1 && ws.c_il != nullptr;
+  TcIl ilp;
+  ilp.rows_p = ws.rows_p; ilp.C_il = ws.c_il; ilp.C_rm_out = nullptr;
+  if (il) {
+    const size_t hb = (size_t)ws.rows_p * h * sizeof(__half);
+    if (flags & IADMM_F_ZERO_STATE) {
+      IADMM_CUDA(cudaMemsetAsync(ws.tc.h_hi[0], 0, hb, st));
+      IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[0], 0, hb, st));
+      IADMM_CUDA(cudaMemsetAsync(ws.c_il, 0, (size_t)ws.rows_p * h * sizeof(float), st));
+    } else {
+      if ((rc = launch_split_state_il(H, ws.tc.h_hi[0], ws.tc.h_lo[0], rows, h, st))) return rc;
+      if ((rc = launch_c_to_il(C, ws.c_il, rows, h, st))) return rc;
+    }
+  } else if (tc) {
     if (flags & IADMM_F_ZERO_STATE) rc = launch_zero_state(ws.tc.h_hi[0], ws.tc.h_lo[0], rows, h, nprod, st);
     else                            rc = launch_split_state(H, ws.tc.h_hi[0], ws.tc.h_lo[0], rows, h, nprod, st);
     if (rc) return rc;
@@ -213,8 +238,10 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
     if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st))) return rc;
     prof_record(1, st);
     if (tc) {
+      ilp.C_rm_out = (k == K - 1) ? C : nullptr;
       rc = launch_gates_tc(packed_weights, L, xv, ws.s.g, ws.tc.h_hi[cur], ws.tc.h_lo[cur], ws.tc.h_hi[cur ^ 1],
-                           ws.tc.h_lo[cur ^ 1], (k == K - 1) ? H : nullptr, C, ws.head_part, rows, h, nprod, st);
+                           ws.tc.h_lo[cur ^ 1], (k == K - 1) ? H : nullptr, C, ws.head_part, rows, h, nprod, st, nullptr,
+                           il ? &ilp : nullptr);
     } else {
       rc = launch_gates_simt(packed_weights, L, xv, ws.s.g, hbuf[cur], hbuf[cur ^ 1], C, ws.head_part, rows, h, st);
     }

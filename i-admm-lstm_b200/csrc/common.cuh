@@ -66,6 +66,9 @@ struct WeightLayout {
   size_t off_u32lo;   // fp16 [h][4h]   lo part
   size_t off_uq8;     // e4m3 [4h][q8_pitch(h)]: per 64-wide K block 64 B of residual (U*2^s - fp16(U*2^s)) * 2^6 followed by
                       //                64 B of the coarse copy fp16(U*2^s) * 2^-5   (F16F8 mode; one 128-byte TMA row)
+  size_t off_uhi_il;  // fp16 [h/8][4h][8]: row-interleaved image of fp16(U*2^s) (16-byte K groups of consecutive gate columns adjacent;
+                      //                the no-swizzle UMMA core-matrix order, see gates_tc.cu "row-interleaved layout")
+  size_t off_uq8_il;  // e4m3 [ceil(h/16)][2][4h][16]: residual plane, coarse plane per 16-wide K group
   size_t total;
 };
 WeightLayout weight_layout(int h, int length);
@@ -209,10 +212,20 @@ static inline size_t q8_pitch(int h) { return (size_t)((h + 63) / 64) * 128; }
 constexpr int kQ8HLoShift = 5, kQ8HHiShift = -6, kQ8UHiShift = -5, kQ8ULoShift = 6;
 int  tc_gate_tiles(int h);
 size_t tc_state_bytes(long rows, int h);
+// Row-interleaved state layout of the fused solve (F16F8 mode): every per-row array is stored [column group][row][16 or 32 B]
+// so that the thread-per-row epilogue reads and writes whole 128-byte lines (see gates_tc.cu).  rows_p = rows rounded up to 128.
+struct TcIl {
+  long   rows_p;
+  float* C_il;        // fp32 [h/8][rows_p][8], the cell state between iterations
+  float* C_rm_out;    // non-NULL on the last iteration: also write the caller's row-major C [rows][h]
+};
+static inline long il_rows(long rows) { return (rows + 127) / 128 * 128; }
 int  launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g,
                      const __half* Hin_hi, const __half* Hin_lo, __half* Hout_hi, __half* Hout_lo,
                      float* H_out_f32 /* may be NULL */, float* C, float* head_part, long rows, int h,
-                     int nprod, cudaStream_t st, float* gates_out = nullptr);
+                     int nprod, cudaStream_t st, float* gates_out = nullptr, const TcIl* il = nullptr);
+int  launch_split_state_il(const float* H, __half* hi, __half* q8, long rows, int h, cudaStream_t st);
+int  launch_c_to_il(const float* C, float* C_il, long rows, int h, cudaStream_t st);
 int  launch_split_state(const float* H, __half* hi, __half* lo, long rows, int h, int nprod, cudaStream_t st);
 int  launch_zero_state(__half* hi, __half* lo, long rows, int h, int nprod, cudaStream_t st);
 size_t tc_lo_bytes(long rows, int h);   // size of one `lo` buffer (fits both the fp16 and the packed e4m3 form)

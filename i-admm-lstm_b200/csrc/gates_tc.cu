@@ -63,7 +63,11 @@ struct TcParams {
   float*  head_part;      // [2*unit_tiles][rows]
   long rows;
   int  h, unit_tiles, k_blocks, stages, nprod;
+  int  exp;               // development experiments (IADMM_TC_EXP, results are garbage): 1 = epilogue reads TMEM only,
+                          // 2 = no TMA / MMA, 3 = no global traffic in the epilogue, 4 = no cell math, 5 = all rows alias 1024 rows (no DRAM)
   long num_tiles;
+  long rows_p;            // row-interleaved layout (EPI 4): rows rounded up to 128; C, hout_hi, hout_lo are [group][rows_p][..]
+  float* c_rm_out;        // row-interleaved layout, last iteration: the caller's row-major C
   size_t q8_pitch;        // bytes per row of the packed e4m3 image (NPROD 2)
 };
 
@@ -79,6 +83,7 @@ struct EpiRow {
   float c[kChunksPerHalf][8];
 };
 
+template <bool IL = false>
 __device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRow& R, int quarter, int half, int lane, int ut,
                                                        long row_base) {
   R.row = row_base + quarter * 32 + lane;
@@ -88,8 +93,9 @@ __device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRow
 #pragma unroll
   for (int cc = 0; cc < kChunksPerHalf; ++cc) {
     const int unit0 = ut * kTcUnits + (half * kChunksPerHalf + cc) * 8;
-    if (R.row_ok && unit0 < P.h) {
-      ld_global_v8(P.C + (size_t)R.row * P.h + unit0, R.c[cc]);
+    if (R.row_ok && unit0 < P.h && P.exp != 3) {
+      if (IL) ld_global_v8(P.C + ((size_t)(unit0 >> 3) * P.rows_p + R.row) * 8, R.c[cc]);
+      else    ld_global_v8(P.C + (size_t)((P.exp == 5) ? (R.row & 1023) : R.row) * P.h + unit0, R.c[cc]);
     } else {
 #pragma unroll
       for (int u = 0; u < 8; ++u) R.c[cc][u] = 0.f;
@@ -177,6 +183,220 @@ __device__ __forceinline__ void lstm_epilogue_tile(const TcParams& P, const EpiR
     }
   }
   if (R.row_ok) P.head_part[((size_t)ut * 2 + half) * P.rows + R.row] = hp;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Packed-fp32 epilogue (EPI 1, 2).  Power measurements (profiles/r01_gate_power_experiments.json) show the gate
+// kernel to be bound by the 1 kW board power cap, not by a pipe: the MMA main loop alone runs at 1.55 GHz, with the
+// cell epilogue the SM clock drops to 1.14 GHz, and the epilogue's ~70 instructions per hidden unit are ~20 % of the
+// energy.  sm_100 has two-wide fp32 instructions (fma/mul/add.f32x2 -> FFMA2/FMUL2/FADD2): the pre-activations, the
+// activation arguments, the tanh polynomials and the state update of two hidden units are issued as pairs, ~40 %
+// fewer instructions for bit-identical results (each lane is the same IEEE operation as the scalar form; the cell
+// update c = i*u + f*c stays scalar because ptxas contracts mul.f32x2 + add.f32x2 into FFMA2).
+// EPI 2 additionally uses the exp-only tanh (absolute error 3e-7, as in the resident kernel).
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ u64 bc2(float a) { u64 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// 1 / (1 + 2^t) for both lanes
+__device__ __forceinline__ void rcp1p_ex2_2(u64 t, float& r0, float& r1) {
+  float t0, t1;
+  upk2(t, t0, t1);
+  float d0, d1;
+  upk2(add2(pk2(ex2_approx(t0), ex2_approx(t1)), bc2(1.0f)), d0, d1);
+  r0 = rcp_approx(d0);
+  r1 = rcp_approx(d1);
+}
+// packed form of split_hidden8 (gate_math.cuh): same roundings lane by lane (the scalings are powers of two, the
+// residual s - fp16(s) is exact)
+template <int NPROD>
+__device__ __forceinline__ void split_hidden8_x2(const u64 (&hn2)[4], uint32_t (&hi)[4], uint32_t (&lo)[4], uint32_t (&res)[2],
+                                                 uint32_t (&crs)[2]) {
+  const u64 hs2 = bc2((float)(1 << kHShift));
+  __nv_fp8x2_storage_t r2[4], c2[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const u64 S = mul2(hn2[u], hs2);
+    float s0, s1;
+    upk2(S, s0, s1);
+    const __half2 hh = __floats2half2_rn(s0, s1);
+    hi[u] = *reinterpret_cast<const uint32_t*>(&hh);
+    const float2 back = __half22float2(hh);
+    u64 D;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(S), "l"(pk2(back.x, back.y)));
+    if (NPROD == 3) {
+      float d0, d1;
+      upk2(D, d0, d1);
+      const __half2 hl = __floats2half2_rn(d0, d1);
+      lo[u] = *reinterpret_cast<const uint32_t*>(&hl);
+    }
+    if (NPROD == 2) {
+      float r0, r1, c0, c1;
+      upk2(mul2(D, bc2(32.0f)), r0, r1);
+      upk2(mul2(S, bc2(0.015625f)), c0, c1);
+      r2[u] = __nv_cvt_float2_to_fp8x2(make_float2(r0, r1), __NV_SATFINITE, __NV_E4M3);
+      c2[u] = __nv_cvt_float2_to_fp8x2(make_float2(c0, c1), __NV_SATFINITE, __NV_E4M3);
+    }
+  }
+  if (NPROD == 2) {
+    res[0] = (uint32_t)r2[0] | ((uint32_t)r2[1] << 16); res[1] = (uint32_t)r2[2] | ((uint32_t)r2[3] << 16);
+    crs[0] = (uint32_t)c2[0] | ((uint32_t)c2[1] << 16); crs[1] = (uint32_t)c2[2] | ((uint32_t)c2[3] << 16);
+  }
+}
+
+// tanh of two values: tanh_fast (FAST = false) or tanh_exp (FAST = true) lane by lane
+template <bool FAST>
+__device__ __forceinline__ u64 tanh2(float x0, float x1, float big0, float big1) {
+  // big0/big1 = 1 - 2/(e^{2x}+1) already evaluated by the caller
+  if (FAST) return pk2(big0, big1);
+  const u64 X = pk2(x0, x1);
+  const u64 T = mul2(X, X);
+  u64 Q = fma2(T, bc2(0.016433170300270403f), bc2(-0.052669384762106176f));
+  Q = fma2(Q, T, bc2(0.133206865150314f));
+  Q = fma2(Q, T, bc2(-0.33332945121698027f));
+  float s0, s1;
+  upk2(fma2(mul2(X, T), Q, X), s0, s1);
+  return pk2((fabsf(x0) < 0.55f) ? s0 : big0, (fabsf(x1) < 0.55f) ? s1 : big1);
+}
+
+template <int NPROD, bool FAST, bool SAVE, bool IL>
+__device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const EpiRow& R, const float* sp, uint32_t tmem_base, int buf,
+                                                      int quarter, int half, int ut, float dequant) {
+  u64 hp2 = 0ull;                                       // (even units, odd units) partial head dots
+  const bool wide = (P.h % 16) == 0;
+  uint32_t hi_st[4], lo_st[4], res_st[2], crs_st[2];
+  const u64 xr2 = bc2(R.xr), gr2 = bc2(R.gr), dq2 = bc2(dequant);
+  const float kL = 1.4426950408889634f;
+  const u64 k_if = bc2(-kL), k_ou = pk2(-kL, 2.0f * kL), k_t = bc2(2.0f * kL);
+  const size_t rowoff = (size_t)((P.exp == 5) ? (R.row & 1023) : R.row);
+#pragma unroll
+  for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+    const int chunk = half * kChunksPerHalf + cc;
+    const int unit0 = ut * kTcUnits + chunk * 8;          // first hidden unit of this chunk
+    uint32_t v[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kTcBN + chunk * kTcChunk);
+    tc_ld32(taddr, v);
+    tc_wait_ld();
+    if (R.row_ok && unit0 < P.h) {
+      const size_t o = rowoff * P.h + unit0;
+      float cnew[8], hnew[8];
+      u64 hn2[4];
+      const float4* w0 = reinterpret_cast<const float4*>(sp + chunk * kTcChunk);
+      const float4* w1 = reinterpret_cast<const float4*>(sp + kTcBN + chunk * kTcChunk);
+      const float4* bb = reinterpret_cast<const float4*>(sp + 2 * kTcBN + chunk * kTcChunk);
+      const float2* wh = reinterpret_cast<const float2*>(sp + 3 * kTcBN + chunk * 8);
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        if (P.exp == 4) {
+          cnew[u] = R.c[cc][u] + __uint_as_float(v[u * 4]); hnew[u] = __uint_as_float(v[u * 4 + 1]);
+          cnew[u + 1] = R.c[cc][u + 1] + __uint_as_float(v[u * 4 + 4]); hnew[u + 1] = __uint_as_float(v[u * 4 + 5]);
+          hn2[u >> 1] = pk2(hnew[u], hnew[u + 1]);
+          continue;
+        }
+        u64 pif[2], pou[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float4 a0 = w0[u + j], a1 = w1[u + j], ab = bb[u + j];
+          const int b = (u + j) * 4;
+          // pre_g = xv*W0 + grad*W1 + (H@U) + b   (models/lstm.py:74-77), gates (i,f) and (o,u) as pairs
+          pif[j] = fma2(pk2(__uint_as_float(v[b]), __uint_as_float(v[b + 1])), dq2,
+                        fma2(gr2, pk2(a1.x, a1.y), fma2(xr2, pk2(a0.x, a0.y), pk2(ab.x, ab.y))));
+          pou[j] = fma2(pk2(__uint_as_float(v[b + 2]), __uint_as_float(v[b + 3])), dq2,
+                        fma2(gr2, pk2(a1.z, a1.w), fma2(xr2, pk2(a0.z, a0.w), pk2(ab.z, ab.w))));
+        }
+        float gi[2], gf[2], go[2], bigu[2], pu[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          rcp1p_ex2_2(mul2(pif[j], k_if), gi[j], gf[j]);           // sigmoid(p_i), sigmoid(p_f)
+          float ru, po_unused;
+          rcp1p_ex2_2(mul2(pou[j], k_ou), go[j], ru);              // sigmoid(p_o), 1/(e^{2 p_u}+1)
+          upk2(pou[j], po_unused, pu[j]);
+          bigu[j] = fmaf(-2.0f, ru, 1.0f);
+        }
+        float gu[2];
+        upk2(tanh2<FAST>(pu[0], pu[1], bigu[0], bigu[1]), gu[0], gu[1]);
+        float cn[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          cn[j] = __fadd_rn(__fmul_rn(gi[j], gu[j]), __fmul_rn(gf[j], R.c[cc][u + j]));   // lstm.py:78
+        float rt0, rt1;
+        rcp1p_ex2_2(mul2(pk2(cn[0], cn[1]), k_t), rt0, rt1);
+        float bt0, bt1;
+        upk2(fma2(pk2(rt0, rt1), bc2(-2.0f), bc2(1.0f)), bt0, bt1);
+        const u64 HN = mul2(pk2(go[0], go[1]), tanh2<FAST>(cn[0], cn[1], bt0, bt1));      // lstm.py:79
+        upk2(HN, hnew[u], hnew[u + 1]);
+        hn2[u >> 1] = HN;
+        cnew[u] = cn[0]; cnew[u + 1] = cn[1];
+        const float2 whp = wh[u >> 1];
+        hp2 = fma2(HN, pk2(whp.x, whp.y), hp2);                                           // lstm.py:80 (partial)
+        if (SAVE) {           // training forward: keep the activations for the hand-written backward
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<float4*>(P.gates_out + (size_t)R.row * 4 * P.h + 4 * (size_t)(unit0 + u + j)) =
+                make_float4(gi[j], gf[j], go[j], gu[j]);
+        }
+      }
+      if (P.exp == 3) { hp2 = add2(hp2, pk2(cnew[0] + cnew[7], hnew[3])); continue; }
+      uint32_t hi[4], lo[4], res[2], crs[2];
+      split_hidden8_x2<NPROD>(hn2, hi, lo, res, crs);
+      if (IL) {
+        // row-interleaved arrays [8-unit group][row][8]: the 32 rows of a warp are adjacent, every access is whole lines
+        const size_t gi = (size_t)(unit0 >> 3) * P.rows_p + R.row;
+        st_global_v8(P.C + gi * 8, cnew);
+        if (P.c_rm_out) st_global_v8(P.c_rm_out + o, cnew);
+        if (P.hout_f32) st_global_v8(P.hout_f32 + o, hnew);
+        *reinterpret_cast<uint4*>(P.hout_hi + gi * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if ((cc & 1) == 0) {
+          res_st[0] = res[0]; res_st[1] = res[1]; crs_st[0] = crs[0]; crs_st[1] = crs[1];
+        } else {
+          // e4m3 planes [16-unit group][residual | coarse][row][16]
+          uint8_t* q = reinterpret_cast<uint8_t*>(P.hout_lo) + ((size_t)(unit0 >> 4) * 2 * P.rows_p + R.row) * 16;
+          *reinterpret_cast<uint4*>(q)                        = make_uint4(res_st[0], res_st[1], res[0], res[1]);
+          *reinterpret_cast<uint4*>(q + (size_t)P.rows_p * 16) = make_uint4(crs_st[0], crs_st[1], crs[0], crs[1]);
+        }
+        continue;
+      }
+      st_global_v8(P.C + o, cnew);
+      if (P.hout_f32) st_global_v8(P.hout_f32 + o, hnew);
+      uint8_t* q8row = reinterpret_cast<uint8_t*>(P.hout_lo) + rowoff * P.q8_pitch;
+      if (!wide) {
+        *reinterpret_cast<uint4*>(P.hout_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (NPROD == 3) *reinterpret_cast<uint4*>(P.hout_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (NPROD == 2) {
+          uint8_t* q = q8row + (size_t)(unit0 >> 6) * 128 + (unit0 & 63);
+          *reinterpret_cast<uint2*>(q)      = make_uint2(res[0], res[1]);
+          *reinterpret_cast<uint2*>(q + 64) = make_uint2(crs[0], crs[1]);
+        }
+      } else if ((cc & 1) == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { hi_st[u] = hi[u]; lo_st[u] = lo[u]; }
+        res_st[0] = res[0]; res_st[1] = res[1]; crs_st[0] = crs[0]; crs_st[1] = crs[1];
+      } else {
+        const size_t o2 = o - 8;                           // first unit of the chunk pair (multiple of 16)
+        const uint32_t w8[8] = {hi_st[0], hi_st[1], hi_st[2], hi_st[3], hi[0], hi[1], hi[2], hi[3]};
+        st_global_v8u(P.hout_hi + o2, w8);
+        if (NPROD == 3) {
+          const uint32_t l8[8] = {lo_st[0], lo_st[1], lo_st[2], lo_st[3], lo[0], lo[1], lo[2], lo[3]};
+          st_global_v8u(P.hout_lo + o2, l8);
+        }
+        if (NPROD == 2) {
+          const int u2 = unit0 - 8;
+          uint8_t* q = q8row + (size_t)(u2 >> 6) * 128 + (u2 & 63);
+          *reinterpret_cast<uint4*>(q)      = make_uint4(res_st[0], res_st[1], res[0], res[1]);
+          *reinterpret_cast<uint4*>(q + 64) = make_uint4(crs_st[0], crs_st[1], crs[0], crs[1]);
+        }
+      }
+    }
+  }
+  float hpa, hpb;
+  upk2(hp2, hpa, hpb);
+  if (R.row_ok) P.head_part[((size_t)ut * 2 + half) * P.rows + R.row] = hpa + hpb;
 }
 
 // stage this tile's W rows / bias / W_h slice (shared by all rows) into shared memory
@@ -362,7 +582,7 @@ constexpr int kPairBBoxRows = 64;                         // U tiles are fetched
 // CL = cluster size: 2 = one CTA pair; 4 = two pairs working on the SAME unit tile for two different row tiles,
 // which lets each 64-row piece of the U tile be fetched from L2 once and multicast to both pairs (the kernel is
 // L2->SM fill bound, profiles/README.md): U-tile L2 reads halve, at the price of 132 instead of 148 usable SMs.
-template <int NPROD, int CL>
+template <int NPROD, int CL, int EPI>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kTcThreads, 1)
 gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -371,8 +591,11 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
   // Stage layout: A_hi16 | A_lo | B_hi16 | B_lo, 16 KB each, every row 128 bytes (128B swizzle).  NPROD 3: lo = fp16
   // residual.  NPROD 2: lo = packed e4m3 image, bytes [0,64) of a row = residual, [64,128) = coarse copy.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int kStageBytes = (NPROD == 1) ? (kPairABytes + kPairBBytes) : 2 * (kPairABytes + kPairBBytes);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool IL = (EPI >= 4);                     // row-interleaved operands and state (no swizzle); EPI 5: 32-wide K stages, 6: exp-only tanh
+  constexpr int kIlBK = (EPI == 5) ? 32 : 64;
+  constexpr uint32_t kIlSub = kIlBK * 256;            // bytes of one operand box: [K groups][128 rows][16 B]
+  constexpr int kStageBytes = IL ? 4 * (int)kIlSub : (NPROD == 1) ? (kPairABytes + kPairBBytes) : 2 * (kPairABytes + kPairBBytes);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS, not generic LD)
   const int stages = P.stages;
   float* sparam = reinterpret_cast<float*>(smem + (size_t)stages * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sparam + 2 * kParamFloats);
@@ -417,7 +640,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA) =====================
-    if (lane == 0) {
+    if (lane == 0 && P.exp != 2) {
       int stage = 0; uint32_t phase = 0;
       constexpr uint32_t kATotal = (NPROD == 1) ? kPairABytes : 2 * kPairABytes;          // bytes of H operands per CTA and stage
       constexpr uint32_t kBBoxTotal = ((NPROD == 1) ? 1 : 2) * kPairBBoxRows * kPairBK * 2; // bytes of one 64-row box of every U operand
@@ -435,10 +658,21 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         for (int kb = 0; kb < P.k_blocks; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
-          if (leader) mbar_expect_tx(fb_local, 2u * (kATotal + (uint32_t)b_boxes * kBBoxTotal));   // both CTAs of the pair
+          if (leader && !IL) mbar_expect_tx(fb_local, 2u * (kATotal + (uint32_t)b_boxes * kBBoxTotal));   // both CTAs of the pair
           const uint32_t fb = map_to_cta(fb_local, leader_rank);
           uint8_t* sbase = smem + (size_t)stage * kStageBytes;
           const int k0 = kb * kPairBK;
+          if (IL) {
+            // row-interleaved operands: four boxes per stage, each [K group][128 rows][16 B] (no swizzle)
+            if (leader) mbar_expect_tx(fb_local, 2u * 4u * kIlSub);
+            const uint32_t sb = smem_u32(sbase);
+            tma_load_3d_pair(sb,              &map_a_hi, fb, 0, row0 >> 3, kb * (kIlBK / 8));
+            tma_load_4d_pair(sb + kIlSub,     &map_a_lo, fb, 0, row0 >> 3, 0, kb * (kIlBK / 16));
+            tma_load_3d_pair(sb + 2 * kIlSub, &map_b_hi, fb, 0, col0 >> 3, kb * (kIlBK / 8));
+            tma_load_4d_pair(sb + 3 * kIlSub, &map_b_lo, fb, 0, col0 >> 3, 0, kb * (kIlBK / 16));
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           auto load_u = [&](const CUtensorMap* map, uint32_t region, int kc) {
             constexpr uint32_t kBoxBytes = kPairBBoxRows * 128;
             if (mcast) {
@@ -479,15 +713,25 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcBN);
         uint32_t acc = 0;
-        for (int kb = 0; kb < P.k_blocks; ++kb) {
+        for (int kb = 0; kb < (P.exp == 2 ? 0 : P.k_blocks); ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + (size_t)stage * kStageBytes);
-          const int k_len = min(kPairBK, P.h - kb * kPairBK);
+          const int k_len = IL ? min(kIlBK, P.h - kb * kIlBK) : min(kPairBK, P.h - kb * kPairBK);
           const int k_steps = (k_len + kTcUK - 1) / kTcUK;
           for (int ks = 0; ks < k_steps; ++ks) {
             const uint32_t koff = (uint32_t)(ks * kTcUK * 2);      // bytes inside the 128-byte swizzled row
-            if (NPROD == 3) {
+            if (IL) {
+              // no-swizzle core-matrix tiles: fp16 K-step = two 8-wide K groups 2048 B apart; e4m3 K-step (32 wide) = two
+              // 16-wide K groups 4096 B apart, residual plane at +0, coarse plane at +2048
+              if ((ks & 1) == 0) {
+                const uint32_t a8 = sbase + kIlSub + (uint32_t)(ks >> 1) * 8192, b8 = sbase + 3 * kIlSub + (uint32_t)(ks >> 1) * 8192;
+                tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8, 4096), make_smem_desc_il(b8 + 2048, 4096), idesc, acc); acc = 1;
+                tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8 + 2048, 4096), make_smem_desc_il(b8, 4096), idesc, 1);
+              }
+              tc_mma_f16_pair(d_tmem, make_smem_desc_il(sbase + (uint32_t)ks * 4096, 2048),
+                              make_smem_desc_il(sbase + 2 * kIlSub + (uint32_t)ks * 4096, 2048), idesc, 1);
+            } else if (NPROD == 3) {
               const uint64_t a_hi = make_smem_desc_sw128(sbase + koff);
               const uint64_t a_lo = make_smem_desc_sw128(sbase + kPairABytes + koff);
               const uint64_t b_hi = make_smem_desc_sw128(sbase + 2 * kPairABytes + koff);
@@ -538,12 +782,20 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       float* sp = sparam + buf * kParamFloats;
       stage_tile_params(P, sp, et, ut);
       EpiRow R;
-      lstm_epilogue_prefetch(P, R, quarter, half, lane, ut,
-                             (rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM) + (long)(rank & 1u) * kTcBM);
+      lstm_epilogue_prefetch<IL>(P, R, quarter, half, lane, ut,
+                                       (rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM) + (long)(rank & 1u) * kTcBM);
       asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1);
       tc_fence_after();
-      lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, half, ut, dequant);
+      if (P.exp == 1) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kTcBN + half * 128), v);
+        tc_wait_ld();
+      } else if (EPI == 0) {
+        lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, half, ut, dequant);
+      } else {
+        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6, EPI == 3, IL>(P, R, sp, tmem_base, buf, quarter, half, ut, dequant);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), leader_rank));
@@ -593,6 +845,32 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows_total, int h, int
   return IADMM_OK;
 }
 
+int make_map_il(CUtensorMap* map, const void* base, uint64_t rows_total, int groups, bool q8, int box_k) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) IADMM_FAIL(IADMM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (rows_total % 8) IADMM_FAIL(IADMM_ESHAPE, "row-interleaved tensor map needs rows %% 8 == 0");
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r;
+  if (!q8) {
+    const cuuint64_t dims[3] = {64, (cuuint64_t)(rows_total / 8), (cuuint64_t)groups};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)rows_total * 16};
+    const cuuint32_t box[3] = {64, 16, (cuuint32_t)(box_k / 8)};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[4] = {128, (cuuint64_t)(rows_total / 8), 2, (cuuint64_t)groups};
+    const cuuint64_t strides[3] = {128, (cuuint64_t)rows_total * 16, (cuuint64_t)rows_total * 32};
+    const cuuint32_t box[4] = {128, 16, 2, (cuuint32_t)(box_k / 16)};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) IADMM_FAIL(IADMM_ECUDA, "cuTensorMapEncodeTiled (interleaved) failed with CUresult %d (rows=%llu groups=%d)", (int)r,
+                                    (unsigned long long)rows_total, groups);
+  return IADMM_OK;
+}
+
 static bool use_quads() {
   static int v = -1;
   if (v < 0) {
@@ -624,7 +902,7 @@ static int set_smem_attr(KernelT kernel, bool* done) {
 
 int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g, const __half* Hin_hi,
                     const __half* Hin_lo, __half* Hout_hi, __half* Hout_lo, float* H_out_f32, float* C,
-                    float* head_part, long rows, int h, int nprod, cudaStream_t st, float* gates_out) {
+                    float* head_part, long rows, int h, int nprod, cudaStream_t st, float* gates_out, const TcIl* il) {
   if (h % 8 != 0) IADMM_FAIL(IADMM_EMODE, "tensor-core gate path needs hidden_dim %% 8 == 0");
   if (rows > 0x7fffffffL - 2 * kTcBM) IADMM_FAIL(IADMM_ESHAPE, "too many rows for one launch");
   static int num_sms = 0;
@@ -645,6 +923,15 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   int rc;
   const int b_box_rows = pair ? kPairBBoxRows : kTcBN;
   const int bk = pair ? kPairBK : kTcBK;
+  static int il_bk = 0;
+  if (!il_bk) { const char* e = getenv("IADMM_TC_IL_BK"); il_bk = (e && atoi(e) == 32) ? 32 : 64; }   // development switch
+  if (il) {
+    if (!pair || nprod != 2 || gates_out) IADMM_FAIL(IADMM_EMODE, "the row-interleaved layout is the F16F8 CTA-pair solve path only");
+    if ((rc = make_map_il(&ma_hi, Hin_hi, (uint64_t)il->rows_p, h / 8, false, il_bk))) return rc;
+    if ((rc = make_map_il(&ma_lo, Hin_lo, (uint64_t)il->rows_p, h / 16, true, il_bk))) return rc;
+    if ((rc = make_map_il(&mb_hi, base + L.off_uhi_il, (uint64_t)4 * h, h / 8, false, il_bk))) return rc;
+    if ((rc = make_map_il(&mb_lo, base + L.off_uq8_il, (uint64_t)4 * h, h / 16, true, il_bk))) return rc;
+  } else {
   if ((rc = make_map(&ma_hi, Hin_hi, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
   if ((rc = make_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
   if (nprod == 2) {
@@ -656,6 +943,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
     if ((rc = make_map(&ma_lo, Hin_lo, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
     if ((rc = make_map(&mb_lo, base + L.off_ulo, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
   }
+  }
 
   TcParams P;
   P.wc = reinterpret_cast<const float*>(base + L.off_wc);
@@ -664,18 +952,29 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.scale = reinterpret_cast<const float*>(base + L.off_scale);
   P.xv = xv; P.g = g;
   P.hout_hi = Hout_hi; P.hout_lo = Hout_lo; P.hout_f32 = H_out_f32; P.C = C; P.head_part = head_part;
-  P.gates_out = gates_out;
+  P.gates_out = gates_out; P.exp = 0;
+  P.rows_p = il ? il->rows_p : 0; P.c_rm_out = il ? il->C_rm_out : nullptr;
+  if (il) P.C = il->C_il;
   P.rows = rows; P.h = h; P.q8_pitch = q8_pitch(h);
   P.unit_tiles = cdiv(h, kTcUnits);
-  P.k_blocks = cdiv(h, bk);
+  P.k_blocks = cdiv(h, il ? il_bk : bk);
   P.nprod = nprod;
+  static int exp_mode = -1, epi = -1;
+  if (exp_mode < 0) {
+    const char* e = getenv("IADMM_TC_EXP");           // development experiments, see TcParams::exp
+    exp_mode = e ? atoi(e) : 0;
+    const char* w = getenv("IADMM_TC_EPI");           // development switch: 0 = scalar epilogue, 1 = packed fp32 (default), 2 = packed + exp-only tanh
+    epi = w ? atoi(w) : 1;
+    if (epi < 0 || epi > 2) epi = 1;
+  }
+  P.exp = exp_mode;
   // cluster size: 4 (two pairs sharing each U tile through TMA multicast) when there is enough work, else 2
   static int max_quads = -1;
   int cl = 1;
   if (pair) {
     cl = 2;
     const long row_tiles = (rows + 2 * kTcBM - 1) / (2 * kTcBM);
-    if (use_quads() && row_tiles >= 2 && num_sms >= 4) cl = 4;
+    if (use_quads() && row_tiles >= 2 && num_sms >= 4 && !gates_out && !il) cl = 4;
   }
   const int tile_rows = (pair ? 2 * kTcBM : kTcBM) * (cl == 4 ? 2 : 1);
   P.num_tiles = ((rows + tile_rows - 1) / tile_rows) * P.unit_tiles;
@@ -683,7 +982,8 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   const int b_bytes = pair ? kPairBBytes : kTcBBytes;
   const int stage_bytes = (nprod == 1) ? (a_bytes + b_bytes) : 2 * (a_bytes + b_bytes);
   P.stages = (192 * 1024) / stage_bytes;                 // 4 / 8 (single CTA, 32-wide K), 3 / 6 (pair, 64-wide K)
-  const size_t smem = 1024 + (size_t)P.stages * stage_bytes + 2 * kParamFloats * sizeof(float) +
+  if (il) P.stages = (192 * 1024) / (il_bk * 1024);      // 3 x 64 KB or 6 x 32 KB
+  const size_t smem = 1024 + (size_t)P.stages * (il ? il_bk * 1024 : stage_bytes) + 2 * kParamFloats * sizeof(float) +
                       (2 * P.stages + 4) * sizeof(uint64_t) + 16;
 
   if (pair) {
@@ -710,14 +1010,28 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
       return IADMM_OK;
     };
     static bool a34 = false, a24 = false, a14 = false, a32 = false, a22 = false, a12 = false;
-    if (cl == 4) {
-      if (nprod == 3)      rc = launch(gates_tc_pair_kernel<3, 4>, &a34, 4);
-      else if (nprod == 2) rc = launch(gates_tc_pair_kernel<2, 4>, &a24, 4);
-      else                 rc = launch(gates_tc_pair_kernel<1, 4>, &a14, 4);
+    static bool e0 = false, e2 = false, s2 = false, s3 = false, s1 = false;
+    static bool i4 = false;
+    if (il) {
+      static bool i5 = false;
+      static bool i6 = false;
+      if (epi == 2)         rc = launch(gates_tc_pair_kernel<2, 2, 6>, &i6, 2);
+      else if (il_bk == 32) rc = launch(gates_tc_pair_kernel<2, 2, 5>, &i5, 2);
+      else             rc = launch(gates_tc_pair_kernel<2, 2, 4>, &i4, 2);
+    } else if (gates_out) {        // training forward: the epilogue also stores the gate activations
+      if (nprod == 1)      rc = launch(gates_tc_pair_kernel<1, 2, 0>, &s1, 2);
+      else if (nprod == 3)       rc = launch(gates_tc_pair_kernel<3, 2, 3>, &s3, 2);
+      else                       rc = launch(gates_tc_pair_kernel<2, 2, 3>, &s2, 2);
+    } else if (cl == 4) {
+      if (nprod == 3)      rc = launch(gates_tc_pair_kernel<3, 4, 1>, &a34, 4);
+      else if (nprod == 2) rc = launch(gates_tc_pair_kernel<2, 4, 1>, &a24, 4);
+      else                 rc = launch(gates_tc_pair_kernel<1, 4, 1>, &a14, 4);
     } else {
-      if (nprod == 3)      rc = launch(gates_tc_pair_kernel<3, 2>, &a32, 2);
-      else if (nprod == 2) rc = launch(gates_tc_pair_kernel<2, 2>, &a22, 2);
-      else                 rc = launch(gates_tc_pair_kernel<1, 2>, &a12, 2);
+      if (nprod == 3)      rc = launch(gates_tc_pair_kernel<3, 2, 1>, &a32, 2);
+      else if (nprod == 2 && epi == 0) rc = launch(gates_tc_pair_kernel<2, 2, 0>, &e0, 2);
+      else if (nprod == 2 && epi == 2) rc = launch(gates_tc_pair_kernel<2, 2, 2>, &e2, 2);
+      else if (nprod == 2) rc = launch(gates_tc_pair_kernel<2, 2, 1>, &a22, 2);
+      else                 rc = launch(gates_tc_pair_kernel<1, 2, 1>, &a12, 2);
     }
     if (rc) return rc;
     IADMM_LAUNCH_CHECK("gates_tc_pair_kernel");

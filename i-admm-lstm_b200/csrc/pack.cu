@@ -32,6 +32,8 @@ WeightLayout weight_layout(int h, int length) {
   L.off_u32hi = take(4 * H * H * sizeof(__half));
   L.off_u32lo = take(4 * H * H * sizeof(__half));
   L.off_uq8   = take(4 * H * q8_pitch(h));
+  L.off_uhi_il = take((size_t)((h + 7) / 8) * 4 * H * 8 * sizeof(__half));
+  L.off_uq8_il = take((size_t)((h + 15) / 16) * 2 * 4 * H * 16);
   L.total = off;
   return L;
 }
@@ -93,6 +95,7 @@ __device__ __forceinline__ uint8_t to_e4m3(float v) {
 __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __restrict__ u32, __half* __restrict__ uhi,
                                                      __half* __restrict__ ulo, __half* __restrict__ u32hi,
                                                      __half* __restrict__ u32lo, uint8_t* __restrict__ uq8,
+                                                     __half* __restrict__ uhi_il, uint8_t* __restrict__ uq8_il,
                                                      float* __restrict__ scale) {
   const float mx = scale[2];
   float us = 1.f;
@@ -120,6 +123,12 @@ __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __
     uint8_t* q = uq8 + (size_t)c * q8_pitch_dev(h) + (size_t)(k >> 6) * 128 + (k & 63);
     q[0]  = to_e4m3(ldexpf(vs - __half2float(hi), kQ8ULoShift));      // residual
     q[64] = to_e4m3(ldexpf(__half2float(hi), kQ8UHiShift));           // coarse copy
+    // row-interleaved images: [K group][gate column][16 bytes]
+    const size_t c4 = (size_t)4 * h;
+    uhi_il[((size_t)(k >> 3) * c4 + c) * 8 + (k & 7)] = hi;
+    uint8_t* qi = uq8_il + ((size_t)(k >> 4) * 2 * c4 + c) * 16 + (k & 15);
+    qi[0]       = q[0];
+    qi[c4 * 16] = q[64];
   }
 }
 
@@ -143,12 +152,15 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
   IADMM_LAUNCH_CHECK("pack_absmax_kernel");
   // padding bytes of the packed e4m3 rows (last K block when h % 64 != 0) are read by the K=32 MMAs: keep them zero
   IADMM_CUDA(cudaMemsetAsync(base + L.off_uq8, 0, (size_t)4 * h * q8_pitch(h), st));
+  IADMM_CUDA(cudaMemsetAsync(base + L.off_uhi_il, 0, L.total - L.off_uhi_il, st));      // K-group padding of the interleaved images
   pack_u_kernel<<<blocks, 256, 0, st>>>(S, h, reinterpret_cast<float*>(base + L.off_u32),
                                         reinterpret_cast<__half*>(base + L.off_uhi),
                                         reinterpret_cast<__half*>(base + L.off_ulo),
                                         reinterpret_cast<__half*>(base + L.off_u32hi),
                                         reinterpret_cast<__half*>(base + L.off_u32lo),
-                                        reinterpret_cast<uint8_t*>(base + L.off_uq8), scale);
+                                        reinterpret_cast<uint8_t*>(base + L.off_uq8),
+                                        reinterpret_cast<__half*>(base + L.off_uhi_il),
+                                        reinterpret_cast<uint8_t*>(base + L.off_uq8_il), scale);
   IADMM_LAUNCH_CHECK("pack_u_kernel");
   return IADMM_OK;
 }
@@ -194,6 +206,66 @@ int launch_split_state(const float* H, __half* hi, __half* lo, long rows, int h,
     split_state_kernel<false><<<grid, 256, 0, st>>>(H, hi, lo, count, h);
   }
   IADMM_LAUNCH_CHECK("split_state_kernel");
+  return IADMM_OK;
+}
+
+// ---- row-interleaved images (fused solve, F16F8 mode): hi [h/8][rows_p][8] fp16, q8 [h/16][2][rows_p][16] e4m3 ----
+__global__ void __launch_bounds__(256) split_state_il_kernel(const float* __restrict__ H, __half* __restrict__ hi,
+                                                             uint8_t* __restrict__ q8, long rows, long rows_p, int h) {
+  // one thread per (row, 8-unit group): 32-byte read, one 16-byte fp16 store and two 8-byte e4m3 stores
+  const float s = (float)(1 << kHShift);
+  const int groups = h / 8;
+  const size_t total = (size_t)rows * groups;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kg = (int)(i / (size_t)rows);                 // consecutive threads -> consecutive rows (coalesced stores)
+    const size_t r = i - (size_t)kg * rows;
+    const float* src = H + r * h + (size_t)kg * 8;
+    __half a[8];
+    uint8_t res[8], crs[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float v = src[u] * s;
+      a[u] = __float2half_rn(v);
+      res[u] = to_e4m3(ldexpf(v - __half2float(a[u]), kQ8HLoShift));
+      crs[u] = to_e4m3(ldexpf(v, kQ8HHiShift));
+    }
+    *reinterpret_cast<uint4*>(hi + ((size_t)kg * rows_p + r) * 8) = *reinterpret_cast<const uint4*>(a);
+    uint8_t* q = q8 + ((size_t)(kg >> 1) * 2 * rows_p + r) * 16 + (kg & 1) * 8;
+    *reinterpret_cast<uint2*>(q) = *reinterpret_cast<const uint2*>(res);
+    *reinterpret_cast<uint2*>(q + (size_t)rows_p * 16) = *reinterpret_cast<const uint2*>(crs);
+  }
+}
+
+__global__ void __launch_bounds__(256) c_to_il_kernel(const float* __restrict__ C, float* __restrict__ C_il, long rows,
+                                                      long rows_p, int h) {
+  const int groups = h / 8;
+  const size_t total = (size_t)rows * groups;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kg = (int)(i / (size_t)rows);
+    const size_t r = i - (size_t)kg * rows;
+    const float4* src = reinterpret_cast<const float4*>(C + r * h + (size_t)kg * 8);
+    float4* dst = reinterpret_cast<float4*>(C_il + ((size_t)kg * rows_p + r) * 8);
+    dst[0] = src[0];
+    dst[1] = src[1];
+  }
+}
+
+int launch_split_state_il(const float* H, __half* hi, __half* q8, long rows, int h, cudaStream_t st) {
+  const long rows_p = il_rows(rows);
+  const size_t total = (size_t)rows * (h / 8);
+  const size_t blocks = (total + 255) / 256;
+  split_state_il_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(
+      H, hi, reinterpret_cast<uint8_t*>(q8), rows, rows_p, h);
+  IADMM_LAUNCH_CHECK("split_state_il_kernel");
+  return IADMM_OK;
+}
+
+int launch_c_to_il(const float* C, float* C_il, long rows, int h, cudaStream_t st) {
+  const long rows_p = il_rows(rows);
+  const size_t total = (size_t)rows * (h / 8);
+  const size_t blocks = (total + 255) / 256;
+  c_to_il_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(C, C_il, rows, rows_p, h);
+  IADMM_LAUNCH_CHECK("c_to_il_kernel");
   return IADMM_OK;
 }
 

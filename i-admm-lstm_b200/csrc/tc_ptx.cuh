@@ -123,6 +123,19 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // arrives on the barrier at this CTA-relative offset in every CTA of `cta_mask` once the issued MMAs retire
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar_local, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_local),
@@ -189,6 +202,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t saddr) {
   d |= (uint64_t)6 << 61;                            // layout type SWIZZLE_32B
   return d;
 }
+// K-major operand tile WITHOUT swizzle (the canonical "interleaved" layout): core matrices of 8 rows x 16 bytes are
+// 128 contiguous bytes; consecutive 8-row groups are 128 B apart (stride byte offset), the next 16-byte K chunk of the
+// same rows is `lbo_bytes` away (leading byte offset).  This is the order [K group][row][16 B] the row-interleaved
+// global layout is stored in, so a TMA box lands in it unchanged.
+__device__ __forceinline__ uint64_t make_smem_desc_il(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;                            // layout type 0 = no swizzle
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n_cols
 __device__ __forceinline__ uint32_t make_idesc_f16(int n_cols, int m_rows = kTcBM) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n_cols >> 3) << 17) |
@@ -204,5 +229,9 @@ EncodeTiledFn get_encode_fn();
 // 2D row-major [rows_total][cols] tensor of fp16 (elem_bytes 2) or bytes (elem_bytes 1); box = [box_rows][box_k
 // elements]; swizzle follows the box row size (128/64/32 bytes); out-of-bounds elements read as zero
 int make_map(CUtensorMap* map, const void* base, uint64_t rows_total, int cols, int box_rows, int elem_bytes, int box_k);
+// row-interleaved operand images (no swizzle): fp16 [groups][rows_total][8] as a 3D tensor {64 elements = 8 rows x 16 B,
+// rows_total/8, groups}, box {64, 16, 8} = 128 rows x 64 K; e4m3 [groups16][2][rows_total][16] as a 4D tensor
+// {128 bytes, rows_total/8, 2, groups16}, box {128, 16, 2, 4}.  rows_total % 8 == 0.
+int make_map_il(CUtensorMap* map, const void* base, uint64_t rows_total, int groups, bool q8, int box_k = 64);
 
 }  // namespace iadmm
