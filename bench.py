@@ -337,8 +337,10 @@ def run_ours(args):
                          "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,
                          "flops_per_launch": gate_flops, "ms_per_launch": gate_avg_ms,
                          "share_of_step": gate_ms.value / ms,
+                         "issued_frac": gate_tflops * {"tc_3xfp16": 3, "tc_f16f8": 2}.get(args.gate_mode, 1) / tf_sus,
                          "note": "logical fp32 flops 8*rows*h^2; the operand split issues %dx that in fp16-equivalent MMA work "
-                                 "(tc_3xfp16: 3 fp16 products, tc_f16f8: 1 fp16 + 2 e4m3 at twice the rate; issued rate %.1f TFLOP/s)"
+                                 "(tc_3xfp16: 3 fp16 products, tc_f16f8: 1 fp16 + 2 e4m3 at twice the rate; issued rate %.1f TFLOP/s "
+                                 "= issued_frac of the peak); the kernel runs at the board power cap (see clocks), DESIGN.md section 4"
                                  % ({"tc_3xfp16": 3, "tc_f16f8": 2}.get(args.gate_mode, 1),
                                     gate_tflops * {"tc_3xfp16": 3, "tc_f16f8": 2}.get(args.gate_mode, 1))},
             "roofline_kkt": {"kernel": "kkt_pass1+combine1+pass2+combine2", "bound": "hbm", "achieved": kkt_gbs,

@@ -66,6 +66,7 @@ struct TcParams {
   int  exp;               // development experiments (IADMM_TC_EXP, results are garbage): 1 = epilogue reads TMEM only,
                           // 2 = no TMA / MMA, 3 = no global traffic in the epilogue, 4 = no cell math, 5 = all rows alias 1024 rows (no DRAM)
   long num_tiles;
+  uint32_t wait_ns;       // suspend-time hint of the mbarrier waits (development switch IADMM_TC_WAIT_NS)
   long rows_p;            // row-interleaved layout (EPI 4): rows rounded up to 128; C, hout_hi, hout_lo are [group][rows_p][..]
   float* c_rm_out;        // row-interleaved layout, last iteration: the caller's row-major C
   size_t q8_pitch;        // bytes per row of the packed e4m3 image (NPROD 2)
@@ -656,7 +657,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const int  b_boxes = mcast ? 2 : (n_cols / 2 + kPairBBoxRows - 1) / kPairBBoxRows;   // boxes landing in this CTA
         const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank ^ 2u)));
         for (int kb = 0; kb < P.k_blocks; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, P.wait_ns);
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
           if (leader && !IL) mbar_expect_tx(fb_local, 2u * (kATotal + (uint32_t)b_boxes * kBBoxTotal));   // both CTAs of the pair
           const uint32_t fb = map_to_cta(fb_local, leader_rank);
@@ -709,12 +710,12 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const uint32_t idesc = make_idesc_f16(n_cols, 2 * kTcBM);
         const int buf = (int)(it & 1);
         const uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1) ^ 1);     // both CTAs' epilogues drained this accumulator
+        mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1) ^ 1, P.wait_ns);     // both CTAs' epilogues drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcBN);
         uint32_t acc = 0;
         for (int kb = 0; kb < (P.exp == 2 ? 0 : P.k_blocks); ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          mbar_wait(smem_u32(&full_bar[stage]), phase, P.wait_ns);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + (size_t)stage * kStageBytes);
           const int k_len = IL ? min(kIlBK, P.h - kb * kIlBK) : min(kPairBK, P.h - kb * kPairBK);
@@ -785,7 +786,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       lstm_epilogue_prefetch<IL>(P, R, quarter, half, lane, ut,
                                        (rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM) + (long)(rank & 1u) * kTcBM);
       asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
-      mbar_wait(smem_u32(&tfull_bar[buf]), use & 1);
+      mbar_wait(smem_u32(&tfull_bar[buf]), use & 1, P.wait_ns);
       tc_fence_after();
       if (P.exp == 1) {
         uint32_t v[32];
@@ -952,7 +953,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.scale = reinterpret_cast<const float*>(base + L.off_scale);
   P.xv = xv; P.g = g;
   P.hout_hi = Hout_hi; P.hout_lo = Hout_lo; P.hout_f32 = H_out_f32; P.C = C; P.head_part = head_part;
-  P.gates_out = gates_out; P.exp = 0;
+  P.gates_out = gates_out; P.exp = 0; P.wait_ns = IADMM_MBAR_SUSPEND_NS;
   P.rows_p = il ? il->rows_p : 0; P.c_rm_out = il ? il->C_rm_out : nullptr;
   if (il) P.C = il->C_il;
   P.rows = rows; P.h = h; P.q8_pitch = q8_pitch(h);
@@ -968,6 +969,9 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
     if (epi < 0 || epi > 2) epi = 1;
   }
   P.exp = exp_mode;
+  static int wait_ns = -1;
+  if (wait_ns < 0) { const char* e = getenv("IADMM_TC_WAIT_NS"); wait_ns = e ? atoi(e) : IADMM_MBAR_SUSPEND_NS; }
+  P.wait_ns = (uint32_t)wait_ns;
   // cluster size: 4 (two pairs sharing each U tile through TMA multicast) when there is enough work, else 2
   static int max_quads = -1;
   int cl = 1;
