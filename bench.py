@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--nvar", type=int, default=N_VAR, help="variables per QP (the metric is quoted at 1000; 5000 = BASELINE config 5, "
+                                                             "with num_ineq = num_eq = nvar/2)")
     ap.add_argument("--hidden", type=int, default=HIDDEN, help="hidden_dim (the metric is quoted at 800; 200 is configs/QP.yaml's default)")
     return ap.parse_args()
 
@@ -177,8 +179,10 @@ def measured_peaks():
     return 6650.0, 1400.0, 1590.0, "fallback"
 
 
-def ncu_traffic(kind, batch, mode):
+def ncu_traffic(kind, batch, mode, headline=True):
     """DRAM bytes per launch from the committed ncu --set full capture of this config, if any."""
+    if not headline:
+        return None
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
         try:
@@ -202,8 +206,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
-    B, n, mi, me, h, K = args.batch, N_VAR, N_INEQ, N_EQ, args.hidden, args.iters
-    m, N = mi + me, N_VAR + N_INEQ + N_EQ
+    B, n, mi, me, h, K = args.batch, args.nvar, args.nvar // 2, args.nvar // 2, args.hidden, args.iters
+    m, N = mi + me, n + mi + me
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     L = ia.lib()
 
@@ -320,7 +324,8 @@ def run_ours(args):
             "metric": METRIC, "value": n_gpus * B * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if h == HIDDEN else WORKLOAD.replace("hidden_dim=800", "hidden_dim=%d" % h),
+            "config": {"workload": (WORKLOAD if h == HIDDEN else WORKLOAD.replace("hidden_dim=800", "hidden_dim=%d" % h)) if n == N_VAR else
+                                   "config5-style: dense QP n=%d, %d ineq + %d eq, hidden_dim=%d, --scaling, K=%d (NOT the headline workload)" % (n, mi, me, h, K),
                        "batch_per_gpu": B, "iters": K, "gate_mode": args.gate_mode,
                        "gate_arithmetic": {"tc_3xfp16": "tcgen05 fp16 hi/lo split, 3 MMAs, fp32 accumulate",
                                            "tc_f16f8": "tcgen05 fp16 MMA + 2 e4m3 correction MMAs, fp32 accumulate",
@@ -333,7 +338,7 @@ def run_ours(args):
             "gpu_launches": steps * launches_per_step,
             "roofline": {"kernel": "gates_tc_pair_kernel" if args.gate_mode != "simt_fp32" else "gates_simt_kernel",
                          "bound": "tensor", "achieved": gate_tflops, "peak": tf_sus, "unit": "TFLOP/s",
-                         "frac": gate_tflops / tf_sus, "traffic": ncu_traffic("gates", B, args.gate_mode),
+                         "frac": gate_tflops / tf_sus, "traffic": ncu_traffic("gates", B, args.gate_mode, h == HIDDEN and n == N_VAR),
                          "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,
                          "flops_per_launch": gate_flops, "ms_per_launch": gate_avg_ms,
                          "share_of_step": gate_ms.value / ms,
@@ -345,7 +350,7 @@ def run_ours(args):
                                     gate_tflops * {"tc_3xfp16": 3, "tc_f16f8": 2}.get(args.gate_mode, 1))},
             "roofline_kkt": {"kernel": "kkt_pass1+combine1+pass2+combine2", "bound": "hbm", "achieved": kkt_gbs,
                              "peak": hbm_gbs, "unit": "GB/s", "frac": kkt_gbs / hbm_gbs,
-                             "traffic": ncu_traffic("kkt", B, args.gate_mode),
+                             "traffic": ncu_traffic("kkt", B, args.gate_mode, n == N_VAR),
                              "bytes_per_iteration": kkt_bytes, "ms_per_iteration": kkt_avg_ms,
                              "share_of_step": kkt_ms.value / ms, "peak_kind": "%s hbm_gbs" % peak_kind},
             "hbm_roofline_frac_whole_path": hbm_frac_whole,

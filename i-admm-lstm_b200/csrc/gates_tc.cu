@@ -64,7 +64,8 @@ struct TcParams {
   long rows;
   int  h, unit_tiles, k_blocks, stages, nprod;
   int  exp;               // development experiments (IADMM_TC_EXP, results are garbage): 1 = epilogue reads TMEM only,
-                          // 2 = no TMA / MMA, 3 = no global traffic in the epilogue, 4 = no cell math, 5 = all rows alias 1024 rows (no DRAM)
+                          // 2 = no TMA / MMA, 3 = no global traffic in the epilogue, 4 = no cell math, 5 = all rows alias 1024 rows (no DRAM),
+                          // 6 = only one of the two e4m3 correction MMAs (cost proxy for half-price corrections)
   long num_tiles;
   uint32_t wait_ns;       // suspend-time hint of the mbarrier waits (development switch IADMM_TC_WAIT_NS)
   long rows_p;            // row-interleaved layout (EPI 4): rows rounded up to 128; C, hout_hi, hout_lo are [group][rows_p][..]
@@ -728,7 +729,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
               if ((ks & 1) == 0) {
                 const uint32_t a8 = sbase + kIlSub + (uint32_t)(ks >> 1) * 8192, b8 = sbase + 3 * kIlSub + (uint32_t)(ks >> 1) * 8192;
                 tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8, 4096), make_smem_desc_il(b8 + 2048, 4096), idesc, acc); acc = 1;
-                tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8 + 2048, 4096), make_smem_desc_il(b8, 4096), idesc, 1);
+                if (P.exp != 6) tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8 + 2048, 4096), make_smem_desc_il(b8, 4096), idesc, 1);
               }
               tc_mma_f16_pair(d_tmem, make_smem_desc_il(sbase + (uint32_t)ks * 4096, 2048),
                               make_smem_desc_il(sbase + 2 * kIlSub + (uint32_t)ks * 4096, 2048), idesc, 1);

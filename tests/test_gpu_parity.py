@@ -548,3 +548,34 @@ def test_error_behaviour():
     assert L.iadmm_solve(*bad, *tail, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()) == -2                 # IADMM_EALIGN (NULL Q)
     assert L.iadmm_solve(*base, *tail, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()) == 0
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("shape", [(3, 100, 20, 17, 208), (2, 260, 70, 54, 48), (1, 130, 0, 0, 16)])
+def test_row_interleaved_solve_matches_row_major_steps(shape):
+    """The fused F16F8 solve (K >= 2) keeps H, C and the e4m3 planes row-interleaved ([column group][row][16/32 B],
+    no-swizzle UMMA tiles); single steps (K = 1) use the row-major / 128B-swizzle kernel.  Both issue the same MMAs on
+    the same operand values, so from a carried NON-zero state (exercises the layout conversion on entry) the fused
+    solve must reproduce the step-by-step iterates up to the fp32 round trip of H at the call boundary, and agree with
+    the fp32 CUDA-core path; rows % 128 != 0, h % 64 != 0 (K tail), narrow last unit tile, m = 0."""
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h = shape
+    K = 5
+    qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=77).items()}
+    prm = orc.lstm_parameters(h, K + 2, seed=77, scale=3.0)
+    args = (qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6)
+    tc = make_model(prm, h, K + 2, "tc_f16f8")
+    ref = make_model(prm, h, K + 2, "simt_fp32")
+    with torch.no_grad():
+        a = tc.solve(2, mi, me, *args)                                   # a non-zero state to continue from
+        st = (a.x, a.y, a.z, a.xv, a.H, a.C)
+        fused = tc.solve(K, mi, me, *args, state=st, t0=2)
+        r32 = ref.solve(K, mi, me, *args, state=st, t0=2)
+        s = st
+        for t in range(K):
+            one = tc.solve(1, mi, me, *args, state=s, t0=2 + t)
+            s = (one.x, one.y, one.z, one.xv, one.H, one.C)
+    for k, v in zip(("x", "y", "z", "xv", "H", "C"), s):
+        assert rel_err(getattr(fused, k), v) <= 1e-5, ("steps", k, rel_err(getattr(fused, k), v))
+        assert torch.isfinite(getattr(fused, k)).all()
+    for k in ("x", "z", "xv", "H", "C"):
+        assert rel_err(getattr(fused, k), getattr(r32, k)) <= 1e-4, ("fp32", k, rel_err(getattr(fused, k), getattr(r32, k)))
