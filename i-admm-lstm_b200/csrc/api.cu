@@ -248,7 +248,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
     if (rc) return rc;
     prof_record(2, st);
     cur ^= 1;
-    if ((rc = launch_tail(ws.d, ws.head_part, ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st, metric_trace ? &ws.s : nullptr))) return rc;
+    if ((rc = launch_tail(ws.d, ws.head_part, tc ? tc_head_slots(h, il) : ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st, metric_trace ? &ws.s : nullptr))) return rc;
     prof_record(3, st);
     if (g_prof.on && g_prof.used < g_prof.cap) ++g_prof.used;
   }

@@ -66,6 +66,8 @@ struct WeightLayout {
   size_t off_u32lo;   // fp16 [h][4h]   lo part
   size_t off_uq8;     // e4m3 [4h][q8_pitch(h)]: per 64-wide K block 64 B of residual (U*2^s - fp16(U*2^s)) * 2^6 followed by
                       //                64 B of the coarse copy fp16(U*2^s) * 2^-5   (F16F8 mode; one 128-byte TMA row)
+  size_t off_tilep;   // fp32 [ceil(h/64)][832]: per 64-unit tile the W row 0 | W row 1 | bias (256 gate columns each) | W_h (64) block the
+                      //                gate kernel's epilogue reads, contiguous so ONE bulk copy stages it in shared memory
   size_t off_uhi_il;  // fp16 [h/8][4h][8]: row-interleaved image of fp16(U*2^s) (16-byte K groups of consecutive gate columns adjacent;
                       //                the no-swizzle UMMA core-matrix order, see gates_tc.cu "row-interleaved layout")
   size_t off_uq8_il;  // e4m3 [ceil(h/16)][2][4h][16]: residual plane, coarse plane per 16-wide K group
@@ -210,7 +212,8 @@ static inline size_t q8_pitch(int h) { return (size_t)((h + 63) / 64) * 128; }
 // F16F8 scalings (powers of two, exact): residual of H*2^14 is < 4 -> *2^5 < 128; H*2^14*2^-6 < 256;
 // fp16(U*2^s) < 2^13 -> *2^-5 < 256; residual of U*2^s is < 2 -> *2^6 < 128  (e4m3 max = 448)
 constexpr int kQ8HLoShift = 5, kQ8HHiShift = -6, kQ8UHiShift = -5, kQ8ULoShift = 6;
-int  tc_gate_tiles(int h);
+int  tc_gate_tiles(int h);                    // head-partial slots to allocate
+int  tc_head_slots(int h, bool interleaved);  // slots the gate kernel writes (= what the tail sums)
 size_t tc_state_bytes(long rows, int h);
 // Row-interleaved state layout of the fused solve (F16F8 mode): every per-row array is stored [column group][row][16 or 32 B]
 // so that the thread-per-row epilogue reads and writes whole 128-byte lines (see gates_tc.cu).  rows_p = rows rounded up to 128.

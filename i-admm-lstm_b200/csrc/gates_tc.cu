@@ -42,7 +42,7 @@ constexpr int kTcABytes = kTcBM * kTcBK * 2;     // 8 KB
 constexpr int kTcBBytes = kTcBN * kTcBK * 2;     // 16 KB
 constexpr int kTcChunk = 32;                     // TMEM columns per epilogue step (8 units)
 
-int tc_gate_tiles(int h) { return 2 * cdiv(h, kTcUnits); }   // two head partials per unit tile
+int tc_gate_tiles(int h) { return 4 * cdiv(h, kTcUnits); }   // workspace slots: up to four head partials per unit tile (16-warp epilogue)
 size_t tc_state_bytes(long rows, int h) { return (size_t)rows * h * sizeof(__half) * 4; }
 
 // ------------------------------------------------------------------------------------------------
@@ -53,6 +53,7 @@ struct TcParams {
   const float* bias;      // [4h]
   const float* wh;        // [h]
   const float* scale;     // [4]: [1] = dequant
+  const float* tilep;     // [unit_tiles][832] per-tile parameter blocks (W0 | W1 | bias | W_h)
   const float* xv;        // [rows]
   const float* g;         // [rows]
   __half* hout_hi;        // [rows][h]
@@ -78,23 +79,25 @@ struct TcParams {
 // Split in two so the C loads are in flight while the warp waits for the accumulator.
 constexpr int kChunksPerHalf = kTcBN / kTcChunk / 2;   // 4
 
-struct EpiRow {
+template <int NCH = kChunksPerHalf>
+struct EpiRowT {
   long row;
   bool row_ok;
   float xr, gr;
-  float c[kChunksPerHalf][8];
+  float c[NCH][8];
 };
+typedef EpiRowT<kChunksPerHalf> EpiRow;
 
-template <bool IL = false>
-__device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRow& R, int quarter, int half, int lane, int ut,
+template <bool IL = false, int NCH = kChunksPerHalf>
+__device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRowT<NCH>& R, int quarter, int half, int lane, int ut,
                                                        long row_base) {
   R.row = row_base + quarter * 32 + lane;
   R.row_ok = R.row < P.rows;
   R.xr = R.row_ok ? __ldg(P.xv + R.row) : 0.f;
   R.gr = R.row_ok ? __ldg(P.g + R.row) : 0.f;
 #pragma unroll
-  for (int cc = 0; cc < kChunksPerHalf; ++cc) {
-    const int unit0 = ut * kTcUnits + (half * kChunksPerHalf + cc) * 8;
+  for (int cc = 0; cc < NCH; ++cc) {
+    const int unit0 = ut * kTcUnits + (half * NCH + cc) * 8;
     if (R.row_ok && unit0 < P.h && P.exp != 3) {
       if (IL) ld_global_v8(P.C + ((size_t)(unit0 >> 3) * P.rows_p + R.row) * 8, R.c[cc]);
       else    ld_global_v8(P.C + (size_t)((P.exp == 5) ? (R.row & 1023) : R.row) * P.h + unit0, R.c[cc]);
@@ -267,8 +270,8 @@ __device__ __forceinline__ u64 tanh2(float x0, float x1, float big0, float big1)
   return pk2((fabsf(x0) < 0.55f) ? s0 : big0, (fabsf(x1) < 0.55f) ? s1 : big1);
 }
 
-template <int NPROD, bool FAST, bool SAVE, bool IL>
-__device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const EpiRow& R, const float* sp, uint32_t tmem_base, int buf,
+template <int NPROD, bool FAST, bool SAVE, bool IL, int NCH = kChunksPerHalf>
+__device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const EpiRowT<NCH>& R, const float* sp, uint32_t tmem_base, int buf,
                                                       int quarter, int half, int ut, float dequant) {
   u64 hp2 = 0ull;                                       // (even units, odd units) partial head dots
   const bool wide = (P.h % 16) == 0;
@@ -278,8 +281,8 @@ __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const E
   const u64 k_if = bc2(-kL), k_ou = pk2(-kL, 2.0f * kL), k_t = bc2(2.0f * kL);
   const size_t rowoff = (size_t)((P.exp == 5) ? (R.row & 1023) : R.row);
 #pragma unroll
-  for (int cc = 0; cc < kChunksPerHalf; ++cc) {
-    const int chunk = half * kChunksPerHalf + cc;
+  for (int cc = 0; cc < NCH; ++cc) {
+    const int chunk = half * NCH + cc;
     const int unit0 = ut * kTcUnits + chunk * 8;          // first hidden unit of this chunk
     uint32_t v[32];
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kTcBN + chunk * kTcChunk);
@@ -398,7 +401,7 @@ __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const E
   }
   float hpa, hpb;
   upk2(hp2, hpa, hpb);
-  if (R.row_ok) P.head_part[((size_t)ut * 2 + half) * P.rows + R.row] = hpa + hpb;
+  if (R.row_ok) P.head_part[((size_t)ut * (8 / NCH) + half) * P.rows + R.row] = hpa + hpb;   // 2 (NCH 4) or 4 (NCH 2) partials per unit tile
 }
 
 // stage this tile's W rows / bias / W_h slice (shared by all rows) into shared memory
@@ -584,8 +587,15 @@ constexpr int kPairBBoxRows = 64;                         // U tiles are fetched
 // CL = cluster size: 2 = one CTA pair; 4 = two pairs working on the SAME unit tile for two different row tiles,
 // which lets each 64-row piece of the U tile be fetched from L2 once and multicast to both pairs (the kernel is
 // L2->SM fill bound, profiles/README.md): U-tile L2 reads halve, at the price of 132 instead of 148 usable SMs.
+// EPI 7: the row-interleaved kernel with SIXTEEN epilogue warps (four per scheduler, two 8-unit chunks per warp and tile) for the
+// regime where the cell epilogue, not the MMAs or the power cap, sets the pace (hidden_dim <~ 400: a tile's MMAs take a quarter of
+// the time of its epilogue).  20 warps (five per scheduler, so 96 registers per thread; the two-chunk epilogue needs 90): warps 0-3 =
+// TMA producer, MMA issuer and two idle warps, warps 4-19 = epilogue (lane quarter = warp % 4).
+constexpr int pair_threads(int epi) { return epi == 7 ? 640 : kTcThreads; }
+constexpr int kEpi16MaxHidden = 256;   // measured: 16 warps win at hidden_dim 208 (0.667 vs 0.739 ms), lose at 400 and 800 (power-capped regime)
+
 template <int NPROD, int CL, int EPI>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kTcThreads, 1)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(pair_threads(EPI), 1)
 gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                      const TcParams P) {
@@ -594,6 +604,8 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
   // residual.  NPROD 2: lo = packed e4m3 image, bytes [0,64) of a row = residual, [64,128) = coarse copy.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool IL = (EPI >= 4);                     // row-interleaved operands and state (no swizzle); EPI 5: 32-wide K stages, 6: exp-only tanh
+  constexpr int kEpiWarps = (EPI == 7) ? 16 : kTcEpiWarps;
+  constexpr int kFirstEpiWarp = (EPI == 7) ? 4 : 2;
   constexpr int kIlBK = (EPI == 5) ? 32 : 64;
   constexpr uint32_t kIlSub = kIlBK * 256;            // bytes of one operand box: [K groups][128 rows][16 B]
   constexpr int kStageBytes = IL ? 4 * (int)kIlSub : (NPROD == 1) ? (kPairABytes + kPairBBytes) : 2 * (kPairABytes + kPairBBytes);
@@ -605,7 +617,9 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
   uint64_t* empty_bar = bars + stages;           // [stages]   both CTAs
   uint64_t* tfull_bar = bars + 2 * stages;       // [2]        both CTAs
   uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]        leader's copy is the live one
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint64_t* pfull_bar = bars + 2 * stages + 4;   // [2]        this CTA's parameter block for accumulator buffer b has landed
+  uint64_t* pempty_bar = bars + 2 * stages + 6;  // [2]        ... has been consumed by all epilogue warps of this CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -622,7 +636,8 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     // a stage is refilled only after the MMAs of EVERY pair of the cluster have consumed it (multicast writes
     // land in the sibling pair's shared memory too)
     for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), kPairsPerCluster); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kTcEpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kEpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&pfull_bar[b]), 1); mbar_init(smem_u32(&pempty_bar[b]), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -640,15 +655,29 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
   // work unit of a cluster = (unit tile, kPairsPerCluster consecutive 256-row tiles); `pair`/`num_pairs` count clusters
   const long pair = blockIdx.x / CL, num_pairs = gridDim.x / CL;
 
+  if (warp < kFirstEpiWarp) {
   if (warp == 0) {
     // ===================== TMA producer (every CTA) =====================
-    if (lane == 0 && P.exp != 2) {
+    if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       constexpr uint32_t kATotal = (NPROD == 1) ? kPairABytes : 2 * kPairABytes;          // bytes of H operands per CTA and stage
       constexpr uint32_t kBBoxTotal = ((NPROD == 1) ? 1 : 2) * kPairBBoxRows * kPairBK * 2; // bytes of one 64-row box of every U operand
-      for (long tile = pair; tile < P.num_tiles; tile += num_pairs) {
+      long pit = 0;
+      for (long tile = pair; tile < P.num_tiles; tile += num_pairs, ++pit) {
         const int  ut = (int)(tile % unit_tiles);
         const long rt = tile / unit_tiles;
+        // this tile's epilogue parameters: one bulk copy into the buffer of its accumulator (no thread of the epilogue stages
+        // anything, no CTA barrier).  Issued after the tile's first operand stages are in flight: the buffer frees up when the
+        // epilogue of the tile two back is done, which is also what this tile's MMAs wait for.
+        auto stage_params = [&]() {
+          const int pb = (int)(pit & 1);
+          mbar_wait(smem_u32(&pempty_bar[pb]), (((uint32_t)(pit >> 1)) & 1) ^ 1, P.wait_ns);
+          mbar_expect_tx(smem_u32(&pfull_bar[pb]), kParamFloats * 4);
+          bulk_load(smem_u32(sparam + pb * kParamFloats), P.tilep + (size_t)ut * kParamFloats, kParamFloats * 4, smem_u32(&pfull_bar[pb]));
+        };
+        const int kb_count = (P.exp == 2) ? 0 : P.k_blocks;
+        const int kb_params = min(2, kb_count - 1);
+        if (kb_count == 0) stage_params();
         const int n_cols = min(kTcBN, h4 - ut * kTcBN);
         const int row0 = (int)((rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM)) + (int)(rank & 1u) * kTcBM;   // this CTA's 128 rows of H
         const int col0 = ut * kTcBN + (int)(rank & 1u) * (n_cols / 2);        // first row of this CTA's half of the U tile
@@ -657,7 +686,8 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const bool mcast = (CL == 4) && (n_cols == kTcBN);
         const int  b_boxes = mcast ? 2 : (n_cols / 2 + kPairBBoxRows - 1) / kPairBBoxRows;   // boxes landing in this CTA
         const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank ^ 2u)));
-        for (int kb = 0; kb < P.k_blocks; ++kb) {
+        for (int kb = 0; kb < kb_count; ++kb) {
+          if (kb == kb_params) stage_params();
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, P.wait_ns);
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
           if (leader && !IL) mbar_expect_tx(fb_local, 2u * (kATotal + (uint32_t)b_boxes * kBBoxTotal));   // both CTAs of the pair
@@ -768,12 +798,13 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         tc_commit_pair(smem_u32(&tfull_bar[buf]), pair_mask);      // accumulators complete in both CTAs of this pair
       }
     }
+  }
   } else {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
-    const int ew = warp - 2;
+    constexpr int NCH = 32 / kEpiWarps;            // 8-unit chunks per warp and tile: 4 (8 warps) or 2 (16 warps)
+    const int ew = warp - kFirstEpiWarp;
     const int quarter = warp & 3;
-    const int half = (ew >= 4) ? 1 : 0;
-    const int et = threadIdx.x - 64;
+    const int part = ew >> 2;                      // which NCH-chunk slice of the tile's 8 column chunks
     const float dequant = P.scale[1];
     long it = 0;
     for (long tile = pair; tile < P.num_tiles; tile += num_pairs, ++it) {
@@ -782,25 +813,27 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       const int buf = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       float* sp = sparam + buf * kParamFloats;
-      stage_tile_params(P, sp, et, ut);
-      EpiRow R;
-      lstm_epilogue_prefetch<IL>(P, R, quarter, half, lane, ut,
-                                       (rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM) + (long)(rank & 1u) * kTcBM);
-      asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
+      EpiRowT<NCH> R;
+      lstm_epilogue_prefetch<IL, NCH>(P, R, quarter, part, lane, ut,
+                                      (rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM) + (long)(rank & 1u) * kTcBM);
+      mbar_wait(smem_u32(&pfull_bar[buf]), use & 1, P.wait_ns);      // parameter block (bulk copy issued by the producer warp)
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1, P.wait_ns);
       tc_fence_after();
       if (P.exp == 1) {
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kTcBN + half * 128), v);
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kTcBN + part * NCH * kTcChunk), v);
         tc_wait_ld();
       } else if (EPI == 0) {
-        lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, half, ut, dequant);
+        if constexpr (NCH == kChunksPerHalf) lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
       } else {
-        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6, EPI == 3, IL>(P, R, sp, tmem_base, buf, quarter, half, ut, dequant);
+        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6, EPI == 3, IL, NCH>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), leader_rank));
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&pempty_bar[buf]));
+        mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), leader_rank));
+      }
     }
   }
 
@@ -871,6 +904,18 @@ int make_map_il(CUtensorMap* map, const void* base, uint64_t rows_total, int gro
   if (r != CUDA_SUCCESS) IADMM_FAIL(IADMM_ECUDA, "cuTensorMapEncodeTiled (interleaved) failed with CUresult %d (rows=%llu groups=%d)", (int)r,
                                     (unsigned long long)rows_total, groups);
   return IADMM_OK;
+}
+
+// epilogue warps of the row-interleaved kernel: 16 where the cell epilogue paces the kernel (few K blocks per tile), 8 where
+// the MMAs and the power cap do (profiles/README.md); IADMM_TC_EPI_WARPS=8|16 overrides
+static int select_epi_warps(int h) {
+  static int env = -1;
+  if (env < 0) { const char* w = getenv("IADMM_TC_EPI_WARPS"); env = w ? atoi(w) : 0; }
+  return (env == 8 || env == 16) ? env : (h <= kEpi16MaxHidden ? 16 : 8);
+}
+// head partials per launch that the tail has to sum: per unit tile one per epilogue warp slice
+int tc_head_slots(int h, bool interleaved) {
+  return ((interleaved && select_epi_warps(h) == 16) ? 4 : 2) * cdiv(h, kTcUnits);
 }
 
 static bool use_quads() {
@@ -952,6 +997,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.bias = reinterpret_cast<const float*>(base + L.off_bias);
   P.wh = reinterpret_cast<const float*>(base + L.off_wh);
   P.scale = reinterpret_cast<const float*>(base + L.off_scale);
+  P.tilep = reinterpret_cast<const float*>(base + L.off_tilep);
   P.xv = xv; P.g = g;
   P.hout_hi = Hout_hi; P.hout_lo = Hout_lo; P.hout_f32 = H_out_f32; P.C = C; P.head_part = head_part;
   P.gates_out = gates_out; P.exp = 0; P.wait_ns = IADMM_MBAR_SUSPEND_NS;
@@ -969,6 +1015,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
     epi = w ? atoi(w) : 1;
     if (epi < 0 || epi > 2) epi = 1;
   }
+  const int epi_warps = select_epi_warps(h);
   P.exp = exp_mode;
   static int wait_ns = -1;
   if (wait_ns < 0) { const char* e = getenv("IADMM_TC_WAIT_NS"); wait_ns = e ? atoi(e) : IADMM_MBAR_SUSPEND_NS; }
@@ -989,8 +1036,9 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.stages = (192 * 1024) / stage_bytes;                 // 4 / 8 (single CTA, 32-wide K), 3 / 6 (pair, 64-wide K)
   if (il) P.stages = (192 * 1024) / (il_bk * 1024);      // 3 x 64 KB or 6 x 32 KB
   const size_t smem = 1024 + (size_t)P.stages * (il ? il_bk * 1024 : stage_bytes) + 2 * kParamFloats * sizeof(float) +
-                      (2 * P.stages + 4) * sizeof(uint64_t) + 16;
+                      (2 * P.stages + 8) * sizeof(uint64_t) + 16;
 
+  int threads = kTcThreads;
   if (pair) {
     auto launch = [&](auto kernel, bool* attr_done, int cluster) -> int {
       int rc2;
@@ -1011,13 +1059,16 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
         clusters = max_quads < num_sms / 4 ? max_quads : num_sms / 4;
       }
       if (P.num_tiles < clusters) clusters = P.num_tiles;
-      kernel<<<(unsigned)(cluster * clusters), kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+      kernel<<<(unsigned)(cluster * clusters), threads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
       return IADMM_OK;
     };
     static bool a34 = false, a24 = false, a14 = false, a32 = false, a22 = false, a12 = false;
     static bool e0 = false, e2 = false, s2 = false, s3 = false, s1 = false;
-    static bool i4 = false;
-    if (il) {
+    static bool i4 = false, i7 = false;
+    if (il && epi_warps == 16) {
+      threads = pair_threads(7);
+      rc = launch(gates_tc_pair_kernel<2, 2, 7>, &i7, 2);
+    } else if (il) {
       static bool i5 = false;
       static bool i6 = false;
       if (epi == 2)         rc = launch(gates_tc_pair_kernel<2, 2, 6>, &i6, 2);

@@ -32,6 +32,7 @@ WeightLayout weight_layout(int h, int length) {
   L.off_u32hi = take(4 * H * H * sizeof(__half));
   L.off_u32lo = take(4 * H * H * sizeof(__half));
   L.off_uq8   = take(4 * H * q8_pitch(h));
+  L.off_tilep = take((size_t)((h + 63) / 64) * 832 * sizeof(float));
   L.off_uhi_il = take((size_t)((h + 7) / 8) * 4 * H * 8 * sizeof(__half));
   L.off_uq8_il = take((size_t)((h + 15) / 16) * 2 * 4 * H * 16);
   L.total = off;
@@ -48,9 +49,23 @@ struct PackSrc {
 __global__ void __launch_bounds__(256) pack_small_kernel(PackSrc S, int h, int length, float* __restrict__ wc,
                                                          float* __restrict__ bias, float* __restrict__ wh,
                                                          float* __restrict__ bh, float* __restrict__ sched,
-                                                         float* __restrict__ scale) {
+                                                         float* __restrict__ scale, float* __restrict__ tilep) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
+  // per-tile parameter blocks of the tensor-core gate kernel (zero padded past 4h / h)
+  const int tiles = (h + 63) / 64;
+  for (int i = tid; i < tiles * 832; i += stride) {
+    const int t = i / 832, o = i - t * 832;
+    float v = 0.f;
+    if (o < 768) {
+      const int a = o >> 8, c = t * 256 + (o & 255);
+      if (c < 4 * h) { const int j = c >> 2, g = c & 3; v = (a == 0) ? S.W[g][j] : (a == 1) ? S.W[g][h + j] : S.b[g][j]; }
+    } else {
+      const int u = t * 64 + (o - 768);
+      if (u < h) v = S.W_h[u];
+    }
+    tilep[i] = v;
+  }
   for (int i = tid; i < 4 * h; i += stride) {
     const int j = i >> 2, g = i & 3;
     wc[i]         = S.W[g][j];
@@ -144,7 +159,7 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
   pack_small_kernel<<<cdiv(4 * h > length ? 4 * h : length, 256), 256, 0, st>>>(
       S, h, length, reinterpret_cast<float*>(base + L.off_wc), reinterpret_cast<float*>(base + L.off_bias),
       reinterpret_cast<float*>(base + L.off_wh), reinterpret_cast<float*>(base + L.off_bh),
-      reinterpret_cast<float*>(base + L.off_sched), scale);
+      reinterpret_cast<float*>(base + L.off_sched), scale, reinterpret_cast<float*>(base + L.off_tilep));
   IADMM_LAUNCH_CHECK("pack_small_kernel");
   const size_t total = (size_t)4 * h * h;
   const int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);

@@ -567,7 +567,7 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
   if (nprod == 2) IADMM_CUDA(cudaMemsetAsync(W.h_lo_out, 0, tc_lo_bytes((long)rows, h), st));
   if ((rc = launch_gates_tc(packed_weights, L, xv, W.s.g, W.h_hi, W.h_lo, W.h_hi_out, W.h_lo_out, H_o, C_o, W.head_part,
                             (long)rows, h, nprod, st, gates_save))) return rc;
-  return launch_tail(W.d, W.head_part, tc_gate_tiles(h), b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
+  return launch_tail(W.d, W.head_part, tc_head_slots(h, false), b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
 }
 
 int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,

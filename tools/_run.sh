@@ -1,4 +1,6 @@
-mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; cat gpurun_out/bench_n2.json | cut -c1-400; tail -2 gpurun_out/bench_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/train_window.py --batch 2 --windows 3 2>&1 | tail -1 | cut -c1-500
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 2>&1 | tail -1 | cut -c1-300
+mkdir -p gpurun_out; rm -f gpurun_out/probe11.*
+for h in 208 800; do for ew in 8 16; do
+  PROBE_H=$h IADMM_TC_EPI_WARPS=$ew timeout 300 python tools/gate_probe.py >> gpurun_out/probe11.jsonl 2>> gpurun_out/probe11.err
+done; done
+tail -5 gpurun_out/probe11.err
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
