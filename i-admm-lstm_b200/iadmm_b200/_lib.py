@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p, POINTER
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libiadmm_b200.so")
+LIB_PATH = os.environ.get("IADMM_B200_LIB") or os.path.join(_HERE, "libiadmm_b200.so")   # the override is a development aid (A/B of two builds)
 
 GATES_SIMT_FP32 = 0
 GATES_TC_3XFP16 = 1
