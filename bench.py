@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--iters", type=int, default=K_ITERS, help="unrolled iterations per solve (metric is quoted at 100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--cpu-batch", type=int, default=4, help="instances per CPU step of the reference arm (~0.8 s each on 16 cores)")
     ap.add_argument("--nvar", type=int, default=N_VAR, help="variables per QP (the metric is quoted at 1000; 5000 = BASELINE config 5, "
                                                              "with num_ineq = num_eq = nvar/2)")
     ap.add_argument("--hidden", type=int, default=HIDDEN, help="hidden_dim (the metric is quoted at 800; 200 is configs/QP.yaml's default)")
@@ -361,7 +361,7 @@ def run_ours(args):
             line["e2e"] = {"value": n_gpus * B * steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms / steps}
         if n_gpus == 1 and not args.no_cpu_baseline:
-            val, cms, cores, sample = cpu_reference_solves_per_s(1, 0, max(2, args.cpu_batch), K)
+            val, cms, cores, sample = cpu_reference_solves_per_s(1, 0, max(12, args.cpu_batch), K)     # ~10 s of CPU work
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
