@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256, help="instances per GPU")
     ap.add_argument("--iters", type=int, default=K_ITERS, help="unrolled iterations per solve (metric is quoted at 100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: keep equal shards instead of sharding the N*batch instances by each GPU's measured rate")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=4, help="instances per CPU step of the reference arm (~0.8 s each on 16 cores)")
     ap.add_argument("--nvar", type=int, default=N_VAR, help="variables per QP (the metric is quoted at 1000; 5000 = BASELINE config 5, "
@@ -204,6 +206,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     B, n, mi, me, h, K = args.batch, args.nvar, args.nvar // 2, args.nvar // 2, args.hidden, args.iters
@@ -213,7 +216,15 @@ def run_ours(args):
 
     torch.manual_seed(17)                                    # identical random-init weights on every rank
     model = ia.LSTM(None, 2, h, K, dev, gate_mode=args.gate_mode).eval()
-    Q, p, A0, zl, zu = device_qp_batch(B, n, mi, me, 17 + rank, dev)
+    # N > 1: the job is N*B independent instances.  GPUs of one box differ by several per cent under the power cap, so after
+    # the warm-up the instances are re-sharded in proportion to each GPU's measured rate (iadmm_b200.dist.balance_by_rate: one
+    # all-gather of a float per rank at set-up; the solve itself has no collective).  Every rank generates some spare instances.
+    balance = world > 1 and not args.no_balance
+    B_cap = B + max(8, B // 8) if balance else B
+    Q, p, A0, zl, zu = device_qp_batch(B_cap, n, mi, me, 17 + rank, dev)
+    full_inputs = (Q, p, A0, zl, zu)
+    Q, p, A0, zl, zu = (t[:B] for t in full_inputs)
+    shares = [B] * world
     scaling = ia.Scaling(n, m, RUIZ_ITS, dev)
 
     def hot_step():
@@ -229,6 +240,19 @@ def run_ours(args):
         for _ in range(warmup):
             r = hot_step()
         barrier()
+        if balance:
+            from iadmm_b200.dist import balance_by_rate
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            for _ in range(2):
+                r = hot_step()
+            w1.record()
+            torch.cuda.synchronize()
+            B_mine, shares = balance_by_rate(world * B, 2 * B / (w0.elapsed_time(w1) * 1e-3), cap=B_cap)
+            Q, p, A0, zl, zu = (t[:B_mine] for t in full_inputs)
+            r = hot_step()                                   # workspace for the new share, untimed
+            B = B_mine
+            barrier()
         sampler = ClockSampler(dev) if rank == 0 else None
         if sampler:
             sampler.start()
@@ -321,19 +345,20 @@ def run_ours(args):
         hbm_frac_whole = (iter_bytes * K / step_s / 1e9) / hbm_gbs
         launches_per_step = K * 6 + 2 + (3 + 2 * RUIZ_ITS)
         line = {
-            "metric": METRIC, "value": n_gpus * B * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
+            "metric": METRIC, "value": sum(shares) * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": (WORKLOAD if h == HIDDEN else WORKLOAD.replace("hidden_dim=800", "hidden_dim=%d" % h)) if n == N_VAR else
                                    "config5-style: dense QP n=%d, %d ineq + %d eq, hidden_dim=%d, --scaling, K=%d (NOT the headline workload)" % (n, mi, me, h, K),
-                       "batch_per_gpu": B, "iters": K, "gate_mode": args.gate_mode,
+                       "batch_per_gpu": args.batch, "instances_per_gpu": shares, "iters": K, "gate_mode": args.gate_mode,
                        "gate_arithmetic": {"tc_3xfp16": "tcgen05 fp16 hi/lo split, 3 MMAs, fp32 accumulate",
                                            "tc_f16f8": "tcgen05 fp16 MMA + 2 e4m3 correction MMAs, fp32 accumulate",
                                            "tc_1xfp16": "tcgen05 single fp16 MMA, fp32 accumulate",
                                            "simt_fp32": "fp32 FMA"}[args.gate_mode],
                        "cache": "inputs larger than L2: Q+A0 %.2f GB and LSTM state %.2f GB per GPU per iteration vs 126 MB L2"
                                 % (kkt_bytes / 2 / 1e9, 16.0 * rows * h / 1e9),
-                       "parallelism": "instances sharded over %d GPU(s), no collective" % n_gpus,
+                       "parallelism": ("%d x %d independent instances sharded over %d GPU(s)%s, no collective in the solve"
+                                       % (n_gpus, args.batch, n_gpus, " in proportion to each GPU's measured warm-up rate" if balance else "")),
                        "results_finite": finite},
             "gpu_launches": steps * launches_per_step,
             "roofline": {"kernel": "gates_tc_pair_kernel" if args.gate_mode != "simt_fp32" else "gates_simt_kernel",
@@ -358,7 +383,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         if e2e:
-            line["e2e"] = {"value": n_gpus * B * steps / (e2e_ms * 1e-3), "unit": UNIT,
+            line["e2e"] = {"value": sum(shares) * steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms / steps}
         if n_gpus == 1 and not args.no_cpu_baseline:
             val, cms, cores, sample = cpu_reference_solves_per_s(1, 0, max(12, args.cpu_batch), K)     # ~10 s of CPU work

@@ -16,6 +16,48 @@ def shard_range(batch, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def balanced_shares(total, rates, cap=None):
+    """Split `total` independent instances over ranks in proportion to their measured rates (instances/s): the GPUs of
+    one box differ by several per cent under the power cap, and with equal shards the job runs at the pace of the slowest.
+    Largest-remainder rounding; every rank gets at least one instance, at most `cap`; the shares sum to `total`
+    (if the caps allow it)."""
+    n = len(rates)
+    tot = float(sum(rates))
+    if tot <= 0 or any(r <= 0 for r in rates):
+        base, extra = divmod(int(total), n)
+        return [base + (1 if i < extra else 0) for i in range(n)]
+    ideal = [total * r / tot for r in rates]
+    shares = [max(1, int(x)) for x in ideal]
+    if cap is not None:
+        shares = [min(s_, int(cap)) for s_ in shares]
+    order = sorted(range(n), key=lambda i: ideal[i] - int(ideal[i]), reverse=True)
+    k = 0
+    while sum(shares) < total and k < 4 * n:
+        i = order[k % n]
+        if cap is None or shares[i] < cap:
+            shares[i] += 1
+        k += 1
+    k = 0
+    while sum(shares) > total and k < 4 * n:
+        i = order[-1 - (k % n)]
+        if shares[i] > 1:
+            shares[i] -= 1
+        k += 1
+    return shares
+
+
+def balance_by_rate(total, my_rate, cap=None, group=None):
+    """All-gather every rank's measured rate and return (my_share, all_shares).  The only communication of a sharded
+    solve, once at set-up; tiny (one float per rank)."""
+    world = dist.get_world_size(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.tensor([float(my_rate)], dtype=torch.float64, device=dev)
+    out = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    shares = balanced_shares(total, [float(o.item()) for o in out], cap)
+    return shares[dist.get_rank(group)], shares
+
+
 def shard_instances(tensors, rank, world):
     """Slice every [B, ...] tensor of a dict (or tuple) to this rank's chunk."""
     if isinstance(tensors, dict):

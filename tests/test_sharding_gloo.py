@@ -48,6 +48,43 @@ def test_shard_ranges():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_balanced_shares():
+    sys.path.insert(0, os.path.join(ROOT, "i-admm-lstm_b200"))
+    from iadmm_b200.dist import balanced_shares
+    assert balanced_shares(512, [1.0, 1.0]) == [256, 256]
+    sh = balanced_shares(2048, [440., 465., 430., 470., 450., 455., 445., 460.])
+    assert sum(sh) == 2048 and max(sh) - min(sh) <= 25
+    assert sh[3] == max(sh) and sh[2] == min(sh)                       # faster GPUs take more instances
+    t = [s_ / r for s_, r in zip(sh, [440., 465., 430., 470., 450., 455., 445., 460.])]
+    assert max(t) / min(t) < 1.01                                      # finish together within 1 %
+    assert balanced_shares(10, [0.0, 1.0]) == [5, 5]                   # no usable measurement: equal shards
+    assert balanced_shares(7, [1.0, 100.0]) == [1, 6]                  # nobody is left without work
+    assert sum(balanced_shares(600, [1.0, 3.0], cap=320)) <= 600 and max(balanced_shares(600, [1.0, 3.0], cap=320)) == 320
+
+
+def _balance_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "i-admm-lstm_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from iadmm_b200.dist import balance_by_rate
+    mine, shares = balance_by_rate(512, 400.0 if rank == 0 else 440.0)
+    q.put((rank, mine, shares))
+    dist.destroy_process_group()
+
+
+def test_two_rank_balance_by_rate():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    ps = [ctx.Process(target=_balance_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in ps: p_.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p_ in ps: p_.join(timeout=60)
+    assert res[0][2] == res[1][2] and sum(res[0][2]) == 512
+    assert res[0][1] == res[0][2][0] and res[1][1] == res[1][2][1] and res[1][1] > res[0][1]
+
+
 def test_two_rank_sharded_solve_matches_single():
     mgr = mp.Manager()
     out = mgr.dict()
