@@ -86,6 +86,17 @@ struct Sched {  // one schedule row, already in fp32 exactly as models/lstm.py:6
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// sm_100 two-wide fp32 arithmetic (FFMA2 / FMUL2 / FADD2): each lane of a pair is the same IEEE operation as the scalar
+// instruction, at half the issue slots.  NOTE: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even with .rn, so keep
+// products that the reference rounds separately in scalar __fmul_rn/__fadd_rn form.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ u64 bc2(float a) { u64 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // streaming 128-bit load: read-only path, do not allocate in L1 (matrix data is touched once per pass)
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;
