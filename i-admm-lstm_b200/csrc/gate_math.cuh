@@ -61,6 +61,26 @@ __device__ __forceinline__ void gates4_shared_rcp(float pi, float pf, float po, 
   gu = fmaf(-2.0f, rcd * c, 1.0f);
 }
 
+// Same with the pre-activations delivered as packed pairs (p_i, p_f) and (p_o, p_u) and the multiplies / adds issued two-wide
+// (FMUL2 / FADD2): lane by lane the same operations as gates4_shared_rcp, 15 instead of 22 issue slots.
+__device__ __forceinline__ void gates4_shared_rcp_x2(u64 pif, u64 pou, float& gi, float& gf, float& go, float& gu) {
+  const float kL = 1.4426950408889634f;
+  float t0, t1, t2, t3;
+  upk2(mul2(pif, bc2(-kL)), t0, t1);
+  upk2(mul2(pou, pk2(-kL, 2.0f * kL)), t2, t3);
+  float a, b, c, d;
+  upk2(add2(pk2(ex2_approx(fminf(t0, 30.0f)), ex2_approx(fminf(t1, 30.0f))), bc2(1.0f)), a, b);
+  upk2(add2(pk2(ex2_approx(fminf(t2, 30.0f)), ex2_approx(fminf(t3, 30.0f))), bc2(1.0f)), c, d);
+  const float ab = a * b, cd = c * d;
+  const float r = rcp_approx(ab * cd);
+  float rab, rcd;
+  upk2(mul2(bc2(r), pk2(cd, ab)), rab, rcd);
+  upk2(mul2(bc2(rab), pk2(b, a)), gi, gf);
+  float guh;
+  upk2(mul2(bc2(rcd), pk2(d, c)), go, guh);
+  gu = fmaf(-2.0f, guh, 1.0f);
+}
+
 // 256-bit global accesses (sm_100): one request per 32-byte sector instead of two
 __device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
   asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
         const bool row_ok = row < N;
         const float xr = row_ok ? (row < n ? S.xt[row] : S.v[row - n]) : 0.f, gr = row_ok ? S.g[row] : 0.f;
         float hp = 0.f;
+        const u64 xr2 = bc2(xr), gr2 = bc2(gr), dq2 = bc2(dequant);
 #pragma unroll
         for (int cc = 0; cc < kResChunks; ++cc) {
           const int chunk = grp * kResChunks + cc;
@@ -468,12 +469,13 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float4 a0 = w0[u], a1 = w1[u], ab = bb[u];
-              const float pi = fmaf(__uint_as_float(acc[u * 4 + 0]), dequant, fmaf(gr, a1.x, fmaf(xr, a0.x, ab.x)));
-              const float pf = fmaf(__uint_as_float(acc[u * 4 + 1]), dequant, fmaf(gr, a1.y, fmaf(xr, a0.y, ab.y)));
-              const float po = fmaf(__uint_as_float(acc[u * 4 + 2]), dequant, fmaf(gr, a1.z, fmaf(xr, a0.z, ab.z)));
-              const float pu = fmaf(__uint_as_float(acc[u * 4 + 3]), dequant, fmaf(gr, a1.w, fmaf(xr, a0.w, ab.w)));
+              // pre-activations of the gate pairs (i,f) and (o,u) two-wide (FFMA2): lane by lane the scalar fmaf chain
+              const u64 pif = fma2(pk2(__uint_as_float(acc[u * 4 + 0]), __uint_as_float(acc[u * 4 + 1])), dq2,
+                                   fma2(gr2, pk2(a1.x, a1.y), fma2(xr2, pk2(a0.x, a0.y), pk2(ab.x, ab.y))));
+              const u64 pou = fma2(pk2(__uint_as_float(acc[u * 4 + 2]), __uint_as_float(acc[u * 4 + 3])), dq2,
+                                   fma2(gr2, pk2(a1.z, a1.w), fma2(xr2, pk2(a0.z, a0.w), pk2(ab.z, ab.w))));
               float gi, gf, go, gu;
-              gates4_shared_rcp(pi, pf, po, pu, gi, gf, go, gu);
+              gates4_shared_rcp_x2(pif, pou, gi, gf, go, gu);
               const float cn = __fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, creg[t][cc][u]));
               const float hn = __fmul_rn(go, tanh_exp(cn));
               creg[t][cc][u] = cn;
