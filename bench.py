@@ -386,7 +386,8 @@ def run_ours(args):
             line["e2e"] = {"value": sum(shares) * steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms / steps}
         if n_gpus == 1 and not args.no_cpu_baseline:
-            val, cms, cores, sample = cpu_reference_solves_per_s(1, 0, max(12, args.cpu_batch), K)     # ~10 s of CPU work
+            val, cms, cores, sample = cpu_reference_solves_per_s(3, 1, 4, K)     # 16 instances, ~12 s of CPU work; batches of 4 are the CPU path's best
+            # operating point here (measured 1.3 solves/s at batch 1-4, 0.56 at batch 12: the dense KKT build falls out of cache)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -64,7 +64,8 @@ struct TcParams {
   float*  head_part;      // [2*unit_tiles][rows]
   long rows;
   int  h, unit_tiles, k_blocks, stages, nprod;
-  int  exp;               // development experiments (IADMM_TC_EXP, results are garbage): 1 = epilogue reads TMEM only,
+  int  exp;               // development experiments (IADMM_TC_EXP, row-interleaved kernel only, compiled into the EPI 8 instantiation;
+                          // results are garbage): 1 = epilogue reads TMEM only,
                           // 2 = no TMA / MMA, 3 = no global traffic in the epilogue, 4 = no cell math, 5 = all rows alias 1024 rows (no DRAM),
                           // 6 = only one of the two e4m3 correction MMAs (cost proxy for half-price corrections)
   long num_tiles;
@@ -88,9 +89,10 @@ struct EpiRowT {
 };
 typedef EpiRowT<kChunksPerHalf> EpiRow;
 
-template <bool IL = false, int NCH = kChunksPerHalf>
+template <bool IL = false, int NCH = kChunksPerHalf, bool ABL = false>
 __device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRowT<NCH>& R, int quarter, int half, int lane, int ut,
                                                        long row_base) {
+  const int ex = ABL ? P.exp : 0;        // ablation switches exist only in the EPI 8 instantiation (IADMM_TC_EXP)
   R.row = row_base + quarter * 32 + lane;
   R.row_ok = R.row < P.rows;
   R.xr = R.row_ok ? __ldg(P.xv + R.row) : 0.f;
@@ -98,9 +100,9 @@ __device__ __forceinline__ void lstm_epilogue_prefetch(const TcParams& P, EpiRow
 #pragma unroll
   for (int cc = 0; cc < NCH; ++cc) {
     const int unit0 = ut * kTcUnits + (half * NCH + cc) * 8;
-    if (R.row_ok && unit0 < P.h && P.exp != 3) {
+    if (R.row_ok && unit0 < P.h && ex != 3) {
       if (IL) ld_global_v8(P.C + ((size_t)(unit0 >> 3) * P.rows_p + R.row) * 8, R.c[cc]);
-      else    ld_global_v8(P.C + (size_t)((P.exp == 5) ? (R.row & 1023) : R.row) * P.h + unit0, R.c[cc]);
+      else    ld_global_v8(P.C + (size_t)((ex == 5) ? (R.row & 1023) : R.row) * P.h + unit0, R.c[cc]);
     } else {
 #pragma unroll
       for (int u = 0; u < 8; ++u) R.c[cc][u] = 0.f;
@@ -262,16 +264,17 @@ __device__ __forceinline__ u64 tanh2(float x0, float x1, float big0, float big1)
   return pk2((fabsf(x0) < 0.55f) ? s0 : big0, (fabsf(x1) < 0.55f) ? s1 : big1);
 }
 
-template <int NPROD, bool FAST, bool SAVE, bool IL, int NCH = kChunksPerHalf>
+template <int NPROD, bool FAST, bool SAVE, bool IL, int NCH = kChunksPerHalf, bool ABL = false>
 __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const EpiRowT<NCH>& R, const float* sp, uint32_t tmem_base, int buf,
                                                       int quarter, int half, int ut, float dequant) {
+  const int ex = ABL ? P.exp : 0;
   u64 hp2 = 0ull;                                       // (even units, odd units) partial head dots
   const bool wide = (P.h % 16) == 0;
   uint32_t hi_st[4], lo_st[4], res_st[2], crs_st[2];
   const u64 xr2 = bc2(R.xr), gr2 = bc2(R.gr), dq2 = bc2(dequant);
   const float kL = 1.4426950408889634f;
   const u64 k_if = bc2(-kL), k_ou = pk2(-kL, 2.0f * kL), k_t = bc2(2.0f * kL);
-  const size_t rowoff = (size_t)((P.exp == 5) ? (R.row & 1023) : R.row);
+  const size_t rowoff = (size_t)((ex == 5) ? (R.row & 1023) : R.row);
 #pragma unroll
   for (int cc = 0; cc < NCH; ++cc) {
     const int chunk = half * NCH + cc;
@@ -290,7 +293,7 @@ __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const E
       const float2* wh = reinterpret_cast<const float2*>(sp + 3 * kTcBN + chunk * 8);
 #pragma unroll
       for (int u = 0; u < 8; u += 2) {
-        if (P.exp == 4) {
+        if (ex == 4) {
           cnew[u] = R.c[cc][u] + __uint_as_float(v[u * 4]); hnew[u] = __uint_as_float(v[u * 4 + 1]);
           cnew[u + 1] = R.c[cc][u + 1] + __uint_as_float(v[u * 4 + 4]); hnew[u + 1] = __uint_as_float(v[u * 4 + 5]);
           hn2[u >> 1] = pk2(hnew[u], hnew[u + 1]);
@@ -339,7 +342,7 @@ __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const E
                 make_float4(gi[j], gf[j], go[j], gu[j]);
         }
       }
-      if (P.exp == 3) { hp2 = add2(hp2, pk2(cnew[0] + cnew[7], hnew[3])); continue; }
+      if (ex == 3) { hp2 = add2(hp2, pk2(cnew[0] + cnew[7], hnew[3])); continue; }
       uint32_t hi[4], lo[4], res[2], crs[2];
       split_hidden8_x2<NPROD>(hn2, hi, lo, res, crs);
       if (IL) {
@@ -595,7 +598,10 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
   // Stage layout: A_hi16 | A_lo | B_hi16 | B_lo, 16 KB each, every row 128 bytes (128B swizzle).  NPROD 3: lo = fp16
   // residual.  NPROD 2: lo = packed e4m3 image, bytes [0,64) of a row = residual, [64,128) = coarse copy.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr bool IL = (EPI >= 4);                     // row-interleaved operands and state (no swizzle); EPI 5: 32-wide K stages, 6: exp-only tanh
+  constexpr bool IL = (EPI >= 4);                     // row-interleaved operands and state (no swizzle); EPI 5: 32-wide K stages, 6: exp-only tanh,
+                                                      // 7: 16 epilogue warps, 8: EPI 4 plus the ablation switches of IADMM_TC_EXP
+  constexpr bool ABL = (EPI == 8);
+  const int ex = ABL ? P.exp : 0;
   constexpr int kEpiWarps = (EPI == 7) ? 16 : kTcEpiWarps;
   constexpr int kFirstEpiWarp = (EPI == 7) ? 4 : 2;
   constexpr int kIlBK = (EPI == 5) ? 32 : 64;
@@ -667,7 +673,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
           mbar_expect_tx(smem_u32(&pfull_bar[pb]), kParamFloats * 4);
           bulk_load(smem_u32(sparam + pb * kParamFloats), P.tilep + (size_t)ut * kParamFloats, kParamFloats * 4, smem_u32(&pfull_bar[pb]));
         };
-        const int kb_count = (P.exp == 2) ? 0 : P.k_blocks;
+        const int kb_count = (ex == 2) ? 0 : P.k_blocks;
         const int kb_params = min(2, kb_count - 1);
         if (kb_count == 0) stage_params();
         const int n_cols = min(kTcBN, h4 - ut * kTcBN);
@@ -737,7 +743,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcBN);
         uint32_t acc = 0;
-        for (int kb = 0; kb < (P.exp == 2 ? 0 : P.k_blocks); ++kb) {
+        for (int kb = 0; kb < (ex == 2 ? 0 : P.k_blocks); ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase, P.wait_ns);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + (size_t)stage * kStageBytes);
@@ -751,7 +757,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
               if ((ks & 1) == 0) {
                 const uint32_t a8 = sbase + kIlSub + (uint32_t)(ks >> 1) * 8192, b8 = sbase + 3 * kIlSub + (uint32_t)(ks >> 1) * 8192;
                 tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8, 4096), make_smem_desc_il(b8 + 2048, 4096), idesc, acc); acc = 1;
-                if (P.exp != 6) tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8 + 2048, 4096), make_smem_desc_il(b8, 4096), idesc, 1);
+                if (ex != 6) tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8 + 2048, 4096), make_smem_desc_il(b8, 4096), idesc, 1);
               }
               tc_mma_f16_pair(d_tmem, make_smem_desc_il(sbase + (uint32_t)ks * 4096, 2048),
                               make_smem_desc_il(sbase + 2 * kIlSub + (uint32_t)ks * 4096, 2048), idesc, 1);
@@ -806,19 +812,19 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       const uint32_t use = (uint32_t)(it >> 1);
       float* sp = sparam + buf * kParamFloats;
       EpiRowT<NCH> R;
-      lstm_epilogue_prefetch<IL, NCH>(P, R, quarter, part, lane, ut,
+      lstm_epilogue_prefetch<IL, NCH, ABL>(P, R, quarter, part, lane, ut,
                                       (rt * kPairsPerCluster + pair_in_cluster) * (2 * kTcBM) + (long)(rank & 1u) * kTcBM);
       mbar_wait(smem_u32(&pfull_bar[buf]), use & 1, P.wait_ns);      // parameter block (bulk copy issued by the producer warp)
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1, P.wait_ns);
       tc_fence_after();
-      if (P.exp == 1) {
+      if (ex == 1) {
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kTcBN + part * NCH * kTcChunk), v);
         tc_wait_ld();
       } else if (EPI == 0) {
         if constexpr (NCH == kChunksPerHalf) lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
       } else {
-        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6, EPI == 3, IL, NCH>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
+        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6, EPI == 3, IL, NCH, ABL>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
       }
       tc_fence_before();
       __syncwarp();
@@ -1056,8 +1062,10 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
     };
     static bool a34 = false, a24 = false, a14 = false, a32 = false, a22 = false, a12 = false;
     static bool e0 = false, e2 = false, s2 = false, s3 = false, s1 = false;
-    static bool i4 = false, i7 = false;
-    if (il && epi_warps == 16) {
+    static bool i4 = false, i7 = false, i8 = false;
+    if (il && exp_mode != 0) {
+      rc = launch(gates_tc_pair_kernel<2, 2, 8>, &i8, 2);          // development ablations (results are garbage)
+    } else if (il && epi_warps == 16) {
       threads = pair_threads(7);
       rc = launch(gates_tc_pair_kernel<2, 2, 7>, &i7, 2);
     } else if (il) {
