@@ -22,7 +22,7 @@ for dt, tag in ((torch.float32, "oracle_fp32"), (torch.float64, "oracle_fp64")):
 print("oracle runs: %.1f s" % (time.time() - t0), flush=True)
 qp = orc.qp_instances(B, n, mi, me, seed=seed)
 prm = orc.lstm_parameters(h, K, seed=seed, scale=wscale)
-for mode in ("simt_fp32", "tc_f16f8", "tc_3xfp16"):
+for mode in ("simt_fp32", "tc_f16f8", "tc_3xfp16", "tc_1xfp16"):
     model = ia.LSTM(None, 2, h, K, "cuda:0", gate_mode=mode)
     with torch.no_grad():
         for k, v in prm.items(): getattr(model, k).copy_(v.cuda())
@@ -31,7 +31,7 @@ for mode in ("simt_fp32", "tc_f16f8", "tc_3xfp16"):
         res[mode] = model.solve(K, mi, me, Q, p, A0, zl, zu, 6e-6)
     torch.cuda.synchronize()
 out = {}
-for a in ("oracle_fp32", "simt_fp32", "tc_f16f8", "tc_3xfp16"):
+for a in ("oracle_fp32", "simt_fp32", "tc_f16f8", "tc_3xfp16", "tc_1xfp16"):
     for b in ("oracle_fp64", "oracle_fp32"):
         if a == b: continue
         out[f"{a} vs {b}"] = {k: float("%.2e" % rel_err(getattr(res[a], k).double().cpu(), getattr(res[b], k).double())) for k in ("x", "y", "z", "pri", "dual")}
