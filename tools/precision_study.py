@@ -53,6 +53,10 @@ def make_cell(mode):
             # K is the last dim of H and the FIRST dim of U: block along K for both operands
             qU = lambda M: q_e2m1_block(M.t().contiguous(), blk).t()
             prod = prod + (q_e2m1_block(Rh, blk) @ qU(Uh)) + (q_e2m1_block(Hs, blk) @ qU(Ru))
+        elif mode == "f16+T1":          # only the correction for the rounding of H (fresh noise every iteration)
+            prod = prod + (q_e4m3(Rh * 32.0) @ q_e4m3(Uh / 32.0))
+        elif mode == "f16+T2":          # only the correction for the rounding of U (a fixed perturbation of the model)
+            prod = prod + (q_e4m3(Hs / 64.0) @ q_e4m3(Ru * 64.0))
         elif mode == "f16+exact":
             prod = prod + Rh @ Uh + Hh @ Ru
         HU = prod / (16384.0 * us)
@@ -83,11 +87,12 @@ if __name__ == "__main__":
         with torch.no_grad():
             orc.lstm_cell = plain
             ref = orc.solve(prm, K, n // 2, n // 2, Qs, ps, As, zls, zus, 6e-6, h, form="block")
-            for mode in ("fp16x1", "f16f8", "fp4b16", "fp4b32", "f16+exact"):
+            for mode in os.environ.get("MODES", "fp16x1,f16f8,fp4b16,fp4b32,f16+exact").split(","):
                 orc.lstm_cell = make_cell(mode)
                 r = orc.solve(prm, K, n // 2, n // 2, Qs, ps, As, zls, zus, 6e-6, h, form="block")
                 row = {"seed": seed, "mode": mode, **{k: float("%.2e" % rel(getattr(r, k), getattr(ref, k))) for k in ("x", "y", "z", "pri", "dual")}}
                 rows.append(row); print(json.dumps(row), flush=True)
         orc.lstm_cell = plain
-    json.dump({"what": __doc__.split("\n\n")[0], "n": n, "hidden": h, "K": K, "rows": rows},
+    if not os.environ.get("MODES"):
+      json.dump({"what": __doc__.split("\n\n")[0], "n": n, "hidden": h, "K": K, "rows": rows},
               open(os.path.join(ROOT, "profiles", "r01_precision_study_cpu.json"), "w"), indent=1)
