@@ -67,7 +67,8 @@ struct TcParams {
   int  exp;               // development experiments (IADMM_TC_EXP, row-interleaved kernel only, compiled into the EPI 8 instantiation;
                           // results are garbage): 1 = epilogue reads TMEM only,
                           // 2 = no TMA / MMA, 3 = no global traffic in the epilogue, 4 = no cell math, 5 = all rows alias 1024 rows (no DRAM),
-                          // 6 = only one of the two e4m3 correction MMAs (cost proxy for half-price corrections)
+                          // 6 = without the U-rounding correction MMA, 7 = without the H-rounding correction MMA (valid numerics of a
+                          // U-correction-only mode: the 1.5-unit candidate of DESIGN.md 6b)
   long num_tiles;
   uint32_t wait_ns;       // suspend-time hint of the mbarrier waits (development switch IADMM_TC_WAIT_NS)
   long rows_p;            // row-interleaved layout (EPI 4): rows rounded up to 128; C, hout_hi, hout_lo are [group][rows_p][..]
@@ -756,11 +757,12 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
               // 16-wide K groups 4096 B apart, residual plane at +0, coarse plane at +2048
               if ((ks & 1) == 0) {
                 const uint32_t a8 = sbase + kIlSub + (uint32_t)(ks >> 1) * 8192, b8 = sbase + 3 * kIlSub + (uint32_t)(ks >> 1) * 8192;
-                tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8, 4096), make_smem_desc_il(b8 + 2048, 4096), idesc, acc); acc = 1;
-                if (ex != 6) tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8 + 2048, 4096), make_smem_desc_il(b8, 4096), idesc, 1);
+                if (ex != 7) { tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8, 4096), make_smem_desc_il(b8 + 2048, 4096), idesc, acc); acc = 1; }
+                if (ex != 6) { tc_mma_f8_pair(d_tmem, make_smem_desc_il(a8 + 2048, 4096), make_smem_desc_il(b8, 4096), idesc, acc); acc = 1; }
               }
               tc_mma_f16_pair(d_tmem, make_smem_desc_il(sbase + (uint32_t)ks * 4096, 2048),
-                              make_smem_desc_il(sbase + 2 * kIlSub + (uint32_t)ks * 4096, 2048), idesc, 1);
+                              make_smem_desc_il(sbase + 2 * kIlSub + (uint32_t)ks * 4096, 2048), idesc, acc);
+              acc = 1;
             } else if (NPROD == 3) {
               const uint64_t a_hi = make_smem_desc_sw128(sbase + koff);
               const uint64_t a_lo = make_smem_desc_sw128(sbase + kPairABytes + koff);
