@@ -36,7 +36,33 @@ def q_e2m1_block(x, block):
     q = q.reshape(*x.shape)
     return q[..., :k] if pad else q
 
+def fp16_neighbours(x):
+    """(down, up) fp16 neighbours of x (fp32 tensor of finite values in fp16's normal range) and the position of x between them"""
+    r = x.half().float()
+    up_of_r = torch.nextafter(r.half(), torch.tensor(float("inf")).half()).float()
+    dn_of_r = torch.nextafter(r.half(), torch.tensor(float("-inf")).half()).float()
+    dn = torch.where(r <= x, r, dn_of_r)
+    up = torch.where(r <= x, up_of_r, r)
+    up = torch.where(dn == x, dn, up)                       # exactly representable: no rounding at all
+    f = torch.where(up > dn, (x - dn) / (up - dn).clamp(min=1e-30), torch.zeros_like(x))
+    return dn, up, f
+
+_DITHER = {}
+def dithered_uh(Us, V, it):
+    """variant `it % V` of a V-way stratified dithered fp16 rounding of Us: element e rounds up in round(f_e V) of the V
+    variants (a per-element random phase decides which), so the average over V consecutive iterations is within ulp/(2V)."""
+    key = (Us.data_ptr(), V)
+    if key not in _DITHER:
+        dn, up, f = fp16_neighbours(Us)
+        g = torch.Generator().manual_seed(1234)
+        phase = torch.randint(0, V, Us.shape, generator=g)
+        _DITHER.clear(); _DITHER[key] = (dn, up, f, phase)
+    dn, up, f, phase = _DITHER[key]
+    thr = (((it + phase) % V).float() + 0.5) / V
+    return torch.where(f > thr, up, dn)
+
 def make_cell(mode):
+    counter = {"it": 0}
     def cell(prm, feats, H, C):
         Ucat = torch.cat([prm[f"U_{g}"] for g in orc.GATES], dim=1)          # [h, 4h]
         mxu = float(Ucat.abs().max())
@@ -45,16 +71,20 @@ def make_cell(mode):
         Hh = Hs.half().float(); Rh = Hs - Hh
         Us = Ucat * us
         Uh = Us.half().float(); Ru = Us - Uh
+        if "_d" in mode:                 # dithered rounding of U, a different variant every iteration
+            V = int(mode.split("_d")[1])
+            Uh = dithered_uh(Us, V, counter["it"]); counter["it"] += 1
+            Ru = Us - Uh
         prod = Hh @ Uh
-        if mode == "f16f8":
+        if mode.startswith("f16+T1"):
+            prod = prod + (q_e4m3(Rh * 32.0) @ q_e4m3(Uh / 32.0))
+        elif mode == "f16f8":
             prod = prod + (q_e4m3(Rh * 32.0) @ q_e4m3(Uh / 32.0)) + (q_e4m3(Hs / 64.0) @ q_e4m3(Ru * 64.0))
         elif mode.startswith("fp4b"):
             blk = int(mode[4:])
             # K is the last dim of H and the FIRST dim of U: block along K for both operands
             qU = lambda M: q_e2m1_block(M.t().contiguous(), blk).t()
             prod = prod + (q_e2m1_block(Rh, blk) @ qU(Uh)) + (q_e2m1_block(Hs, blk) @ qU(Ru))
-        elif mode == "f16+T1":          # only the correction for the rounding of H (fresh noise every iteration)
-            prod = prod + (q_e4m3(Rh * 32.0) @ q_e4m3(Uh / 32.0))
         elif mode == "f16+T2":          # only the correction for the rounding of U (a fixed perturbation of the model)
             prod = prod + (q_e4m3(Hs / 64.0) @ q_e4m3(Ru * 64.0))
         elif mode == "f16+exact":
