@@ -68,7 +68,14 @@ def make_cell(mode):
         mxu = float(Ucat.abs().max())
         us = 2.0 ** (12 - math.frexp(mxu)[1] + 1) if mxu > 0 else 1.0        # max|U| us in [2^12, 2^13)
         Hs = H * 16384.0
-        Hh = Hs.half().float(); Rh = Hs - Hh
+        if "_fb" in mode:                # temporal error feedback on the fp16 image of H (first-order noise shaping)
+            carry = counter.get("carry")
+            tgt = Hs if carry is None or carry.shape != Hs.shape else Hs + carry
+            Hh = tgt.half().float()
+            counter["carry"] = q_e4m3((tgt - Hh) * 32.0) / 32.0       # the residual is kept as the e4m3 plane
+            Rh = Hs - Hh
+        else:
+            Hh = Hs.half().float(); Rh = Hs - Hh
         Us = Ucat * us
         Uh = Us.half().float(); Ru = Us - Uh
         if "_d" in mode:                 # dithered rounding of U, a different variant every iteration
@@ -85,7 +92,7 @@ def make_cell(mode):
             # K is the last dim of H and the FIRST dim of U: block along K for both operands
             qU = lambda M: q_e2m1_block(M.t().contiguous(), blk).t()
             prod = prod + (q_e2m1_block(Rh, blk) @ qU(Uh)) + (q_e2m1_block(Hs, blk) @ qU(Ru))
-        elif mode == "f16+T2":          # only the correction for the rounding of U (a fixed perturbation of the model)
+        elif mode.startswith("f16+T2"):          # only the correction for the rounding of U (a fixed perturbation of the model)
             prod = prod + (q_e4m3(Hs / 64.0) @ q_e4m3(Ru * 64.0))
         elif mode == "f16+exact":
             prod = prod + Rh @ Uh + Hh @ Ru
