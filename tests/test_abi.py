@@ -91,3 +91,24 @@ def test_state_dict_contract():
     for k, v in sd.items():
         assert tuple(v.shape) == tuple(g["shape_" + k])
     assert model.name() == "lstm"
+
+
+def test_header_is_plain_c_and_links(libpath, tmp_path):
+    """include/iadmm.h is the drop-in boundary: it must compile as plain C99 (no C++-isms, no torch/CUDA types) and a C
+    program must link against the shared library and call a non-compute entry point."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "iadmm.h"\n#include <stdio.h>\n'
+                   'int main(void) { size_t b = 0; int rc = iadmm_weights_bytes(64, 10, &b);\n'
+                   '  printf("%d %d %lu\\n", iadmm_abi_version(), rc, (unsigned long)b);\n'
+                   '  return (iadmm_abi_version() == IADMM_ABI_VERSION && rc == IADMM_OK && b > 0) ? 0 : 1; }\n')
+    exe = tmp_path / "c_abi"
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                           libpath, "-Wl,-rpath," + os.path.dirname(libpath)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
