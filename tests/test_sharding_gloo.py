@@ -146,3 +146,28 @@ def test_two_rank_gradient_allreduce_matches_single():
     port = 29900 + (os.getpid() % 90)
     mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
     assert out["max_rel"] < 1e-10
+
+
+def test_balanced_shares_properties():
+    """Property test (hypothesis): the shares always sum to the total, nobody is left without work, and a faster GPU never
+    gets fewer instances than a slower one (up to the one instance of rounding)."""
+    sys.path.insert(0, os.path.join(ROOT, "i-admm-lstm_b200"))
+    from hypothesis import given, settings, strategies as st
+    from iadmm_b200.dist import balanced_shares
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.floats(min_value=50.0, max_value=1000.0), min_size=1, max_size=8), st.integers(min_value=8, max_value=4096))
+    def check(rates, per_rank):
+        total = per_rank * len(rates)
+        sh = balanced_shares(total, rates)
+        assert sum(sh) == total and min(sh) >= 1
+        for i in range(len(rates)):
+            for j in range(len(rates)):
+                if rates[i] > rates[j]:
+                    assert sh[i] >= sh[j] - 1
+        # finishing times within one instance's worth of the ideal
+        t = [s_ / r for s_, r in zip(sh, rates)]
+        ideal = total / sum(rates)
+        assert max(t) <= ideal + 1.5 / min(rates)
+
+    check()
