@@ -1,6 +1,11 @@
 """Build libiadmm_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
     python i-admm-lstm_b200/build.py [--force] [--verbose]
+    IADMM_DEV_BUILD=1 python i-admm-lstm_b200/build.py      # -> libiadmm_b200_dev.so with the development switches
+
+The release library never reads the environment; the IADMM_TC_* / IADMM_RESIDENT / ... development switches used by
+tools/ exist only in the development build (-DIADMM_DEV_SWITCHES), which is loaded explicitly with
+IADMM_B200_LIB=<path to libiadmm_b200_dev.so>.
 
 The library has no torch / libcuda link-time dependency (cudart is linked statically; the one driver
 entry point needed for TMA descriptors is resolved at run time), so it loads on a CPU-only box for the
@@ -34,11 +39,14 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, dev=None):
     nvcc = _nvcc()
+    dev = (os.environ.get("IADMM_DEV_BUILD") == "1") if dev is None else dev
+    target = OUT.replace(".so", "_dev.so") if dev else OUT
+    flags = NVCC_FLAGS + (["-DIADMM_DEV_SWITCHES"] if dev else [])
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(HERE, "..", "include", "iadmm.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", "dev") if dev else os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -47,7 +55,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -57,10 +65,10 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _stale(OUT, objs):
-        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+    if force or procs or _stale(target, objs):
+        cmd = [nvcc, "-shared", "-o", target] + objs + ["-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
         subprocess.check_call(cmd)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":

@@ -18,6 +18,28 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+const char* dev_env(const char* name) {
+#ifdef IADMM_DEV_SWITCHES
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
+int device_sm_count(int* sms) {
+  static int cache[kMaxDevices] = {0};
+  int dev = 0;
+  IADMM_CUDA(cudaGetDevice(&dev));
+  int v = (dev >= 0 && dev < kMaxDevices) ? __atomic_load_n(&cache[dev], __ATOMIC_RELAXED) : 0;
+  if (!v) {
+    IADMM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < kMaxDevices) __atomic_store_n(&cache[dev], v, __ATOMIC_RELAXED);
+  }
+  *sms = v;
+  return IADMM_OK;
+}
+
 // implemented in the other translation units
 int pack_weights_impl(const float* const W[4], const float* const U[4], const float* const b[4], const float* W_h,
                       const float* b_h, const float* rho, const float* alpha, int h, int length, void* packed,
@@ -64,12 +86,15 @@ static inline void prof_record(int slot, cudaStream_t st) {
   if (g_prof.on && g_prof.used < g_prof.cap) cudaEventRecord(g_prof.ev[(size_t)g_prof.used * 4 + slot], st);
 }
 
-static int is_tc(int mode) { return mode == IADMM_GATES_TC_3XFP16 || mode == IADMM_GATES_TC_1XFP16 || mode == IADMM_GATES_TC_F16F8; }
+static int is_tc(int mode) {
+  return mode == IADMM_GATES_TC_3XFP16 || mode == IADMM_GATES_TC_1XFP16 || mode == IADMM_GATES_TC_F16F8 || mode == IADMM_GATES_TC_F16F8U;
+}
+static int is_f16f8(int mode) { return mode == IADMM_GATES_TC_F16F8 || mode == IADMM_GATES_TC_F16F8U; }
 
 static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, void* base, SolveWs* ws) {
   if (mode != IADMM_GATES_SIMT_FP32 && !is_tc(mode)) IADMM_FAIL(IADMM_EMODE, "unknown gate mode %d", mode);
   if (is_tc(mode) && (h % 8 != 0)) IADMM_FAIL(IADMM_EMODE, "tensor-core gate modes need hidden_dim %% 8 == 0 (got %d)", h);
-  if (mode == IADMM_GATES_TC_F16F8 && (h % 16 != 0)) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0 (got %d)", h);
+  if (is_f16f8(mode) && (h % 16 != 0)) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0 (got %d)", h);
   ws->d = make_kkt_dims(B, n, m, num_ineq);
   const size_t rows = (size_t)B * (n + m);
   ws->tiles = is_tc(mode) ? tc_gate_tiles(h) : simt_gate_tiles(h);
@@ -83,7 +108,7 @@ static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, vo
   memset(&ws->tc, 0, sizeof(ws->tc));
   if (is_tc(mode)) {
     // the F16F8 solve keeps its state row-interleaved: rows padded to a multiple of 128
-    const bool il = (mode == IADMM_GATES_TC_F16F8);
+    const bool il = is_f16f8(mode);
     ws->rows_p = il ? il_rows((long)rows) : (long)rows;
     const size_t rp = (size_t)ws->rows_p;
     const size_t hb = rp * (size_t)h * sizeof(__half);
@@ -193,7 +218,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   const float* b_h = reinterpret_cast<const float*>(wbase + L.off_bh);
   const long rows = (long)B * (n + m);
   const bool tc = is_tc(mode);
-  const int nprod = (mode == IADMM_GATES_TC_3XFP16) ? 3 : (mode == IADMM_GATES_TC_F16F8 ? 2 : 1);
+  const int nprod = (mode == IADMM_GATES_TC_3XFP16) ? 3 : (is_f16f8(mode) ? 2 : 1);
   const bool want_trace = pri_trace || dual_trace || pri_trace_u || dual_trace_u || metric_trace;
 
   // small instances: one persistent CTA per instance keeps the whole iteration on chip (resident.cu)
@@ -205,11 +230,11 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   int cur = 0;
   // Row-interleaved state for the fused F16F8 solve (K >= 2; a single step would only pay the layout conversion):
   // the epilogue of the gate kernel then touches whole 128-byte lines instead of one 32-byte sector per row.
-  static int il_env = -1;
-  if (il_env < 0) { const char* e = getenv("IADMM_TC_INTERLEAVED"); il_env = (e && e[0] == '0') ? 0 : 1; }   // development switch
-  const bool il = tc && nprod == 2 && K >= 2 && il_env == 1 && ws.c_il != nullptr;
+  const char* il_sw = dev_env("IADMM_TC_INTERLEAVED");     // development switch: 0 = row-major state
+  const bool il = tc && nprod == 2 && K >= 2 && !(il_sw && il_sw[0] == '0') && ws.c_il != nullptr;
   TcIl ilp;
   ilp.rows_p = ws.rows_p; ilp.C_il = ws.c_il; ilp.C_rm_out = nullptr;
+  ilp.drop_h_correction = (mode == IADMM_GATES_TC_F16F8U) ? 1 : 0;
   if (il) {
     const size_t hb = (size_t)ws.rows_p * h * sizeof(__half);
     if (flags & IADMM_F_ZERO_STATE) {
@@ -248,7 +273,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
     if (rc) return rc;
     prof_record(2, st);
     cur ^= 1;
-    if ((rc = launch_tail(ws.d, ws.head_part, tc ? tc_head_slots(h, il) : ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st, metric_trace ? &ws.s : nullptr))) return rc;
+    if ((rc = launch_tail(ws.d, ws.head_part, tc ? tc_head_slots(h, il, il && ilp.drop_h_correction) : ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st, metric_trace ? &ws.s : nullptr))) return rc;
     prof_record(3, st);
     if (g_prof.on && g_prof.used < g_prof.cap) ++g_prof.used;
   }
@@ -328,7 +353,7 @@ int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, 
   const int m = num_ineq + num_eq;
   if (B <= 0 || n <= 0 || m < 0 || t < 0 || t >= length) IADMM_FAIL(IADMM_ESHAPE, "build_kkt: B=%d n=%d m=%d t=%d length=%d", B, n, m, t, length);
   if (B > 65535 || n + m > 65535) IADMM_FAIL(IADMM_ESHAPE, "build_kkt: B and n+m must be <= 65535");
-  if (!packed_weights || !Q || !p || !x || !Kmat || !rhs) IADMM_FAIL(IADMM_EALIGN, "build_kkt: NULL pointer");
+  if (!packed_weights || !Q || !p || !x || !rhs) IADMM_FAIL(IADMM_EALIGN, "build_kkt: NULL pointer");
   int rc = check_device();
   if (rc) return rc;
   const WeightLayout L = weight_layout(h, length);

@@ -40,6 +40,31 @@ void set_error(const char* fmt, ...);
     }                                                                                          \
   } while (0)
 
+// ------------------------------------------------------------------------------------------------
+// per-device facts and opt-ins.  cudaFuncSetAttribute and the SM count are per DEVICE: a process that drives several GPUs
+// (the Python layer wraps every call in torch.cuda.device(dev)) needs the opt-in on each of them, so the "already done"
+// marks are bit masks over the device ordinal, never plain process-wide flags.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce { unsigned long long done = 0ull; };     // bit d: attribute set on device d (benign if set twice)
+int device_sm_count(int* sms);                                // SM count of the CURRENT device (cached per ordinal)
+
+template <typename KernelT>
+static inline int ensure_dyn_smem(KernelT kernel, int bytes, PerDeviceOnce* once) {
+  int dev = 0;
+  IADMM_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = (dev >= 0 && dev < kMaxDevices) ? (1ull << dev) : 0ull;
+  if (bit && (__atomic_load_n(&once->done, __ATOMIC_ACQUIRE) & bit)) return IADMM_OK;
+  IADMM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (bit) __atomic_fetch_or(&once->done, bit, __ATOMIC_RELEASE);
+  return IADMM_OK;
+}
+
+// Development switches (IADMM_TC_*, IADMM_RESIDENT, ...) are read from the environment ONLY in a development build
+// (`IADMM_DEV_BUILD=1 python i-admm-lstm_b200/build.py` -> libiadmm_b200_dev.so, compiled with -DIADMM_DEV_SWITCHES).
+// The release library never calls getenv: no environment variable can change what it computes.
+const char* dev_env(const char* name);
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int    cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline bool   aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -224,7 +249,7 @@ static inline size_t q8_pitch(int h) { return (size_t)((h + 63) / 64) * 128; }
 // fp16(U*2^s) < 2^13 -> *2^-5 < 256; residual of U*2^s is < 2 -> *2^6 < 128  (e4m3 max = 448)
 constexpr int kQ8HLoShift = 5, kQ8HHiShift = -6, kQ8UHiShift = -5, kQ8ULoShift = 6;
 int  tc_gate_tiles(int h);                    // head-partial slots to allocate
-int  tc_head_slots(int h, bool interleaved);  // slots the gate kernel writes (= what the tail sums)
+int  tc_head_slots(int h, bool interleaved, bool eight_warps = false);  // slots the gate kernel writes (= what the tail sums)
 size_t tc_state_bytes(long rows, int h);
 // Row-interleaved state layout of the fused solve (F16F8 mode): every per-row array is stored [column group][row][16 or 32 B]
 // so that the thread-per-row epilogue reads and writes whole 128-byte lines (see gates_tc.cu).  rows_p = rows rounded up to 128.
@@ -232,6 +257,7 @@ struct TcIl {
   long   rows_p;
   float* C_il;        // fp32 [h/8][rows_p][8], the cell state between iterations
   float* C_rm_out;    // non-NULL on the last iteration: also write the caller's row-major C [rows][h]
+  int    drop_h_correction;   // IADMM_GATES_TC_F16F8U: the e4m3 product that corrects the fp16 rounding of H is not issued
 };
 static inline long il_rows(long rows) { return (rows + 127) / 128 * 128; }
 int  launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g,

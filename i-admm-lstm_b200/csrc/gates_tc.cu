@@ -909,45 +909,64 @@ int make_map_il(CUtensorMap* map, const void* base, uint64_t rows_total, int gro
   return IADMM_OK;
 }
 
+// Encoding a tensor map costs a driver call; a K=100 solve would encode 400 of them for the same six (pointer, shape) pairs
+// (two ping-pong state images x two operands, two weight images).  Small per-thread cache keyed by everything that goes
+// into the encoding; a map only holds the address and the shape, so a hit is valid whatever the buffer contains.
+struct MapKey {
+  const void* base; uint64_t rows; int a, b, c, kind;
+  bool operator==(const MapKey& o) const { return base == o.base && rows == o.rows && a == o.a && b == o.b && c == o.c && kind == o.kind; }
+};
+struct MapCache {
+  static constexpr int kSlots = 16;
+  MapKey key[kSlots];
+  CUtensorMap map[kSlots];
+  int used = 0, next = 0;
+};
+template <typename MakeFn>
+static int cached_map(CUtensorMap* out, const MapKey& k, MakeFn make) {
+  static thread_local MapCache cache;
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.key[i] == k) { *out = cache.map[i]; return IADMM_OK; }
+  int rc = make(out);
+  if (rc) return rc;
+  const int slot = cache.next;
+  cache.key[slot] = k; cache.map[slot] = *out;
+  cache.next = (cache.next + 1) % MapCache::kSlots;
+  if (cache.used < MapCache::kSlots) ++cache.used;
+  return IADMM_OK;
+}
+static int get_map(CUtensorMap* map, const void* base, uint64_t rows_total, int h, int box_rows, int elem_bytes, int box_k) {
+  return cached_map(map, MapKey{base, rows_total, h, box_rows, box_k, elem_bytes},
+                    [&](CUtensorMap* m) { return make_map(m, base, rows_total, h, box_rows, elem_bytes, box_k); });
+}
+static int get_map_il(CUtensorMap* map, const void* base, uint64_t rows_total, int groups, bool q8, int box_k) {
+  return cached_map(map, MapKey{base, rows_total, groups, q8 ? 1 : 0, box_k, 16},
+                    [&](CUtensorMap* m) { return make_map_il(m, base, rows_total, groups, q8, box_k); });
+}
+
 // epilogue warps of the row-interleaved kernel: 16 where the cell epilogue paces the kernel (few K blocks per tile), 8 where
-// the MMAs and the power cap do (profiles/README.md); IADMM_TC_EPI_WARPS=8|16 overrides
+// the MMAs and the power cap do (profiles/README.md); development switch IADMM_TC_EPI_WARPS=8|16 overrides
 static int select_epi_warps(int h) {
-  static int env = -1;
-  if (env < 0) { const char* w = getenv("IADMM_TC_EPI_WARPS"); env = w ? atoi(w) : 0; }
+  const char* w = dev_env("IADMM_TC_EPI_WARPS");
+  const int env = w ? atoi(w) : 0;
   return (env == 8 || env == 16) ? env : (h <= kEpi16MaxHidden ? 16 : 8);
 }
 // head partials per launch that the tail has to sum: per unit tile one per epilogue warp slice
-int tc_head_slots(int h, bool interleaved) {
-  return ((interleaved && select_epi_warps(h) == 16) ? 4 : 2) * cdiv(h, kTcUnits);
+int tc_head_slots(int h, bool interleaved, bool eight_warps) {
+  const bool dev_exp = dev_env("IADMM_TC_EXP") != nullptr && atoi(dev_env("IADMM_TC_EXP")) != 0;
+  return ((interleaved && !eight_warps && !dev_exp && select_epi_warps(h) == 16) ? 4 : 2) * cdiv(h, kTcUnits);
 }
 
 static bool use_quads() {
-  static int v = -1;
-  if (v < 0) {
-    // 4-CTA multicast clusters are bit-identical to plain pairs but measured 3-4 % slower on B200 (the kernel is
-    // bound by the per-SM request port, not by L2 reads, and only 132 SMs host 4-CTA clusters): opt-in only.
-    const char* e = getenv("IADMM_TC_QUAD");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
+  // 4-CTA multicast clusters are bit-identical to plain pairs but measured 3-4 % slower on B200 (the kernel is
+  // bound by the per-SM request port, not by L2 reads, and only 132 SMs host 4-CTA clusters): development switch only.
+  const char* e = dev_env("IADMM_TC_QUAD");
+  return e && e[0] == '1';
 }
 
 static bool use_cta_pairs() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("IADMM_TC_CTA_PAIR");      // development switch: 0 = single-CTA tiles
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-template <typename KernelT>
-static int set_smem_attr(KernelT kernel, bool* done) {
-  if (!*done) {
-    IADMM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    *done = true;
-  }
-  return IADMM_OK;
+  const char* e = dev_env("IADMM_TC_CTA_PAIR");      // development switch: 0 = single-CTA tiles
+  return !(e && e[0] == '0');
 }
 
 int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g, const __half* Hin_hi,
@@ -955,13 +974,9 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
                     float* head_part, long rows, int h, int nprod, cudaStream_t st, float* gates_out, const TcIl* il) {
   if (h % 8 != 0) IADMM_FAIL(IADMM_EMODE, "tensor-core gate path needs hidden_dim %% 8 == 0");
   if (rows > 0x7fffffffL - 2 * kTcBM) IADMM_FAIL(IADMM_ESHAPE, "too many rows for one launch");
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    IADMM_CUDA(cudaGetDevice(&dev));
-    IADMM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  if (const char* e = getenv("IADMM_TC_MAX_SMS")) {      // development switch: restrict the persistent grid
+  int num_sms = 0, rc;
+  if ((rc = device_sm_count(&num_sms))) return rc;
+  if (const char* e = dev_env("IADMM_TC_MAX_SMS")) {      // development switch: restrict the persistent grid (this call only)
     const int v = atoi(e);
     if (v >= 2 && v < num_sms) num_sms = v;
   }
@@ -970,29 +985,28 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   if (nprod == 2 && !pair) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode runs on CTA pairs only");
   if (nprod == 2 && h % 16 != 0) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  int rc;
   const int b_box_rows = pair ? kPairBBoxRows : kTcBN;
   const int bk = pair ? kPairBK : kTcBK;
-  static int il_bk = 0;
-  if (!il_bk) { const char* e = getenv("IADMM_TC_IL_BK"); il_bk = (e && atoi(e) == 32) ? 32 : 64; }   // development switch
+  int il_bk = 64;
+  if (const char* e = dev_env("IADMM_TC_IL_BK")) il_bk = (atoi(e) == 32) ? 32 : 64;   // development switch
   if (il) {
     if (!pair || nprod != 2 || gates_out) IADMM_FAIL(IADMM_EMODE, "the row-interleaved layout is the F16F8 CTA-pair solve path only");
-    if ((rc = make_map_il(&ma_hi, Hin_hi, (uint64_t)il->rows_p, h / 8, false, il_bk))) return rc;
-    if ((rc = make_map_il(&ma_lo, Hin_lo, (uint64_t)il->rows_p, h / 16, true, il_bk))) return rc;
-    if ((rc = make_map_il(&mb_hi, base + L.off_uhi_il, (uint64_t)4 * h, h / 8, false, il_bk))) return rc;
-    if ((rc = make_map_il(&mb_lo, base + L.off_uq8_il, (uint64_t)4 * h, h / 16, true, il_bk))) return rc;
+    if ((rc = get_map_il(&ma_hi, Hin_hi, (uint64_t)il->rows_p, h / 8, false, il_bk))) return rc;
+    if ((rc = get_map_il(&ma_lo, Hin_lo, (uint64_t)il->rows_p, h / 16, true, il_bk))) return rc;
+    if ((rc = get_map_il(&mb_hi, base + L.off_uhi_il, (uint64_t)4 * h, h / 8, false, il_bk))) return rc;
+    if ((rc = get_map_il(&mb_lo, base + L.off_uq8_il, (uint64_t)4 * h, h / 16, true, il_bk))) return rc;
   } else {
-  if ((rc = make_map(&ma_hi, Hin_hi, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
-  if ((rc = make_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
-  if (nprod == 2) {
-    // packed e4m3 images: byte tensors [rows][q8_pitch], one 128-byte box row per 64-wide K block
-    const int pitch = (int)q8_pitch(h);
-    if ((rc = make_map(&ma_lo, Hin_lo, (uint64_t)rows, pitch, kTcBM, 1, 128))) return rc;
-    if ((rc = make_map(&mb_lo, base + L.off_uq8, (uint64_t)4 * h, pitch, b_box_rows, 1, 128))) return rc;
-  } else {
-    if ((rc = make_map(&ma_lo, Hin_lo, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
-    if ((rc = make_map(&mb_lo, base + L.off_ulo, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
-  }
+    if ((rc = get_map(&ma_hi, Hin_hi, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
+    if ((rc = get_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
+    if (nprod == 2) {
+      // packed e4m3 images: byte tensors [rows][q8_pitch], one 128-byte box row per 64-wide K block
+      const int pitch = (int)q8_pitch(h);
+      if ((rc = get_map(&ma_lo, Hin_lo, (uint64_t)rows, pitch, kTcBM, 1, 128))) return rc;
+      if ((rc = get_map(&mb_lo, base + L.off_uq8, (uint64_t)4 * h, pitch, b_box_rows, 1, 128))) return rc;
+    } else {
+      if ((rc = get_map(&ma_lo, Hin_lo, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
+      if ((rc = get_map(&mb_lo, base + L.off_ulo, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;
+    }
   }
 
   TcParams P;
@@ -1010,21 +1024,19 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.unit_tiles = cdiv(h, kTcUnits);
   P.k_blocks = cdiv(h, il ? il_bk : bk);
   P.nprod = nprod;
-  static int exp_mode = -1, epi = -1;
-  if (exp_mode < 0) {
-    const char* e = getenv("IADMM_TC_EXP");           // development experiments, see TcParams::exp
-    exp_mode = e ? atoi(e) : 0;
-    const char* w = getenv("IADMM_TC_EPI");           // development switch: 0 = scalar epilogue, 1 = packed fp32 (default), 2 = packed + exp-only tanh
-    epi = w ? atoi(w) : 1;
+  int exp_mode = 0, epi = 1;
+  if (const char* e = dev_env("IADMM_TC_EXP")) exp_mode = atoi(e);          // development experiments, see TcParams::exp
+  if (const char* w = dev_env("IADMM_TC_EPI")) {    // development switch: 0 = scalar epilogue, 1 = packed fp32 (default), 2 = packed + exp-only tanh
+    epi = atoi(w);
     if (epi < 0 || epi > 2) epi = 1;
   }
-  const int epi_warps = select_epi_warps(h);
+  // IADMM_GATES_TC_F16F8U: the H-rounding correction product is not issued (TcParams::exp 7 is exactly that and numerically valid)
+  const bool drop_h = il && il->drop_h_correction;
+  if (drop_h && exp_mode == 0) exp_mode = 7;
+  const int epi_warps = (drop_h || exp_mode) ? 8 : select_epi_warps(h);     // the switch lives in the 8-warp instantiation
   P.exp = exp_mode;
-  static int wait_ns = -1;
-  if (wait_ns < 0) { const char* e = getenv("IADMM_TC_WAIT_NS"); wait_ns = e ? atoi(e) : IADMM_MBAR_SUSPEND_NS; }
-  P.wait_ns = (uint32_t)wait_ns;
+  if (const char* e = dev_env("IADMM_TC_WAIT_NS")) P.wait_ns = (uint32_t)atoi(e);
   // cluster size: 4 (two pairs sharing each U tile through TMA multicast) when there is enough work, else 2
-  static int max_quads = -1;
   int cl = 1;
   if (pair) {
     cl = 2;
@@ -1043,44 +1055,38 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
 
   int threads = kTcThreads;
   if (pair) {
-    auto launch = [&](auto kernel, bool* attr_done, int cluster) -> int {
+    auto launch = [&](auto kernel, PerDeviceOnce* attr_done, int cluster) -> int {
       int rc2;
-      if ((rc2 = set_smem_attr(kernel, attr_done))) return rc2;
+      if ((rc2 = ensure_dyn_smem(kernel, 220 * 1024, attr_done))) return rc2;
       long clusters = num_sms / cluster;
       if (cluster == 4) {
-        if (max_quads < 0) {      // co-resident 4-CTA clusters (GPC granularity: 33 on a 148-SM B200)
-          cudaLaunchConfig_t cfg{};
-          cfg.gridDim = dim3((unsigned)(num_sms / 4 * 4)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem;
-          cudaLaunchAttribute at[1];
-          at[0].id = cudaLaunchAttributeClusterDimension;
-          at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-          cfg.attrs = at; cfg.numAttrs = 1;
-          int n = 0;
-          if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) n = num_sms / 4 - 4;
-          max_quads = n;
-        }
-        clusters = max_quads < num_sms / 4 ? max_quads : num_sms / 4;
+        // co-resident 4-CTA clusters (GPC granularity: 33 on a 148-SM B200)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(num_sms / 4 * 4)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) n = num_sms / 4 - 4;
+        clusters = n < num_sms / 4 ? n : num_sms / 4;
       }
       if (P.num_tiles < clusters) clusters = P.num_tiles;
       kernel<<<(unsigned)(cluster * clusters), threads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
       return IADMM_OK;
     };
-    static bool a34 = false, a24 = false, a14 = false, a32 = false, a22 = false, a12 = false;
-    static bool e0 = false, e2 = false, s2 = false, s3 = false, s1 = false;
-    static bool i4 = false, i7 = false;
-    if (il && epi_warps == 16 && exp_mode == 0) {
+    static PerDeviceOnce a34, a24, a14, a32, a22, a12, e0, e2, s2, s3, s1, i4, i5, i6, i7;
+    if (il && epi_warps == 16) {
       threads = pair_threads(7);
       rc = launch(gates_tc_pair_kernel<2, 2, 7>, &i7, 2);
     } else if (il) {
-      static bool i5 = false;
-      static bool i6 = false;
       if (epi == 2)         rc = launch(gates_tc_pair_kernel<2, 2, 6>, &i6, 2);
       else if (il_bk == 32) rc = launch(gates_tc_pair_kernel<2, 2, 5>, &i5, 2);
-      else             rc = launch(gates_tc_pair_kernel<2, 2, 4>, &i4, 2);
+      else                  rc = launch(gates_tc_pair_kernel<2, 2, 4>, &i4, 2);
     } else if (gates_out) {        // training forward: the epilogue also stores the gate activations
       if (nprod == 1)      rc = launch(gates_tc_pair_kernel<1, 2, 0>, &s1, 2);
-      else if (nprod == 3)       rc = launch(gates_tc_pair_kernel<3, 2, 3>, &s3, 2);
-      else                       rc = launch(gates_tc_pair_kernel<2, 2, 3>, &s2, 2);
+      else if (nprod == 3) rc = launch(gates_tc_pair_kernel<3, 2, 3>, &s3, 2);
+      else                 rc = launch(gates_tc_pair_kernel<2, 2, 3>, &s2, 2);
     } else if (cl == 4) {
       if (nprod == 3)      rc = launch(gates_tc_pair_kernel<3, 4, 1>, &a34, 4);
       else if (nprod == 2) rc = launch(gates_tc_pair_kernel<2, 4, 1>, &a24, 4);
@@ -1097,12 +1103,12 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
     return IADMM_OK;
   }
   const long grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
-  static bool a3 = false, a1 = false;
+  static PerDeviceOnce a3, a1;
   if (nprod == 3) {
-    if ((rc = set_smem_attr(gates_tc_kernel<3>, &a3))) return rc;
+    if ((rc = ensure_dyn_smem(gates_tc_kernel<3>, 220 * 1024, &a3))) return rc;
     gates_tc_kernel<3><<<(unsigned)grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
   } else {
-    if ((rc = set_smem_attr(gates_tc_kernel<1>, &a1))) return rc;
+    if ((rc = ensure_dyn_smem(gates_tc_kernel<1>, 220 * 1024, &a1))) return rc;
     gates_tc_kernel<1><<<(unsigned)grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
   }
   IADMM_LAUNCH_CHECK("gates_tc_kernel");

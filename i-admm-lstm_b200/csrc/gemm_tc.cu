@@ -194,17 +194,10 @@ int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi
   P.n_tiles = (int)((N + kGmBN - 1) / kGmBN);
   P.k_blocks = (int)((K + kGmBK - 1) / kGmBK);
   P.num_tiles = ((M + kTcBM - 1) / kTcBM) * P.n_tiles;
-  static int num_sms = 0;
-  static bool attr = false;
-  if (!num_sms) {
-    int dev = 0;
-    IADMM_CUDA(cudaGetDevice(&dev));
-    IADMM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  if (!attr) {
-    IADMM_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr = true;
-  }
+  int num_sms = 0;
+  static PerDeviceOnce attr;
+  if ((rc = device_sm_count(&num_sms))) return rc;
+  if ((rc = ensure_dyn_smem(tc_gemm_nt_kernel, 220 * 1024, &attr))) return rc;
   const size_t smem = 1024 + (size_t)kGmStages * kGmStageBytes + (2 * kGmStages + 4) * sizeof(uint64_t) + 16;
   const long grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
   tc_gemm_nt_kernel<<<(unsigned)grid, kGmThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);

@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(256) build_kkt_kernel(int B, int n, int m, int
   const int r = blockIdx.y;                       // row of K
   const float rho_r = (r >= n) ? ((r - n < num_ineq) ? sched->rho_ineq : sched->rho_eq) : 0.f;
   const float inv_r = (r >= n) ? ((r - n < num_ineq) ? sched->inv_rho_ineq : sched->inv_rho_eq) : 0.f;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < (int)N; c += gridDim.x * blockDim.x) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; K != nullptr && c < (int)N; c += gridDim.x * blockDim.x) {
     float v;
     if (r < n) {
       if (c < n) { v = Q[(b * n + r) * n + c]; if (c == r) v = __fadd_rn(v, sigma); }
@@ -672,7 +672,7 @@ int launch_build_kkt(int B, int n, int m, int num_ineq, const float* Q, const fl
                      const float* x, const float* y, const float* z, const Sched* sched_t, float sigma,
                      float* K, float* rhs, float* rho_vec, cudaStream_t st) {
   const int N = n + m;
-  const dim3 grid(cdiv(N, 256) > 8 ? 8 : cdiv(N, 256), N, B);
+  const dim3 grid(K == nullptr ? 1 : (cdiv(N, 256) > 8 ? 8 : cdiv(N, 256)), N, B);
   build_kkt_kernel<<<grid, 256, 0, st>>>(B, n, m, num_ineq, Q, p, A0, x, y, z, sched_t, sigma, K, rhs, rho_vec);
   IADMM_LAUNCH_CHECK("build_kkt_kernel");
   return IADMM_OK;

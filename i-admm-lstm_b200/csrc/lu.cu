@@ -337,11 +337,9 @@ int iadmm_lu_solve(const float* LU, const int* perm, float* rhs, int B, int N, v
   if (!LU || !perm || !rhs) IADMM_FAIL(IADMM_EALIGN, "lu_solve: NULL pointer");
   const size_t smem = ((size_t)((N + 31) / 32) * 32 + 32 * 33) * sizeof(float);
   if (smem > 200 * 1024) IADMM_FAIL(IADMM_EMODE, "lu_solve: N=%d does not fit the shared-memory right-hand side", N);
-  static bool attr = false;
-  if (!attr) {
-    IADMM_CUDA(cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  static PerDeviceOnce attr;
+  int rc;
+  if ((rc = ensure_dyn_smem(lu_solve_kernel, 200 * 1024, &attr))) return rc;
   lu_solve_kernel<<<B, kLuSolveThreads, smem, static_cast<cudaStream_t>(stream)>>>(LU, perm, rhs, N);
   IADMM_LAUNCH_CHECK("lu_solve_kernel");
   return IADMM_OK;

@@ -582,12 +582,8 @@ __global__ void __launch_bounds__(kResThreads, 1) solve_resident_kernel(const Re
 // host side
 // ------------------------------------------------------------------------------------------------
 bool resident_eligible(int n, int m, int h, int nprod, int flags) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("IADMM_RESIDENT");          // development switch: 0 = always the streaming path
-    enabled = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!enabled || (flags & IADMM_F_STREAMING)) return false;
+  const char* e = dev_env("IADMM_RESIDENT");           // development switch: 0 = always the streaming path
+  if ((e && e[0] == '0') || (flags & IADMM_F_STREAMING)) return false;
   if (h != kResH || n + m > kResMaxN || nprod < 1 || nprod > 3) return false;
   return res_fixed_bytes(n, m) <= (size_t)kResSmemLimit;
 }
@@ -616,13 +612,11 @@ int launch_solve_resident(const void* packed, const WeightLayout& L, const float
   const size_t mats = (size_t)(n + m) * res_ld(n) * sizeof(float);
   A.cache_mats = (fixed + mats <= (size_t)kResSmemLimit) ? 1 : 0;
   const size_t smem = fixed + (A.cache_mats ? mats : 0);
-  static bool attr[8] = {false, false, false, false, false, false, false, false};
+  static PerDeviceOnce attr[8];
   auto go = [&](auto kernel) -> int {
     const int slot = nprod * 2 + A.cache_mats - 2;
-    if (!attr[slot]) {
-      IADMM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemLimit));
-      attr[slot] = true;
-    }
+    int rc2;
+    if ((rc2 = ensure_dyn_smem(kernel, kResSmemLimit, &attr[slot]))) return rc2;
     kernel<<<B, kResThreads, smem, st>>>(A);
     return IADMM_OK;
   };

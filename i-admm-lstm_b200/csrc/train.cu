@@ -32,12 +32,8 @@ int launch_split_both(const float* X, long R, long Cc, long Rp, const float* sca
                       cudaStream_t st);
 
 static bool use_tc_backward() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("IADMM_TRAIN_SIMT_GEMM");     // development switch: 1 = fp32 CUDA-core GEMMs in the backward
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
+  const char* e = dev_env("IADMM_TRAIN_SIMT_GEMM");      // development switch: 1 = fp32 CUDA-core GEMMs in the backward
+  return !(e && e[0] == '1');
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -555,8 +551,8 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
   // the state converted at the boundary; both keep the gate activations for the backward
   int nprod = 0;
   if (mode == IADMM_GATES_TC_3XFP16 && h % 8 == 0) nprod = 3;
-  else if (mode == IADMM_GATES_TC_F16F8 && h % 16 == 0) nprod = 2;
-  else if (mode == IADMM_GATES_TC_F16F8 && h % 8 == 0) nprod = 3;
+  else if ((mode == IADMM_GATES_TC_F16F8 || mode == IADMM_GATES_TC_F16F8U) && h % 16 == 0) nprod = 2;   // training keeps both corrections
+  else if ((mode == IADMM_GATES_TC_F16F8 || mode == IADMM_GATES_TC_F16F8U) && h % 8 == 0) nprod = 3;
   else if (mode == IADMM_GATES_TC_1XFP16 && h % 8 == 0) nprod = 1;
   else if (mode != IADMM_GATES_SIMT_FP32 && h % 8 == 0) IADMM_FAIL(IADMM_EMODE, "step_fwd: unknown gate mode %d", mode);
   if (nprod == 0) {

@@ -16,7 +16,9 @@ GATES_SIMT_FP32 = 0
 GATES_TC_3XFP16 = 1
 GATES_TC_1XFP16 = 2
 GATES_TC_F16F8 = 3
-GATE_MODES = {"simt_fp32": GATES_SIMT_FP32, "tc_3xfp16": GATES_TC_3XFP16, "tc_1xfp16": GATES_TC_1XFP16, "tc_f16f8": GATES_TC_F16F8}
+GATES_TC_F16F8U = 4
+GATE_MODES = {"simt_fp32": GATES_SIMT_FP32, "tc_3xfp16": GATES_TC_3XFP16, "tc_1xfp16": GATES_TC_1XFP16, "tc_f16f8": GATES_TC_F16F8,
+              "tc_f16f8u": GATES_TC_F16F8U}
 
 F_ZERO_STATE = 1
 F_SKIP_FINAL_RESID = 2

@@ -19,30 +19,37 @@ def shard_range(batch, rank, world):
 def balanced_shares(total, rates, cap=None):
     """Split `total` independent instances over ranks in proportion to their measured rates (instances/s): the GPUs of
     one box differ by several per cent under the power cap, and with equal shards the job runs at the pace of the slowest.
-    Largest-remainder rounding; every rank gets at least one instance, at most `cap`; the shares sum to `total`
-    (if the caps allow it)."""
+    Largest-remainder rounding; every rank gets at least one instance when there are enough of them (a rank may get 0
+    when total < number of ranks), at most `cap`.  The shares ALWAYS sum to `total`; if the caps make that impossible a
+    ValueError is raised -- instances are never silently dropped or double-counted."""
     n = len(rates)
+    total = int(total)
+    if total < 0:
+        raise ValueError("balanced_shares: negative total")
+    if cap is not None and int(cap) * n < total:
+        raise ValueError(f"balanced_shares: {n} ranks x cap {cap} cannot hold {total} instances")
     tot = float(sum(rates))
     if tot <= 0 or any(r <= 0 for r in rates):
-        base, extra = divmod(int(total), n)
-        return [base + (1 if i < extra else 0) for i in range(n)]
-    ideal = [total * r / tot for r in rates]
-    shares = [max(1, int(x)) for x in ideal]
+        base, extra = divmod(total, n)
+        shares = [base + (1 if i < extra else 0) for i in range(n)]
+        ideal = [float(s_) for s_ in shares]
+    else:
+        ideal = [total * r / tot for r in rates]
+        floor = 1 if total >= n else 0
+        shares = [max(floor, int(x)) for x in ideal]
     if cap is not None:
         shares = [min(s_, int(cap)) for s_ in shares]
     order = sorted(range(n), key=lambda i: ideal[i] - int(ideal[i]), reverse=True)
-    k = 0
-    while sum(shares) < total and k < 4 * n:
-        i = order[k % n]
-        if cap is None or shares[i] < cap:
-            shares[i] += 1
-        k += 1
-    k = 0
-    while sum(shares) > total and k < 4 * n:
-        i = order[-1 - (k % n)]
-        if shares[i] > 1:
-            shares[i] -= 1
-        k += 1
+    floor = 1 if total >= n else 0
+    while sum(shares) < total:                      # terminates: cap * n >= total was checked above
+        for i in order:
+            if sum(shares) < total and (cap is None or shares[i] < cap):
+                shares[i] += 1
+    while sum(shares) > total:                      # terminates: floor * n <= total
+        for i in reversed(order):
+            if sum(shares) > total and shares[i] > floor:
+                shares[i] -= 1
+    assert sum(shares) == total and all(s_ >= 0 for s_ in shares)
     return shares
 
 
@@ -69,10 +76,17 @@ def shard_instances(tensors, rank, world):
     return tuple(v[lo:hi].contiguous() for v in tensors)
 
 
-def gather_batch(local, batch, dim=0, group=None):
-    """All-gather per-rank chunks (sizes from shard_range) along `dim` into the full batch, on every rank."""
+def gather_batch(local, batch, dim=0, group=None, sizes=None):
+    """All-gather per-rank chunks along `dim` into the full batch, on every rank.  `sizes` = the per-rank chunk sizes
+    (e.g. the shares of `balance_by_rate`); default: the equal split of `shard_range`."""
     world = dist.get_world_size(group)
-    sizes = [shard_range(batch, r, world)[1] - shard_range(batch, r, world)[0] for r in range(world)]
+    if sizes is None:
+        sizes = [shard_range(batch, r, world)[1] - shard_range(batch, r, world)[0] for r in range(world)]
+    sizes = [int(s_) for s_ in sizes]
+    if len(sizes) != world or sum(sizes) != int(batch):
+        raise ValueError(f"gather_batch: sizes {sizes} do not describe a batch of {batch} over {world} ranks")
+    if local.shape[dim] != sizes[dist.get_rank(group)]:
+        raise ValueError(f"gather_batch: this rank holds {local.shape[dim]} rows, expected {sizes[dist.get_rank(group)]}")
     mx = max(sizes)
     loc = local.movedim(dim, 0).contiguous()
     pad = torch.zeros((mx,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
@@ -83,20 +97,39 @@ def gather_batch(local, batch, dim=0, group=None):
     return full.movedim(0, dim)
 
 
-def allreduce_gradients(module, group=None):
-    """Data-parallel training: average the LSTM weight gradients over the ranks with ONE
+def allreduce_gradients(module, group=None, local_batch=None):
+    """Data-parallel training: combine the LSTM weight gradients of the ranks with ONE
     all-reduce of the flat gradient buffer (2,570,601 floats at h=800, K=100) per TBPTT window, then the
-    unchanged Adam step runs on every rank.  The loss is a batch mean (main.py:347), so with equal shards
-    this equals single-process training on the concatenated batch.  NCCL on GPUs, gloo in the CPU tests."""
+    unchanged Adam step runs on every rank.  Each rank's loss is the mean over ITS instances (main.py:347), so the
+    gradient of the mean over the concatenated batch is sum_r (B_r / B) * grad_r: pass `local_batch` = B_r when the
+    shards are unequal (`shard_range` remainders, `balance_by_rate`); without it equal shards are assumed (plain
+    average).  The flat buffer covers EVERY parameter (zeros where `.grad` is None), so all ranks issue the same
+    collective whatever their local graph touched.  NCCL on GPUs, gloo in the CPU tests."""
     world = dist.get_world_size(group)
-    grads = [p.grad for p in module.parameters() if p.grad is not None]
-    if not grads or world == 1:
+    params = list(module.parameters())
+    if not params or world == 1:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat /= world
+    dev = params[0].device
+    total = sum(p.numel() for p in params)
+    # one extra slot carries the local batch size, so the weights need no second collective
+    flat = torch.zeros((total + 1,), dtype=params[0].dtype, device=dev)
+    w = float(local_batch) if local_batch is not None else 1.0
     off = 0
-    for g in grads:
-        k = g.numel()
-        g.copy_(flat[off:off + k].view_as(g))
+    for p in params:
+        k = p.numel()
+        if p.grad is not None:
+            flat[off:off + k].copy_(p.grad.reshape(-1))
+        off += k
+    flat[:total] *= w
+    flat[total] = w
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat[:total] /= flat[total]
+    off = 0
+    for p in params:
+        k = p.numel()
+        g = flat[off:off + k].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
         off += k

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import ops as _ops          # registers torch.ops.iadmm.*
 
 PARAM_ORDER = ("W_i", "U_i", "b_i", "W_f", "U_f", "b_f", "W_o", "U_o", "b_o",
                "W_u", "U_u", "b_u", "W_h", "b_h", "rho", "alpha")
@@ -89,14 +90,20 @@ class LSTM(nn.Module):
         mode = self.gate_mode
         if isinstance(mode, str):
             mode = _lib.GATE_MODES[mode]
-        if mode == _lib.GATES_TC_F16F8 and self.hidden_dim % 16 != 0:
+        if mode in (_lib.GATES_TC_F16F8, _lib.GATES_TC_F16F8U) and self.hidden_dim % 16 != 0:
             mode = _lib.GATES_TC_3XFP16    # fp8 operand rows must be 16-byte multiples
         if mode != _lib.GATES_SIMT_FP32 and self.hidden_dim % 8 != 0:
             mode = _lib.GATES_SIMT_FP32    # the tcgen05 tiles need 16-byte rows of fp16
         return mode
 
+    def invalidate_packed(self):
+        """Force a re-pack at the next call.  The cache below notices optimizer steps, `load_state_dict`, `copy_` and
+        every other in-place op on the parameters (they bump `param._version`); an edit through `param.data`
+        (`p.data.add_(...)`, weight surgery in older code) does NOT -- call this after one."""
+        self._packed_key = None
+
     def packed_weights(self):
-        """Device buffer in the kernels' layout; re-packed when any parameter changed."""
+        """Device buffer in the kernels' layout; re-packed when any parameter changed (see `invalidate_packed`)."""
         prm = [getattr(self, k) for k in PARAM_ORDER]
         key = tuple((p.data_ptr(), p._version) for p in prm)
         if self._packed is None or key != self._packed_key:
@@ -158,13 +165,12 @@ class LSTM(nn.Module):
         sd = se = sc = None
         if scaling is not None:
             sd, se, sc = scaling.d, scaling.e, scaling.c_vec
-        with torch.cuda.device(dev):
-            _lib.check(L.iadmm_solve(_lib.ptr(packed), _lib.ptr(Q), _lib.ptr(p), _lib.ptr(A0), _lib.ptr(zl), _lib.ptr(zu),
-                                     _lib.ptr(sd), _lib.ptr(se), _lib.ptr(sc),
-                                     _lib.ptr(x), _lib.ptr(y), _lib.ptr(z), _lib.ptr(xv), _lib.ptr(H), _lib.ptr(C),
-                                     _lib.ptr(pri), _lib.ptr(dual), _lib.ptr(pri_u), _lib.ptr(dual_u), _lib.ptr(met),
-                                     B, n, int(num_ineq), int(num_eq), h, self.length, int(t0), int(K),
-                                     float(sigma), mode, flags, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        for name, v in (("x", x), ("y", y), ("z", z), ("xv", xv), ("H", H), ("C", C)):
+            if not v.is_contiguous():
+                raise _lib.IadmmError(f"state tensor {name} must be contiguous")
+        # the one thin custom op of the forward path (iadmm_b200/ops.py -> iadmm_solve of include/iadmm.h)
+        torch.ops.iadmm.solve(packed, Q, p, A0, zl, zu, sd, se, sc, x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met, ws,
+                              int(num_ineq), int(num_eq), h, self.length, int(t0), int(K), float(sigma), mode, flags)
         return SolveResult(x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met)
 
     # -- one truncated-BPTT window, forward + backward, in one library call ------------------------
@@ -209,6 +215,20 @@ class LSTM(nn.Module):
             off += k
         return loss[0], (x, y, z, xv, H, C)
 
+    def _kkt_tuple(self, t, num_ineq, num_eq, Q, p, A0, x, y, z, sigma, dense=True):
+        """(A_tild, b_tild, rho_vec) of models/lstm.py:61-69 for the iterate BEFORE iteration t; A_tild is None unless `dense`."""
+        dev = Q.device
+        B, n = Q.shape[0], Q.shape[1]
+        m = num_ineq + num_eq
+        N = n + m
+        A_tild = torch.empty((B, N, N), device=dev) if dense else None
+        b_tild = torch.empty((B, N, 1), device=dev)
+        rho_vec = torch.empty((B, m, 1), device=dev)
+        Qc, pc, Ac, xc, yc, zc = (_lib.f32(v, dev) for v in (Q, p, A0, x, y, z))
+        torch.ops.iadmm.build_kkt(self.packed_weights(), Qc, pc, Ac, xc, yc, zc, A_tild, b_tild, rho_vec,
+                                  int(num_ineq), int(num_eq), self.hidden_dim, self.length, int(t), float(sigma))
+        return A_tild, b_tild, rho_vec
+
     # -- the reference's per-iteration interface -------------------------------------------------
     def forward(self, t, num_ineq, num_eq, x, y, z, xv, sigma, H_t, C_t, **kwargs):
         """One iteration; returns (x, y, z, xv, H_t, C_t, A_tild, b_tild, rho_vec) like models/lstm.py:96.
@@ -223,7 +243,14 @@ class LSTM(nn.Module):
             _lib.require_cuda(Q, p, A0, zl, zu, x, y, z, xv, H_t, C_t)
             outs = StepFunction.apply(self, int(t), int(num_ineq), int(num_eq), float(sigma), Q, p, A0, zl, zu,
                                       x, y, z, xv, H_t, C_t, *[getattr(self, k) for k in _ORDER])
-            return (*outs, None, None, None)
+            # models/lstm.py:96 always returns A_tild, b_tild, rho_vec.  The training loop (main.py:339) discards them, so
+            # here they are plain (detached) tensors: b_tild and rho_vec always, the dense A_tild only when
+            # `materialize_kkt` asks for it (16 MB per instance at n=m=1000 -- exactly what the tape-free design avoids).
+            # NOTE: forward and backward nodes share one workspace (`model._train_ws`): single-stream use only.
+            with torch.no_grad():
+                kkt = self._kkt_tuple(int(t), num_ineq, num_eq, Q, p, A0, x.detach(), y.detach(), z.detach(), sigma,
+                                      dense=bool(self.materialize_kkt))
+            return (*outs, *kkt)
         if not (0 <= int(t) < self.length):
             raise IndexError(f"index {t} is out of bounds for dimension 0 with size {self.length}")
         L = _lib.lib()
@@ -231,18 +258,8 @@ class LSTM(nn.Module):
         dev = Q.device
         B, n = Q.shape[0], Q.shape[1]
         m = num_ineq + num_eq
-        A_tild = b_tild = rho_vec = None
-        if self.materialize_kkt:
-            N = n + m
-            A_tild = torch.empty((B, N, N), device=dev)
-            b_tild = torch.empty((B, N, 1), device=dev)
-            rho_vec = torch.empty((B, m, 1), device=dev)
-            Qc, pc, Ac, xc, yc, zc = (_lib.f32(v, dev) for v in (Q, p, A0, x, y, z))
-            with torch.cuda.device(dev):
-                _lib.check(L.iadmm_build_kkt(_lib.ptr(self.packed_weights()), _lib.ptr(Qc), _lib.ptr(pc), _lib.ptr(Ac),
-                                             _lib.ptr(xc), _lib.ptr(yc), _lib.ptr(zc), _lib.ptr(A_tild), _lib.ptr(b_tild),
-                                             _lib.ptr(rho_vec), B, n, int(num_ineq), int(num_eq), self.hidden_dim,
-                                             self.length, int(t), float(sigma), _lib.stream_ptr()))
+        A_tild, b_tild, rho_vec = self._kkt_tuple(int(t), num_ineq, num_eq, Q, p, A0, x, y, z, sigma,
+                                                  dense=bool(self.materialize_kkt))
         r = self.solve(1, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state=(x, y, z, xv, H_t, C_t), t0=int(t),
                        traces=False)
         return r.x, r.y, r.z, r.xv, r.H, r.C, A_tild, b_tild, rho_vec

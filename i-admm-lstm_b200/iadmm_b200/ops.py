@@ -1,0 +1,69 @@
+"""torch custom ops around the C ABI (north_star: "the model's forward path calls one thin C-ABI torch custom op").
+
+    torch.ops.iadmm.solve       -> iadmm_solve        (K unrolled iterations + residual/metric traces, in place)
+    torch.ops.iadmm.ruiz        -> iadmm_ruiz         (Scaling.scale_data)
+    torch.ops.iadmm.residuals   -> iadmm_residuals    (primal_dual_loss)
+    torch.ops.iadmm.build_kkt   -> iadmm_build_kkt    (A_tild / b_tild / rho_vec of LSTM.forward's return tuple)
+
+Each op is a few lines: it turns tensors into device pointers and calls the library on the current CUDA stream of the
+tensors' device.  They are registered for the CUDA dispatch key ONLY -- calling one with CPU tensors fails in the
+dispatcher ("no kernel for CPU"): there is no fallback.  State and trace tensors are declared as mutated arguments, so
+the ops are safe under torch's functionalisation / graph capture; nothing is allocated inside (the caller passes the
+workspace), nothing synchronises.
+"""
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_P = _lib.ptr
+
+
+@torch.library.custom_op("iadmm::solve", mutates_args=("x", "y", "z", "xv", "H", "C", "pri", "dual", "pri_u", "dual_u",
+                                                        "metrics", "workspace"), device_types="cuda")
+def solve(packed: Tensor, Q: Tensor, p: Tensor, A0: Tensor, zl: Tensor, zu: Tensor,
+          sd: Optional[Tensor], se: Optional[Tensor], sc: Optional[Tensor],
+          x: Tensor, y: Tensor, z: Tensor, xv: Tensor, H: Tensor, C: Tensor,
+          pri: Optional[Tensor], dual: Optional[Tensor], pri_u: Optional[Tensor], dual_u: Optional[Tensor],
+          metrics: Optional[Tensor], workspace: Tensor,
+          num_ineq: int, num_eq: int, h: int, length: int, t0: int, K: int, sigma: float, mode: int, flags: int) -> None:
+    B, n = Q.shape[0], Q.shape[1]
+    with torch.cuda.device(Q.device):
+        _lib.check(_lib.lib().iadmm_solve(_P(packed), _P(Q), _P(p), _P(A0), _P(zl), _P(zu), _P(sd), _P(se), _P(sc),
+                                          _P(x), _P(y), _P(z), _P(xv), _P(H), _P(C),
+                                          _P(pri), _P(dual), _P(pri_u), _P(dual_u), _P(metrics),
+                                          B, n, num_ineq, num_eq, h, length, t0, K, sigma, mode, flags,
+                                          _P(workspace), workspace.numel(), _lib.stream_ptr()))
+
+
+@torch.library.custom_op("iadmm::ruiz", mutates_args=("Qs", "ps", "A0s", "zls", "zus", "d", "e", "c", "workspace"),
+                         device_types="cuda")
+def ruiz(Q: Tensor, p: Tensor, A0: Tensor, zl: Tensor, zu: Tensor,
+         Qs: Tensor, ps: Tensor, A0s: Tensor, zls: Tensor, zus: Tensor, d: Tensor, e: Tensor, c: Tensor,
+         workspace: Tensor, iterations: int) -> None:
+    B, n, m = Q.shape[0], Q.shape[1], A0.shape[1]
+    with torch.cuda.device(Q.device):
+        _lib.check(_lib.lib().iadmm_ruiz(_P(Q), _P(p), _P(A0), _P(zl), _P(zu), _P(Qs), _P(ps), _P(A0s), _P(zls), _P(zus),
+                                         _P(d), _P(e), _P(c), B, n, m, iterations, _P(workspace), workspace.numel(),
+                                         _lib.stream_ptr()))
+
+
+@torch.library.custom_op("iadmm::residuals", mutates_args=("pri", "dual", "workspace"), device_types="cuda")
+def residuals(x: Tensor, y: Tensor, z: Tensor, Q: Tensor, p: Tensor, A0: Tensor, pri: Tensor, dual: Tensor,
+              workspace: Tensor) -> None:
+    B, n, m = Q.shape[0], Q.shape[1], A0.shape[1]
+    with torch.cuda.device(Q.device):
+        _lib.check(_lib.lib().iadmm_residuals(_P(x), _P(y), _P(z), _P(Q), _P(p), _P(A0), _P(pri), _P(dual), B, n, m,
+                                              _P(workspace), workspace.numel(), _lib.stream_ptr()))
+
+
+@torch.library.custom_op("iadmm::build_kkt", mutates_args=("Kmat", "rhs", "rho_vec"), device_types="cuda")
+def build_kkt(packed: Tensor, Q: Tensor, p: Tensor, A0: Tensor, x: Tensor, y: Tensor, z: Tensor,
+              Kmat: Optional[Tensor], rhs: Tensor, rho_vec: Tensor,
+              num_ineq: int, num_eq: int, h: int, length: int, t: int, sigma: float) -> None:
+    B, n = Q.shape[0], Q.shape[1]
+    with torch.cuda.device(Q.device):
+        _lib.check(_lib.lib().iadmm_build_kkt(_P(packed), _P(Q), _P(p), _P(A0), _P(x), _P(y), _P(z), _P(Kmat), _P(rhs),
+                                              _P(rho_vec), B, n, num_ineq, num_eq, h, length, t, sigma, _lib.stream_ptr()))

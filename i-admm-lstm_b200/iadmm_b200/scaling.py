@@ -10,6 +10,7 @@ from ctypes import byref, c_size_t
 import torch
 
 from . import _lib
+from . import ops as _ops          # registers torch.ops.iadmm.*
 
 
 class Scaling(object):
@@ -64,9 +65,5 @@ class Scaling(object):
         nbytes = c_size_t()
         _lib.check(L.iadmm_ruiz_workspace_bytes(B, n, m, byref(nbytes)))
         ws = _lib.workspace(nbytes.value, dev)
-        with torch.cuda.device(dev):
-            _lib.check(L.iadmm_ruiz(_lib.ptr(Q), _lib.ptr(p), _lib.ptr(A0), _lib.ptr(zl), _lib.ptr(zu),
-                                    _lib.ptr(Qs), _lib.ptr(ps), _lib.ptr(A0s), _lib.ptr(zls), _lib.ptr(zus),
-                                    _lib.ptr(self.d), _lib.ptr(self.e), _lib.ptr(self.c_vec),
-                                    B, n, m, int(self.scaling_ites), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        torch.ops.iadmm.ruiz(Q, p, A0, zl, zu, Qs, ps, A0s, zls, zus, self.d, self.e, self.c_vec, ws, int(self.scaling_ites))
         return Qs, ps, A0s, zls, zus

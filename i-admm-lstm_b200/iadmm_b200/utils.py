@@ -9,6 +9,7 @@ from ctypes import byref, c_size_t
 import torch
 
 from . import _lib
+from . import ops as _ops          # registers torch.ops.iadmm.*
 
 
 def primal_dual_loss(x, y, z, Q, p, A0):
@@ -29,10 +30,7 @@ def primal_dual_loss(x, y, z, Q, p, A0):
     nbytes = c_size_t()
     _lib.check(L.iadmm_residuals_workspace_bytes(B, n, m, byref(nbytes)))
     ws = _lib.workspace(nbytes.value, dev)
-    with torch.cuda.device(dev):
-        _lib.check(L.iadmm_residuals(_lib.ptr(x), _lib.ptr(y), _lib.ptr(z), _lib.ptr(Q), _lib.ptr(p), _lib.ptr(A0),
-                                     _lib.ptr(pri), _lib.ptr(dual), B, n, m, _lib.ptr(ws), ws.numel(),
-                                     _lib.stream_ptr()))
+    torch.ops.iadmm.residuals(x, y, z, Q, p, A0, pri, dual, ws)
     pri = pri.reshape(B, 1, 1)
     dual = dual.reshape(B, 1, 1)
     return pri, dual, pri + dual

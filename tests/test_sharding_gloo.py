@@ -59,7 +59,11 @@ def test_balanced_shares():
     assert max(t) / min(t) < 1.01                                      # finish together within 1 %
     assert balanced_shares(10, [0.0, 1.0]) == [5, 5]                   # no usable measurement: equal shards
     assert balanced_shares(7, [1.0, 100.0]) == [1, 6]                  # nobody is left without work
-    assert sum(balanced_shares(600, [1.0, 3.0], cap=320)) <= 600 and max(balanced_shares(600, [1.0, 3.0], cap=320)) == 320
+    assert balanced_shares(600, [1.0, 3.0], cap=320) == [280, 320]     # the cap moves work to the slower rank, nothing is dropped
+    assert sorted(balanced_shares(2, [1.0, 1.0, 1.0, 1.0])) == [0, 0, 1, 1]   # fewer instances than ranks: zero-size shares
+    import pytest
+    with pytest.raises(ValueError):
+        balanced_shares(700, [1.0, 3.0], cap=320)                      # impossible under the caps: loud, never silent
 
 
 def _balance_worker(rank, world, port, q):
@@ -130,11 +134,19 @@ def _dp_worker(rank, world, port, out):
     mod = Params(prm)
     window(mod, shard_instances({k: qp[k] for k in ("Q", "p", "A0", "zl", "zu")}, rank, world))
     allreduce_gradients(mod)
+    # unequal shards (3 + 1 instances): each rank's loss is the mean over ITS instances, so the ranks are weighted B_r / B
+    cut = 3
+    mine = {k: (qp[k][:cut] if rank == 0 else qp[k][cut:]) for k in ("Q", "p", "A0", "zl", "zu")}
+    mod_u = Params(prm)
+    window(mod_u, mine)
+    allreduce_gradients(mod_u, local_batch=mine["Q"].shape[0])
     if rank == 0:
         full = Params(prm)
         window(full, qp)
         out["max_rel"] = max(float((a.grad - b.grad).norm() / (b.grad.norm() + 1e-300))
                              for a, b in zip(mod.parameters(), full.parameters()))
+        out["max_rel_unequal"] = max(float((a.grad - b.grad).norm() / (b.grad.norm() + 1e-300))
+                                     for a, b in zip(mod_u.parameters(), full.parameters()))
     dist.destroy_process_group()
 
 
@@ -146,6 +158,7 @@ def test_two_rank_gradient_allreduce_matches_single():
     port = 29900 + (os.getpid() % 90)
     mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
     assert out["max_rel"] < 1e-10
+    assert out["max_rel_unequal"] < 1e-10
 
 
 def test_balanced_shares_properties():
