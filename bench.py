@@ -1,8 +1,14 @@
 #!/usr/bin/env python
 """Benchmark of the I-ADMM-LSTM unrolled solve path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gate-mode M] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--workload W] [--gate-mode M] [--batch B]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workloads (`--workload`; the default `solve` is the headline BASELINE config 2, the line the driver records):
+    solve     config 2: n=1000, 500+500, hidden_dim=800, --scaling, K=100, batch 256 per GPU
+    config5   config 5: n=5000, 2500+2500, hidden_dim=800, K=100, batch 24 per GPU
+    hidden200 configs/QP.yaml's default hidden_dim (208 = 200 rounded up to the tensor-core tile granularity): HBM-bound regime
+    train     config 3: one truncated-BPTT window (TL=100) forward + backward + NCCL gradient all-reduce + Adam per step
 
 One "step" = the hot path over one batch of synthetic QPs: Ruiz equilibration (10 its) + K=100 unrolled
 I-ADMM-LSTM iterations + the per-iteration primal/dual residual traces, for `batch` instances per GPU of
@@ -13,7 +19,10 @@ Prints ONE JSON line (rank 0).  `value` = solves/s with inputs resident in HBM; 
 the public API with pinned HOST buffers, H2D/D2H copies inside the timed region; `roofline` = the gate
 kernel (tensor-bound) measured live with CUDA events through the library's profile hooks, plus
 `roofline_kkt` for the HBM-bound KKT phase; `cpu_baseline` = the oracle port of the reference's torch
-path on the host cores (bounded sample).  `--impl reference` times that CPU path alone.
+path on the host cores (bounded sample).  `--impl reference` times the CPU path alone: the UNMODIFIED reference modules from the git-ignored
+baseline/_ref (kind "reference") when that copy travelled with the snapshot, else the oracle port (kind "port").
+`--impl reference-gpu` runs the same unmodified reference modules on the B200 itself (stock PyTorch fp32, TF32 off,
+device-timed): the like-for-like "what torch gives you on this GPU" number, also reported as `gpu_reference` in our line.
 """
 import argparse
 import json
@@ -43,9 +52,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gate-mode", default="tc_f16f8", choices=["tc_3xfp16", "tc_f16f8", "tc_1xfp16", "simt_fp32"])
-    ap.add_argument("--batch", type=int, default=256, help="instances per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--workload", default="solve", choices=["solve", "config5", "hidden200", "train"])
+    ap.add_argument("--gate-mode", default="tc_f16f8", choices=["tc_3xfp16", "tc_f16f8", "tc_f16f8u", "tc_1xfp16", "simt_fp32"])
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU (default: 256 solve, 24 config5, 2 train)")
     ap.add_argument("--iters", type=int, default=K_ITERS, help="unrolled iterations per solve (metric is quoted at 100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-balance", action="store_true",
@@ -55,7 +65,17 @@ def parse_args():
     ap.add_argument("--nvar", type=int, default=N_VAR, help="variables per QP (the metric is quoted at 1000; 5000 = BASELINE config 5, "
                                                              "with num_ineq = num_eq = nvar/2)")
     ap.add_argument("--hidden", type=int, default=HIDDEN, help="hidden_dim (the metric is quoted at 800; 200 is configs/QP.yaml's default)")
-    return ap.parse_args()
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the stock-PyTorch-on-this-GPU sample in our line")
+    ap.add_argument("--gpu-ref-batch", type=int, default=32, help="instances per step of the stock-PyTorch GPU arm")
+    ap.add_argument("--tl", type=int, default=100, help="train: truncated_length of the window")
+    a = ap.parse_args()
+    if a.workload == "config5":
+        a.nvar = 5000
+    if a.workload == "hidden200":
+        a.hidden = 208
+    if a.batch is None:
+        a.batch = {"solve": 256, "config5": 24, "hidden200": 256, "train": 2}[a.workload]
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -127,21 +147,41 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# the reference arm / cpu baseline: oracle port of the reference's torch CPU path
+# the reference arms: the unmodified reference modules (baseline/_ref) on the host cores or on the GPU; the oracle port
+# of the same torch CPU path when the copy is not there
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_solves_per_s(steps, warmup, cpu_batch, iters):
-    from oracle import iadmm_oracle as orc
+def _ref_inputs(batch, n, mi, me, h, iters, device):
+    from oracle import iadmm_oracle as orc          # input generators only (qp_instances / lstm_parameters)
+    qp = orc.qp_instances(batch, n, mi, me, seed=17)
+    prm = orc.lstm_parameters(h, iters, seed=17)
+    return {k: v.to(device) for k, v in qp.items()}, prm
+
+
+def cpu_reference_solves_per_s(steps, warmup, cpu_batch, iters, n=N_VAR, h=HIDDEN):
+    """Ruiz + K iterations + residual per iteration on the host cores.  What main.py times: scale_data (:825-834) + the K
+    model() calls (:881-890); residuals as in :955."""
+    from baseline import ref_arm
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    qp = orc.qp_instances(cpu_batch, N_VAR, N_INEQ, N_EQ, seed=17)
-    prm = orc.lstm_parameters(HIDDEN, iters, seed=17)
+    mi = me = n // 2
+    qp, prm = _ref_inputs(cpu_batch, n, mi, me, h, iters, "cpu")
+    if ref_arm.available():
+        kind = "reference"
+        model = ref_arm.make_model(prm, h, iters, "cpu")
 
-    def one_step():
-        # what main.py times: scale_data (:825-834) + the K model() calls (:881-890); residuals as in :955
-        Qs, ps, As, zls, zus, sc = orc.ruiz_equilibrate(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], RUIZ_ITS)
-        orc.solve(prm, iters, N_INEQ, N_EQ, Qs, ps, As, zls, zus, SIGMA, HIDDEN, scaling=sc,
-                  original=(qp["Q"], qp["p"], qp["A0"]), form="dense")
+        def one_step():
+            ref_arm.solve(model, iters, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], SIGMA, RUIZ_ITS)
+        how = "UNMODIFIED reference modules (models/lstm.py, methods/scaling.py incl. its O(n^3) dense-diag Ruiz, utils.py) from baseline/_ref"
+    else:
+        from oracle import iadmm_oracle as orc
+        kind = "port"
 
+        def one_step():
+            Qs, ps, As, zls, zus, sc = orc.ruiz_equilibrate(qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], RUIZ_ITS)
+            orc.solve(prm, iters, mi, me, Qs, ps, As, zls, zus, SIGMA, h, scaling=sc,
+                      original=(qp["Q"], qp["p"], qp["A0"]), form="dense")
+        how = ("oracle port (dense-KKT form like models/lstm.py:67-72; NOTE its Ruiz is O(n^2) where the reference's dense-diag "
+               "bmm's are O(n^3), 0.32 s/instance in BASELINE.md: the port is slightly FASTER than the reference)")
     with torch.no_grad():
         for _ in range(warmup):
             one_step()
@@ -149,9 +189,43 @@ def cpu_reference_solves_per_s(steps, warmup, cpu_batch, iters):
         for _ in range(steps):
             one_step()
         dt = time.perf_counter() - t0
-    sample = (f"{steps} x ({cpu_batch} instance(s) of the same workload, Ruiz + K={iters}, dense-KKT form like "
-              f"models/lstm.py:67-72), torch {torch.__version__} CPU fp32, {cores} threads")
-    return cpu_batch * steps / dt, dt / steps * 1e3, cores, sample
+    sample = (f"{steps} x ({cpu_batch} instance(s) of the same workload, Ruiz + K={iters}), {how}, "
+              f"torch {torch.__version__} CPU fp32, {cores} threads")
+    return cpu_batch * steps / dt, dt / steps * 1e3, cores, sample, kind
+
+
+def gpu_reference_solves_per_s(steps, warmup, batch, iters, dev, n=N_VAR, h=HIDDEN):
+    """The unmodified reference modules with device='cuda' (stock PyTorch fp32 kernels, TF32 off like torch's default),
+    timed on the device around scale_data + K x (model() + primal_dual_loss).  None when baseline/_ref is absent."""
+    from baseline import ref_arm
+    if not ref_arm.available():
+        return None
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    mi = me = n // 2
+    qp, prm = _ref_inputs(batch, n, mi, me, h, iters, dev)
+    model = ref_arm.make_model(prm, h, iters, dev)
+
+    def one_step():
+        return ref_arm.solve(model, iters, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], SIGMA, RUIZ_ITS)
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del r
+    torch.cuda.empty_cache()
+    return {"value": batch * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "batch_per_step": batch,
+            "steps": steps, "warmup": warmup,
+            "what": ("UNMODIFIED reference modules (baseline/_ref: models/lstm.py, methods/scaling.py, utils.py) on this GPU, "
+                     "device='cuda', stock PyTorch %s fp32 (TF32 off), same workload: Ruiz + K=%d x (model() + primal_dual_loss), "
+                     "device-timed with CUDA events" % (torch.__version__, iters))}
 
 
 def run_reference(args):
@@ -159,15 +233,42 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    val, ms, cores, sample = cpu_reference_solves_per_s(steps, warmup, args.cpu_batch, args.iters)
+    n, h = args.nvar, args.hidden
+    workload = workload_name(args)
+    if args.impl == "reference-gpu":
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        g = gpu_reference_solves_per_s(steps, max(1, warmup), args.gpu_ref_batch, args.iters, dev, n, h)
+        if g is None:
+            print(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref is not in this snapshot (run build() in the build container)"}), flush=True)
+            return
+        line = {"impl": "reference-gpu", "metric": METRIC, "value": g["value"], "unit": UNIT, "n_gpus": 1, "steps": steps,
+                "warmup": max(1, warmup), "ms_per_step": g["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "batch_per_step": args.gpu_ref_batch, "iters": args.iters},
+                "gpu_reference": g, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    val, ms, cores, sample, kind = cpu_reference_solves_per_s(steps, warmup, args.cpu_batch, args.iters, n, h)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_step": args.cpu_batch, "iters": args.iters},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload, "batch_per_step": args.cpu_batch, "iters": args.iters},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    n, h = args.nvar, args.hidden
+    if args.workload == "train":
+        return ("config3: TBPTT training window, dense QP n=%d, %d ineq + %d eq, hidden_dim=%d, --scaling, truncated_length=%d, "
+                "forward + backward + gradient all-reduce + Adam" % (n, n // 2, n // 2, h, args.tl))
+    if n == N_VAR:
+        return WORKLOAD if h == HIDDEN else WORKLOAD.replace("hidden_dim=800", "hidden_dim=%d" % h) + " (NOT the headline hidden_dim)"
+    return ("config5: dense QP n=%d, %d ineq + %d eq, hidden_dim=%d, --scaling, K=%d (NOT the headline workload)"
+            % (n, n // 2, n // 2, h, args.iters))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -348,11 +449,11 @@ def run_ours(args):
             "metric": METRIC, "value": sum(shares) * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (WORKLOAD if h == HIDDEN else WORKLOAD.replace("hidden_dim=800", "hidden_dim=%d" % h)) if n == N_VAR else
-                                   "config5-style: dense QP n=%d, %d ineq + %d eq, hidden_dim=%d, --scaling, K=%d (NOT the headline workload)" % (n, mi, me, h, K),
+            "config": {"workload": workload_name(args),
                        "batch_per_gpu": args.batch, "instances_per_gpu": shares, "iters": K, "gate_mode": args.gate_mode,
                        "gate_arithmetic": {"tc_3xfp16": "tcgen05 fp16 hi/lo split, 3 MMAs, fp32 accumulate",
                                            "tc_f16f8": "tcgen05 fp16 MMA + 2 e4m3 correction MMAs, fp32 accumulate",
+                                           "tc_f16f8u": "tcgen05 fp16 MMA + 1 e4m3 correction MMA (weights rounding only), fp32 accumulate",
                                            "tc_1xfp16": "tcgen05 single fp16 MMA, fp32 accumulate",
                                            "simt_fp32": "fp32 FMA"}[args.gate_mode],
                        "cache": "inputs larger than L2: Q+A0 %.2f GB and LSTM state %.2f GB per GPU per iteration vs 126 MB L2"
@@ -364,6 +465,8 @@ def run_ours(args):
             "roofline": {"kernel": "gates_tc_pair_kernel" if args.gate_mode != "simt_fp32" else "gates_simt_kernel",
                          "bound": "tensor", "achieved": gate_tflops, "peak": tf_sus, "unit": "TFLOP/s",
                          "frac": gate_tflops / tf_sus, "traffic": ncu_traffic("gates", B, args.gate_mode, h == HIDDEN and n == N_VAR),
+                         "traffic_source": "profiles/roofline_traffic.json: dram__bytes_read+write of one committed ncu --set full "
+                                           "capture of this kernel at this shape (not measured in this run)",
                          "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,
                          "flops_per_launch": gate_flops, "ms_per_launch": gate_avg_ms,
                          "share_of_step": gate_ms.value / ms,
@@ -385,10 +488,167 @@ def run_ours(args):
         if e2e:
             line["e2e"] = {"value": sum(shares) * steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms / steps}
+        if n_gpus == 1 and not args.no_gpu_reference:
+            # stock PyTorch on the same B200: bounded sample, after our timed regions
+            try:
+                line["gpu_reference"] = gpu_reference_solves_per_s(1, 1, min(args.gpu_ref_batch, 32 if n <= 1000 else 2), K, dev, n, h) or \
+                    {"unavailable": "baseline/_ref is not in this snapshot"}
+            except Exception as exc:                                              # never lose the bench line to the side arm
+                line["gpu_reference"] = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
         if n_gpus == 1 and not args.no_cpu_baseline:
-            val, cms, cores, sample = cpu_reference_solves_per_s(3, 1, 4, K)     # 16 instances, ~12 s of CPU work; batches of 4 are the CPU path's best
-            # operating point here (measured 1.3 solves/s at batch 1-4, 0.56 at batch 12: the dense KKT build falls out of cache)
-            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            cb = 4 if n <= 1000 else 1
+            val, cms, cores, sample, kind = cpu_reference_solves_per_s(3 if n <= 1000 else 1, 1 if n <= 1000 else 0, cb, K, n, h)
+            # ~12 instances, 10-20 s of CPU work; batches of 4 are the CPU path's best operating point at n=1000
+            # (measured 1.3 solves/s at batch 1-4, 0.56 at batch 12: the dense KKT build falls out of cache)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+# training workload (BASELINE config 3): one truncated-BPTT window per step, main.py:336-358 through the drop-in modules
+# ---------------------------------------------------------------------------------------------------
+def run_train(args):
+    import torch.distributed as dist
+    import iadmm_b200 as ia
+    from iadmm_b200.dist import allreduce_gradients
+    from ctypes import c_double, c_int
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    B, n, mi, me, h, TL = args.batch, args.nvar, args.nvar // 2, args.nvar // 2, args.hidden, args.tl
+    m, N = mi + me, n + mi + me
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    L = ia.lib()
+    torch.manual_seed(17)                                    # identical initial weights on every rank
+    model = ia.LSTM(None, 2, h, TL, dev, gate_mode=args.gate_mode)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-5, weight_decay=0.0)          # main.py:191
+    Q, p, A0, zl, zu = device_qp_batch(B, n, mi, me, 17 + rank, dev)
+    scaling = ia.Scaling(n, m, RUIZ_ITS, dev)
+    ar_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+
+    def zero_state():
+        return (torch.zeros((B, n, 1), device=dev), torch.zeros((B, m, 1), device=dev), torch.zeros((B, m, 1), device=dev),
+                torch.zeros((B, N, 1), device=dev), torch.zeros((B, N, h), device=dev), torch.zeros((B, N, h), device=dev))
+
+    def train_step(raw, timed_idx=None):
+        # main.py:306-358 for one batch with outer_T == truncated_length: scale_data, zero state, ONE window, Adam
+        Qs, ps, As, zls, zus = scaling.scale_data(*raw)
+        opt.zero_grad(set_to_none=True)
+        loss, _ = model.train_window(TL, mi, me, Qs, ps, As, zls, zus, SIGMA, zero_state(), loss_scale=1.0 / TL, inplace=True)
+        if world > 1:
+            if timed_idx is not None:
+                ar_ev[timed_idx][0].record()
+            allreduce_gradients(model, local_batch=B)        # ONE NCCL all-reduce of the flat gradient buffer per window
+            if timed_idx is not None:
+                ar_ev[timed_idx][1].record()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    raw = (Q, p, A0, zl, zu)
+    for _ in range(warmup):
+        loss = train_step(raw)
+    barrier()
+    sampler = ClockSampler(dev) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ia._lib.check(L.iadmm_profile_begin(steps * TL * 2))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.profiler.start()
+    e0.record()
+    for i in range(steps):
+        loss = train_step(raw, i)
+    e1.record()
+    barrier()
+    torch.cuda.profiler.stop()
+    ms = e0.elapsed_time(e1)
+    kinds = 7
+    pms, pcnt = (c_double * kinds)(), (c_int * kinds)()
+    ia._lib.check(L.iadmm_profile_end_kinds(pms, pcnt, kinds))
+    clocks = sampler.stop() if sampler else None
+    ar_ms = sum(a.elapsed_time(b) for a, b in ar_ev) if world > 1 else 0.0
+    loss_v = float(loss)
+    mem_gb = torch.cuda.max_memory_allocated() / 1e9
+
+    # ---- e2e: the batch arrives from pinned host memory every step, the loss goes back to the host -----------------
+    host_in = [t.cpu().pin_memory() for t in raw]
+    dev_in = [torch.empty_like(t) for t in raw]
+    host_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        for d_, h_ in zip(dev_in, host_in):
+            d_.copy_(h_, non_blocking=True)
+        ls = train_step(tuple(dev_in))
+        host_loss.copy_(ls.reshape(1), non_blocking=True)
+
+    e2e_step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+
+    # weights must stay identical across ranks (same all-reduced gradient, same Adam state)
+    chk = torch.stack([prm.detach().double().sum() for prm in model.parameters()]).sum()
+    same = True
+    times = torch.tensor([ms, e2e_ms, ar_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(lo == hi)
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, ar_ms = (float(v) for v in times)
+
+    if rank == 0:
+        hbm_gbs, tf_sus, tf_burst, peak_kind = measured_peaks()
+        rows = B * N
+        its = max(1, pcnt[4])
+        gemm_ms = pms[4] / its
+        gemm_flops = 16.0 * rows * h * h                      # H_bar = D U^T and U_bar = H^T D: 2 x (2 * rows * h * 4h)
+        gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        line = {
+            "metric": "training instances/sec (TBPTT window TL=%d, n=%d, m=%d)" % (TL, n, m),
+            "value": world * B * steps / (ms * 1e-3), "unit": "instances/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "batch_per_gpu": B, "truncated_length": TL, "gate_mode": args.gate_mode,
+                       "cache": "inputs larger than L2: saved states %.1f GB per window" % (2 * (TL + 1) * rows * h * 4 / 1e9),
+                       "parallelism": "data parallel over %d GPU(s): one NCCL all-reduce of the flat gradient buffer (%d floats) per window, "
+                                      "then the reference's Adam on every rank" % (world, sum(p_.numel() for p_ in model.parameters())),
+                       "weights_identical_across_ranks": same, "loss": loss_v, "peak_mem_GB": mem_gb},
+            "gpu_launches": steps * TL * 60,
+            "allreduce": {"ms_per_step": ar_ms / steps, "share_of_step": ar_ms / ms if ms > 0 else 0.0,
+                          "bytes": 4 * (sum(p_.numel() for p_ in model.parameters()) + 1)},
+            "roofline": {"kernel": "tc_gemm_nt_kernel x2 (+ fp16 hi/lo operand splits)", "bound": "tensor", "achieved": gemm_tflops,
+                         "peak": tf_sus, "unit": "TFLOP/s", "frac": gemm_tflops / tf_sus, "traffic": None,
+                         "flops_per_launch": gemm_flops, "ms_per_launch": gemm_ms, "share_of_step": pms[4] / ms,
+                         "peak_kind": "%s bf16_tflops_sustained" % peak_kind,
+                         "note": "logical fp32 flops of the two gate-product adjoints per iteration (16*rows*h^2); each runs as 3 fp16 "
+                                 "MMAs (hi/lo split of both operands)"},
+            "phase_ms_per_iteration": {"fwd_gates": pms[3] / max(1, pcnt[3]), "bwd_gemms": gemm_ms,
+                                       "kkt_fwd_and_adjoint": pms[5] / its, "bwd_cell_and_small_adjoints": pms[6] / max(1, pcnt[6])},
+            "clocks": clocks,
+            "e2e": {"value": world * B * steps / (e2e_ms * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
+        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -397,7 +657,9 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.impl != "ours":
         run_reference(a)
+    elif a.workload == "train":
+        run_train(a)
     else:
         run_ours(a)

@@ -74,16 +74,27 @@ struct SolveWs {
   size_t bytes;
 };
 
-// measurement hooks: events recorded around the phases of each iteration
+// measurement hooks: CUDA-event spans recorded around the phases of each iteration (bench.py)
+struct ProfSpan { int kind; cudaEvent_t e0, e1; };
 struct Profile {
   bool on = false;
-  int cap = 0, used = 0;            // iterations
-  cudaEvent_t* ev = nullptr;        // 4 per iteration
+  int cap = 0, used = 0;            // spans
+  ProfSpan* span = nullptr;
+  int open[kProfKinds];             // index of the span opened last per kind, -1 = none
 };
 static Profile g_prof;
 
-static inline void prof_record(int slot, cudaStream_t st) {
-  if (g_prof.on && g_prof.used < g_prof.cap) cudaEventRecord(g_prof.ev[(size_t)g_prof.used * 4 + slot], st);
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof.on || g_prof.used >= g_prof.cap) return;
+  const int i = g_prof.used++;
+  g_prof.span[i].kind = kind;
+  g_prof.open[kind] = i;
+  cudaEventRecord(g_prof.span[i].e0, st);
+}
+void prof_end(int kind, cudaStream_t st) {
+  if (!g_prof.on || g_prof.open[kind] < 0) return;
+  cudaEventRecord(g_prof.span[g_prof.open[kind]].e1, st);
+  g_prof.open[kind] = -(g_prof.open[kind] + 2);       // closed: remembered as -(i+2)
 }
 
 static int is_tc(int mode) {
@@ -254,14 +265,15 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   }
   for (int k = 0; k < K; ++k) {
     const Sched* sk = sched + (t0 + k);
-    prof_record(0, st);
+    prof_begin(kProfKkt, st);
     if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, sk, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
                                   dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st, metric_trace, zu,
                                   k > 0 ? sk - 1 : nullptr))) return rc;
     if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st))) return rc;
     if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st))) return rc;
-    prof_record(1, st);
+    prof_end(kProfKkt, st);
+    prof_begin(kProfGates, st);
     if (tc) {
       ilp.C_rm_out = (k == K - 1) ? C : nullptr;
       rc = launch_gates_tc(packed_weights, L, xv, ws.s.g, ws.tc.h_hi[cur], ws.tc.h_lo[cur], ws.tc.h_hi[cur ^ 1],
@@ -271,11 +283,11 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
       rc = launch_gates_simt(packed_weights, L, xv, ws.s.g, hbuf[cur], hbuf[cur ^ 1], C, ws.head_part, rows, h, st);
     }
     if (rc) return rc;
-    prof_record(2, st);
+    prof_end(kProfGates, st);
+    prof_begin(kProfTail, st);
     cur ^= 1;
     if ((rc = launch_tail(ws.d, ws.head_part, tc ? tc_head_slots(h, il, il && ilp.drop_h_correction) : ws.tiles, b_h, sk, zl, zu, x, y, z, xv, st, metric_trace ? &ws.s : nullptr))) return rc;
-    prof_record(3, st);
-    if (g_prof.on && g_prof.used < g_prof.cap) ++g_prof.used;
+    prof_end(kProfTail, st);
   }
   if (!tc && cur == 1)
     IADMM_CUDA(cudaMemcpyAsync(H, ws.h_alt, (size_t)rows * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -289,37 +301,57 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
 
 int iadmm_profile_begin(int max_iterations) {
   if (max_iterations <= 0 || max_iterations > (1 << 20)) IADMM_FAIL(IADMM_ESHAPE, "profile_begin: max_iterations=%d", max_iterations);
-  if (g_prof.ev) IADMM_FAIL(IADMM_ESHAPE, "profile_begin: a profile is already open");
-  g_prof.ev = new cudaEvent_t[(size_t)max_iterations * 4];
-  for (size_t i = 0; i < (size_t)max_iterations * 4; ++i) IADMM_CUDA(cudaEventCreate(&g_prof.ev[i]));
-  g_prof.cap = max_iterations; g_prof.used = 0; g_prof.on = true;
+  if (g_prof.span) IADMM_FAIL(IADMM_ESHAPE, "profile_begin: a profile is already open");
+  const size_t cap = (size_t)max_iterations * 8;       // at most 8 spans per iteration (3 in the solve, 7 in a training iteration)
+  g_prof.span = new ProfSpan[cap];
+  for (size_t i = 0; i < cap; ++i) {
+    IADMM_CUDA(cudaEventCreate(&g_prof.span[i].e0));
+    IADMM_CUDA(cudaEventCreate(&g_prof.span[i].e1));
+  }
+  for (int k = 0; k < kProfKinds; ++k) g_prof.open[k] = -1;
+  g_prof.cap = (int)cap; g_prof.used = 0; g_prof.on = true;
   return IADMM_OK;
 }
 
-int iadmm_profile_end(double* kkt_ms, double* gates_ms, double* tail_ms, int* iterations) {
-  if (!g_prof.ev) IADMM_FAIL(IADMM_ESHAPE, "profile_end: no open profile");
+int iadmm_profile_end_kinds(double* ms_by_kind, int* spans_by_kind, int kinds) {
+  if (!g_prof.span) IADMM_FAIL(IADMM_ESHAPE, "profile_end: no open profile");
+  if (kinds < 0 || kinds > kProfKinds) IADMM_FAIL(IADMM_ESHAPE, "profile_end: kinds=%d (the library records %d)", kinds, kProfKinds);
   g_prof.on = false;
-  double k = 0, g = 0, t = 0;
+  double ms[kProfKinds] = {0};
+  int cnt[kProfKinds] = {0};
   int rc = IADMM_OK;
-  if (g_prof.used > 0) {
-    cudaError_t e = cudaEventSynchronize(g_prof.ev[(size_t)(g_prof.used - 1) * 4 + 3]);
-    if (e != cudaSuccess) { set_error("profile_end: %s", cudaGetErrorString(e)); rc = IADMM_ECUDA; }
-    for (int i = 0; i < g_prof.used && rc == IADMM_OK; ++i) {
-      float a = 0, b = 0, c = 0;
-      cudaEvent_t* ev = g_prof.ev + (size_t)i * 4;
-      cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
-      k += a; g += b; t += c;
+  // every recorded event must have completed: wait for the device once (measurement code, not the hot path)
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { set_error("profile_end: %s", cudaGetErrorString(e)); rc = IADMM_ECUDA; }
+  for (int i = 0; i < g_prof.used && rc == IADMM_OK; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.span[i].e0, g_prof.span[i].e1) == cudaSuccess) {   // fails for a span that was never closed
+      ms[g_prof.span[i].kind] += t;
+      ++cnt[g_prof.span[i].kind];
     }
   }
-  for (size_t i = 0; i < (size_t)g_prof.cap * 4; ++i) cudaEventDestroy(g_prof.ev[i]);
-  delete[] g_prof.ev;
-  g_prof.ev = nullptr;
-  if (kkt_ms) *kkt_ms = k;
-  if (gates_ms) *gates_ms = g;
-  if (tail_ms) *tail_ms = t;
-  if (iterations) *iterations = g_prof.used;
+  (void)cudaGetLastError();
+  for (int i = 0; i < g_prof.cap; ++i) { cudaEventDestroy(g_prof.span[i].e0); cudaEventDestroy(g_prof.span[i].e1); }
+  delete[] g_prof.span;
+  g_prof.span = nullptr;
   g_prof.cap = g_prof.used = 0;
+  for (int k = 0; k < kinds; ++k) {
+    if (ms_by_kind) ms_by_kind[k] = ms[k];
+    if (spans_by_kind) spans_by_kind[k] = cnt[k];
+  }
   return rc;
+}
+
+int iadmm_profile_end(double* kkt_ms, double* gates_ms, double* tail_ms, int* iterations) {
+  double ms[kProfKinds];
+  int cnt[kProfKinds];
+  int rc = iadmm_profile_end_kinds(ms, cnt, kProfKinds);
+  if (rc) return rc;
+  if (kkt_ms) *kkt_ms = ms[kProfKkt];
+  if (gates_ms) *gates_ms = ms[kProfGates];
+  if (tail_ms) *tail_ms = ms[kProfTail];
+  if (iterations) *iterations = cnt[kProfGates];
+  return IADMM_OK;
 }
 
 int iadmm_residuals_workspace_bytes(int B, int n, int m, size_t* bytes) {

@@ -65,6 +65,16 @@ static inline int ensure_dyn_smem(KernelT kernel, int bytes, PerDeviceOnce* once
 // The release library never calls getenv: no environment variable can change what it computes.
 const char* dev_env(const char* name);
 
+// measurement spans (iadmm_profile_begin/_end, include/iadmm.h): no-ops unless a profile is open
+enum { kProfKkt = 0, kProfGates = 1, kProfTail = 2,            // iadmm_solve: KKT passes+combines | gate kernel | tail
+       kProfTrainGates = 3,                                     // training forward: gate kernel (+ state split)
+       kProfTrainGemm = 4,                                      // training backward: the two gate-product adjoint GEMMs (+ operand splits)
+       kProfTrainKkt = 5,                                       // training: KKT passes of forward, residuals and adjoint
+       kProfTrainCell = 6,                                      // training backward: cell adjoint + small parameter adjoints
+       kProfKinds = 7 };
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int    cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline bool   aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -540,6 +540,7 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
   }
   IADMM_CUDA(cudaMemcpyAsync(xv_o, xv, rows * fb, cudaMemcpyDeviceToDevice, st));
   IADMM_CUDA(cudaMemcpyAsync(C_o, C, rows * h * fb, cudaMemcpyDeviceToDevice, st));
+  prof_begin(kProfTrainKkt, st);
   if ((rc = launch_kkt_pass1(W.d, Q, A0, xv, x, y, W.s, st))) return rc;
   if ((rc = launch_kkt_combine1(W.d, p, xv, x, y, z, sk, sigma, W.s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                 nullptr, -1, 0, st))) return rc;
@@ -547,6 +548,7 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
   if ((rc = launch_kkt_pass2(W.d, Q, A0, W.s, st))) return rc;
   if ((rc = launch_kkt_combine2(W.d, sk, sigma, W.s, st))) return rc;
   IADMM_CUDA(cudaMemcpyAsync(g_save, W.s.g, rows * fb, cudaMemcpyDeviceToDevice, st));
+  prof_end(kProfTrainKkt, st);
   // gate contraction of the forward: fp32 CUDA cores, or the tensor-core kernel (same arithmetic as the solve) with
   // the state converted at the boundary; both keep the gate activations for the backward
   int nprod = 0;
@@ -559,10 +561,12 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
     if ((rc = launch_gates_simt(packed_weights, L, xv, W.s.g, H, H_o, C_o, W.head_part, (long)rows, h, st, gates_save))) return rc;
     return launch_tail(W.d, W.head_part, W.tiles, b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
   }
+  prof_begin(kProfTrainGates, st);
   if ((rc = launch_split_state(H, W.h_hi, W.h_lo, (long)rows, h, nprod, st))) return rc;
   if (nprod == 2) IADMM_CUDA(cudaMemsetAsync(W.h_lo_out, 0, tc_lo_bytes((long)rows, h), st));
   if ((rc = launch_gates_tc(packed_weights, L, xv, W.s.g, W.h_hi, W.h_lo, W.h_hi_out, W.h_lo_out, H_o, C_o, W.head_part,
                             (long)rows, h, nprod, st, gates_save))) return rc;
+  prof_end(kProfTrainGates, st);
   return launch_tail(W.d, W.head_part, tc_head_slots(h, false), b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
 }
 
@@ -604,6 +608,7 @@ int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, c
   IADMM_CUDA(cudaMemsetAsync(W.acc, 0, 4 * sizeof(double), st));
 
   // 1. tail
+  prof_begin(kProfTrainCell, st);
   tail_bwd_kernel<<<row_blocks, 256, 0, st>>>(W.d, sk, zl, zu, x, y, z, xv_o, gx_o, gy_o, gz_o, gxv_o, W.Xbar, gx, gy, gz, W.acc);
   IADMM_LAUNCH_CHECK("tail_bwd_kernel");
   // 2. cell non-linearities -> D, gC
@@ -626,8 +631,10 @@ int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, c
     colsum_final_kernel<<<cdiv(h4, 64), 256, 0, st>>>(W.cs_part, W.cs_parts, 3, h4, W.bbar, W.w0bar, W.w1bar);
     IADMM_LAUNCH_CHECK("colsum_final_kernel");
   }
+  prof_end(kProfTrainCell, st);
   // 4. (input adjoints of the cell, xv direct and g: produced by cell_bwd_kernel)
   // 5. the two GEMMs: H_bar = D U^T ; U_bar = H^T D
+  prof_begin(kProfTrainGemm, st);
   if (use_tc_backward() && h % 16 == 0 && rows / 32 < 65535) {
     // tensor cores, fp16 hi/lo split of D * s_D (s_D from max|D|), U * s_U, H * 2^14: fp32-class products
     const float* wscale = reinterpret_cast<const float*>(wbase + L.off_scale);            // [0] = s_U
@@ -649,12 +656,15 @@ int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, c
     if ((rc = launch_sgemm<false, true>(W.D, u32, gH, (long)rows, h, h4, h4, h4, h, st))) return rc;
     if ((rc = launch_sgemm<true, false>(H, W.D, W.u32bar, h, h4, (long)rows, h, h4, h4, st))) return rc;
   }
+  prof_end(kProfTrainGemm, st);
   // 6. KKT adjoint: w_bar = K g_bar (pass 1 with zero rhs), then K^T w_bar (pass 2)
+  prof_begin(kProfTrainKkt, st);
   if ((rc = launch_kkt_pass1(W.d, Q, A0, W.gbar, W.zeros, W.zeros, W.s, st))) return rc;
   if ((rc = launch_kkt_combine1(W.d, W.zeros, W.gbar, W.zeros, W.zeros, W.zeros, sk, sigma, W.s, nullptr, nullptr, nullptr,
                                 nullptr, nullptr, nullptr, nullptr, -1, 0, st))) return rc;
   if ((rc = launch_kkt_pass2(W.d, Q, A0, W.s, st))) return rc;
   if ((rc = launch_kkt_combine2(W.d, sk, sigma, W.s, st))) return rc;
+  prof_end(kProfTrainKkt, st);
   // 7. assemble
   step_bwd_final_kernel<<<row_blocks, 256, 0, st>>>(W.d, sk, sigma, xv, y, w_save, W.gbar, W.s.w, W.s.g, W.Xbar, W.xvbar_cell,
                                                     gxv, gx, gy, gz, W.acc);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "iadmm_residuals_bwd": ([_P] * 11 + [_I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_profile_begin": ([_I], c_int),
     "iadmm_profile_end": ([POINTER(ctypes.c_double)] * 3 + [POINTER(_I)], c_int),
+    "iadmm_profile_end_kinds": ([POINTER(ctypes.c_double), POINTER(_I), _I], c_int),
 }
 
 

@@ -236,6 +236,11 @@ int iadmm_train_window(const void* packed_weights,
  * Process-wide, not thread safe; recording costs four event records per iteration. */
 int iadmm_profile_begin(int max_iterations);
 int iadmm_profile_end(double* kkt_ms, double* gates_ms, double* tail_ms, int* iterations);
+/* Same, every span kind the library records: [0] KKT phase, [1] gate kernel, [2] tail of iadmm_solve; of the training
+ * entry points [3] forward gate kernel, [4] the two gate-product adjoint GEMMs of the backward (with their operand
+ * splits), [5] KKT passes (forward, residuals, adjoint), [6] cell adjoint and small parameter adjoints.
+ * ms_by_kind / spans_by_kind: arrays of `kinds` (<= 7) entries, either may be NULL.  Synchronises the device. */
+int iadmm_profile_end_kinds(double* ms_by_kind, int* spans_by_kind, int kinds);
 
 #ifdef __cplusplus
 }

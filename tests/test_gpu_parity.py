@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import load_golden, golden_params, golden_qp, rel_err, t
+from helpers import load_golden, golden_params, golden_qp, rel_err, t, assert_parity
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -273,15 +273,19 @@ def test_config5_shape_vs_oracle():
     with torch.no_grad():
         r = model.solve(K, mi, me, Qd, pd, Ad, zld, zud, 6e-6, scaling=sc)
     torch.cuda.synchronize()
-    errs = {k: rel_err(getattr(r, k), getattr(ref, k)) for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual")}
+    errs = {k: rel_err(getattr(r, k), getattr(ref, k)) for k in ("x", "z", "xv", "H", "C", "pri", "dual")}
     errs["pri_u"] = rel_err(r.pri_unscaled, ref.pri_unscaled)
     errs["dual_u"] = rel_err(r.dual_unscaled, ref.dual_unscaled)
     print("config5-shape", {k: f"{v:.1e}" for k, v in errs.items()})
-    # y = y + rho (z~ - z) carries ~rho*ulp(z) = 3e-5 of absolute rounding noise on equality rows whatever the
-    # implementation (two fp32 evaluations in different summation orders decorrelate it); early iterates have
-    # small |y|, so its relative error is bounded looser here than after K=100 (golden tests: <= 1e-5)
     for k, v in errs.items():
-        assert v < (5e-4 if k == "y" else 3e-5), (k, v)
+        assert v < 3e-5, (k, v)
+    # y = y + rho (z~ - z) carries ~rho*ulp(z) = 3e-5 of absolute rounding noise on equality rows whatever the
+    # implementation (two fp32 evaluations in different summation orders decorrelate it) and early iterates have small
+    # |y|: the bar is north_star's 1e-4 against the fp32 oracle, or -- if the fp32 oracle itself is further than that from
+    # the same computation in float64 -- being as close to the float64 result as the fp32 oracle is (helpers.assert_parity)
+    ref64 = orc.solve({k: v.double() for k, v in prm.items()}, K, mi, me,
+                      *orc.ruiz_equilibrate(Q.double(), p.double(), A0.double(), zl.double(), zu.double(), 10)[:5], 6e-6, h, form="block")
+    print("config5-shape y", assert_parity("y", r.y, ref.y, ref64.y))
 
 
 def test_cuda_graph_capture_of_solve():

@@ -59,9 +59,14 @@ def test_resident_vs_oracle_k100():
     with torch.no_grad():
         r = model.solve(K, mi, me, *data, sigma=6e-6, traces=True)
     ref = orc.solve(prm, K, mi, me, *(qp[k].cpu() for k in ("Q", "p", "A0", "zl", "zu")), 6e-6, 64, form="block")
+    ref64 = orc.solve({k: v.double() for k, v in prm.items()}, K, mi, me, *(qp[k].cpu().double() for k in ("Q", "p", "A0", "zl", "zu")),
+                      6e-6, 64, form="block")
     for name in ("x", "z"):
         _close(getattr(r, name), getattr(ref, name), 1e-4, name)
-    _close(r.y, ref.y, 1e-3, "y")
+    # y: 1e-4 against the fp32 oracle, or as close to the float64 result as the fp32 oracle itself (un-scaled data, seed 11:
+    # the reference's own fp32 run is a few 1e-4 off its float64 run on y -- helpers.assert_parity states that explicitly)
+    from helpers import assert_parity
+    print("resident K=100 y", assert_parity("y", r.y, ref.y, ref64.y))
     _close(r.pri, ref.pri, 1e-4, "pri")
     _close(r.dual, ref.dual, 1e-4, "dual")
 
