@@ -9,6 +9,8 @@ Workloads (`--workload`; the default `solve` is the headline BASELINE config 2, 
     config5   config 5: n=5000, 2500+2500, hidden_dim=800, K=100, batch 24 per GPU
     hidden200 configs/QP.yaml's default hidden_dim (208 = 200 rounded up to the tensor-core tile granularity): HBM-bound regime
     train     config 3: one truncated-BPTT window (TL=100) forward + backward + NCCL gradient all-reduce + Adam per step
+    sparse    a sparse family of generate_data.py:96-228 (--family Random_QP | Equality_QP | SVM) at n=1000: Q / A0 streamed in the
+              bitmap-slab form (--sparse auto) or densified like main.py:243-296 (--sparse off)
 
 One "step" = the hot path over one batch of synthetic QPs: Ruiz equilibration (10 its) + K=100 unrolled
 I-ADMM-LSTM iterations + the per-iteration primal/dual residual traces, for `batch` instances per GPU of
@@ -53,7 +55,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
-    ap.add_argument("--workload", default="solve", choices=["solve", "config5", "hidden200", "train"])
+    ap.add_argument("--workload", default="solve", choices=["solve", "config5", "hidden200", "train", "sparse"])
+    ap.add_argument("--family", default="Random_QP", choices=["Random_QP", "Equality_QP", "SVM"],
+                    help="sparse workload: problem family of generate_data.py:96-228")
+    ap.add_argument("--sparse", default="auto", choices=["auto", "off"], help="sparse workload: bitmap-slab form of Q / A0, or the densified problem")
     ap.add_argument("--gate-mode", default="tc_f16f8", choices=["tc_3xfp16", "tc_f16f8", "tc_f16f8u", "tc_1xfp16", "simt_fp32"])
     ap.add_argument("--batch", type=int, default=None, help="instances per GPU (default: 256 solve, 24 config5, 2 train)")
     ap.add_argument("--iters", type=int, default=K_ITERS, help="unrolled iterations per solve (metric is quoted at 100)")
@@ -74,7 +79,7 @@ def parse_args():
     if a.workload == "hidden200":
         a.hidden = 208
     if a.batch is None:
-        a.batch = {"solve": 256, "config5": 24, "hidden200": 256, "train": 2}[a.workload]
+        a.batch = {"solve": 256, "config5": 24, "hidden200": 256, "train": 2, "sparse": 128}[a.workload]
     return a
 
 
@@ -262,6 +267,11 @@ def run_reference(args):
 
 def workload_name(args):
     n, h = args.nvar, args.hidden
+    if args.workload == "sparse":
+        return ("sparse family %s of generate_data.py:96-228 at num_var=%d (densified on load like main.py:243-296), hidden_dim=%d, "
+                "--scaling, K=%d; Q / A0 %s (NOT the headline workload)"
+                % (args.family, n, h, args.iters, "streamed in the bitmap-slab sparse form where below 75 %% density" if args.sparse == "auto"
+                   else "streamed dense"))
     if args.workload == "train":
         return ("config3: TBPTT training window, dense QP n=%d, %d ineq + %d eq, hidden_dim=%d, --scaling, truncated_length=%d, "
                 "forward + backward + gradient all-reduce + Adam" % (n, n // 2, n // 2, h, args.tl))
@@ -322,15 +332,35 @@ def run_ours(args):
     # all-gather of a float per rank at set-up; the solve itself has no collective).  Every rank generates some spare instances.
     balance = world > 1 and not args.no_balance
     B_cap = B + max(8, B // 8) if balance else B
-    Q, p, A0, zl, zu = device_qp_batch(B_cap, n, mi, me, 17 + rank, dev)
+    sparse_mode = args.workload == "sparse"
+    if sparse_mode:
+        from iadmm_b200.data import generate_family_batch
+        fam = generate_family_batch(args.family, B_cap, n if args.family != "SVM" else n // 2, num_ineq=n if args.family == "Random_QP" else n // 2,
+                                    num_eq=n, seed=17 + rank, device=dev)
+        Q, p, A0, zl, zu = (fam[k] for k in ("Q", "p", "A0", "zl", "zu"))
+        n, mi, me = fam["num_var"], fam["num_ineq"], fam["num_eq"]
+        m, N = mi + me, n + mi + me
+    else:
+        Q, p, A0, zl, zu = device_qp_batch(B_cap, n, mi, me, 17 + rank, dev)
     full_inputs = (Q, p, A0, zl, zu)
     Q, p, A0, zl, zu = (t[:B] for t in full_inputs)
     shares = [B] * world
     scaling = ia.Scaling(n, m, RUIZ_ITS, dev)
 
+    sp_caps = {}
+
     def hot_step():
         Qs, ps, As, zls, zus = scaling.scale_data(Q, p, A0, zl, zu)
-        return model.solve(K, mi, me, Qs, ps, As, zls, zus, SIGMA, scaling=scaling)
+        if sparse_mode and args.sparse == "auto":
+            # the first call measures the densities (host sync) and decides per matrix; later calls re-pack with the same
+            # capacities without synchronising (packing is part of the step: it has to follow the Ruiz scaling)
+            if not sp_caps:
+                for key, M_ in (("q", Qs), ("a", As)):
+                    sb = ia.SparseBatch.pack(M_, ia.lstm.SPARSE_AUTO_DENSITY)
+                    sp_caps[key] = None if sb is None else (sb.cap, sb.density, sb.bytes_per_instance)
+            pair = tuple(None if sp_caps[key] is None else ia.SparseBatch.pack(M_, cap=sp_caps[key][0]) for key, M_ in (("q", Qs), ("a", As)))
+            return model.solve(K, mi, me, Qs, ps, As, zls, zus, SIGMA, scaling=scaling, sparse=pair, streaming=True)
+        return model.solve(K, mi, me, Qs, ps, As, zls, zus, SIGMA, scaling=scaling, streaming=sparse_mode)
 
     def barrier():
         if world > 1:
@@ -440,6 +470,14 @@ def run_ours(args):
         gate_flops = 8.0 * rows * h * h                      # logical fp32 flops of H@U (no credit for the 3-way split)
         gate_tflops = gate_flops / (gate_avg_ms * 1e-3) / 1e12 if gate_avg_ms > 0 else 0.0
         kkt_bytes = 8.0 * B * (n * n + m * n)                # Q and A0 streamed once per pass, two passes
+        kkt_dense_bytes = kkt_bytes
+        sparse_info = None
+        if sparse_mode and args.sparse == "auto":
+            per_pass = (sp_caps["q"][2] if sp_caps.get("q") else 4.0 * n * n) + (sp_caps["a"][2] if sp_caps.get("a") else 4.0 * m * n)
+            kkt_bytes = 2.0 * B * per_pass
+            sparse_info = {"Q": None if not sp_caps.get("q") else {"density": sp_caps["q"][1], "bytes_per_pass": sp_caps["q"][2]},
+                           "A0": None if not sp_caps.get("a") else {"density": sp_caps["a"][1], "bytes_per_pass": sp_caps["a"][2]},
+                           "dense_bytes_per_pass": 4.0 * (n * n + m * n), "stored_bytes_per_pass": per_pass}
         kkt_gbs = kkt_bytes / (kkt_avg_ms * 1e-3) / 1e9 if kkt_avg_ms > 0 else 0.0
         iter_bytes = kkt_bytes + 16.0 * rows * h + 64.0 * rows       # SURVEY section 8(d) bytes per iteration
         step_s = ms / steps * 1e-3
@@ -479,7 +517,8 @@ def run_ours(args):
             "roofline_kkt": {"kernel": "kkt_pass1+combine1+pass2+combine2", "bound": "hbm", "achieved": kkt_gbs,
                              "peak": hbm_gbs, "unit": "GB/s", "frac": kkt_gbs / hbm_gbs,
                              "traffic": ncu_traffic("kkt", B, args.gate_mode, n == N_VAR),
-                             "bytes_per_iteration": kkt_bytes, "ms_per_iteration": kkt_avg_ms,
+                             "bytes_per_iteration": kkt_bytes, "dense_bytes_per_iteration": kkt_dense_bytes, "sparse": sparse_info,
+                             "ms_per_iteration": kkt_avg_ms,
                              "share_of_step": kkt_ms.value / ms, "peak_kind": "%s hbm_gbs" % peak_kind},
             "hbm_roofline_frac_whole_path": hbm_frac_whole,
             "phase_ms_per_iteration": {"kkt": kkt_avg_ms, "gates": gate_avg_ms, "tail": tail_ms.value / nit_v},
@@ -488,14 +527,14 @@ def run_ours(args):
         if e2e:
             line["e2e"] = {"value": sum(shares) * steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms / steps}
-        if n_gpus == 1 and not args.no_gpu_reference:
+        if n_gpus == 1 and not args.no_gpu_reference and not sparse_mode:
             # stock PyTorch on the same B200: bounded sample, after our timed regions
             try:
                 line["gpu_reference"] = gpu_reference_solves_per_s(1, 1, min(args.gpu_ref_batch, 32 if n <= 1000 else 2), K, dev, n, h) or \
                     {"unavailable": "baseline/_ref is not in this snapshot"}
             except Exception as exc:                                              # never lose the bench line to the side arm
                 line["gpu_reference"] = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
-        if n_gpus == 1 and not args.no_cpu_baseline:
+        if n_gpus == 1 and not args.no_cpu_baseline and not sparse_mode:
             cb = 4 if n <= 1000 else 1
             val, cms, cores, sample, kind = cpu_reference_solves_per_s(3 if n <= 1000 else 1, 1 if n <= 1000 else 0, cb, K, n, h)
             # ~12 instances, 10-20 s of CPU work; batches of 4 are the CPU path's best operating point at n=1000

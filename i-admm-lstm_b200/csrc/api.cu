@@ -198,18 +198,19 @@ int iadmm_solve_workspace_bytes(int B, int n, int m, int h, int mode, size_t* by
   return IADMM_OK;
 }
 
-int iadmm_solve(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
+static int solve_impl(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
                 const float* zu, const float* sd, const float* se, const float* sc, float* x, float* y, float* z,
                 float* xv, float* H, float* C, float* pri_trace, float* dual_trace, float* pri_trace_u,
                 float* dual_trace_u, float* metric_trace, int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
-                float sigma, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+                float sigma, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream, const KktSparse* sp) {
   const int m = num_ineq + num_eq;
+  const bool spq = sp && sp->q.vals, spa = sp && sp->a.vals;
   if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || K < 0 || t0 < 0)
     IADMM_FAIL(IADMM_ESHAPE, "solve: B=%d n=%d ineq=%d eq=%d h=%d t0=%d K=%d", B, n, num_ineq, num_eq, h, t0, K);
   if (t0 + K > length) IADMM_FAIL(IADMM_ESHAPE, "solve: iterations %d..%d exceed the schedule length %d (lstm.py:60)", t0, t0 + K - 1, length);
   if (B > 65535) IADMM_FAIL(IADMM_ESHAPE, "solve: batch %d > 65535 per call; shard the batch", B);
-  if (!packed_weights || !Q || !p || !x || !xv || !H || !C || !workspace) IADMM_FAIL(IADMM_EALIGN, "solve: NULL pointer");
-  if (m > 0 && (!A0 || !zl || !zu || !y || !z)) IADMM_FAIL(IADMM_EALIGN, "solve: NULL constraint pointer");
+  if (!packed_weights || (!Q && !spq) || !p || !x || !xv || !H || !C || !workspace) IADMM_FAIL(IADMM_EALIGN, "solve: NULL pointer");
+  if (m > 0 && ((!A0 && !spa) || !zl || !zu || !y || !z)) IADMM_FAIL(IADMM_EALIGN, "solve: NULL constraint pointer");
   if ((pri_trace_u || dual_trace_u) && (!sd || !sc || (m > 0 && !se)))
     IADMM_FAIL(IADMM_EALIGN, "solve: un-scaled traces need the Ruiz diagonals d, e, c");
   if (!aligned16(H) || !aligned16(C) || !aligned16(workspace) || !aligned16(packed_weights))
@@ -233,7 +234,7 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   const bool want_trace = pri_trace || dual_trace || pri_trace_u || dual_trace_u || metric_trace;
 
   // small instances: one persistent CTA per instance keeps the whole iteration on chip (resident.cu)
-  if (tc && resident_eligible(n, m, h, nprod, flags))
+  if (tc && !sp && resident_eligible(n, m, h, nprod, flags))
     return launch_solve_resident(packed_weights, L, Q, p, A0, zl, zu, sd, se, sc, x, y, z, xv, H, C, pri_trace, dual_trace,
                                  pri_trace_u, dual_trace_u, metric_trace, B, n, m, num_ineq, t0, K, sigma, nprod, flags, st);
 
@@ -266,11 +267,11 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   for (int k = 0; k < K; ++k) {
     const Sched* sk = sched + (t0 + k);
     prof_begin(kProfKkt, st);
-    if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
+    if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st, sp))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, sk, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
                                   dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st, metric_trace, zu,
                                   k > 0 ? sk - 1 : nullptr))) return rc;
-    if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st))) return rc;
+    if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st, sp))) return rc;
     if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st))) return rc;
     prof_end(kProfKkt, st);
     prof_begin(kProfGates, st);
@@ -292,11 +293,40 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
   if (!tc && cur == 1)
     IADMM_CUDA(cudaMemcpyAsync(H, ws.h_alt, (size_t)rows * h * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (want_trace && !(flags & IADMM_F_SKIP_FINAL_RESID)) {
-    if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st))) return rc;
+    if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st, sp))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, nullptr, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
                                   dual_trace_u, sd, se, sc, K - 1, 1, st, metric_trace, zu, sched + (t0 + K - 1)))) return rc;
   }
   return IADMM_OK;
+}
+
+int iadmm_solve(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
+                const float* zu, const float* sd, const float* se, const float* sc, float* x, float* y, float* z,
+                float* xv, float* H, float* C, float* pri_trace, float* dual_trace, float* pri_trace_u,
+                float* dual_trace_u, float* metric_trace, int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
+                float sigma, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+  return solve_impl(packed_weights, Q, p, A0, zl, zu, sd, se, sc, x, y, z, xv, H, C, pri_trace, dual_trace, pri_trace_u, dual_trace_u,
+                    metric_trace, B, n, num_ineq, num_eq, h, length, t0, K, sigma, mode, flags, workspace, workspace_bytes, stream,
+                    nullptr);
+}
+
+int iadmm_solve_sparse(const void* packed_weights, const float* Q, const void* Q_sparse, size_t q_cap, const float* p,
+                       const float* A0, const void* A0_sparse, size_t a_cap, const float* zl, const float* zu,
+                       const float* sd, const float* se, const float* sc, float* x, float* y, float* z,
+                       float* xv, float* H, float* C, float* pri_trace, float* dual_trace, float* pri_trace_u,
+                       float* dual_trace_u, float* metric_trace, int B, int n, int num_ineq, int num_eq, int h, int length, int t0,
+                       int K, float sigma, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0) IADMM_FAIL(IADMM_ESHAPE, "solve_sparse: B=%d n=%d ineq=%d eq=%d", B, n, num_ineq, num_eq);
+  if (!Q_sparse && !A0_sparse) IADMM_FAIL(IADMM_EALIGN, "solve_sparse: neither matrix is given in sparse form (use iadmm_solve)");
+  if ((Q_sparse && !aligned16(Q_sparse)) || (A0_sparse && !aligned16(A0_sparse)))
+    IADMM_FAIL(IADMM_EALIGN, "solve_sparse: sparse buffers must be 16-byte aligned");
+  KktSparse sp;
+  memset(&sp, 0, sizeof(sp));
+  if (Q_sparse) sparse_view(Q_sparse, B, n, n, q_cap, &sp.q);
+  if (A0_sparse && num_ineq + num_eq > 0) sparse_view(A0_sparse, B, num_ineq + num_eq, n, a_cap, &sp.a);
+  return solve_impl(packed_weights, Q, p, A0, zl, zu, sd, se, sc, x, y, z, xv, H, C, pri_trace, dual_trace, pri_trace_u, dual_trace_u,
+                    metric_trace, B, n, num_ineq, num_eq, h, length, t0, K, sigma, mode, flags | IADMM_F_STREAMING, workspace,
+                    workspace_bytes, stream, &sp);
 }
 
 int iadmm_profile_begin(int max_iterations) {

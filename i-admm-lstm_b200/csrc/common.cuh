@@ -226,9 +226,21 @@ constexpr int kMetricRows = 6;   // rows of one metric_trace block: objective, i
 size_t kkt_scratch_floats(const KktDims& d);
 void   kkt_scratch_carve(const KktDims& d, float* base, KktScratch* s);
 
+// A matrix batch in "bitmap slab" sparse form (sparse.cu; layout documented at iadmm_sparse_pack in include/iadmm.h)
+struct SpMat {
+  const uint4*    mask;        // [B][rows][S] 128-bit occupancy masks
+  const uint32_t* off;         // [B][rows][S] offset of the slab's first value inside the instance's values
+  const float*    vals;        // [B][cap]     non-zero values, row-major per instance; NULL = matrix not given in sparse form
+  int    S;                    // slabs per row = ceil(n / 128)
+  size_t mask_stride;          // rows * S   (entries per instance of mask and off)
+  size_t vals_stride;          // cap
+};
+struct KktSparse { SpMat q, a; };
+int sparse_view(const void* packed, int B, int rows, int n, size_t cap, SpMat* out);   // carve a packed buffer
+
 // pass 1: qxt,qx,axt,ax and column partials of A0^T v, A0^T y
 int launch_kkt_pass1(const KktDims& d, const float* Q, const float* A0, const float* xv, const float* x,
-                     const float* y, const KktScratch& s, cudaStream_t st);
+                     const float* y, const KktScratch& s, cudaStream_t st, const KktSparse* sp = nullptr);
 // combine 1: w = K xv - rhs ; residual norms of (x,y,z) into trace row `trace_row` (skipped when < 0)
 int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const float* x, const float* y,
                         const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
@@ -237,7 +249,8 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
                         cudaStream_t st, float* metric_trace = nullptr, const float* zu = nullptr,
                         const Sched* sched_prev = nullptr);
 // pass 2: column partials of Q^T w1, A0^T w2 and rows A0 w1
-int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st);
+int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st,
+                     const KktSparse* sp = nullptr);
 // combine 2: g = K^T w
 int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, const KktScratch& s, cudaStream_t st);
 

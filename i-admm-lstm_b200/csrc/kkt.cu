@@ -18,6 +18,8 @@
 // are bit-reproducible run to run.  HBM-bound by design: 8 independent 128-bit loads in flight per lane.
 #include "common.cuh"
 
+#include <string.h>
+
 namespace iadmm {
 
 constexpr int kKktThreads = 256;
@@ -111,8 +113,37 @@ __device__ __forceinline__ void store_cols4(float* __restrict__ v, int col, int 
   if (col + 3 < n) v[col + 3] = a.w;
 }
 
+// Sparse operand ("bitmap slabs", sparse.cu): per row and 128-column slab a 128-bit occupancy mask (bit b of word w <-> column
+// 128*slab + 32*w + b), the offset of the slab's first stored value, and the non-zero values of the instance in row-major
+// order.  A lane of the streaming pass owns 4 consecutive columns = one nibble of the mask, so the dense kernel's work
+// decomposition, accumulation order and therefore every rounding carry over unchanged: the sparse loader returns exactly the
+// values the dense loader would (zeros where the mask is clear) while reading 4*nnz + 20*rows*ceil(n/128) bytes.
+template <bool VEC>
+__device__ __forceinline__ float4 load_cols4_sparse(const SpMat& sp, size_t inst, int row, int slab, int lane) {
+  const size_t rs = (size_t)row * sp.S + slab;
+  const uint4 mk = __ldg(sp.mask + inst * sp.mask_stride + rs);
+  const uint32_t base = __ldg(sp.off + inst * sp.mask_stride + rs);
+  const int w = lane >> 3, sh = (lane & 7) * 4;
+  const uint32_t mine = (w == 0) ? mk.x : (w == 1) ? mk.y : (w == 2) ? mk.z : mk.w;
+  const uint32_t before = ((w > 0) ? __popc(mk.x) : 0) + ((w > 1) ? __popc(mk.y) : 0) + ((w > 2) ? __popc(mk.z) : 0) +
+                          __popc(mine & ((1u << sh) - 1u));
+  const uint32_t nib = (mine >> sh) & 15u;
+  const float* p = sp.vals + inst * sp.vals_stride + base + before;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nib & 1u) r.x = __ldg(p);
+  p += (nib & 1u);
+  if (nib & 2u) r.y = __ldg(p);
+  p += ((nib >> 1) & 1u);
+  if (nib & 4u) r.z = __ldg(p);
+  p += ((nib >> 2) & 1u);
+  if (nib & 8u) r.w = __ldg(p);
+  return r;
+}
+
 struct TileArgs {
   const float* mat;        // first element of the instance's matrix [rows_total, n]
+  SpMat sp;                // SP: the matrix in bitmap-slab form instead
+  size_t inst;             // SP: instance index
   int rows_total, n, r0, R;
   const float* rrhs[2];    // NR vectors of length n      (row products  M r)
   float*       rout[2];    // NR outputs of length rows_total
@@ -121,7 +152,7 @@ struct TileArgs {
 };
 
 // smem: rowscal[2][R] | rowacc[R*2] | rowpart[warps][R*2]
-template <int NR, int NC, bool VEC>
+template <int NR, int NC, bool VEC, bool SP = false>
 __device__ __forceinline__ void tile_pass(const TileArgs& a, float* smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = a.R, n = a.n;
@@ -154,8 +185,10 @@ __device__ __forceinline__ void tile_pass(const TileArgs& a, float* smem) {
 #pragma unroll
       for (int u = 0; u < kRowUnroll; ++u) {
         const int row = a.r0 + rg + u;
-        v[u] = (active && row < a.rows_total) ? load_cols4<VEC>(a.mat + (size_t)row * n, col, n)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (SP) v[u] = (active && row < a.rows_total) ? load_cols4_sparse<VEC>(a.sp, a.inst, row, cc * kKktWarps + warp, lane)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        else    v[u] = (active && row < a.rows_total) ? load_cols4<VEC>(a.mat + (size_t)row * n, col, n)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (NC > 0) {
 #pragma unroll
@@ -222,13 +255,14 @@ static size_t tile_smem_bytes(int R) { return (size_t)(4 * R + kKktWarps * R * 2
 struct Pass1Args {
   KktDims d;
   const float *Q, *A0;
+  SpMat spq, spa;                    // bitmap-slab forms (used by the SPQ / SPA instantiations)
   const float *xt; long xt_stride;   // x~  (first n entries of xv)
   const float *v;  long v_stride;    // v   (last m entries of xv)
   const float *x, *y;                // previous iterate [B,n], [B,m]
   KktScratch s;
 };
 
-template <bool VEC>
+template <bool VEC, bool SPQ = false, bool SPA = false>
 __global__ void __launch_bounds__(kKktThreads) kkt_pass1_kernel(const Pass1Args P) {
   extern __shared__ float smem[];
   const KktDims& d = P.d;
@@ -239,24 +273,25 @@ __global__ void __launch_bounds__(kKktThreads) kkt_pass1_kernel(const Pass1Args 
   a.rrhs[0] = P.xt + (size_t)b * P.xt_stride;
   a.rrhs[1] = P.x + b * n;
   if (chunk < d.chunks_q) {
-    a.mat = P.Q + b * n * n; a.rows_total = d.n; a.r0 = chunk * a.R;
+    a.mat = SPQ ? nullptr : P.Q + b * n * n; a.sp = P.spq; a.inst = b; a.rows_total = d.n; a.r0 = chunk * a.R;
     a.rout[0] = P.s.qxt + b * n; a.rout[1] = P.s.qx + b * n;
     a.crhs[0] = a.crhs[1] = nullptr; a.cpart[0] = a.cpart[1] = nullptr;
-    tile_pass<2, 0, VEC>(a, smem);
+    tile_pass<2, 0, VEC, SPQ>(a, smem);
   } else {
     const int ca = chunk - d.chunks_q;
-    a.mat = P.A0 + b * m * n; a.rows_total = d.m; a.r0 = ca * a.R;
+    a.mat = SPA ? nullptr : P.A0 + b * m * n; a.sp = P.spa; a.inst = b; a.rows_total = d.m; a.r0 = ca * a.R;
     a.rout[0] = P.s.axt + b * m; a.rout[1] = P.s.ax + b * m;
     a.crhs[0] = P.v + (size_t)b * P.v_stride; a.crhs[1] = P.y + b * m;
     float* part = P.s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
     a.cpart[0] = part; a.cpart[1] = part + n;
-    tile_pass<2, 2, VEC>(a, smem);
+    tile_pass<2, 2, VEC, SPA>(a, smem);
   }
 }
 
-template <bool VEC>
+template <bool VEC, bool SPQ = false, bool SPA = false>
 __global__ void __launch_bounds__(kKktThreads) kkt_pass2_kernel(const KktDims d, const float* __restrict__ Q,
-                                                                const float* __restrict__ A0, const KktScratch s) {
+                                                                const float* __restrict__ A0, const KktScratch s,
+                                                                const SpMat spq, const SpMat spa) {
   extern __shared__ float smem[];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const size_t n = d.n, m = d.m, N = n + m;
@@ -266,59 +301,87 @@ __global__ void __launch_bounds__(kKktThreads) kkt_pass2_kernel(const KktDims d,
   const float* w2 = w1 + n;
   a.rrhs[1] = nullptr; a.rout[1] = nullptr; a.crhs[1] = nullptr; a.cpart[1] = nullptr;
   if (chunk < d.chunks_q) {
-    a.mat = Q + b * n * n; a.rows_total = d.n; a.r0 = chunk * a.R;
+    a.mat = SPQ ? nullptr : Q + b * n * n; a.sp = spq; a.inst = b; a.rows_total = d.n; a.r0 = chunk * a.R;
     a.rrhs[0] = nullptr; a.rout[0] = nullptr;
     a.crhs[0] = w1; a.cpart[0] = s.part_q + ((size_t)b * d.chunks_q + chunk) * n;
-    tile_pass<0, 1, VEC>(a, smem);
+    tile_pass<0, 1, VEC, SPQ>(a, smem);
   } else {
     const int ca = chunk - d.chunks_q;
-    a.mat = A0 + b * m * n; a.rows_total = d.m; a.r0 = ca * a.R;
+    a.mat = SPA ? nullptr : A0 + b * m * n; a.sp = spa; a.inst = b; a.rows_total = d.m; a.r0 = ca * a.R;
     a.rrhs[0] = w1; a.rout[0] = s.aw1 + b * m;
     a.crhs[0] = w2; a.cpart[0] = s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
-    tile_pass<1, 1, VEC>(a, smem);
+    tile_pass<1, 1, VEC, SPA>(a, smem);
   }
 }
 
-static bool can_vectorise(const KktDims& d, const void* Q, const void* A0) {
-  return (d.n % 4 == 0) && aligned16(Q) && aligned16(A0);
+static bool can_vectorise(const KktDims& d, const void* Q, const void* A0, const KktSparse* sp) {
+  // the 128-bit path needs 16-byte aligned matrix rows (n % 4 == 0); a matrix given in sparse form has no such constraint
+  return (d.n % 4 == 0) && ((sp && sp->q.vals) || aligned16(Q)) && ((sp && sp->a.vals) || aligned16(A0));
+}
+
+template <bool VEC>
+static void launch_pass1_variant(const Pass1Args& P, bool spq, bool spa, dim3 grid, size_t smem, cudaStream_t st) {
+  if (spq && spa)  kkt_pass1_kernel<VEC, true, true><<<grid, kKktThreads, smem, st>>>(P);
+  else if (spq)    kkt_pass1_kernel<VEC, true, false><<<grid, kKktThreads, smem, st>>>(P);
+  else if (spa)    kkt_pass1_kernel<VEC, false, true><<<grid, kKktThreads, smem, st>>>(P);
+  else             kkt_pass1_kernel<VEC, false, false><<<grid, kKktThreads, smem, st>>>(P);
+}
+
+static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t st) {
+  const KktDims& d = P.d;
+  const bool spq = sp && sp->q.vals, spa = sp && sp->a.vals && d.m > 0;
+  if (spq) P.spq = sp->q;
+  if (spa) P.spa = sp->a;
+  const dim3 grid(d.chunks_q + d.chunks_a, d.B);
+  const size_t smem = tile_smem_bytes(d.rows_per_chunk);
+  if (can_vectorise(d, P.Q, P.A0, sp)) launch_pass1_variant<true>(P, spq, spa, grid, smem, st);
+  else                                 launch_pass1_variant<false>(P, spq, spa, grid, smem, st);
+  IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
+  return IADMM_OK;
 }
 
 int launch_kkt_pass1(const KktDims& d, const float* Q, const float* A0, const float* xv, const float* x,
-                     const float* y, const KktScratch& s, cudaStream_t st) {
+                     const float* y, const KktScratch& s, cudaStream_t st, const KktSparse* sp) {
   Pass1Args P;
+  memset(&P.spq, 0, sizeof(SpMat)); memset(&P.spa, 0, sizeof(SpMat));
   P.d = d; P.Q = Q; P.A0 = A0;
   P.xt = xv; P.xt_stride = d.n + d.m;
   P.v = xv + d.n; P.v_stride = d.n + d.m;
   P.x = x; P.y = y; P.s = s;
-  const dim3 grid(d.chunks_q + d.chunks_a, d.B);
-  const size_t smem = tile_smem_bytes(d.rows_per_chunk);
-  if (can_vectorise(d, Q, A0)) kkt_pass1_kernel<true><<<grid, kKktThreads, smem, st>>>(P);
-  else                         kkt_pass1_kernel<false><<<grid, kKktThreads, smem, st>>>(P);
-  IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
-  return IADMM_OK;
+  return launch_pass1_common(P, sp, st);
 }
 
 // primal_dual_loss on its own (utils.py:68-71): x plays x~ and y plays v, the second product pair is unused
 int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, const float* x, const float* y,
                            const KktScratch& s, cudaStream_t st) {
   Pass1Args P;
+  memset(&P.spq, 0, sizeof(SpMat)); memset(&P.spa, 0, sizeof(SpMat));
   P.d = d; P.Q = Q; P.A0 = A0;
   P.xt = x; P.xt_stride = d.n;
   P.v = y; P.v_stride = d.m;
   P.x = x; P.y = y; P.s = s;
-  const dim3 grid(d.chunks_q + d.chunks_a, d.B);
-  const size_t smem = tile_smem_bytes(d.rows_per_chunk);
-  if (can_vectorise(d, Q, A0)) kkt_pass1_kernel<true><<<grid, kKktThreads, smem, st>>>(P);
-  else                         kkt_pass1_kernel<false><<<grid, kKktThreads, smem, st>>>(P);
-  IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
-  return IADMM_OK;
+  return launch_pass1_common(P, nullptr, st);
 }
 
-int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st) {
+template <bool VEC>
+static void launch_pass2_variant(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, const SpMat& q, const SpMat& a,
+                                 bool spq, bool spa, dim3 grid, size_t smem, cudaStream_t st) {
+  if (spq && spa)  kkt_pass2_kernel<VEC, true, true><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
+  else if (spq)    kkt_pass2_kernel<VEC, true, false><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
+  else if (spa)    kkt_pass2_kernel<VEC, false, true><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
+  else             kkt_pass2_kernel<VEC, false, false><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
+}
+
+int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st, const KktSparse* sp) {
   const dim3 grid(d.chunks_q + d.chunks_a, d.B);
   const size_t smem = tile_smem_bytes(d.rows_per_chunk);
-  if (can_vectorise(d, Q, A0)) kkt_pass2_kernel<true><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s);
-  else                         kkt_pass2_kernel<false><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s);
+  const bool spq = sp && sp->q.vals, spa = sp && sp->a.vals && d.m > 0;
+  SpMat q, a;
+  memset(&q, 0, sizeof(q)); memset(&a, 0, sizeof(a));
+  if (spq) q = sp->q;
+  if (spa) a = sp->a;
+  if (can_vectorise(d, Q, A0, sp)) launch_pass2_variant<true>(d, Q, A0, s, q, a, spq, spa, grid, smem, st);
+  else                             launch_pass2_variant<false>(d, Q, A0, s, q, a, spq, spa, grid, smem, st);
   IADMM_LAUNCH_CHECK("kkt_pass2_kernel");
   return IADMM_OK;
 }

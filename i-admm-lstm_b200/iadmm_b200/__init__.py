@@ -8,11 +8,11 @@ Public surface = the reference's own call boundary for this path:
 All compute goes through the C ABI of libiadmm_b200.so (include/iadmm.h); there is no fallback.
 """
 from ._lib import IadmmError, LIB_PATH, GATE_MODES, lib
-from .lstm import LSTM, SolveResult
+from .lstm import LSTM, SolveResult, SparseBatch
 from .scaling import Scaling
 from .lu import LU
 from . import data
 from .utils import primal_dual_loss, obj_fn, ineq_dist, eq_dist, lb_dist, ub_dist
 
-__all__ = ["LSTM", "SolveResult", "Scaling", "LU", "primal_dual_loss", "obj_fn", "ineq_dist", "eq_dist",
+__all__ = ["LSTM", "SolveResult", "SparseBatch", "Scaling", "LU", "primal_dual_loss", "obj_fn", "ineq_dist", "eq_dist",
            "lb_dist", "ub_dist", "data", "IadmmError", "LIB_PATH", "GATE_MODES", "lib"]

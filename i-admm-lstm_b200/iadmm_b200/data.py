@@ -107,3 +107,61 @@ def generate_qp_batch(batch, n, num_ineq, num_eq, seed, device, as_stored=False)
     zu = torch.cat((c, b), dim=1).contiguous()
     Q = Q0 if as_stored else 2 * Q0
     return dict(Q=Q, p=p, A0=A0, zl=zl, zu=zu, G=G, c=c, A=A, b=b)
+
+
+def generate_family_batch(family, batch, num_var, num_ineq=0, num_eq=0, seed=0, device="cuda", density=None):
+    """The sparse problem families of generate_data.py on `device`, as main.py sees them after loading (densified, Q doubled):
+      Random_QP   (:96-134)  M = N(0,1) masked at 60 %, Q0 = (M M^T + 0.01 I)/2, A0 = N(0,1) masked at 60 % [num_ineq, n],
+                             zl = -U[0,1), zu = U[0,1)
+      Equality_QP (:136-175) same Q at 50 %, A0 = A = N(0,1) masked at 50 % [num_eq, n], zl = zu = b ~ N(0,1)
+      SVM         (:177-228) n = num_var + num_ineq variables, Q0 = diag(I_num_var, 0), p = [0; lambda 1],
+                             A0 = [[diag(b^) A^ , -I], [I_n]] with A^ masked at 50 %, zl = [-inf; -inf; 0], zu = [-1; +inf]
+    `density` overrides the family's mask probability (e.g. 0.01 for a QPLIB-like truly sparse instance).  The OSQP "solved"
+    filter of the reference is skipped.  Returns Q, p, A0, zl, zu (+ the counts main.py derives)."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    B = batch
+
+    def randn(*s):
+        return torch.randn(s, device=dev, generator=g)
+
+    def rand(*s):
+        return torch.rand(s, device=dev, generator=g)
+
+    if family in ("Random_QP", "Equality_QP"):
+        n = num_var
+        sp_ = density if density is not None else (0.6 if family == "Random_QP" else 0.5)
+        M = randn(B, n, n) * (rand(B, n, n) < sp_)
+        Q0 = (M @ M.mT + 0.01 * torch.eye(n, device=dev)) * 0.5
+        p = randn(B, n, 1)
+        if family == "Random_QP":
+            A0 = randn(B, num_ineq, n) * (rand(B, num_ineq, n) < sp_)
+            zl, zu = -rand(B, num_ineq, 1), rand(B, num_ineq, 1)
+            mi, me = num_ineq, 0
+        else:
+            A0 = randn(B, num_eq, n) * (rand(B, num_eq, n) < sp_)
+            zl = randn(B, num_eq, 1)
+            zu = zl.clone()
+            mi, me = 0, num_eq
+        return dict(Q=(2 * Q0).contiguous(), p=p, A0=A0.contiguous(), zl=zl, zu=zu, num_var=n, num_ineq=mi, num_eq=me)
+    if family == "SVM":
+        nv, mi = num_var, num_ineq
+        n = nv + mi
+        sp_ = density if density is not None else 0.5
+        Q0 = torch.zeros((B, n, n), device=dev)
+        Q0[:, :nv, :nv] = torch.eye(nv, device=dev)
+        lamb = 1.0 + randn(B, 1, 1)                                  # np.random.normal(1): mean 1, std 1
+        p = torch.cat((torch.zeros((B, nv, 1), device=dev), lamb * torch.ones((B, mi, 1), device=dev)), 1)
+        half = mi // 2
+        b_hat = torch.cat((torch.ones(half, device=dev), -torch.ones(mi - half, device=dev)))
+        A_hat = torch.cat((1 / nv + randn(B, half, nv) / nv, -1 / nv + randn(B, mi - half, nv) / nv), 1)
+        A_hat = A_hat * (rand(B, mi, nv) < sp_)
+        G = torch.cat((b_hat.view(1, mi, 1) * A_hat, -torch.eye(mi, device=dev).expand(B, mi, mi)), 2)
+        A0 = torch.cat((G, torch.eye(n, device=dev).expand(B, n, n)), 1).contiguous()
+        inf = float("inf")
+        zl = torch.cat((torch.full((B, mi, 1), -inf, device=dev), torch.full((B, nv, 1), -inf, device=dev),
+                        torch.zeros((B, mi, 1), device=dev)), 1)
+        zu = torch.cat((-torch.ones((B, mi, 1), device=dev), torch.full((B, n, 1), inf, device=dev)), 1)
+        # main.py treats every row of A0 as an inequality row for this family (num_eq = 0)
+        return dict(Q=(2 * Q0).contiguous(), p=p, A0=A0, zl=zl, zu=zu, num_var=n, num_ineq=mi + n, num_eq=0)
+    raise ValueError(f"unknown family {family!r}")

@@ -20,6 +20,47 @@ PARAM_ORDER = ("W_i", "U_i", "b_i", "W_f", "U_f", "b_f", "W_o", "U_o", "b_o",
                "W_u", "U_u", "b_u", "W_h", "b_h", "rho", "alpha")
 
 
+SPARSE_AUTO_DENSITY = 0.75     # "auto": a matrix goes to the bitmap-slab form when its densest instance is below this
+
+
+class SparseBatch:
+    """A [B, rows, n] matrix batch in the library's bitmap-slab form (include/iadmm.h, iadmm_sparse_pack)."""
+
+    def __init__(self, buf, cap, shape, nnz):
+        self.buf, self.cap, self.shape, self.nnz = buf, cap, tuple(shape), nnz
+
+    @property
+    def density(self):
+        return float(self.nnz.max()) / max(1, self.shape[1] * self.shape[2])
+
+    @property
+    def bytes_per_instance(self):
+        """What one streaming pass reads per instance (worst instance): 4 nnz + 20 bytes per row and 128-column slab."""
+        return 4 * int(self.nnz.max()) + 20 * self.shape[1] * ((self.shape[2] + 127) // 128)
+
+    @staticmethod
+    def pack(M, max_density=None, cap=None):
+        """Pack a dense CUDA batch.  Without `cap` the value capacity is the densest instance's non-zero count (one host
+        sync) and None is returned when `max_density` is given and exceeded.  With `cap` (e.g. the capacity of a previous
+        batch of the same family, or rows*n) nothing synchronises; check `nnz.max() <= cap` afterwards."""
+        _lib.require_cuda(M)
+        M = _lib.f32(M)
+        B, rows, n = M.shape
+        if rows == 0:
+            return None
+        if cap is None:
+            cnt = int(torch.count_nonzero(M.reshape(B, -1), dim=1).max())
+            if max_density is not None and cnt > max_density * rows * n:
+                return None
+            cap = max(4, (cnt + 3) // 4 * 4)
+        nbytes = c_size_t()
+        _lib.check(_lib.lib().iadmm_sparse_bytes(B, rows, n, cap, byref(nbytes)))
+        buf = torch.empty(nbytes.value, dtype=torch.uint8, device=M.device)
+        nnz = torch.empty((B,), dtype=torch.int32, device=M.device)
+        torch.ops.iadmm.sparse_pack(M, buf, nnz, cap)
+        return SparseBatch(buf, cap, M.shape, nnz)
+
+
 @dataclass
 class SolveResult:
     x: torch.Tensor            # [B,n,1]
@@ -130,12 +171,16 @@ class LSTM(nn.Module):
 
     # -- K fused iterations -------------------------------------------------------------------
     def solve(self, K, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state=None, t0=0, scaling=None,
-              traces=True, inplace=False, streaming=False):
+              traces=True, inplace=False, streaming=False, sparse=None):
         """K iterations of `forward` (t = t0..t0+K-1) plus the residuals of utils.py:68-71 after each,
         in one library call.  Small instances (n+m <= 256, hidden_dim 64, tensor-core modes) run on the
         on-chip-resident kernel (one persistent CTA per instance); `streaming=True` forces the HBM-streaming path.  `state=(x,y,z,xv,H,C)` or None for the zero state of main.py:837-843.
         `scaling` is the `Scaling` object that produced (Q,p,A0,zl,zu): with it the residuals of the
-        un-scaled iterates on the original data (main.py:922-955) are traced too."""
+        un-scaled iterates on the original data (main.py:922-955) are traced too.
+        `sparse`: None = stream Q and A0 dense (the reference densifies every family, main.py:243-296); "auto" = re-lay each of
+        Q, A0 in the bitmap-slab form when its density is below SPARSE_AUTO_DENSITY (Random_QP / Equality_QP / SVM / QPLIB
+        families: the KKT passes then read only the stored bytes, results are bit-identical); True = always; or a pair
+        `(SparseBatch | None, SparseBatch | None)` packed by the caller.  One host sync per packed matrix."""
         L = _lib.lib()
         _lib.require_cuda(Q, p, A0, zl, zu, *[prm for prm in self.parameters()])
         dev = Q.device
@@ -168,6 +213,19 @@ class LSTM(nn.Module):
         for name, v in (("x", x), ("y", y), ("z", z), ("xv", xv), ("H", H), ("C", C)):
             if not v.is_contiguous():
                 raise _lib.IadmmError(f"state tensor {name} must be contiguous")
+        if sparse is not None and sparse is not False:
+            if isinstance(sparse, (tuple, list)):
+                q_sp, a_sp = sparse
+            else:
+                lim = SPARSE_AUTO_DENSITY if sparse == "auto" else None
+                q_sp, a_sp = SparseBatch.pack(Q, lim), SparseBatch.pack(A0, lim)
+            self.last_sparse = (q_sp, a_sp)
+            if q_sp is not None or a_sp is not None:
+                torch.ops.iadmm.solve_sparse(packed, Q, q_sp.buf if q_sp else None, q_sp.cap if q_sp else 0, p,
+                                             A0, a_sp.buf if a_sp else None, a_sp.cap if a_sp else 0, zl, zu, sd, se, sc,
+                                             x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met, ws,
+                                             int(num_ineq), int(num_eq), h, self.length, int(t0), int(K), float(sigma), mode, flags)
+                return SolveResult(x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met)
         # the one thin custom op of the forward path (iadmm_b200/ops.py -> iadmm_solve of include/iadmm.h)
         torch.ops.iadmm.solve(packed, Q, p, A0, zl, zu, sd, se, sc, x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met, ws,
                               int(num_ineq), int(num_eq), h, self.length, int(t0), int(K), float(sigma), mode, flags)

@@ -4,6 +4,7 @@
     torch.ops.iadmm.ruiz        -> iadmm_ruiz         (Scaling.scale_data)
     torch.ops.iadmm.residuals   -> iadmm_residuals    (primal_dual_loss)
     torch.ops.iadmm.build_kkt   -> iadmm_build_kkt    (A_tild / b_tild / rho_vec of LSTM.forward's return tuple)
+    torch.ops.iadmm.sparse_pack / solve_sparse -> iadmm_sparse_pack / iadmm_solve_sparse (sparse problem families)
 
 Each op is a few lines: it turns tensors into device pointers and calls the library on the current CUDA stream of the
 tensors' device.  They are registered for the CUDA dispatch key ONLY -- calling one with CPU tensors fails in the
@@ -67,3 +68,28 @@ def build_kkt(packed: Tensor, Q: Tensor, p: Tensor, A0: Tensor, x: Tensor, y: Te
     with torch.cuda.device(Q.device):
         _lib.check(_lib.lib().iadmm_build_kkt(_P(packed), _P(Q), _P(p), _P(A0), _P(x), _P(y), _P(z), _P(Kmat), _P(rhs),
                                               _P(rho_vec), B, n, num_ineq, num_eq, h, length, t, sigma, _lib.stream_ptr()))
+
+
+@torch.library.custom_op("iadmm::sparse_pack", mutates_args=("packed", "nnz"), device_types="cuda")
+def sparse_pack(M: Tensor, packed: Tensor, nnz: Tensor, cap: int) -> None:
+    B, rows, n = M.shape
+    with torch.cuda.device(M.device):
+        _lib.check(_lib.lib().iadmm_sparse_pack(_P(M), B, rows, n, cap, _P(packed), packed.numel(), _P(nnz), _lib.stream_ptr()))
+
+
+@torch.library.custom_op("iadmm::solve_sparse", mutates_args=("x", "y", "z", "xv", "H", "C", "pri", "dual", "pri_u", "dual_u",
+                                                               "metrics", "workspace"), device_types="cuda")
+def solve_sparse(packed: Tensor, Q: Optional[Tensor], Q_sp: Optional[Tensor], q_cap: int, p: Tensor,
+                 A0: Optional[Tensor], A0_sp: Optional[Tensor], a_cap: int, zl: Tensor, zu: Tensor,
+                 sd: Optional[Tensor], se: Optional[Tensor], sc: Optional[Tensor],
+                 x: Tensor, y: Tensor, z: Tensor, xv: Tensor, H: Tensor, C: Tensor,
+                 pri: Optional[Tensor], dual: Optional[Tensor], pri_u: Optional[Tensor], dual_u: Optional[Tensor],
+                 metrics: Optional[Tensor], workspace: Tensor,
+                 num_ineq: int, num_eq: int, h: int, length: int, t0: int, K: int, sigma: float, mode: int, flags: int) -> None:
+    B, n = x.shape[0], x.shape[1]
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().iadmm_solve_sparse(_P(packed), _P(Q), _P(Q_sp), q_cap, _P(p), _P(A0), _P(A0_sp), a_cap, _P(zl), _P(zu),
+                                                 _P(sd), _P(se), _P(sc), _P(x), _P(y), _P(z), _P(xv), _P(H), _P(C),
+                                                 _P(pri), _P(dual), _P(pri_u), _P(dual_u), _P(metrics),
+                                                 B, n, num_ineq, num_eq, h, length, t0, K, sigma, mode, flags,
+                                                 _P(workspace), workspace.numel(), _lib.stream_ptr()))

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define IADMM_ABI_VERSION 2
+#define IADMM_ABI_VERSION 3
 
 enum {
   IADMM_OK      = 0,
@@ -137,6 +137,32 @@ int iadmm_solve(const void* packed_weights,
                 int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
                 float sigma, int mode, int flags,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- sparse problem families ----------------------------------------------------------------------
+ * Replaces: the `.toarray()` densification of main.py:243-296 for the families generate_data.py:96-228 stores as scipy
+ * csc matrices (Random_QP: A0 60 % dense; Equality_QP: 50 %; SVM: identity blocks) and the QPLIB / Maros-Meszaros
+ * instances.  iadmm_sparse_pack re-lays a dense [B, rows, n] batch (after Ruiz scaling, which keeps the pattern) as
+ * "bitmap slabs": per row and 128-column slab a 128-bit occupancy mask and the offset of its first value, plus the
+ * instance's non-zero values in row-major order -- 4*nnz + 20*rows*ceil(n/128) bytes per instance instead of 4*rows*n.
+ * `cap` = value capacity per instance (>= the largest instance's non-zero count; rows*n always suffices); `nnz` (device,
+ * [B], may be NULL) receives the counts -- values beyond `cap` are NOT stored, so check max(nnz) <= cap.
+ * iadmm_solve_sparse = iadmm_solve with Q and/or A0 given in that form (pass NULL for the form not used; the dense
+ * pointer of a matrix given in sparse form may be NULL).  Same kernels, same lane-to-column assignment and accumulation
+ * order as the dense passes: results are bit-identical to the densified problem, the KKT passes read only the stored bytes.
+ * Always runs the HBM-streaming variant. */
+int iadmm_sparse_bytes(int B, int rows, int n, size_t cap, size_t* bytes);
+int iadmm_sparse_pack(const float* M, int B, int rows, int n, size_t cap, void* packed, size_t packed_bytes, int* nnz,
+                      void* stream);
+int iadmm_solve_sparse(const void* packed_weights,
+                       const float* Q, const void* Q_sparse, size_t q_cap, const float* p,
+                       const float* A0, const void* A0_sparse, size_t a_cap, const float* zl, const float* zu,
+                       const float* d, const float* e, const float* c,
+                       float* x, float* y, float* z, float* xv, float* H, float* C,
+                       float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
+                       float* metric_trace,
+                       int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
+                       float sigma, int mode, int flags,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- adjacent pieces of the reference interface ------------------------------------------------- */
 

@@ -35,7 +35,7 @@ def test_header_symbols_exported(libpath):
 def test_binding_covers_header(libpath):
     from iadmm_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert _lib.lib().iadmm_abi_version() == 2
+    assert _lib.lib().iadmm_abi_version() == 3
 
 
 def test_workspace_sizes(libpath):

@@ -171,8 +171,12 @@ def test_clip_gradient_at_an_exact_double_tie():
     dd = {k: qp[k].to(DEV) for k in ("Q", "p", "A0", "zl", "zu")}
     ours = run(lambda x, y, z, xv, H, C: model(1, mi, me, x, y, z, xv, 6e-6, H, C, Q=dd["Q"], p=dd["p"], A0=dd["A0"], lb=None,
                                                ub=None, zl=dd["zl"], zu=dd["zu"])[:4], DEV, torch.float32)
+    # (gy is exactly zero in exact arithmetic here -- y cancels out of both z' and y' -- so errors are measured against the
+    # largest adjoint, not against each adjoint's own norm)
+    scale = max(float(b.norm()) for b in ref)
     for name, a, b in zip(("gx", "gy", "gz", "gxv"), ours, ref):
-        assert rel_err(a, b) < 1e-4, (name, rel_err(a, b))
+        err = float((a - b).norm()) / scale
+        assert err < 1e-4, (name, err)
     # the tie rows really carry the QUARTER gradient: with the tie made one-sided (zu or zl moved away, derivative 0.5)
     # the reference gradient is a different one
     for delta in (-1.0, 1.0):
