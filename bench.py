@@ -270,7 +270,7 @@ def workload_name(args):
     if args.workload == "sparse":
         return ("sparse family %s of generate_data.py:96-228 at num_var=%d (densified on load like main.py:243-296), hidden_dim=%d, "
                 "--scaling, K=%d; Q / A0 %s (NOT the headline workload)"
-                % (args.family, n, h, args.iters, "streamed in the bitmap-slab sparse form where below 75 %% density" if args.sparse == "auto"
+                % (args.family, n, h, args.iters, "streamed in the bitmap-slab sparse form where below 0.3 %% density" if args.sparse == "auto"
                    else "streamed dense"))
     if args.workload == "train":
         return ("config3: TBPTT training window, dense QP n=%d, %d ineq + %d eq, hidden_dim=%d, --scaling, truncated_length=%d, "

@@ -118,17 +118,13 @@ __device__ __forceinline__ void store_cols4(float* __restrict__ v, int col, int 
 // order.  A lane of the streaming pass owns 4 consecutive columns = one nibble of the mask, so the dense kernel's work
 // decomposition, accumulation order and therefore every rounding carry over unchanged: the sparse loader returns exactly the
 // values the dense loader would (zeros where the mask is clear) while reading 4*nnz + 20*rows*ceil(n/128) bytes.
-template <bool VEC>
-__device__ __forceinline__ float4 load_cols4_sparse(const SpMat& sp, size_t inst, int row, int slab, int lane) {
-  const size_t rs = (size_t)row * sp.S + slab;
-  const uint4 mk = __ldg(sp.mask + inst * sp.mask_stride + rs);
-  const uint32_t base = __ldg(sp.off + inst * sp.mask_stride + rs);
+__device__ __forceinline__ float4 expand_cols4_sparse(const float* __restrict__ vals, const uint4 mk, uint32_t base, int lane) {
   const int w = lane >> 3, sh = (lane & 7) * 4;
   const uint32_t mine = (w == 0) ? mk.x : (w == 1) ? mk.y : (w == 2) ? mk.z : mk.w;
   const uint32_t before = ((w > 0) ? __popc(mk.x) : 0) + ((w > 1) ? __popc(mk.y) : 0) + ((w > 2) ? __popc(mk.z) : 0) +
                           __popc(mine & ((1u << sh) - 1u));
   const uint32_t nib = (mine >> sh) & 15u;
-  const float* p = sp.vals + inst * sp.vals_stride + base + before;
+  const float* p = vals + base + before;
   float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
   if (nib & 1u) r.x = __ldg(p);
   p += (nib & 1u);
@@ -152,7 +148,7 @@ struct TileArgs {
 };
 
 // smem: rowscal[2][R] | rowacc[R*2] | rowpart[warps][R*2]
-template <int NR, int NC, bool VEC, bool SP = false>
+template <int NR, int NC, bool VEC>
 __device__ __forceinline__ void tile_pass(const TileArgs& a, float* smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = a.R, n = a.n;
@@ -185,10 +181,8 @@ __device__ __forceinline__ void tile_pass(const TileArgs& a, float* smem) {
 #pragma unroll
       for (int u = 0; u < kRowUnroll; ++u) {
         const int row = a.r0 + rg + u;
-        if (SP) v[u] = (active && row < a.rows_total) ? load_cols4_sparse<VEC>(a.sp, a.inst, row, cc * kKktWarps + warp, lane)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-        else    v[u] = (active && row < a.rows_total) ? load_cols4<VEC>(a.mat + (size_t)row * n, col, n)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u] = (active && row < a.rows_total) ? load_cols4<VEC>(a.mat + (size_t)row * n, col, n)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (NC > 0) {
 #pragma unroll
@@ -247,7 +241,164 @@ __device__ __forceinline__ void tile_pass(const TileArgs& a, float* smem) {
     }
 }
 
-static size_t tile_smem_bytes(int R) { return (size_t)(4 * R + kKktWarps * R * 2) * sizeof(float); }
+// The same pass over a matrix in bitmap-slab form.  Kept as a separate function so that the dense pass above compiles exactly
+// as before (sharing one body cost the dense kernels 2x the registers).
+// smem: rowscal[2][R] | rowacc[R*2] | rowpart[warps][R*2] | slab masks [warps][R] uint4 | slab offsets [warps][R] u32
+template <int NR, int NC, bool VEC>
+__device__ __forceinline__ void tile_pass_sparse(const TileArgs& a, float* smem) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = a.R, n = a.n;
+  constexpr bool SP = true;
+  float* rowscal = smem;
+  float* rowacc  = smem + 2 * R;
+  float* rowpart = smem + 4 * R;
+
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    for (int r = tid; r < R; r += kKktThreads) {
+      const int row = a.r0 + r;
+      rowscal[c * R + r] = (row < a.rows_total) ? __ldg(a.crhs[c] + row) : 0.f;
+    }
+  for (int i = tid; i < R * NR; i += kKktThreads) rowacc[i] = 0.f;
+  __syncthreads();
+
+  const int nchunk = (n + kChunkCols - 1) / kChunkCols;
+  for (int cc = 0; cc < nchunk; ++cc) {
+    const int  col    = cc * kChunkCols + warp * kSlabCols + lane * 4;
+    const bool active = col < n;
+    float4 rv[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) rv[k] = load_vec4<VEC>(a.rrhs[k], col, n);
+    float4 cacc[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cacc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // SP: stage the masks and value offsets of this warp's 128-column slab for all R rows of the CTA in shared memory with
+    // one round of independent loads (a dependent load per row group would make the pass latency bound), and keep a bit per
+    // row "slab not empty" (R <= 64)
+    uint4* smk = nullptr;
+    uint32_t* sof = nullptr;
+    unsigned long long occ = 0ull;
+    if (SP) {
+      smk = reinterpret_cast<uint4*>(smem + 4 * R + kKktWarps * R * 2) + warp * R;
+      sof = reinterpret_cast<uint32_t*>(reinterpret_cast<uint4*>(smem + 4 * R + kKktWarps * R * 2) + kKktWarps * R) + warp * R;
+      const int slab = cc * kKktWarps + warp;
+      __syncwarp();                                   // the previous column chunk's readers are done
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = i * 32 + lane;
+        uint4 mk = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t of = 0u;
+        if (r < R && slab < a.sp.S && a.r0 + r < a.rows_total) {
+          const size_t rs = a.inst * a.sp.mask_stride + (size_t)(a.r0 + r) * a.sp.S + slab;
+          mk = __ldg(a.sp.mask + rs);
+          of = __ldg(a.sp.off + rs);
+        }
+        if (r < R) { smk[r] = mk; sof[r] = of; }
+        occ |= (unsigned long long)__ballot_sync(kFullMask, (mk.x | mk.y | mk.z | mk.w) != 0u) << (32 * i);
+      }
+      __syncwarp();
+    }
+
+    // SP: only rows whose slab is not empty are visited, 8 at a time in increasing row order (`todo` = their bit set).  A
+    // skipped row contributes exact zeros to every sum, so the results are those of the dense pass bit for bit, and a pass
+    // over identity blocks / truly sparse rows costs the mask bytes plus work proportional to the non-empty (row, slab) pairs.
+    unsigned long long todo = occ;
+    if (SP && NR > 0) {
+      for (int i = lane; i < R * NR; i += 32) rowpart[warp * (R * NR) + i] = 0.f;
+      __syncwarp();
+    }
+    for (int rg = 0; SP ? (todo != 0ull) : (rg < R); rg += kRowUnroll) {
+      float4 v[kRowUnroll];
+      int rsel[kRowUnroll];                      // SP: the CTA-local rows of this group (-1 = none)
+      if (SP) {
+        const float* vals = a.sp.vals + a.inst * a.sp.vals_stride;
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+          rsel[u] = -1;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (todo != 0ull) {
+            const int r = __ffsll((long long)todo) - 1;
+            todo &= todo - 1ull;
+            rsel[u] = r;
+            v[u] = expand_cols4_sparse(vals, smk[r], sof[r], lane);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+          const int row = a.r0 + rg + u;
+          v[u] = (active && row < a.rows_total) ? load_cols4<VEC>(a.mat + (size_t)row * n, col, n)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (NC > 0) {
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const float s = SP ? ((rsel[u] >= 0) ? rowscal[c * R + rsel[u]] : 0.f) : rowscal[c * R + rg + u];
+            cacc[c].x = fmaf(v[u].x, s, cacc[c].x);
+            cacc[c].y = fmaf(v[u].y, s, cacc[c].y);
+            cacc[c].z = fmaf(v[u].z, s, cacc[c].z);
+            cacc[c].w = fmaf(v[u].w, s, cacc[c].w);
+          }
+        }
+      }
+      if (NR > 0) {
+        float rp[kRowUnroll * (NR > 0 ? NR : 1)];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+          for (int k = 0; k < NR; ++k) {
+            float t = v[u].x * rv[k].x;
+            t = fmaf(v[u].y, rv[k].y, t);
+            t = fmaf(v[u].z, rv[k].z, t);
+            t = fmaf(v[u].w, rv[k].w, t);
+            rp[u * NR + k] = t;
+          }
+        }
+        constexpr int NV = kRowUnroll * (NR > 0 ? NR : 1);
+        const float tot = warp_transpose_reduce<NV>(rp, lane);
+        constexpr int kGroup = 32 / NV;              // lanes holding the same value
+        if ((lane % kGroup) == 0) {
+          const int idx = lane / kGroup;             // = u*NR + k
+          if (SP) {
+            int rr = -1;                             // row of slot u = idx / NR (static unroll: rsel stays in registers)
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) if (u == idx / (NR > 0 ? NR : 1)) rr = rsel[u];
+            if (rr >= 0) rowpart[warp * (R * NR) + rr * NR + idx % (NR > 0 ? NR : 1)] = tot;
+          } else {
+            rowpart[warp * (R * NR) + rg * NR + idx] = tot;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) store_cols4<VEC>(a.cpart[c], col, n, cacc[c]);
+
+    if (NR > 0) {
+      __syncthreads();
+      for (int i = tid; i < R * NR; i += kKktThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kKktWarps; ++w) s += rowpart[w * (R * NR) + i];
+        rowacc[i] += s;
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NR; ++k)
+    for (int r = tid; r < R; r += kKktThreads) {
+      const int row = a.r0 + r;
+      if (row < a.rows_total) a.rout[k][row] = rowacc[r * NR + k];
+    }
+}
+
+static size_t tile_smem_bytes(int R, bool sparse = false) {
+  return (size_t)(4 * R + kKktWarps * R * 2) * sizeof(float) + (sparse ? (size_t)kKktWarps * R * 20 : 0);
+}
 
 // ------------------------------------------------------------------------------------------------
 // pass 1 / pass 2 kernels.  grid = (chunks_q + chunks_a, B)
@@ -263,7 +414,7 @@ struct Pass1Args {
 };
 
 template <bool VEC, bool SPQ = false, bool SPA = false>
-__global__ void __launch_bounds__(kKktThreads) kkt_pass1_kernel(const Pass1Args P) {
+__global__ void __launch_bounds__(kKktThreads, (SPQ || SPA) ? 3 : 0) kkt_pass1_kernel(const Pass1Args P) {
   extern __shared__ float smem[];
   const KktDims& d = P.d;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -276,7 +427,7 @@ __global__ void __launch_bounds__(kKktThreads) kkt_pass1_kernel(const Pass1Args 
     a.mat = SPQ ? nullptr : P.Q + b * n * n; a.sp = P.spq; a.inst = b; a.rows_total = d.n; a.r0 = chunk * a.R;
     a.rout[0] = P.s.qxt + b * n; a.rout[1] = P.s.qx + b * n;
     a.crhs[0] = a.crhs[1] = nullptr; a.cpart[0] = a.cpart[1] = nullptr;
-    tile_pass<2, 0, VEC, SPQ>(a, smem);
+    if constexpr (SPQ) tile_pass_sparse<2, 0, VEC>(a, smem); else tile_pass<2, 0, VEC>(a, smem);
   } else {
     const int ca = chunk - d.chunks_q;
     a.mat = SPA ? nullptr : P.A0 + b * m * n; a.sp = P.spa; a.inst = b; a.rows_total = d.m; a.r0 = ca * a.R;
@@ -284,12 +435,12 @@ __global__ void __launch_bounds__(kKktThreads) kkt_pass1_kernel(const Pass1Args 
     a.crhs[0] = P.v + (size_t)b * P.v_stride; a.crhs[1] = P.y + b * m;
     float* part = P.s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
     a.cpart[0] = part; a.cpart[1] = part + n;
-    tile_pass<2, 2, VEC, SPA>(a, smem);
+    if constexpr (SPA) tile_pass_sparse<2, 2, VEC>(a, smem); else tile_pass<2, 2, VEC>(a, smem);
   }
 }
 
 template <bool VEC, bool SPQ = false, bool SPA = false>
-__global__ void __launch_bounds__(kKktThreads) kkt_pass2_kernel(const KktDims d, const float* __restrict__ Q,
+__global__ void __launch_bounds__(kKktThreads, (SPQ || SPA) ? 3 : 0) kkt_pass2_kernel(const KktDims d, const float* __restrict__ Q,
                                                                 const float* __restrict__ A0, const KktScratch s,
                                                                 const SpMat spq, const SpMat spa) {
   extern __shared__ float smem[];
@@ -304,13 +455,13 @@ __global__ void __launch_bounds__(kKktThreads) kkt_pass2_kernel(const KktDims d,
     a.mat = SPQ ? nullptr : Q + b * n * n; a.sp = spq; a.inst = b; a.rows_total = d.n; a.r0 = chunk * a.R;
     a.rrhs[0] = nullptr; a.rout[0] = nullptr;
     a.crhs[0] = w1; a.cpart[0] = s.part_q + ((size_t)b * d.chunks_q + chunk) * n;
-    tile_pass<0, 1, VEC, SPQ>(a, smem);
+    if constexpr (SPQ) tile_pass_sparse<0, 1, VEC>(a, smem); else tile_pass<0, 1, VEC>(a, smem);
   } else {
     const int ca = chunk - d.chunks_q;
     a.mat = SPA ? nullptr : A0 + b * m * n; a.sp = spa; a.inst = b; a.rows_total = d.m; a.r0 = ca * a.R;
     a.rrhs[0] = w1; a.rout[0] = s.aw1 + b * m;
     a.crhs[0] = w2; a.cpart[0] = s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
-    tile_pass<1, 1, VEC, SPA>(a, smem);
+    if constexpr (SPA) tile_pass_sparse<1, 1, VEC>(a, smem); else tile_pass<1, 1, VEC>(a, smem);
   }
 }
 
@@ -333,7 +484,8 @@ static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t s
   if (spq) P.spq = sp->q;
   if (spa) P.spa = sp->a;
   const dim3 grid(d.chunks_q + d.chunks_a, d.B);
-  const size_t smem = tile_smem_bytes(d.rows_per_chunk);
+  if ((spq || spa) && d.rows_per_chunk > 64) IADMM_FAIL(IADMM_EMODE, "sparse KKT pass: at most 64 rows per chunk");
+  const size_t smem = tile_smem_bytes(d.rows_per_chunk, spq || spa);
   if (can_vectorise(d, P.Q, P.A0, sp)) launch_pass1_variant<true>(P, spq, spa, grid, smem, st);
   else                                 launch_pass1_variant<false>(P, spq, spa, grid, smem, st);
   IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
@@ -374,8 +526,9 @@ static void launch_pass2_variant(const KktDims& d, const float* Q, const float* 
 
 int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st, const KktSparse* sp) {
   const dim3 grid(d.chunks_q + d.chunks_a, d.B);
-  const size_t smem = tile_smem_bytes(d.rows_per_chunk);
   const bool spq = sp && sp->q.vals, spa = sp && sp->a.vals && d.m > 0;
+  if ((spq || spa) && d.rows_per_chunk > 64) IADMM_FAIL(IADMM_EMODE, "sparse KKT pass: at most 64 rows per chunk");
+  const size_t smem = tile_smem_bytes(d.rows_per_chunk, spq || spa);
   SpMat q, a;
   memset(&q, 0, sizeof(q)); memset(&a, 0, sizeof(a));
   if (spq) q = sp->q;

@@ -20,7 +20,12 @@ PARAM_ORDER = ("W_i", "U_i", "b_i", "W_f", "U_f", "b_f", "W_o", "U_o", "b_o",
                "W_u", "U_u", "b_u", "W_h", "b_h", "rho", "alpha")
 
 
-SPARSE_AUTO_DENSITY = 0.75     # "auto": a matrix goes to the bitmap-slab form when its densest instance is below this
+# "auto": a matrix goes to the bitmap-slab form when its densest instance is below this density.  Measured crossover on B200
+# (tools/sparse_sweep.py, profiles/r02_sparse_sweep.jsonl, n = m = 1000): the sparse pass is 1.28x faster than the dense one at
+# 0.1 % density (diagonal Q of the QP family, identity blocks of SVM, QPLIB-class matrices) but SLOWER from ~0.5 % upwards
+# although it reads 3-20x fewer bytes -- ncu: the mask expansion makes the pass instruction-issue bound (91 vs ~25 warp
+# instructions per row and 128-column slab), so the 50-60 % dense families stay on the dense streaming pass.
+SPARSE_AUTO_DENSITY = 0.003
 
 
 class SparseBatch:
