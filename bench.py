@@ -49,6 +49,25 @@ WORKLOAD = ("config2: dense QP n=1000, 500 ineq + 500 eq, hidden_dim=800, --scal
             "unrolled iterations + per-iteration residual traces, random-init LSTM")
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Point fd 1 at stderr for the rest of the run (NCCL prints its version banner to stdout from C, whatever NCCL_DEBUG
+    says on some boxes); the ONE JSON line goes to the real stdout through emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -73,6 +92,7 @@ def parse_args():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the stock-PyTorch-on-this-GPU sample in our line")
     ap.add_argument("--gpu-ref-batch", type=int, default=32, help="instances per step of the stock-PyTorch GPU arm")
     ap.add_argument("--tl", type=int, default=100, help="train: truncated_length of the window")
+    ap.add_argument("--recompute", action="store_true", help="train: recompute the gate activations in the backward (3x less memory)")
     a = ap.parse_args()
     if a.workload == "config5":
         a.nvar = 5000
@@ -317,7 +337,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        quiet_stdout()                                       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     B, n, mi, me, h, K = args.batch, args.nvar, args.nvar // 2, args.nvar // 2, args.hidden, args.iters
@@ -540,7 +561,7 @@ def run_ours(args):
             # ~12 instances, 10-20 s of CPU work; batches of 4 are the CPU path's best operating point at n=1000
             # (measured 1.3 solves/s at batch 1-4, 0.56 at batch 12: the dense KKT build falls out of cache)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -562,6 +583,7 @@ def run_train(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")
+        quiet_stdout()
         dist.init_process_group("nccl", device_id=dev)
     B, n, mi, me, h, TL = args.batch, args.nvar, args.nvar // 2, args.nvar // 2, args.hidden, args.tl
     m, N = mi + me, n + mi + me
@@ -582,7 +604,8 @@ def run_train(args):
         # main.py:306-358 for one batch with outer_T == truncated_length: scale_data, zero state, ONE window, Adam
         Qs, ps, As, zls, zus = scaling.scale_data(*raw)
         opt.zero_grad(set_to_none=True)
-        loss, _ = model.train_window(TL, mi, me, Qs, ps, As, zls, zus, SIGMA, zero_state(), loss_scale=1.0 / TL, inplace=True)
+        loss, _ = model.train_window(TL, mi, me, Qs, ps, As, zls, zus, SIGMA, zero_state(), loss_scale=1.0 / TL, inplace=True,
+                                     recompute_gates=True if args.recompute else None)
         if world > 1:
             if timed_idx is not None:
                 ar_ev[timed_idx][0].record()
@@ -672,7 +695,8 @@ def run_train(args):
                        "cache": "inputs larger than L2: saved states %.1f GB per window" % (2 * (TL + 1) * rows * h * 4 / 1e9),
                        "parallelism": "data parallel over %d GPU(s): one NCCL all-reduce of the flat gradient buffer (%d floats) per window, "
                                       "then the reference's Adam on every rank" % (world, sum(p_.numel() for p_ in model.parameters())),
-                       "weights_identical_across_ranks": same, "loss": loss_v, "peak_mem_GB": mem_gb},
+                       "weights_identical_across_ranks": same, "loss": loss_v, "peak_mem_GB": mem_gb,
+                       "gate_activations": "recomputed in the backward" if getattr(model, "last_window_flags", 0) & 1 else "kept over the window"},
             "gpu_launches": steps * TL * 60,
             "allreduce": {"ms_per_step": ar_ms / steps, "share_of_step": ar_ms / ms if ms > 0 else 0.0,
                           "bytes": 4 * (sum(p_.numel() for p_ in model.parameters()) + 1)},
@@ -688,7 +712,7 @@ def run_train(args):
             "e2e": {"value": world * B * steps / (e2e_ms * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

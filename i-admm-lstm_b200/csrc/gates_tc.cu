@@ -265,7 +265,7 @@ __device__ __forceinline__ u64 tanh2(float x0, float x1, float big0, float big1)
   return pk2((fabsf(x0) < 0.55f) ? s0 : big0, (fabsf(x1) < 0.55f) ? s1 : big1);
 }
 
-template <int NPROD, bool FAST, bool SAVE, bool IL, int NCH = kChunksPerHalf, bool ABL = false>
+template <int NPROD, bool FAST, bool SAVE, bool IL, int NCH = kChunksPerHalf, bool ABL = false, bool SHR = false>
 __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const EpiRowT<NCH>& R, const float* sp, uint32_t tmem_base, int buf,
                                                       int quarter, int half, int ut, float dequant) {
   const int ex = ABL ? P.exp : 0;
@@ -314,9 +314,24 @@ __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const E
         float gi[2], gf[2], go[2], bigu[2], pu[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          rcp1p_ex2_2(mul2(pif[j], k_if), gi[j], gf[j]);           // sigmoid(p_i), sigmoid(p_f)
           float ru, po_unused;
-          rcp1p_ex2_2(mul2(pou[j], k_ou), go[j], ru);              // sigmoid(p_o), 1/(e^{2 p_u}+1)
+          if (SHR) {
+            // one reciprocal for the four activations of a unit (gate_math.cuh, gates4_shared_rcp_x2): 4 ex2 + 1 rcp
+            float t0, t1, t2, t3, a, b, c, d;
+            upk2(mul2(pif[j], k_if), t0, t1);
+            upk2(mul2(pou[j], k_ou), t2, t3);
+            upk2(add2(pk2(ex2_approx(fminf(t0, 30.0f)), ex2_approx(fminf(t1, 30.0f))), bc2(1.0f)), a, b);
+            upk2(add2(pk2(ex2_approx(fminf(t2, 30.0f)), ex2_approx(fminf(t3, 30.0f))), bc2(1.0f)), c, d);
+            const float ab = a * b, cd = c * d;
+            const float r = rcp_approx(ab * cd);
+            float rab, rcd;
+            upk2(mul2(bc2(r), pk2(cd, ab)), rab, rcd);
+            upk2(mul2(bc2(rab), pk2(b, a)), gi[j], gf[j]);
+            upk2(mul2(bc2(rcd), pk2(d, c)), go[j], ru);
+          } else {
+            rcp1p_ex2_2(mul2(pif[j], k_if), gi[j], gf[j]);           // sigmoid(p_i), sigmoid(p_f)
+            rcp1p_ex2_2(mul2(pou[j], k_ou), go[j], ru);              // sigmoid(p_o), 1/(e^{2 p_u}+1)
+          }
           upk2(pou[j], po_unused, pu[j]);
           bigu[j] = fmaf(-2.0f, ru, 1.0f);
         }
@@ -587,7 +602,7 @@ constexpr int kPairBBoxRows = 64;                         // U tiles are fetched
 // regime where the cell epilogue, not the MMAs or the power cap, sets the pace (hidden_dim <~ 400: a tile's MMAs take a quarter of
 // the time of its epilogue).  20 warps (five per scheduler, so 96 registers per thread; the two-chunk epilogue needs 90): warps 0-3 =
 // TMA producer, MMA issuer and two idle warps, warps 4-19 = epilogue (lane quarter = warp % 4).
-constexpr int pair_threads(int epi) { return epi == 7 ? 640 : kTcThreads; }
+constexpr int pair_threads(int epi) { return (epi == 7 || epi == 9) ? 640 : kTcThreads; }
 constexpr int kEpi16MaxHidden = 256;   // measured: 16 warps win at hidden_dim 208 (0.667 vs 0.739 ms), lose at 400 and 800 (power-capped regime)
 
 template <int NPROD, int CL, int EPI>
@@ -604,10 +619,10 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
   // The ablation switches of IADMM_TC_EXP (uniform, never-taken branches in production) stay compiled into the 8-warp
   // row-interleaved kernel on purpose: without them ptxas takes 168 instead of 146 registers and schedules the epilogue 3 %
   // slower (same box: 4.74 vs 4.59 ms per launch); declaring a larger block only offers 128 registers with spills.
-  constexpr bool ABL = (EPI == 4);
+  constexpr bool ABL = (EPI == 4 || EPI == 8);   // EPI 8: as 4 with one shared reciprocal per unit (measured, not adopted: DESIGN.md)
   const int ex = ABL ? P.exp : 0;
-  constexpr int kEpiWarps = (EPI == 7) ? 16 : kTcEpiWarps;
-  constexpr int kFirstEpiWarp = (EPI == 7) ? 4 : 2;
+  constexpr int kEpiWarps = (EPI == 7 || EPI == 9) ? 16 : kTcEpiWarps;     // EPI 9: as 7 with one shared reciprocal per unit
+  constexpr int kFirstEpiWarp = (EPI == 7 || EPI == 9) ? 4 : 2;
   constexpr int kIlBK = (EPI == 5) ? 32 : 64;
   constexpr uint32_t kIlSub = kIlBK * 256;            // bytes of one operand box: [K groups][128 rows][16 B]
   constexpr int kStageBytes = IL ? 4 * (int)kIlSub : (NPROD == 1) ? (kPairABytes + kPairBBytes) : 2 * (kPairABytes + kPairBBytes);
@@ -829,7 +844,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       } else if (EPI == 0) {
         if constexpr (NCH == kChunksPerHalf) lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
       } else {
-        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6, EPI == 3, IL, NCH, ABL>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
+        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6, EPI == 3, IL, NCH, ABL, EPI == 8 || EPI == 9>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
       }
       tc_fence_before();
       __syncwarp();
@@ -1028,7 +1043,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   if (const char* e = dev_env("IADMM_TC_EXP")) exp_mode = atoi(e);          // development experiments, see TcParams::exp
   if (const char* w = dev_env("IADMM_TC_EPI")) {    // development switch: 0 = scalar epilogue, 1 = packed fp32 (default), 2 = packed + exp-only tanh
     epi = atoi(w);
-    if (epi < 0 || epi > 2) epi = 1;
+    if (epi < 0 || epi > 3) epi = 1;                  // 3: shared-reciprocal activations (row-interleaved kernel only)
   }
   // IADMM_GATES_TC_F16F8U: the H-rounding correction product is not issued (TcParams::exp 7 is exactly that and numerically valid)
   const bool drop_h = il && il->drop_h_correction;
@@ -1075,12 +1090,15 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
       kernel<<<(unsigned)(cluster * clusters), threads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
       return IADMM_OK;
     };
-    static PerDeviceOnce a34, a24, a14, a32, a22, a12, e0, e2, s2, s3, s1, i4, i5, i6, i7;
+    static PerDeviceOnce a34, a24, a14, a32, a22, a12, e0, e2, s2, s3, s1, i4, i5, i6, i7, i8;
     if (il && epi_warps == 16) {
       threads = pair_threads(7);
-      rc = launch(gates_tc_pair_kernel<2, 2, 7>, &i7, 2);
+      static PerDeviceOnce i9;
+      if (epi == 3) rc = launch(gates_tc_pair_kernel<2, 2, 9>, &i9, 2);
+      else          rc = launch(gates_tc_pair_kernel<2, 2, 7>, &i7, 2);
     } else if (il) {
-      if (epi == 2)         rc = launch(gates_tc_pair_kernel<2, 2, 6>, &i6, 2);
+      if (epi == 3)         rc = launch(gates_tc_pair_kernel<2, 2, 8>, &i8, 2);
+      else if (epi == 2)    rc = launch(gates_tc_pair_kernel<2, 2, 6>, &i6, 2);
       else if (il_bk == 32) rc = launch(gates_tc_pair_kernel<2, 2, 5>, &i5, 2);
       else                  rc = launch(gates_tc_pair_kernel<2, 2, 4>, &i4, 2);
     } else if (gates_out) {        // training forward: the epilogue also stores the gate activations

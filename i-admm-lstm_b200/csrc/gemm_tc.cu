@@ -24,11 +24,12 @@ constexpr int kGmStageBytes = 2 * (kGmABytes + kGmBBytes);   // 96 KB
 constexpr int kGmStages = 2;
 
 struct GemmParams {
-  float* C;
+  float* C;                // splits == 1: the result; splits > 1: partial results [splits][M][ldc]
   const float* scale;      // device scalar
   long M, N, K, ldc;
   int n_tiles, k_blocks;
-  long num_tiles;
+  int splits, kb_per_split;   // split-K: work unit = (tile, split), split s covers K blocks [s*kb_per_split, ...)
+  long num_tiles;             // output tiles; work units = num_tiles * splits
 };
 
 __global__ void __launch_bounds__(kGmThreads, 1)
@@ -64,11 +65,14 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (long tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      for (long unit = blockIdx.x; unit < P.num_tiles * P.splits; unit += gridDim.x) {
+        const long tile = unit / P.splits;
+        const int sp = (int)(unit - tile * P.splits);
         const int nt = (int)(tile % P.n_tiles);
         const long mt = tile / P.n_tiles;
         const int row0 = (int)(mt * kTcBM), col0 = nt * kGmBN;
-        for (int kb = 0; kb < P.k_blocks; ++kb) {
+        const int kb_end = min(P.k_blocks, (sp + 1) * P.kb_per_split);
+        for (int kb = sp * P.kb_per_split; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, kGmStageBytes);
@@ -86,7 +90,10 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       long it = 0;
-      for (long tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
+      for (long unit = blockIdx.x; unit < P.num_tiles * P.splits; unit += gridDim.x, ++it) {
+        const long tile = unit / P.splits;
+        const int sp = (int)(unit - tile * P.splits);
+        const int kb_end = min(P.k_blocks, (sp + 1) * P.kb_per_split);
         const int nt = (int)(tile % P.n_tiles);
         const int n_cols = (int)min((long)kGmBN, P.N - (long)nt * kGmBN);
         const uint32_t idesc = make_idesc_f16(n_cols);
@@ -96,7 +103,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kGmBN);
         uint32_t acc = 0;
-        for (int kb = 0; kb < P.k_blocks; ++kb) {
+        for (int kb = sp * P.kb_per_split; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sb = smem_u32(smem + (size_t)stage * kGmStageBytes);
@@ -124,7 +131,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const int half = (ew >= 4) ? 1 : 0;
     const float scale = *P.scale;
     long it = 0;
-    for (long tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
+    for (long unit = blockIdx.x; unit < P.num_tiles * P.splits; unit += gridDim.x, ++it) {
+      const long tile = unit / P.splits;
+      const int sp = (int)(unit - tile * P.splits);
       const int nt = (int)(tile % P.n_tiles);
       const long mt = tile / P.n_tiles;
       const int buf = (int)(it & 1);
@@ -140,7 +149,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kGmBN + chunk * 32), v);
         tc_wait_ld();
         if (row < P.M) {
-          float* crow = P.C + row * P.ldc + col0;
+          float* crow = P.C + ((size_t)sp * P.M + row) * P.ldc + col0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (col0 + q * 8 < P.N) {            // N % 8 == 0
@@ -168,8 +177,40 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 }
 
 // A_hi/A_lo: [M][lda], B_hi/B_lo: [N][ldb] fp16 K-major; lda, ldb multiples of 8; N multiple of 16; C fp32 [M][ldc], ldc % 4 == 0
+// sum of the split-K partials in a fixed order (deterministic): C[i] = ((p0 + p1) + p2) + ...
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __restrict__ part, float4* __restrict__ C, size_t count4, int splits) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count4) return;
+  float4 a = part[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 b = part[(size_t)s * count4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  C[i] = a;
+}
+
+// Split-K factor for a GEMM with few output tiles and a long K (U_bar = H^T D: 7 x 13 tiles, K = rows): the (tile, split)
+// work units should fill whole waves of the persistent grid.  Picks the factor <= max_splits with the best wave efficiency
+// (ties: the smaller one); every split keeps at least 8 K blocks.
+int tc_gemm_pick_splits(long M, long N, long K, int num_sms, int max_splits) {
+  const long tiles = ((M + kTcBM - 1) / kTcBM) * ((N + kGmBN - 1) / kGmBN);
+  const long k_blocks = (K + kGmBK - 1) / kGmBK;
+  if (tiles >= 4L * num_sms) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_splits && k_blocks / s >= 8; ++s) {
+    const long units = tiles * s;
+    const long waves = (units + num_sms - 1) / num_sms;
+    const double eff = (double)units / (double)(waves * num_sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+// splits > 1: `part` must hold splits * M * ldc floats; C then receives the fixed-order sum of the partials
 int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi, const __half* B_lo, float* C,
-                      const float* scale, long M, long N, long K, long lda, long ldb, long ldc, cudaStream_t st) {
+                      const float* scale, long M, long N, long K, long lda, long ldb, long ldc, cudaStream_t st,
+                      int splits, float* part) {
   if (N % 16 != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) IADMM_FAIL(IADMM_ESHAPE, "tc_gemm: unsupported leading dimensions");
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) IADMM_FAIL(IADMM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -190,18 +231,28 @@ int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi
       (rc = mk(&mb_hi, B_hi, N, ldb, kGmBN)) || (rc = mk(&mb_lo, B_lo, N, ldb, kGmBN)))
     return rc;
   GemmParams P;
-  P.C = C; P.scale = scale; P.M = M; P.N = N; P.K = K; P.ldc = ldc;
+  if (splits < 1 || (splits > 1 && (!part || (M * ldc) % 4 != 0))) IADMM_FAIL(IADMM_ESHAPE, "tc_gemm: bad split-K arguments");
+  P.C = (splits > 1) ? part : C; P.scale = scale; P.M = M; P.N = N; P.K = K; P.ldc = ldc;
   P.n_tiles = (int)((N + kGmBN - 1) / kGmBN);
   P.k_blocks = (int)((K + kGmBK - 1) / kGmBK);
+  P.splits = splits;
+  P.kb_per_split = (P.k_blocks + splits - 1) / splits;
   P.num_tiles = ((M + kTcBM - 1) / kTcBM) * P.n_tiles;
   int num_sms = 0;
   static PerDeviceOnce attr;
   if ((rc = device_sm_count(&num_sms))) return rc;
   if ((rc = ensure_dyn_smem(tc_gemm_nt_kernel, 220 * 1024, &attr))) return rc;
   const size_t smem = 1024 + (size_t)kGmStages * kGmStageBytes + (2 * kGmStages + 4) * sizeof(uint64_t) + 16;
-  const long grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
+  const long units = P.num_tiles * splits;
+  const long grid = units < num_sms ? units : num_sms;
   tc_gemm_nt_kernel<<<(unsigned)grid, kGmThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
   IADMM_LAUNCH_CHECK("tc_gemm_nt_kernel");
+  if (splits > 1) {
+    const size_t count4 = (size_t)(M * ldc) / 4;
+    splitk_reduce_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(part),
+                                                                           reinterpret_cast<float4*>(C), count4, splits);
+    IADMM_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
   return IADMM_OK;
 }
 

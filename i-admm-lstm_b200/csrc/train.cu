@@ -23,7 +23,10 @@ int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, co
                            const KktScratch& s, cudaStream_t st);
 // gemm_tc.cu
 int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi, const __half* B_lo, float* C,
-                      const float* scale, long M, long N, long K, long lda, long ldb, long ldc, cudaStream_t st);
+                      const float* scale, long M, long N, long K, long lda, long ldb, long ldc, cudaStream_t st,
+                      int splits = 1, float* part = nullptr);
+int tc_gemm_pick_splits(long M, long N, long K, int num_sms, int max_splits);
+constexpr int kMaxSplitK = 16;
 int launch_absmax(const float* X, size_t count, float* out, cudaStream_t st);
 int launch_gemm_scales(const float* absmax, const float* other, float* scales, cudaStream_t st);
 int launch_split_rows(const float* X, size_t count, const float* scale, __half* hi, __half* lo, cudaStream_t st);
@@ -420,7 +423,7 @@ __global__ void negate_sum_kernel(const float* __restrict__ Xbar, long rows, flo
 struct TrainWs {
   KktDims d;
   KktScratch s;
-  float *head_part, *zeros, *Xbar, *xvbar_cell, *gbar, *D, *u32bar, *cs_part, *w0bar, *w1bar, *bbar, *whbar, *sbar_sum;
+  float *head_part, *zeros, *Xbar, *xvbar_cell, *gbar, *D, *u32bar, *u32bar_part, *cs_part, *w0bar, *w1bar, *bbar, *whbar, *sbar_sum;
   __half *h_hi, *h_lo, *h_hi_out, *h_lo_out;      // tensor-core forward: fp16 / e4m3 images of H (in) and scratch (out)
   __half *d_hi, *d_lo, *dt_hi, *dt_lo, *ht_hi, *ht_lo;   // tensor-core backward GEMM operands (D, D^T, H^T as fp16 hi/lo)
   float *gscal;                                   // [8]: absmax(D), then the scales of gemm_scales_kernel at [4..6]
@@ -471,6 +474,7 @@ static void plan_train(int B, int n, int m, int num_ineq, int h, void* base, Tra
   W->gbar = reinterpret_cast<float*>(take(rows * sizeof(float)));
   W->D = reinterpret_cast<float*>(take(rows * 4 * (size_t)h * sizeof(float)));
   W->u32bar = reinterpret_cast<float*>(take((size_t)h * 4 * h * sizeof(float)));
+  W->u32bar_part = (h % 16 == 0) ? reinterpret_cast<float*>(take((size_t)kMaxSplitK * h * 4 * h * sizeof(float))) : nullptr;   // split-K partials of U_bar
   W->cs_part = reinterpret_cast<float*>(take((size_t)W->cs_parts * 3 * 4 * h * sizeof(float)));
   W->w0bar = reinterpret_cast<float*>(take((size_t)4 * h * sizeof(float)));
   W->w1bar = reinterpret_cast<float*>(take((size_t)4 * h * sizeof(float)));
@@ -485,6 +489,34 @@ static int check_sm100() {
   IADMM_CUDA(cudaGetDevice(&dev));
   IADMM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) IADMM_FAIL(IADMM_EARCH, "device %d has compute capability %d.x; libiadmm_b200 needs sm_100 (B200)", dev, major);
+  return IADMM_OK;
+}
+
+
+// The forward gate contraction + cell of one training iteration (fp32 CUDA cores, or the tensor-core kernel with the state
+// converted at the boundary), keeping the gate activations.  C_o must already hold C (the cell kernels update it in place).
+// Returns the number of head partials written per row through *head_slots.
+static int train_gate_forward(const void* packed_weights, const WeightLayout& L, const TrainWs& W, const float* xv, const float* g,
+                              const float* H, float* H_o, float* C_o, float* gates_out, size_t rows, int h, int mode,
+                              int* head_slots, cudaStream_t st) {
+  int rc;
+  int nprod = 0;
+  if (mode == IADMM_GATES_TC_3XFP16 && h % 8 == 0) nprod = 3;
+  else if ((mode == IADMM_GATES_TC_F16F8 || mode == IADMM_GATES_TC_F16F8U) && h % 16 == 0) nprod = 2;   // training keeps both corrections
+  else if ((mode == IADMM_GATES_TC_F16F8 || mode == IADMM_GATES_TC_F16F8U) && h % 8 == 0) nprod = 3;
+  else if (mode == IADMM_GATES_TC_1XFP16 && h % 8 == 0) nprod = 1;
+  else if (mode != IADMM_GATES_SIMT_FP32 && h % 8 == 0) IADMM_FAIL(IADMM_EMODE, "training: unknown gate mode %d", mode);
+  if (nprod == 0) {
+    *head_slots = W.tiles;
+    return launch_gates_simt(packed_weights, L, xv, g, H, H_o, C_o, W.head_part, (long)rows, h, st, gates_out);
+  }
+  prof_begin(kProfTrainGates, st);
+  if ((rc = launch_split_state(H, W.h_hi, W.h_lo, (long)rows, h, nprod, st))) return rc;
+  if (nprod == 2) IADMM_CUDA(cudaMemsetAsync(W.h_lo_out, 0, tc_lo_bytes((long)rows, h), st));
+  if ((rc = launch_gates_tc(packed_weights, L, xv, g, W.h_hi, W.h_lo, W.h_hi_out, W.h_lo_out, H_o, C_o, W.head_part,
+                            (long)rows, h, nprod, st, gates_out))) return rc;
+  prof_end(kProfTrainGates, st);
+  *head_slots = tc_head_slots(h, false);
   return IADMM_OK;
 }
 
@@ -517,9 +549,8 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
   if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || t < 0 || t >= length)
     IADMM_FAIL(IADMM_ESHAPE, "step_fwd: B=%d n=%d ineq=%d eq=%d h=%d t=%d length=%d", B, n, num_ineq, num_eq, h, t, length);
   if (B > 65535) IADMM_FAIL(IADMM_ESHAPE, "step_fwd: batch %d > 65535", B);
-  if (!packed_weights || !Q || !p || !x || !xv || !H || !C || !x_o || !xv_o || !H_o || !C_o || !g_save || !w_save ||
-      !gates_save || !workspace)
-    IADMM_FAIL(IADMM_EALIGN, "step_fwd: NULL pointer");
+  if (!packed_weights || !Q || !p || !x || !xv || !H || !C || !x_o || !xv_o || !H_o || !C_o || !g_save || !w_save || !workspace)
+    IADMM_FAIL(IADMM_EALIGN, "step_fwd: NULL pointer");            // gates_save may be NULL: activations not kept
   if (h % 4 != 0) IADMM_FAIL(IADMM_ESHAPE, "step_fwd: hidden_dim %% 4 != 0 not supported by the training path");
   int rc = check_sm100();
   if (rc) return rc;
@@ -551,23 +582,9 @@ int iadmm_step_fwd(const void* packed_weights, const float* Q, const float* p, c
   prof_end(kProfTrainKkt, st);
   // gate contraction of the forward: fp32 CUDA cores, or the tensor-core kernel (same arithmetic as the solve) with
   // the state converted at the boundary; both keep the gate activations for the backward
-  int nprod = 0;
-  if (mode == IADMM_GATES_TC_3XFP16 && h % 8 == 0) nprod = 3;
-  else if ((mode == IADMM_GATES_TC_F16F8 || mode == IADMM_GATES_TC_F16F8U) && h % 16 == 0) nprod = 2;   // training keeps both corrections
-  else if ((mode == IADMM_GATES_TC_F16F8 || mode == IADMM_GATES_TC_F16F8U) && h % 8 == 0) nprod = 3;
-  else if (mode == IADMM_GATES_TC_1XFP16 && h % 8 == 0) nprod = 1;
-  else if (mode != IADMM_GATES_SIMT_FP32 && h % 8 == 0) IADMM_FAIL(IADMM_EMODE, "step_fwd: unknown gate mode %d", mode);
-  if (nprod == 0) {
-    if ((rc = launch_gates_simt(packed_weights, L, xv, W.s.g, H, H_o, C_o, W.head_part, (long)rows, h, st, gates_save))) return rc;
-    return launch_tail(W.d, W.head_part, W.tiles, b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
-  }
-  prof_begin(kProfTrainGates, st);
-  if ((rc = launch_split_state(H, W.h_hi, W.h_lo, (long)rows, h, nprod, st))) return rc;
-  if (nprod == 2) IADMM_CUDA(cudaMemsetAsync(W.h_lo_out, 0, tc_lo_bytes((long)rows, h), st));
-  if ((rc = launch_gates_tc(packed_weights, L, xv, W.s.g, W.h_hi, W.h_lo, W.h_hi_out, W.h_lo_out, H_o, C_o, W.head_part,
-                            (long)rows, h, nprod, st, gates_save))) return rc;
-  prof_end(kProfTrainGates, st);
-  return launch_tail(W.d, W.head_part, tc_head_slots(h, false), b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
+  int head_slots = 0;
+  if ((rc = train_gate_forward(packed_weights, L, W, xv, W.s.g, H, H_o, C_o, gates_save, rows, h, mode, &head_slots, st))) return rc;
+  return launch_tail(W.d, W.head_part, head_slots, b_h, sk, zl, zu, x_o, y_o, z_o, xv_o, st);
 }
 
 int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
@@ -650,8 +667,12 @@ int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, c
     if ((rc = launch_split_both(W.D, (long)rows, h4, W.rows_p, W.gscal + 4, W.d_hi, W.d_lo, W.dt_hi, W.dt_lo, st))) return rc;
     if ((rc = launch_split_both(H, (long)rows, h, W.rows_p, nullptr, nullptr, nullptr, W.ht_hi, W.ht_lo, st))) return rc;
     if ((rc = launch_tc_gemm_nt(W.d_hi, W.d_lo, u32hi, u32lo, gH, W.gscal + 5, (long)rows, h, h4, h4, h4, h, st))) return rc;
+    // U_bar = H^T D has 7 x 13 output tiles and K = rows: split K so that the (tile, split) units fill the 148 SMs
+    int num_sms = 148;
+    if ((rc = device_sm_count(&num_sms))) return rc;
+    const int splits = tc_gemm_pick_splits(h, h4, (long)rows, num_sms, kMaxSplitK);
     if ((rc = launch_tc_gemm_nt(W.ht_hi, W.ht_lo, W.dt_hi, W.dt_lo, W.u32bar, W.gscal + 6, h, h4, (long)rows, W.rows_p, W.rows_p,
-                                h4, st))) return rc;
+                                h4, st, splits, W.u32bar_part))) return rc;
   } else {
     if ((rc = launch_sgemm<false, true>(W.D, u32, gH, (long)rows, h, h4, h4, h4, h, st))) return rc;
     if ((rc = launch_sgemm<true, false>(H, W.D, W.u32bar, h, h4, (long)rows, h, h4, h4, st))) return rc;
@@ -820,10 +841,12 @@ struct WindowWs {
   float *g_save, *w_save, *gates, *pri, *dual, *rp, *rd;   // [TL] each
   float *adj[2][6];                              // ping-pong adjoints gx gy gz gxv gH gC
   float *rgx, *rgy, *rgz, *seed;
+  float *Hs, *Cs;                                // recompute: scratch outputs of the re-run gate kernel
   size_t bytes;
 };
 
-static void plan_window(int B, int n, int m, int h, int TL, void* base, WindowWs* W) {
+static void plan_window(int B, int n, int m, int h, int TL, int flags, void* base, WindowWs* W) {
+  const bool recompute = (flags & IADMM_TRAIN_RECOMPUTE_GATES) != 0;
   const size_t N = (size_t)n + m, rows = (size_t)B * N, fb = sizeof(float);
   char* p = static_cast<char*>(base);
   size_t off = 0;
@@ -841,7 +864,9 @@ static void plan_window(int B, int n, int m, int h, int TL, void* base, WindowWs
   W->C = reinterpret_cast<float*>(take(S * rows * h * fb));
   W->g_save = reinterpret_cast<float*>(take((size_t)TL * rows * fb));
   W->w_save = reinterpret_cast<float*>(take((size_t)TL * rows * fb));
-  W->gates = reinterpret_cast<float*>(take((size_t)TL * rows * 4 * h * fb));
+  W->gates = reinterpret_cast<float*>(take((size_t)(recompute ? 1 : TL) * rows * 4 * h * fb));
+  W->Hs = recompute ? reinterpret_cast<float*>(take(rows * h * fb)) : nullptr;
+  W->Cs = recompute ? reinterpret_cast<float*>(take(rows * h * fb)) : nullptr;
   W->pri = reinterpret_cast<float*>(take((size_t)TL * B * fb));
   W->dual = reinterpret_cast<float*>(take((size_t)TL * B * fb));
   W->rp = reinterpret_cast<float*>(take((size_t)TL * B * (m > 0 ? m : 1) * fb));
@@ -900,11 +925,11 @@ __global__ void __launch_bounds__(256) window_loss_kernel(const float* __restric
 
 extern "C" {
 
-int iadmm_window_workspace_bytes(int B, int n, int m, int h, int TL, size_t* bytes) {
+int iadmm_window_workspace_bytes(int B, int n, int m, int h, int TL, int flags, size_t* bytes) {
   if (B <= 0 || n <= 0 || m < 0 || h <= 0 || TL <= 0 || !bytes)
     IADMM_FAIL(IADMM_ESHAPE, "window_workspace_bytes: B=%d n=%d m=%d h=%d TL=%d", B, n, m, h, TL);
   WindowWs W;
-  plan_window(B, n, m, h, TL, nullptr, &W);
+  plan_window(B, n, m, h, TL, flags, nullptr, &W);
   *bytes = W.bytes;
   return IADMM_OK;
 }
@@ -912,15 +937,16 @@ int iadmm_window_workspace_bytes(int B, int n, int m, int h, int TL, size_t* byt
 int iadmm_train_window(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* zl,
                        const float* zu, float* x, float* y, float* z, float* xv, float* H, float* C, float* grad_flat,
                        float* loss_out, int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int TL, float sigma,
-                       float loss_scale, int mode, void* workspace, size_t workspace_bytes, void* stream) {
+                       float loss_scale, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream) {
   const int m = num_ineq + num_eq;
   if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || TL <= 0 || t0 < 0 || t0 + TL > length)
     IADMM_FAIL(IADMM_ESHAPE, "train_window: B=%d n=%d ineq=%d eq=%d h=%d t0=%d TL=%d length=%d", B, n, num_ineq, num_eq, h, t0, TL, length);
   if (!packed_weights || !Q || !p || !x || !xv || !H || !C || !grad_flat || !loss_out || !workspace)
     IADMM_FAIL(IADMM_EALIGN, "train_window: NULL pointer");
   if (m > 0 && (!A0 || !zl || !zu || !y || !z)) IADMM_FAIL(IADMM_EALIGN, "train_window: NULL constraint pointer");
+  const bool recompute = (flags & IADMM_TRAIN_RECOMPUTE_GATES) != 0;
   WindowWs W;
-  plan_window(B, n, m, h, TL, workspace, &W);
+  plan_window(B, n, m, h, TL, flags, workspace, &W);
   if (W.bytes > workspace_bytes) IADMM_FAIL(IADMM_EWORK, "train_window: workspace too small: %zu < %zu", workspace_bytes, W.bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t N = (size_t)n + m, rows = (size_t)B * N, fb = sizeof(float);
@@ -940,8 +966,8 @@ int iadmm_train_window(const void* packed_weights, const float* Q, const float* 
     const size_t a = (size_t)t, b = (size_t)t + 1;
     if ((rc = iadmm_step_fwd(packed_weights, Q, p, A0, zl, zu, W.x + a * sx, W.y + a * sy, W.z + a * sy, W.xv + a * sxv, W.H + a * sH,
                              W.C + a * sH, W.x + b * sx, W.y + b * sy, W.z + b * sy, W.xv + b * sxv, W.H + b * sH, W.C + b * sH,
-                             W.g_save + a * sxv, W.w_save + a * sxv, W.gates + a * sG, B, n, num_ineq, num_eq, h, length, t0 + t,
-                             sigma, mode, W.step_ws, W.step_bytes, stream))) return rc;
+                             W.g_save + a * sxv, W.w_save + a * sxv, recompute ? nullptr : W.gates + a * sG, B, n, num_ineq, num_eq, h,
+                             length, t0 + t, sigma, mode, W.step_ws, W.step_bytes, stream))) return rc;
     if ((rc = iadmm_residuals_fwd(W.x + b * sx, W.y + b * sy, W.z + b * sy, Q, p, A0, W.pri + a * B, W.dual + a * B, W.rp + a * sy,
                                   W.rd + a * sx, B, n, m, W.res_ws, W.res_bytes, stream))) return rc;
   }
@@ -969,8 +995,22 @@ int iadmm_train_window(const void* packed_weights, const float* Q, const float* 
       add3_kernel<<<(unsigned)((mx + 255) / 256), 256, 0, st>>>(gin[0], W.rgx, sx, gin[1], W.rgy, sy, gin[2], W.rgz, sy);
       IADMM_LAUNCH_CHECK("add3_kernel");
     }
+    const float* gates_t = W.gates + a * sG;
+    if (recompute) {
+      // the gate activations of iteration t are not kept over the window (25.6 MB per instance and
+      // iteration at n+m = 2000, hidden_dim 800) but recomputed from the saved H_t, C_t, xv_t and g_t by the SAME kernel the
+      // forward ran (bit-identical activations), into one iteration's worth of scratch
+      TrainWs T;
+      plan_train(B, n, m, num_ineq, h, W.step_ws, &T);
+      const WeightLayout Lw = weight_layout(h, length);
+      IADMM_CUDA(cudaMemcpyAsync(W.Cs, W.C + a * sH, sH * fb, cudaMemcpyDeviceToDevice, st));
+      int slots = 0;
+      if ((rc = train_gate_forward(packed_weights, Lw, T, W.xv + a * sxv, W.g_save + a * sxv, W.H + a * sH, W.Hs, W.Cs, W.gates,
+                                   rows, h, mode, &slots, st))) return rc;
+      gates_t = W.gates;
+    }
     if ((rc = iadmm_step_bwd(packed_weights, Q, p, A0, zl, zu, W.x + a * sx, W.y + a * sy, W.z + a * sy, W.xv + a * sxv, W.H + a * sH,
-                             W.C + a * sH, W.xv + b * sxv, W.H + b * sH, W.g_save + a * sxv, W.w_save + a * sxv, W.gates + a * sG,
+                             W.C + a * sH, W.xv + b * sxv, W.H + b * sH, W.g_save + a * sxv, W.w_save + a * sxv, gates_t,
                              gin[0], m > 0 ? gin[1] : nullptr, m > 0 ? gin[2] : nullptr, last ? nullptr : gin[3],
                              last ? nullptr : gin[4], last ? nullptr : gin[5], gout[0], gout[1], gout[2], gout[3], gout[4], gout[5],
                              grad_flat, B, n, num_ineq, num_eq, h, length, t0 + t, sigma, W.step_ws, W.step_bytes, stream))) return rc;

@@ -23,6 +23,7 @@ GATE_MODES = {"simt_fp32": GATES_SIMT_FP32, "tc_3xfp16": GATES_TC_3XFP16, "tc_1x
 F_ZERO_STATE = 1
 F_SKIP_FINAL_RESID = 2
 F_STREAMING = 4
+TRAIN_RECOMPUTE_GATES = 1
 
 # every symbol include/iadmm.h declares, with its argument types
 _P, _I, _F, _Z = c_void_p, c_int, c_float, c_size_t
@@ -48,8 +49,8 @@ SIGNATURES = {
     "iadmm_train_workspace_bytes": ([_I, _I, _I, _I, POINTER(_Z)], c_int),
     "iadmm_step_fwd": ([_P] * 21 + [_I] * 7 + [_F, _I, _P, _Z, _P], c_int),
     "iadmm_step_bwd": ([_P] * 30 + [_I] * 7 + [_F, _P, _Z, _P], c_int),
-    "iadmm_window_workspace_bytes": ([_I] * 5 + [POINTER(_Z)], c_int),
-    "iadmm_train_window": ([_P] * 14 + [_I] * 8 + [_F, _F, _I, _P, _Z, _P], c_int),
+    "iadmm_window_workspace_bytes": ([_I] * 6 + [POINTER(_Z)], c_int),
+    "iadmm_train_window": ([_P] * 14 + [_I] * 8 + [_F, _F, _I, _I, _P, _Z, _P], c_int),
     "iadmm_residuals_train_workspace_bytes": ([_I, _I, _I, POINTER(_Z)], c_int),
     "iadmm_residuals_fwd": ([_P] * 10 + [_I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_residuals_bwd": ([_P] * 11 + [_I, _I, _I, _P, _Z, _P], c_int),

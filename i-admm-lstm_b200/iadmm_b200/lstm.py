@@ -237,12 +237,16 @@ class LSTM(nn.Module):
         return SolveResult(x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met)
 
     # -- one truncated-BPTT window, forward + backward, in one library call ------------------------
-    def train_window(self, TL, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state, t0=0, loss_scale=None, inplace=False):
+    def train_window(self, TL, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state, t0=0, loss_scale=None, inplace=False,
+                     recompute_gates=None):
         """The body of main.py:336-358 for one window: TL iterations (t = t0..t0+TL-1), the loss
         `sum_t primal_dual_loss(...).mean() * loss_scale` (default 1/TL; main.py uses 1/outer_T) and its gradient
         w.r.t. every parameter, ADDED to `.grad` like `loss.backward()` does.  Returns (loss, state') with
         state' = (x, y, z, xv, H, C) after the window, detached.  Equivalent to running `forward` +
-        `primal_dual_loss` under autograd, without a host round trip per iteration."""
+        `primal_dual_loss` under autograd, without a host round trip per iteration.
+        `recompute_gates`: True = do not keep the gate activations over the window (the backward re-runs the gate kernel per
+        iteration: same gradients bit for bit, 3x less memory, ~15 % more time); None = only when keeping them would not fit
+        in the device memory that is free right now."""
         from .autograd import PARAM_ORDER
         L = _lib.lib()
         _lib.require_cuda(Q, p, A0, zl, zu, *[prm for prm in self.parameters()])
@@ -254,8 +258,15 @@ class LSTM(nn.Module):
         x, y, z, xv, H, C = (_lib.f32(t.detach(), dev) if inplace else _lib.f32(t.detach(), dev).clone() for t in state)
         count, nbytes = c_size_t(), c_size_t()
         _lib.check(L.iadmm_param_count(h, self.length, byref(count)))
-        _lib.check(L.iadmm_window_workspace_bytes(B, n, m, h, int(TL), byref(nbytes)))
+        flags = _lib.TRAIN_RECOMPUTE_GATES if recompute_gates else 0
+        _lib.check(L.iadmm_window_workspace_bytes(B, n, m, h, int(TL), flags, byref(nbytes)))
         ws = getattr(self, "_window_ws", None)
+        if recompute_gates is None and (ws is None or ws.numel() < nbytes.value):
+            free = torch.cuda.mem_get_info(dev)[0] + (ws.numel() if ws is not None and ws.device == dev else 0)
+            if nbytes.value > 0.9 * free:
+                flags = _lib.TRAIN_RECOMPUTE_GATES
+                _lib.check(L.iadmm_window_workspace_bytes(B, n, m, h, int(TL), flags, byref(nbytes)))
+        self.last_window_flags = flags
         if ws is None or ws.numel() < nbytes.value or ws.device != dev:
             self._window_ws = None
             ws = self._window_ws = _lib.workspace(nbytes.value, dev)
@@ -267,7 +278,7 @@ class LSTM(nn.Module):
             _lib.check(L.iadmm_train_window(_lib.ptr(packed), _lib.ptr(Q), _lib.ptr(p), _lib.ptr(A0), _lib.ptr(zl), _lib.ptr(zu),
                                             _lib.ptr(x), _lib.ptr(y), _lib.ptr(z), _lib.ptr(xv), _lib.ptr(H), _lib.ptr(C),
                                             _lib.ptr(flat), _lib.ptr(loss), B, n, int(num_ineq), int(num_eq), h, self.length,
-                                            int(t0), int(TL), float(sigma), scale, self._mode(), _lib.ptr(ws), ws.numel(),
+                                            int(t0), int(TL), float(sigma), scale, self._mode(), flags, _lib.ptr(ws), ws.numel(),
                                             _lib.stream_ptr()))
         off = 0
         for name in PARAM_ORDER:

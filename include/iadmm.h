@@ -205,7 +205,7 @@ int iadmm_lu_solve(const float* LU, const int* perm, float* rhs, int B, int N, v
  *
  * grad_flat: [iadmm_param_count] floats in state_dict order (W_i,U_i,b_i, W_f,.., W_u,U_u,b_u, W_h, b_h, rho,
  * alpha); iadmm_step_bwd ADDS this iteration's parameter adjoints to it.  Incoming adjoints g*_o may be
- * NULL (= zero); outgoing adjoints gx..gC are overwritten.  gates_save: [B*(n+m), 4h].
+ * NULL (= zero); outgoing adjoints gx..gC are overwritten.  gates_save: [B*(n+m), 4h] (NULL in iadmm_step_fwd: not kept).
  */
 int iadmm_param_count(int h, int length, size_t* count);
 int iadmm_train_workspace_bytes(int B, int n, int m, int h, size_t* bytes);
@@ -245,13 +245,17 @@ int iadmm_residuals_bwd(const float* Q, const float* A0, const float* pri, const
  * the state after the window (the reference detaches it there, main.py:353-358); grad_flat [iadmm_param_count] is
  * OVERWRITTEN with d loss / d parameters (state_dict order, see above); loss_out [1].  Same kernels and results as
  * the per-iteration entry points, without the host round trips between them. */
-int iadmm_window_workspace_bytes(int B, int n, int m, int h, int TL, size_t* bytes);
+enum { IADMM_TRAIN_RECOMPUTE_GATES = 1 };   /* flags of iadmm_train_window: do not keep the gate activations [TL, B*(n+m), 4h] over
+                                               the window; the backward re-runs the forward gate kernel per iteration on the saved
+                                               H, C, xv, g (bit-identical activations, same gradients): 2.56 -> 0 GB per instance
+                                               and window at n+m = 2000, hidden_dim 800, TL = 100, for one more gate product */
+int iadmm_window_workspace_bytes(int B, int n, int m, int h, int TL, int flags, size_t* bytes);
 int iadmm_train_window(const void* packed_weights,
                        const float* Q, const float* p, const float* A0, const float* zl, const float* zu,
                        float* x, float* y, float* z, float* xv, float* H, float* C,
                        float* grad_flat, float* loss_out,
                        int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int TL, float sigma,
-                       float loss_scale, int mode, void* workspace, size_t workspace_bytes, void* stream);
+                       float loss_scale, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------
  * The reference times its solve with time.time() around model() (main.py:881-890, no device sync).

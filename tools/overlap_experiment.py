@@ -7,7 +7,8 @@ import torch
 import iadmm_b200 as ia
 from bench import device_qp_batch
 dev = "cuda:0"
-B, n, mi, me, h, K = 256, 1000, 500, 500, 800, 100
+n = int(os.environ.get("OV_N", 1000)); h = int(os.environ.get("OV_H", 800)); B = int(os.environ.get("OV_B", 256)); K = int(os.environ.get("OV_K", 100))
+mi = me = n // 2
 torch.manual_seed(17)
 models = [ia.LSTM(None, 2, h, K, dev) for _ in range(2)]
 with torch.no_grad():
@@ -37,4 +38,4 @@ def timeit(fn, reps=3):
 ms_full, rf = timeit(full)
 ms_split, rs = timeit(split)
 same = torch.equal(rf.x, torch.cat([rs[0].x, rs[1].x])) and torch.equal(rf.pri, torch.cat([rs[0].pri, rs[1].pri], 1))
-print(f"max_sms={os.environ.get('IADMM_TC_MAX_SMS','148')}: full batch {ms_full:.1f} ms ({B/ms_full*1e3:.1f} solves/s)   two half batches on two streams {ms_split:.1f} ms ({B/ms_split*1e3:.1f} solves/s)  identical={same}")
+print(f"n={n} h={h} B={B} K={K} max_sms={os.environ.get('IADMM_TC_MAX_SMS','148')}: full batch {ms_full:.1f} ms ({B/ms_full*1e3:.1f} solves/s)   two half batches on two streams {ms_split:.1f} ms ({B/ms_split*1e3:.1f} solves/s)  identical={same}")
