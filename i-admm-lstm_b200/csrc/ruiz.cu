@@ -7,8 +7,17 @@
 // and reproduce the reference's fp32 values exactly (the only order-dependent quantity is the mean of
 // the n column norms in the cost scaling, accumulated here in double).  The cost factor c_t of
 // iteration k is applied lazily by the matrix pass of iteration k+1 (rounding commutes with the
-// column max because c_t > 0), so one iteration is one read+write pass: (1 + 2*ites + 1/2) * 4(n^2+mn)
-// bytes in total instead of O(n^3) flops.
+// column max because c_t > 0).
+//
+// Traffic.  Round 1 rescaled the matrices in place every iteration (one read + one write pass each: (1 + 2*ites + 1/2) *
+// 4(n^2+mn) bytes, 21.5 passes at 10 iterations).  The entries themselves are only needed at the end: iteration k needs the
+// inf-norms of the matrix scaled by the diagonals of iterations 0..k-1.  The "chain" passes therefore read the ORIGINAL
+// matrices and re-apply, in registers and in the same order, the rounded products of all previous iterations (3 fp32
+// multiplies per entry and iteration for Q, 2 for A0 -- the pass stays HBM bound up to 10 iterations), take the norms, and
+// write nothing; one last pass applies the whole chain and writes the result: ites + 2 reads + 1 write = 13 passes instead of
+// 21.5, bit-identical to the in-place form (same operands, same IEEE multiplies, same order).  Needs the per-iteration
+// diagonals (ites * (n+m) floats per instance) instead of the current ones; more than kRzMaxChain iterations fall back to the
+// in-place form.
 #include "common.cuh"
 
 namespace iadmm {
@@ -17,6 +26,7 @@ constexpr int kRzThreads = 256;
 constexpr int kRzWarps   = 8;
 constexpr int kRzUnroll  = 8;
 constexpr int kRzChunkCols = 128 * kRzWarps;
+constexpr int kRzMaxChain = 10;        // iterations the chain passes re-apply from registers (scaling_ites of every config)
 constexpr float kMinScaling = 1e-4f;   // scaling.py:12
 constexpr float kMaxScaling = 1e4f;    // scaling.py:13
 
@@ -26,9 +36,11 @@ __device__ __forceinline__ float limit_scaling(float v) {   // scaling.py:31-38
 }
 
 struct RuizWs {            // per-instance vectors, fp32
-  float* sd;               // [B,n] current D_temp diagonal
-  float* se;               // [B,m] current E_temp diagonal
-  float* cprev;            // [B]   cost factor of the previous iteration, not yet applied to Q
+  float* sd;               // [hist][B,n] D_temp diagonal of iteration k at slot k*hist_on (hist = 1: the current one only)
+  float* se;               // [hist][B,m] E_temp diagonal
+  float* cprev;            // [hist+1][B] cost factor of iteration k-1 (applied lazily by iteration k) at slot k*hist_on
+  int hist_on;             // 1: per-iteration history kept (chain passes), 0: slot 0 is overwritten every iteration
+  int B;
   float* rowmax;           // [B,m] row inf-norms of the current A0
   float* partq;            // [B,chunks_q,n] column inf-norm partials of the current (pre-cost) Q
   float* parta;            // [B,chunks_a,n]
@@ -145,6 +157,132 @@ ruiz_pass_kernel(const float* Qsrc, const float* Asrc, float* Qdst, float* Adst,
   }
 }
 
+// Chain pass: reads the ORIGINAL matrices, re-applies the scale steps 0..steps-1 in registers (same rounded products, same
+// order as the in-place form) and either takes the norms of the result (WRITE = false: the matrix iteration `steps` sees)
+// or applies the last cost factor and writes it (WRITE = true).  grid = (chunks_q + chunks_a, B).
+template <bool WRITE, bool VEC>
+__global__ void __launch_bounds__(kRzThreads)
+ruiz_chain_kernel(const float* __restrict__ Qsrc, const float* __restrict__ Asrc, float* __restrict__ Qdst, float* __restrict__ Adst,
+                  int n, int m, int steps, RuizWs W) {
+  __shared__ float rowpart[kRzWarps][128];
+  __shared__ float srow_s[kRzMaxChain][128];       // left diagonal factors of this CTA's rows, per step (R <= 128)
+  __shared__ float cstep[kRzMaxChain + 1];         // Q: cost factor applied before step j; [steps] = the pending last one
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const bool isQ = chunk < W.chunks_q;
+  const int ca = isQ ? chunk : chunk - W.chunks_q;
+  const int rows_total = isQ ? n : m;
+  const int R = W.R, r0 = ca * R;
+  const float* src = isQ ? Qsrc + (size_t)b * n * n : Asrc + (size_t)b * m * n;
+  float*       dst = WRITE ? (isQ ? Qdst + (size_t)b * n * n : Adst + (size_t)b * m * n) : nullptr;
+  float* colpart = isQ ? W.partq + ((size_t)b * W.chunks_q + ca) * n : W.parta + ((size_t)b * W.chunks_a + ca) * n;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rlen = isQ ? n : m;
+  const float* left = isQ ? W.sd : W.se;
+  for (int i = tid; i < steps * R; i += kRzThreads) {
+    const int j = i / R, r = i - j * R, row = r0 + r;
+    srow_s[j][r] = (row < rows_total) ? left[((size_t)j * W.B + b) * rlen + row] : 1.0f;
+  }
+  if (tid < steps + (WRITE ? 1 : 0)) cstep[tid] = isQ ? W.cprev[(size_t)tid * W.B + b] : 1.0f;
+  __syncthreads();
+
+  const int nchunk = (n + kRzChunkCols - 1) / kRzChunkCols;
+  for (int cc = 0; cc < nchunk; ++cc) {
+    const int  col    = cc * kRzChunkCols + warp * 128 + lane * 4;
+    const bool active = col < n;
+    u64 sc[kRzMaxChain][2];                         // right diagonal factors of this lane's 4 columns, per step, as pairs
+#pragma unroll
+    for (int j = 0; j < kRzMaxChain; ++j) {
+      float t[4] = {1.f, 1.f, 1.f, 1.f};
+      if (j < steps) {
+        const float* sdj = W.sd + ((size_t)j * W.B + b) * n;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (col + e < n) t[e] = sdj[col + e];
+      }
+      sc[j][0] = pk2(t[0], t[1]); sc[j][1] = pk2(t[2], t[3]);
+    }
+    float cmax[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int rg = 0; rg < R; rg += kRzUnroll) {
+      u64 v[kRzUnroll][2];
+#pragma unroll
+      for (int u = 0; u < kRzUnroll; ++u) {
+        const int row = r0 + rg + u;
+        const bool ok = active && row < rows_total;
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ok && VEC) {
+          const float4 q = ldg_stream4(src + (size_t)row * n + col);
+          t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+        } else if (ok) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (col + e < n) t[e] = ldg_stream1(src + (size_t)row * n + col + e);
+        }
+        v[u][0] = pk2(t[0], t[1]); v[u][1] = pk2(t[2], t[3]);
+      }
+      float rmax[kRzUnroll];
+#pragma unroll
+      for (int u = 0; u < kRzUnroll; ++u) {
+        const int row = r0 + rg + u;
+        const bool ok = active && row < rows_total;
+        u64 a0 = v[u][0], a1 = v[u][1];
+#pragma unroll
+        for (int j = 0; j < kRzMaxChain; ++j) {
+          if (j < steps) {
+            if (isQ) { const u64 cj = bc2(cstep[j]); a0 = mul2(cj, a0); a1 = mul2(cj, a1); }   // lazily applied c_{j-1} (scaling.py:101)
+            a0 = mul2(a0, sc[j][0]); a1 = mul2(a1, sc[j][1]);                                     // bmm(M, D_temp)   (scaling.py:80-81)
+            const u64 sr = bc2(srow_s[j][rg + u]);
+            a0 = mul2(sr, a0); a1 = mul2(sr, a1);                                                 // bmm(D_temp|E_temp, .)
+          }
+        }
+        float t[4];
+        if (WRITE) {
+          if (isQ) { const u64 cl = bc2(cstep[steps]); a0 = mul2(cl, a0); a1 = mul2(cl, a1); }  // the last cost factor
+          upk2(a0, t[0], t[1]); upk2(a1, t[2], t[3]);
+          if (ok) {
+            float* drow = dst + (size_t)row * n + col;
+            if (VEC) *reinterpret_cast<float4*>(drow) = make_float4(t[0], t[1], t[2], t[3]);
+            else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (col + e < n) drow[e] = t[e];
+            }
+          }
+          rmax[u] = 0.f;
+        } else {
+          upk2(a0, t[0], t[1]); upk2(a1, t[2], t[3]);
+          float rm = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = fabsf(t[e]);
+            cmax[e] = fmaxf(cmax[e], a);
+            rm = fmaxf(rm, a);
+          }
+          rmax[u] = rm;
+        }
+      }
+      if (!WRITE && !isQ) {
+        const float tot = warp_transpose_reduce<kRzUnroll, true>(rmax, lane);
+        if ((lane & 3) == 0) rowpart[warp][rg + (lane >> 2)] = tot;
+      }
+    }
+    if (!WRITE && active) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (col + e < n) colpart[col + e] = cmax[e];
+    }
+    if (!WRITE && !isQ) {
+      __syncthreads();
+      for (int r = tid; r < R; r += kRzThreads) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRzWarps; ++w) t = fmaxf(t, rowpart[w][r]);
+        const int row = r0 + r;
+        if (row < rows_total) {
+          float* rm = W.rowmax + (size_t)b * m + row;
+          *rm = (cc == 0) ? t : fmaxf(*rm, t);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // One CTA per instance: finish iteration k-1 (cost normalisation, vector updates) and prepare the
 // diagonal factors of iteration k.
 constexpr int kRzVecThreads = 512;
@@ -170,13 +308,17 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
 }
 
 __global__ void __launch_bounds__(kRzVecThreads)
-ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, float* __restrict__ p, float* __restrict__ zl,
+ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, int k, float* __restrict__ p, float* __restrict__ zl,
                 float* __restrict__ zu, float* __restrict__ d, float* __restrict__ e, float* __restrict__ c, RuizWs W) {
+  // k = iteration being finished (finish_prev) and/or the one before the iteration being prepared (prepare_next, k = -1 at the start)
   __shared__ float shf[kRzVecThreads / 32];
   __shared__ double shd[kRzVecThreads / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
-  float* sd = W.sd + (size_t)b * n;
-  float* se = W.se + (size_t)b * m;
+  const size_t kf = (size_t)(k < 0 ? 0 : k) * W.hist_on, kn = (size_t)(k + 1) * W.hist_on;     // history slots
+  const float* sd = W.sd + (kf * W.B + b) * n;
+  const float* se = W.se + (kf * W.B + b) * m;
+  float* sd_next = W.sd + (kn * W.B + b) * n;
+  float* se_next = W.se + (kn * W.B + b) * m;
   const float* partq = W.partq + (size_t)b * W.chunks_q * n;
   const float* parta = W.parta + (size_t)b * W.chunks_a * n;
   p += (size_t)b * n; d += (size_t)b * n;
@@ -207,11 +349,11 @@ ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, float* __restri
     const float cost = limit_scaling(fmaxf(limit_scaling(pmax), mean_col));
     cprev = __frcp_rn(cost);
     for (int j = tid; j < n; j += kRzVecThreads) p[j] = __fmul_rn(cprev, p[j]);
-    if (tid == 0) { c[b] = __fmul_rn(cprev, c[b]); W.cprev[b] = cprev; }
+    if (tid == 0) { c[b] = __fmul_rn(cprev, c[b]); W.cprev[kn * W.B + b] = cprev; }
   } else {
     for (int j = tid; j < n; j += kRzVecThreads) d[j] = 1.0f;
     for (int i = tid; i < m; i += kRzVecThreads) e[i] = 1.0f;
-    if (tid == 0) { c[b] = 1.0f; W.cprev[b] = 1.0f; }
+    if (tid == 0) { c[b] = 1.0f; W.cprev[kn * W.B + b] = 1.0f; }
   }
   if (prepare_next) {
     // scaling.py:66-69 on the matrix as it stands (Q carries the pending factor cprev)
@@ -220,10 +362,10 @@ ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, float* __restri
       for (int ch = 0; ch < W.chunks_q; ++ch) cq = fmaxf(cq, partq[(size_t)ch * n + j]);
       for (int ch = 0; ch < W.chunks_a; ++ch) ca = fmaxf(ca, parta[(size_t)ch * n + j]);
       const float nrm = fmaxf(__fmul_rn(cprev, cq), ca);
-      sd[j] = __frcp_rn(__fsqrt_rn(limit_scaling(nrm)));   // reciprocal(sqrt(.)), two roundings like scaling.py:68-69
+      sd_next[j] = __frcp_rn(__fsqrt_rn(limit_scaling(nrm)));   // reciprocal(sqrt(.)), two roundings like scaling.py:68-69
     }
     const float* rowmax = W.rowmax + (size_t)b * m;
-    for (int i = tid; i < m; i += kRzVecThreads) se[i] = __frcp_rn(__fsqrt_rn(limit_scaling(rowmax[i])));
+    for (int i = tid; i < m; i += kRzVecThreads) se_next[i] = __frcp_rn(__fsqrt_rn(limit_scaling(rowmax[i])));
   }
 }
 
@@ -232,7 +374,8 @@ size_t ruiz_ws_floats(int B, int n, int m, int* R_out, int* cq_out, int* ca_out)
   int R = kd.rows_per_chunk > 128 ? 128 : kd.rows_per_chunk;
   const int cq = cdiv(n, R), ca = cdiv(m, R);
   if (R_out) { *R_out = R; *cq_out = cq; *ca_out = ca; }
-  return (size_t)B * n + (size_t)B * m + B + (size_t)B * m + (size_t)B * cq * n + (size_t)B * ca * n + 64;
+  const size_t hist = kRzMaxChain + 1;          // per-iteration diagonals for the chain passes
+  return hist * ((size_t)B * n + (size_t)B * m + B) + (size_t)B * m + (size_t)B * cq * n + (size_t)B * ca * n + 64 + 4 * 8;
 }
 
 int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, const float* zu, float* Qs, float* ps,
@@ -243,8 +386,13 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
   if (workspace_bytes < need) IADMM_FAIL(IADMM_EWORK, "ruiz workspace too small: %zu < %zu", workspace_bytes, need);
   float* base = static_cast<float*>(workspace);
   auto take = [&](size_t cnt) { float* q = base; base += (cnt + 3) / 4 * 4; return q; };
-  W.sd = take((size_t)B * n); W.se = take((size_t)B * m); W.cprev = take(B); W.rowmax = take((size_t)B * m);
+  const size_t hist = kRzMaxChain + 1;
+  W.B = B;
+  W.sd = take(hist * (size_t)B * n); W.se = take(hist * (size_t)B * m); W.cprev = take(hist * (size_t)B); W.rowmax = take((size_t)B * m);
   W.partq = take((size_t)B * W.chunks_q * n); W.parta = take((size_t)B * W.chunks_a * n);
+  const char* sw = dev_env("IADMM_RUIZ_CHAIN");                       // development switch: 0 = in-place form (round 1)
+  const bool chain = iterations <= kRzMaxChain && !(sw && sw[0] == '0');
+  W.hist_on = chain ? 1 : 0;
 
   IADMM_CUDA(cudaMemcpyAsync(ps, p, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (m > 0) {
@@ -256,22 +404,37 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
   if (iterations == 0) {
     IADMM_CUDA(cudaMemcpyAsync(Qs, Q, (size_t)B * n * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (m > 0) IADMM_CUDA(cudaMemcpyAsync(A0s, A0, (size_t)B * m * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 0, ps, zls, zus, d, e, c, W);
+    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 0, -1, ps, zls, zus, d, e, c, W);
     IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
     return IADMM_OK;
   }
   if (vec) ruiz_pass_kernel<kRzNorm, true><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, W);
   else     ruiz_pass_kernel<kRzNorm, false><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, W);
   IADMM_LAUNCH_CHECK("ruiz_pass_kernel<norm>");
-  ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 1, ps, zls, zus, d, e, c, W);
+  ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 1, -1, ps, zls, zus, d, e, c, W);
   IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+  if (chain) {
+    // iteration k: norms of the original matrices under the scale steps 0..k (read only), then the vector work
+    for (int k = 0; k < iterations; ++k) {
+      if (vec) ruiz_chain_kernel<false, true><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, k + 1, W);
+      else     ruiz_chain_kernel<false, false><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, k + 1, W);
+      IADMM_LAUNCH_CHECK("ruiz_chain_kernel<norm>");
+      ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 1, (k + 1 < iterations) ? 1 : 0, k, ps, zls, zus, d, e, c, W);
+      IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+    }
+    // the only write: all steps and the last cost factor applied to the original entries
+    if (vec) ruiz_chain_kernel<true, true><<<grid, kRzThreads, 0, st>>>(Q, A0, Qs, A0s, n, m, iterations, W);
+    else     ruiz_chain_kernel<true, false><<<grid, kRzThreads, 0, st>>>(Q, A0, Qs, A0s, n, m, iterations, W);
+    IADMM_LAUNCH_CHECK("ruiz_chain_kernel<write>");
+    return IADMM_OK;
+  }
   for (int k = 0; k < iterations; ++k) {
     const float* qsrc = (k == 0) ? Q : Qs;
     const float* asrc = (k == 0) ? A0 : A0s;
     if (vec) ruiz_pass_kernel<kRzScale, true><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, W);
     else     ruiz_pass_kernel<kRzScale, false><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, W);
     IADMM_LAUNCH_CHECK("ruiz_pass_kernel<scale>");
-    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 1, (k + 1 < iterations) ? 1 : 0, ps, zls, zus, d, e, c, W);
+    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 1, (k + 1 < iterations) ? 1 : 0, k, ps, zls, zus, d, e, c, W);
     IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
   }
   if (vec) ruiz_pass_kernel<kRzCost, true><<<grid, kRzThreads, 0, st>>>(Qs, A0s, Qs, A0s, n, m, W);
