@@ -77,7 +77,9 @@ def parse_args():
     ap.add_argument("--workload", default="solve", choices=["solve", "config5", "hidden200", "train", "sparse"])
     ap.add_argument("--family", default="Random_QP", choices=["Random_QP", "Equality_QP", "SVM"],
                     help="sparse workload: problem family of generate_data.py:96-228")
-    ap.add_argument("--sparse", default="auto", choices=["auto", "off"], help="sparse workload: bitmap-slab form of Q / A0, or the densified problem")
+    ap.add_argument("--sparse", default="off", choices=["auto", "off"],
+                    help="Q / A0 in the library's sparse forms where measured density / block structure allow (SparseBatch.auto), or streamed "
+                         "dense like the reference's densified tensors (the default, also for the headline workload)")
     ap.add_argument("--gate-mode", default="tc_f16f8", choices=["tc_3xfp16", "tc_f16f8", "tc_f16f8u", "tc_1xfp16", "simt_fp32"])
     ap.add_argument("--batch", type=int, default=None, help="instances per GPU (default: 256 solve, 24 config5, 2 train)")
     ap.add_argument("--iters", type=int, default=K_ITERS, help="unrolled iterations per solve (metric is quoted at 100)")
@@ -93,6 +95,8 @@ def parse_args():
     ap.add_argument("--gpu-ref-batch", type=int, default=32, help="instances per step of the stock-PyTorch GPU arm")
     ap.add_argument("--tl", type=int, default=100, help="train: truncated_length of the window")
     ap.add_argument("--recompute", action="store_true", help="train: recompute the gate activations in the backward (3x less memory)")
+    ap.add_argument("--graph", action="store_true", help="train: capture scale_data + the window (forward, loss, backward) in ONE CUDA graph "
+                                                          "and replay it per step (the library only enqueues on the caller's stream)")
     a = ap.parse_args()
     if a.workload == "config5":
         a.nvar = 5000
@@ -354,6 +358,8 @@ def run_ours(args):
     balance = world > 1 and not args.no_balance
     B_cap = B + max(8, B // 8) if balance else B
     sparse_mode = args.workload == "sparse"
+    if sparse_mode and "--sparse" not in sys.argv:
+        args.sparse = "auto"
     if sparse_mode:
         from iadmm_b200.data import generate_family_batch
         fam = generate_family_batch(args.family, B_cap, n if args.family != "SVM" else n // 2, num_ineq=n if args.family == "Random_QP" else n // 2,
@@ -372,15 +378,19 @@ def run_ours(args):
 
     def hot_step():
         Qs, ps, As, zls, zus = scaling.scale_data(Q, p, A0, zl, zu)
-        if sparse_mode and args.sparse == "auto":
-            # the first call measures the densities (host sync) and decides per matrix; later calls re-pack with the same
-            # capacities without synchronising (packing is part of the step: it has to follow the Ruiz scaling)
+        if args.sparse == "auto":
+            # the first call measures density / block occupancy (host syncs) and decides per matrix; later calls rebuild the
+            # chosen form without synchronising (it is part of the step: it has to follow the Ruiz scaling)
             if not sp_caps:
                 for key, M_ in (("q", Qs), ("a", As)):
-                    sb = ia.SparseBatch.pack(M_, ia.lstm.SPARSE_AUTO_DENSITY)
-                    sp_caps[key] = None if sb is None else (sb.cap, sb.density, sb.bytes_per_instance)
-            pair = tuple(None if sp_caps[key] is None else ia.SparseBatch.pack(M_, cap=sp_caps[key][0]) for key, M_ in (("q", Qs), ("a", As)))
-            return model.solve(K, mi, me, Qs, ps, As, zls, zus, SIGMA, scaling=scaling, sparse=pair, streaming=True)
+                    sb = ia.SparseBatch.auto(M_)
+                    sp_caps[key] = None if sb is None else (sb.kind, sb.cap, sb.density if sb.kind == "slabs" else sb.occupancy,
+                                                            sb.bytes_per_instance)
+            pair = tuple(None if sp_caps[key] is None else
+                         (ia.SparseBatch.pack(M_, cap=sp_caps[key][1]) if sp_caps[key][0] == "slabs" else ia.SparseBatch.blocks(M_))
+                         for key, M_ in (("q", Qs), ("a", As)))
+            if pair[0] is not None or pair[1] is not None:
+                return model.solve(K, mi, me, Qs, ps, As, zls, zus, SIGMA, scaling=scaling, sparse=pair)
         return model.solve(K, mi, me, Qs, ps, As, zls, zus, SIGMA, scaling=scaling, streaming=sparse_mode)
 
     def barrier():
@@ -493,12 +503,15 @@ def run_ours(args):
         kkt_bytes = 8.0 * B * (n * n + m * n)                # Q and A0 streamed once per pass, two passes
         kkt_dense_bytes = kkt_bytes
         sparse_info = None
-        if sparse_mode and args.sparse == "auto":
-            per_pass = (sp_caps["q"][2] if sp_caps.get("q") else 4.0 * n * n) + (sp_caps["a"][2] if sp_caps.get("a") else 4.0 * m * n)
+        if args.sparse == "auto":
+            per_pass = (sp_caps["q"][3] if sp_caps.get("q") else 4.0 * n * n) + (sp_caps["a"][3] if sp_caps.get("a") else 4.0 * m * n)
             kkt_bytes = 2.0 * B * per_pass
-            sparse_info = {"Q": None if not sp_caps.get("q") else {"density": sp_caps["q"][1], "bytes_per_pass": sp_caps["q"][2]},
-                           "A0": None if not sp_caps.get("a") else {"density": sp_caps["a"][1], "bytes_per_pass": sp_caps["a"][2]},
-                           "dense_bytes_per_pass": 4.0 * (n * n + m * n), "stored_bytes_per_pass": per_pass}
+
+            def info(v):
+                return None if not v else {"form": v[0], "density" if v[0] == "slabs" else "block_occupancy": v[2], "bytes_per_pass": v[3]}
+            sparse_info = {"Q": info(sp_caps.get("q")), "A0": info(sp_caps.get("a")),
+                           "dense_bytes_per_pass": 4.0 * (n * n + m * n), "stored_bytes_per_pass": per_pass,
+                           "note": "opt-in (--sparse auto): structural zeros of Q / A0 are not streamed; results are bit-identical to the dense path"}
         kkt_gbs = kkt_bytes / (kkt_avg_ms * 1e-3) / 1e9 if kkt_avg_ms > 0 else 0.0
         iter_bytes = kkt_bytes + 16.0 * rows * h + 64.0 * rows       # SURVEY section 8(d) bytes per iteration
         step_s = ms / steps * 1e-3
@@ -509,6 +522,9 @@ def run_ours(args):
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args),
+                       "matrix_form": ("dense streaming of Q and A0 (the reference's densified tensors)" if args.sparse != "auto" else
+                                       "OPT-IN --sparse auto: structural zeros not streamed (per matrix: bitmap slabs / block skipping / dense "
+                                       "by measured density and block occupancy); results bit-identical to dense streaming"),
                        "batch_per_gpu": args.batch, "instances_per_gpu": shares, "iters": K, "gate_mode": args.gate_mode,
                        "gate_arithmetic": {"tc_3xfp16": "tcgen05 fp16 hi/lo split, 3 MMAs, fp32 accumulate",
                                            "tc_f16f8": "tcgen05 fp16 MMA + 2 e4m3 correction MMAs, fp32 accumulate",
@@ -624,6 +640,44 @@ def run_train(args):
     for _ in range(warmup):
         loss = train_step(raw)
     barrier()
+    graph = None
+    if args.graph:
+        # Static buffers in, gradients out: the ~6000 launches of a window become one graph launch (at 2 instances per GPU the
+        # per-iteration kernels take 0.5 ms and their launches another 0.13 ms).  The weight re-pack is captured too, so a
+        # replay always sees the parameters Adam just updated; `.grad` tensors are allocated during capture and rewritten by
+        # every replay (so no zero_grad(set_to_none=True) between replays).
+        static_in = [t.clone() for t in raw]
+        static_loss = torch.zeros((), device=dev)
+        opt.zero_grad(set_to_none=True)
+        model.invalidate_packed()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            Qs, ps, As, zls, zus = scaling.scale_data(*static_in)
+            ls, _ = model.train_window(TL, mi, me, Qs, ps, As, zls, zus, SIGMA, zero_state(), loss_scale=1.0 / TL, inplace=True,
+                                       recompute_gates=True if args.recompute else False)
+            static_loss.copy_(ls)
+        torch.cuda.current_stream().wait_stream(side)
+
+        def train_step(raw_, timed_idx=None):                                     # noqa: F811  (graph-replay form of the step)
+            for d_, s_ in zip(static_in, raw_):
+                if d_.data_ptr() != s_.data_ptr():
+                    d_.copy_(s_, non_blocking=True)
+            graph.replay()
+            if world > 1:
+                if timed_idx is not None:
+                    ar_ev[timed_idx][0].record()
+                allreduce_gradients(model, local_batch=B)
+                if timed_idx is not None:
+                    ar_ev[timed_idx][1].record()
+            opt.step()
+            return static_loss
+
+        raw = tuple(static_in)
+        for _ in range(2):
+            loss = train_step(raw)
+        barrier()
     sampler = ClockSampler(dev) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -696,7 +750,8 @@ def run_train(args):
                        "parallelism": "data parallel over %d GPU(s): one NCCL all-reduce of the flat gradient buffer (%d floats) per window, "
                                       "then the reference's Adam on every rank" % (world, sum(p_.numel() for p_ in model.parameters())),
                        "weights_identical_across_ranks": same, "loss": loss_v, "peak_mem_GB": mem_gb,
-                       "gate_activations": "recomputed in the backward" if getattr(model, "last_window_flags", 0) & 1 else "kept over the window"},
+                       "gate_activations": "recomputed in the backward" if getattr(model, "last_window_flags", 0) & 1 else "kept over the window",
+                       "launch": "one CUDA graph per step (scale_data + window)" if graph is not None else "eager (the library enqueues ~60 launches per iteration)"},
             "gpu_launches": steps * TL * 60,
             "allreduce": {"ms_per_step": ar_ms / steps, "share_of_step": ar_ms / ms if ms > 0 else 0.0,
                           "bytes": 4 * (sum(p_.numel() for p_ in model.parameters()) + 1)},

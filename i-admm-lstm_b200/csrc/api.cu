@@ -204,7 +204,7 @@ static int solve_impl(const void* packed_weights, const float* Q, const float* p
                 float* dual_trace_u, float* metric_trace, int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int K,
                 float sigma, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream, const KktSparse* sp) {
   const int m = num_ineq + num_eq;
-  const bool spq = sp && sp->q.vals, spa = sp && sp->a.vals;
+  const bool spq = sp && sp->q.vals, spa = sp && sp->a.vals;     // bitmap-slab form: the dense pointer is not needed
   if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0 || h <= 0 || K < 0 || t0 < 0)
     IADMM_FAIL(IADMM_ESHAPE, "solve: B=%d n=%d ineq=%d eq=%d h=%d t0=%d K=%d", B, n, num_ineq, num_eq, h, t0, K);
   if (t0 + K > length) IADMM_FAIL(IADMM_ESHAPE, "solve: iterations %d..%d exceed the schedule length %d (lstm.py:60)", t0, t0 + K - 1, length);
@@ -310,20 +310,28 @@ int iadmm_solve(const void* packed_weights, const float* Q, const float* p, cons
                     nullptr);
 }
 
-int iadmm_solve_sparse(const void* packed_weights, const float* Q, const void* Q_sparse, size_t q_cap, const float* p,
-                       const float* A0, const void* A0_sparse, size_t a_cap, const float* zl, const float* zu,
+int iadmm_solve_sparse(const void* packed_weights, const float* Q, const void* Q_sparse, size_t q_cap, const void* Q_blocks,
+                       const float* p, const float* A0, const void* A0_sparse, size_t a_cap, const void* A0_blocks,
+                       const float* zl, const float* zu,
                        const float* sd, const float* se, const float* sc, float* x, float* y, float* z,
                        float* xv, float* H, float* C, float* pri_trace, float* dual_trace, float* pri_trace_u,
                        float* dual_trace_u, float* metric_trace, int B, int n, int num_ineq, int num_eq, int h, int length, int t0,
                        int K, float sigma, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream) {
   if (B <= 0 || n <= 0 || num_ineq < 0 || num_eq < 0) IADMM_FAIL(IADMM_ESHAPE, "solve_sparse: B=%d n=%d ineq=%d eq=%d", B, n, num_ineq, num_eq);
-  if (!Q_sparse && !A0_sparse) IADMM_FAIL(IADMM_EALIGN, "solve_sparse: neither matrix is given in sparse form (use iadmm_solve)");
-  if ((Q_sparse && !aligned16(Q_sparse)) || (A0_sparse && !aligned16(A0_sparse)))
+  if (!Q_sparse && !A0_sparse && !Q_blocks && !A0_blocks)
+    IADMM_FAIL(IADMM_EALIGN, "solve_sparse: neither matrix is given in sparse form (use iadmm_solve)");
+  if ((Q_sparse && Q_blocks) || (A0_sparse && A0_blocks)) IADMM_FAIL(IADMM_EMODE, "solve_sparse: one sparse form per matrix");
+  if ((Q_sparse && !aligned16(Q_sparse)) || (A0_sparse && !aligned16(A0_sparse)) || (Q_blocks && !aligned16(Q_blocks)) ||
+      (A0_blocks && !aligned16(A0_blocks)))
     IADMM_FAIL(IADMM_EALIGN, "solve_sparse: sparse buffers must be 16-byte aligned");
+  if ((Q_blocks && !Q) || (A0_blocks && !A0)) IADMM_FAIL(IADMM_EALIGN, "solve_sparse: the block-skip form reads the dense matrix");
   KktSparse sp;
   memset(&sp, 0, sizeof(sp));
+  const int m_ = num_ineq + num_eq;
   if (Q_sparse) sparse_view(Q_sparse, B, n, n, q_cap, &sp.q);
-  if (A0_sparse && num_ineq + num_eq > 0) sparse_view(A0_sparse, B, num_ineq + num_eq, n, a_cap, &sp.a);
+  if (A0_sparse && m_ > 0) sparse_view(A0_sparse, B, m_, n, a_cap, &sp.a);
+  if (Q_blocks) { sp.q.blk = static_cast<const unsigned long long*>(Q_blocks); sp.q.blk_stride = (size_t)(n + 7) / 8; }
+  if (A0_blocks && m_ > 0) { sp.a.blk = static_cast<const unsigned long long*>(A0_blocks); sp.a.blk_stride = (size_t)(m_ + 7) / 8; }
   return solve_impl(packed_weights, Q, p, A0, zl, zu, sd, se, sc, x, y, z, xv, H, C, pri_trace, dual_trace, pri_trace_u, dual_trace_u,
                     metric_trace, B, n, num_ineq, num_eq, h, length, t0, K, sigma, mode, flags | IADMM_F_STREAMING, workspace,
                     workspace_bytes, stream, &sp);

@@ -234,6 +234,9 @@ struct SpMat {
   int    S;                    // slabs per row = ceil(n / 128)
   size_t mask_stride;          // rows * S   (entries per instance of mask and off)
   size_t vals_stride;          // cap
+  // -- or: the dense matrix with block skipping (vals == NULL): one bit per 8-row x 128-column block
+  const unsigned long long* blk;   // [B][ceil(rows/8)] bit s of word g: block (g, s) holds a non-zero; NULL = not given
+  size_t blk_stride;               // ceil(rows/8)
 };
 struct KktSparse { SpMat q, a; };
 int sparse_view(const void* packed, int B, int rows, int n, size_t cap, SpMat* out);   // carve a packed buffer

@@ -140,6 +140,7 @@ struct TileArgs {
   const float* mat;        // first element of the instance's matrix [rows_total, n]
   SpMat sp;                // SP: the matrix in bitmap-slab form instead
   size_t inst;             // SP: instance index
+  const unsigned long long* blk;   // block-skip form: this instance's block-occupancy words [ceil(rows/8)]
   int rows_total, n, r0, R;
   const float* rrhs[2];    // NR vectors of length n      (row products  M r)
   float*       rout[2];    // NR outputs of length rows_total
@@ -178,6 +179,116 @@ __device__ __forceinline__ void tile_pass(const TileArgs& a, float* smem) {
 
     for (int rg = 0; rg < R; rg += kRowUnroll) {
       float4 v[kRowUnroll];
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) {
+        const int row = a.r0 + rg + u;
+        v[u] = (active && row < a.rows_total) ? load_cols4<VEC>(a.mat + (size_t)row * n, col, n)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (NC > 0) {
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const float s = rowscal[c * R + rg + u];
+            cacc[c].x = fmaf(v[u].x, s, cacc[c].x);
+            cacc[c].y = fmaf(v[u].y, s, cacc[c].y);
+            cacc[c].z = fmaf(v[u].z, s, cacc[c].z);
+            cacc[c].w = fmaf(v[u].w, s, cacc[c].w);
+          }
+        }
+      }
+      if (NR > 0) {
+        float rp[kRowUnroll * (NR > 0 ? NR : 1)];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+          for (int k = 0; k < NR; ++k) {
+            float t = v[u].x * rv[k].x;
+            t = fmaf(v[u].y, rv[k].y, t);
+            t = fmaf(v[u].z, rv[k].z, t);
+            t = fmaf(v[u].w, rv[k].w, t);
+            rp[u * NR + k] = t;
+          }
+        }
+        constexpr int NV = kRowUnroll * (NR > 0 ? NR : 1);
+        const float tot = warp_transpose_reduce<NV>(rp, lane);
+        constexpr int kGroup = 32 / NV;              // lanes holding the same value
+        if ((lane % kGroup) == 0) {
+          const int idx = lane / kGroup;             // = u*NR + k
+          rowpart[warp * (R * NR) + rg * NR + idx] = tot;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) store_cols4<VEC>(a.cpart[c], col, n, cacc[c]);
+
+    if (NR > 0) {
+      __syncthreads();
+      for (int i = tid; i < R * NR; i += kKktThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kKktWarps; ++w) s += rowpart[w * (R * NR) + i];
+        rowacc[i] += s;
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NR; ++k)
+    for (int r = tid; r < R; r += kKktThreads) {
+      const int row = a.r0 + r;
+      if (row < a.rows_total) a.rout[k][row] = rowacc[r * NR + k];
+    }
+}
+
+// The dense pass with block skipping (structured sparsity): `a.blk` holds one bit per 8-row x 128-column block of the
+// instance's matrix (bit s of word g <-> rows 8g..8g+7, columns 128s..128s+127 contain a non-zero).  A warp's unit of work IS
+// such a block, so a clear bit skips its 4 KB of loads and its products with a warp-uniform branch and nothing else changes:
+// no decode cost, bit-identical results (the skipped entries are exact zeros), HBM bytes = the non-empty blocks.  Diagonal Q
+// (QP family), identity blocks (SVM) and banded / block-structured QPLIB matrices are the cases this is for.
+template <int NR, int NC, bool VEC>
+__device__ __forceinline__ void tile_pass_blocks(const TileArgs& a, float* smem) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = a.R, n = a.n;
+  float* rowscal = smem;
+  float* rowacc  = smem + 2 * R;
+  float* rowpart = smem + 4 * R;
+
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    for (int r = tid; r < R; r += kKktThreads) {
+      const int row = a.r0 + r;
+      rowscal[c * R + r] = (row < a.rows_total) ? __ldg(a.crhs[c] + row) : 0.f;
+    }
+  for (int i = tid; i < R * NR; i += kKktThreads) rowacc[i] = 0.f;
+  __syncthreads();
+
+  const int nchunk = (n + kChunkCols - 1) / kChunkCols;
+  for (int cc = 0; cc < nchunk; ++cc) {
+    const int  col    = cc * kChunkCols + warp * kSlabCols + lane * 4;
+    const bool active = col < n;
+    float4 rv[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) rv[k] = load_vec4<VEC>(a.rrhs[k], col, n);
+    float4 cacc[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cacc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int rg = 0; rg < R; rg += kRowUnroll) {
+      float4 v[kRowUnroll];
+      {
+        const int g = (a.r0 + rg) >> 3;                       // R and r0 are multiples of 8 (= kRowUnroll)
+        const unsigned long long word = (a.r0 + rg < a.rows_total) ? __ldg(a.blk + g) : 0ull;
+        if (!((word >> (cc * kKktWarps + warp)) & 1ull)) {
+          if (NR > 0) {
+            constexpr int NV0 = kRowUnroll * (NR > 0 ? NR : 1);
+            constexpr int kGroup0 = 32 / NV0;
+            if ((lane % kGroup0) == 0) rowpart[warp * (R * NR) + rg * NR + lane / kGroup0] = 0.f;
+          }
+          continue;
+        }
+      }
 #pragma unroll
       for (int u = 0; u < kRowUnroll; ++u) {
         const int row = a.r0 + rg + u;
@@ -413,8 +524,10 @@ struct Pass1Args {
   KktScratch s;
 };
 
-template <bool VEC, bool SPQ = false, bool SPA = false>
-__global__ void __launch_bounds__(kKktThreads, (SPQ || SPA) ? 3 : 0) kkt_pass1_kernel(const Pass1Args P) {
+// MQ / MA: form of Q / A0 -- 0 dense, 1 bitmap slabs, 2 dense with block skipping
+template <bool VEC, int MQ = 0, int MA = 0>
+__global__ void __launch_bounds__(kKktThreads, (MQ == 1 || MA == 1) ? 3 : 0) kkt_pass1_kernel(const Pass1Args P) {
+  constexpr bool SPQ = (MQ == 1), SPA = (MA == 1);
   extern __shared__ float smem[];
   const KktDims& d = P.d;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -425,24 +538,31 @@ __global__ void __launch_bounds__(kKktThreads, (SPQ || SPA) ? 3 : 0) kkt_pass1_k
   a.rrhs[1] = P.x + b * n;
   if (chunk < d.chunks_q) {
     a.mat = SPQ ? nullptr : P.Q + b * n * n; a.sp = P.spq; a.inst = b; a.rows_total = d.n; a.r0 = chunk * a.R;
+    a.blk = (MQ == 2) ? P.spq.blk + b * P.spq.blk_stride : nullptr;
     a.rout[0] = P.s.qxt + b * n; a.rout[1] = P.s.qx + b * n;
     a.crhs[0] = a.crhs[1] = nullptr; a.cpart[0] = a.cpart[1] = nullptr;
-    if constexpr (SPQ) tile_pass_sparse<2, 0, VEC>(a, smem); else tile_pass<2, 0, VEC>(a, smem);
+    if constexpr (MQ == 1) tile_pass_sparse<2, 0, VEC>(a, smem);
+    else if constexpr (MQ == 2) tile_pass_blocks<2, 0, VEC>(a, smem);
+    else tile_pass<2, 0, VEC>(a, smem);
   } else {
     const int ca = chunk - d.chunks_q;
     a.mat = SPA ? nullptr : P.A0 + b * m * n; a.sp = P.spa; a.inst = b; a.rows_total = d.m; a.r0 = ca * a.R;
+    a.blk = (MA == 2) ? P.spa.blk + b * P.spa.blk_stride : nullptr;
     a.rout[0] = P.s.axt + b * m; a.rout[1] = P.s.ax + b * m;
     a.crhs[0] = P.v + (size_t)b * P.v_stride; a.crhs[1] = P.y + b * m;
     float* part = P.s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
     a.cpart[0] = part; a.cpart[1] = part + n;
-    if constexpr (SPA) tile_pass_sparse<2, 2, VEC>(a, smem); else tile_pass<2, 2, VEC>(a, smem);
+    if constexpr (MA == 1) tile_pass_sparse<2, 2, VEC>(a, smem);
+    else if constexpr (MA == 2) tile_pass_blocks<2, 2, VEC>(a, smem);
+    else tile_pass<2, 2, VEC>(a, smem);
   }
 }
 
-template <bool VEC, bool SPQ = false, bool SPA = false>
-__global__ void __launch_bounds__(kKktThreads, (SPQ || SPA) ? 3 : 0) kkt_pass2_kernel(const KktDims d, const float* __restrict__ Q,
+template <bool VEC, int MQ = 0, int MA = 0>
+__global__ void __launch_bounds__(kKktThreads, (MQ == 1 || MA == 1) ? 3 : 0) kkt_pass2_kernel(const KktDims d, const float* __restrict__ Q,
                                                                 const float* __restrict__ A0, const KktScratch s,
                                                                 const SpMat spq, const SpMat spa) {
+  constexpr bool SPQ = (MQ == 1), SPA = (MA == 1);
   extern __shared__ float smem[];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const size_t n = d.n, m = d.m, N = n + m;
@@ -453,41 +573,55 @@ __global__ void __launch_bounds__(kKktThreads, (SPQ || SPA) ? 3 : 0) kkt_pass2_k
   a.rrhs[1] = nullptr; a.rout[1] = nullptr; a.crhs[1] = nullptr; a.cpart[1] = nullptr;
   if (chunk < d.chunks_q) {
     a.mat = SPQ ? nullptr : Q + b * n * n; a.sp = spq; a.inst = b; a.rows_total = d.n; a.r0 = chunk * a.R;
+    a.blk = (MQ == 2) ? spq.blk + b * spq.blk_stride : nullptr;
     a.rrhs[0] = nullptr; a.rout[0] = nullptr;
     a.crhs[0] = w1; a.cpart[0] = s.part_q + ((size_t)b * d.chunks_q + chunk) * n;
-    if constexpr (SPQ) tile_pass_sparse<0, 1, VEC>(a, smem); else tile_pass<0, 1, VEC>(a, smem);
+    if constexpr (MQ == 1) tile_pass_sparse<0, 1, VEC>(a, smem);
+    else if constexpr (MQ == 2) tile_pass_blocks<0, 1, VEC>(a, smem);
+    else tile_pass<0, 1, VEC>(a, smem);
   } else {
     const int ca = chunk - d.chunks_q;
     a.mat = SPA ? nullptr : A0 + b * m * n; a.sp = spa; a.inst = b; a.rows_total = d.m; a.r0 = ca * a.R;
+    a.blk = (MA == 2) ? spa.blk + b * spa.blk_stride : nullptr;
     a.rrhs[0] = w1; a.rout[0] = s.aw1 + b * m;
     a.crhs[0] = w2; a.cpart[0] = s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
-    if constexpr (SPA) tile_pass_sparse<1, 1, VEC>(a, smem); else tile_pass<1, 1, VEC>(a, smem);
+    if constexpr (MA == 1) tile_pass_sparse<1, 1, VEC>(a, smem);
+    else if constexpr (MA == 2) tile_pass_blocks<1, 1, VEC>(a, smem);
+    else tile_pass<1, 1, VEC>(a, smem);
   }
 }
 
+static int sp_mode(const SpMat* m) { return !m ? 0 : (m->vals ? 1 : (m->blk ? 2 : 0)); }
+
 static bool can_vectorise(const KktDims& d, const void* Q, const void* A0, const KktSparse* sp) {
-  // the 128-bit path needs 16-byte aligned matrix rows (n % 4 == 0); a matrix given in sparse form has no such constraint
+  // the 128-bit path needs 16-byte aligned matrix rows (n % 4 == 0); a matrix given in bitmap-slab form has no such constraint
   return (d.n % 4 == 0) && ((sp && sp->q.vals) || aligned16(Q)) && ((sp && sp->a.vals) || aligned16(A0));
 }
 
+template <bool VEC, int MQ>
+static void launch_pass1_a(const Pass1Args& P, int ma, dim3 grid, size_t smem, cudaStream_t st) {
+  if (ma == 1)      kkt_pass1_kernel<VEC, MQ, 1><<<grid, kKktThreads, smem, st>>>(P);
+  else if (ma == 2) kkt_pass1_kernel<VEC, MQ, 2><<<grid, kKktThreads, smem, st>>>(P);
+  else              kkt_pass1_kernel<VEC, MQ, 0><<<grid, kKktThreads, smem, st>>>(P);
+}
 template <bool VEC>
-static void launch_pass1_variant(const Pass1Args& P, bool spq, bool spa, dim3 grid, size_t smem, cudaStream_t st) {
-  if (spq && spa)  kkt_pass1_kernel<VEC, true, true><<<grid, kKktThreads, smem, st>>>(P);
-  else if (spq)    kkt_pass1_kernel<VEC, true, false><<<grid, kKktThreads, smem, st>>>(P);
-  else if (spa)    kkt_pass1_kernel<VEC, false, true><<<grid, kKktThreads, smem, st>>>(P);
-  else             kkt_pass1_kernel<VEC, false, false><<<grid, kKktThreads, smem, st>>>(P);
+static void launch_pass1_variant(const Pass1Args& P, int mq, int ma, dim3 grid, size_t smem, cudaStream_t st) {
+  if (mq == 1)      launch_pass1_a<VEC, 1>(P, ma, grid, smem, st);
+  else if (mq == 2) launch_pass1_a<VEC, 2>(P, ma, grid, smem, st);
+  else              launch_pass1_a<VEC, 0>(P, ma, grid, smem, st);
 }
 
 static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t st) {
   const KktDims& d = P.d;
-  const bool spq = sp && sp->q.vals, spa = sp && sp->a.vals && d.m > 0;
-  if (spq) P.spq = sp->q;
-  if (spa) P.spa = sp->a;
+  const int mq = sp_mode(sp ? &sp->q : nullptr), ma = d.m > 0 ? sp_mode(sp ? &sp->a : nullptr) : 0;
+  if (mq) P.spq = sp->q;
+  if (ma) P.spa = sp->a;
   const dim3 grid(d.chunks_q + d.chunks_a, d.B);
-  if ((spq || spa) && d.rows_per_chunk > 64) IADMM_FAIL(IADMM_EMODE, "sparse KKT pass: at most 64 rows per chunk");
-  const size_t smem = tile_smem_bytes(d.rows_per_chunk, spq || spa);
-  if (can_vectorise(d, P.Q, P.A0, sp)) launch_pass1_variant<true>(P, spq, spa, grid, smem, st);
-  else                                 launch_pass1_variant<false>(P, spq, spa, grid, smem, st);
+  if ((mq || ma) && (d.rows_per_chunk > 64 || d.rows_per_chunk % 8)) IADMM_FAIL(IADMM_EMODE, "sparse KKT pass: row chunks must be 8..64 rows");
+  if ((mq == 2 || ma == 2) && d.n > 64 * 128) IADMM_FAIL(IADMM_EMODE, "block-skip KKT pass: at most 8192 columns");
+  const size_t smem = tile_smem_bytes(d.rows_per_chunk, mq == 1 || ma == 1);
+  if (can_vectorise(d, P.Q, P.A0, sp)) launch_pass1_variant<true>(P, mq, ma, grid, smem, st);
+  else                                 launch_pass1_variant<false>(P, mq, ma, grid, smem, st);
   IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
   return IADMM_OK;
 }
@@ -515,26 +649,33 @@ int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, co
   return launch_pass1_common(P, nullptr, st);
 }
 
+template <bool VEC, int MQ>
+static void launch_pass2_a(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, const SpMat& q, const SpMat& a,
+                           int ma, dim3 grid, size_t smem, cudaStream_t st) {
+  if (ma == 1)      kkt_pass2_kernel<VEC, MQ, 1><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
+  else if (ma == 2) kkt_pass2_kernel<VEC, MQ, 2><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
+  else              kkt_pass2_kernel<VEC, MQ, 0><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
+}
 template <bool VEC>
 static void launch_pass2_variant(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, const SpMat& q, const SpMat& a,
-                                 bool spq, bool spa, dim3 grid, size_t smem, cudaStream_t st) {
-  if (spq && spa)  kkt_pass2_kernel<VEC, true, true><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
-  else if (spq)    kkt_pass2_kernel<VEC, true, false><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
-  else if (spa)    kkt_pass2_kernel<VEC, false, true><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
-  else             kkt_pass2_kernel<VEC, false, false><<<grid, kKktThreads, smem, st>>>(d, Q, A0, s, q, a);
+                                 int mq, int ma, dim3 grid, size_t smem, cudaStream_t st) {
+  if (mq == 1)      launch_pass2_a<VEC, 1>(d, Q, A0, s, q, a, ma, grid, smem, st);
+  else if (mq == 2) launch_pass2_a<VEC, 2>(d, Q, A0, s, q, a, ma, grid, smem, st);
+  else              launch_pass2_a<VEC, 0>(d, Q, A0, s, q, a, ma, grid, smem, st);
 }
 
 int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st, const KktSparse* sp) {
   const dim3 grid(d.chunks_q + d.chunks_a, d.B);
-  const bool spq = sp && sp->q.vals, spa = sp && sp->a.vals && d.m > 0;
-  if ((spq || spa) && d.rows_per_chunk > 64) IADMM_FAIL(IADMM_EMODE, "sparse KKT pass: at most 64 rows per chunk");
-  const size_t smem = tile_smem_bytes(d.rows_per_chunk, spq || spa);
+  const int mq = sp_mode(sp ? &sp->q : nullptr), ma = d.m > 0 ? sp_mode(sp ? &sp->a : nullptr) : 0;
+  if ((mq || ma) && (d.rows_per_chunk > 64 || d.rows_per_chunk % 8)) IADMM_FAIL(IADMM_EMODE, "sparse KKT pass: row chunks must be 8..64 rows");
+  if ((mq == 2 || ma == 2) && d.n > 64 * 128) IADMM_FAIL(IADMM_EMODE, "block-skip KKT pass: at most 8192 columns");
+  const size_t smem = tile_smem_bytes(d.rows_per_chunk, mq == 1 || ma == 1);
   SpMat q, a;
   memset(&q, 0, sizeof(q)); memset(&a, 0, sizeof(a));
-  if (spq) q = sp->q;
-  if (spa) a = sp->a;
-  if (can_vectorise(d, Q, A0, sp)) launch_pass2_variant<true>(d, Q, A0, s, q, a, spq, spa, grid, smem, st);
-  else                             launch_pass2_variant<false>(d, Q, A0, s, q, a, spq, spa, grid, smem, st);
+  if (mq) q = sp->q;
+  if (ma) a = sp->a;
+  if (can_vectorise(d, Q, A0, sp)) launch_pass2_variant<true>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
+  else                             launch_pass2_variant<false>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
   IADMM_LAUNCH_CHECK("kkt_pass2_kernel");
   return IADMM_OK;
 }

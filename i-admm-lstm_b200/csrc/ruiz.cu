@@ -14,10 +14,11 @@
 // inf-norms of the matrix scaled by the diagonals of iterations 0..k-1.  The "chain" passes therefore read the ORIGINAL
 // matrices and re-apply, in registers and in the same order, the rounded products of all previous iterations (3 fp32
 // multiplies per entry and iteration for Q, 2 for A0 -- the pass stays HBM bound up to 10 iterations), take the norms, and
-// write nothing; one last pass applies the whole chain and writes the result: ites + 2 reads + 1 write = 13 passes instead of
-// 21.5, bit-identical to the in-place form (same operands, same IEEE multiplies, same order).  Needs the per-iteration
-// diagonals (ites * (n+m) floats per instance) instead of the current ones; more than kRzMaxChain iterations fall back to the
-// in-place form.
+// write nothing.  Re-applying ALL previous iterations turned out compute bound (measured: 11.8 ms against 9.0 ms in place at
+// config 2), so the state is materialised every kRzPeriod = 3 iterations: 12 reads + 4 writes = 16 matrix passes instead of 21.5
+// at 10 iterations, bit-identical to the in-place form (same operands, same IEEE multiplies, same order -- checked by hash,
+// tools/ruiz_ab.py).  Needs the per-iteration diagonals ((n+m) floats per instance and iteration); more than kRzMaxHist
+// iterations fall back to the in-place form.
 #include "common.cuh"
 
 namespace iadmm {
@@ -26,7 +27,9 @@ constexpr int kRzThreads = 256;
 constexpr int kRzWarps   = 8;
 constexpr int kRzUnroll  = 8;
 constexpr int kRzChunkCols = 128 * kRzWarps;
-constexpr int kRzMaxChain = 10;        // iterations the chain passes re-apply from registers (scaling_ites of every config)
+constexpr int kRzPeriod = 3;           // chain passes: the state is materialised every kRzPeriod iterations
+constexpr int kRzMaxChain = kRzPeriod; // steps a chain pass re-applies in registers
+constexpr int kRzMaxHist = 32;         // iterations whose diagonals are kept (more: in-place form)
 constexpr float kMinScaling = 1e-4f;   // scaling.py:12
 constexpr float kMaxScaling = 1e4f;    // scaling.py:13
 
@@ -157,13 +160,15 @@ ruiz_pass_kernel(const float* Qsrc, const float* Asrc, float* Qdst, float* Adst,
   }
 }
 
-// Chain pass: reads the ORIGINAL matrices, re-applies the scale steps 0..steps-1 in registers (same rounded products, same
-// order as the in-place form) and either takes the norms of the result (WRITE = false: the matrix iteration `steps` sees)
-// or applies the last cost factor and writes it (WRITE = true).  grid = (chunks_q + chunks_a, B).
-template <bool WRITE, bool VEC>
+// Chain pass: reads a materialised state of the matrices (the originals, or Qs/A0s as written by an earlier chain pass),
+// re-applies the scale steps slot0 .. slot0+steps-1 in registers (same rounded products, same order as the in-place form),
+// and takes the norms of the result (NORM) and/or writes it (WRITE; with final_cost the pending last cost factor is applied
+// first).  src may be dst (every entry is read and then written by the same thread; loads are coherent).
+// grid = (chunks_q + chunks_a, B).
+template <bool NORM, bool WRITE, bool VEC>
 __global__ void __launch_bounds__(kRzThreads)
-ruiz_chain_kernel(const float* __restrict__ Qsrc, const float* __restrict__ Asrc, float* __restrict__ Qdst, float* __restrict__ Adst,
-                  int n, int m, int steps, RuizWs W) {
+ruiz_chain_kernel(const float* Qsrc, const float* Asrc, float* Qdst, float* Adst, int n, int m, int slot0, int steps, int final_cost,
+                  RuizWs W) {
   __shared__ float rowpart[kRzWarps][128];
   __shared__ float srow_s[kRzMaxChain][128];       // left diagonal factors of this CTA's rows, per step (R <= 128)
   __shared__ float cstep[kRzMaxChain + 1];         // Q: cost factor applied before step j; [steps] = the pending last one
@@ -180,9 +185,9 @@ ruiz_chain_kernel(const float* __restrict__ Qsrc, const float* __restrict__ Asrc
   const float* left = isQ ? W.sd : W.se;
   for (int i = tid; i < steps * R; i += kRzThreads) {
     const int j = i / R, r = i - j * R, row = r0 + r;
-    srow_s[j][r] = (row < rows_total) ? left[((size_t)j * W.B + b) * rlen + row] : 1.0f;
+    srow_s[j][r] = (row < rows_total) ? left[((size_t)(slot0 + j) * W.B + b) * rlen + row] : 1.0f;
   }
-  if (tid < steps + (WRITE ? 1 : 0)) cstep[tid] = isQ ? W.cprev[(size_t)tid * W.B + b] : 1.0f;
+  if (tid < steps + (final_cost ? 1 : 0)) cstep[tid] = isQ ? W.cprev[(size_t)(slot0 + tid) * W.B + b] : 1.0f;
   __syncthreads();
 
   const int nchunk = (n + kRzChunkCols - 1) / kRzChunkCols;
@@ -194,7 +199,7 @@ ruiz_chain_kernel(const float* __restrict__ Qsrc, const float* __restrict__ Asrc
     for (int j = 0; j < kRzMaxChain; ++j) {
       float t[4] = {1.f, 1.f, 1.f, 1.f};
       if (j < steps) {
-        const float* sdj = W.sd + ((size_t)j * W.B + b) * n;
+        const float* sdj = W.sd + ((size_t)(slot0 + j) * W.B + b) * n;
 #pragma unroll
         for (int e = 0; e < 4; ++e) if (col + e < n) t[e] = sdj[col + e];
       }
@@ -209,11 +214,11 @@ ruiz_chain_kernel(const float* __restrict__ Qsrc, const float* __restrict__ Asrc
         const bool ok = active && row < rows_total;
         float t[4] = {0.f, 0.f, 0.f, 0.f};
         if (ok && VEC) {
-          const float4 q = ldg_stream4(src + (size_t)row * n + col);
+          const float4 q = ld_stream4_coherent(src + (size_t)row * n + col);
           t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
         } else if (ok) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (col + e < n) t[e] = ldg_stream1(src + (size_t)row * n + col + e);
+          for (int e = 0; e < 4; ++e) if (col + e < n) t[e] = src[(size_t)row * n + col + e];
         }
         v[u][0] = pk2(t[0], t[1]); v[u][1] = pk2(t[2], t[3]);
       }
@@ -234,7 +239,7 @@ ruiz_chain_kernel(const float* __restrict__ Qsrc, const float* __restrict__ Asrc
         }
         float t[4];
         if (WRITE) {
-          if (isQ) { const u64 cl = bc2(cstep[steps]); a0 = mul2(cl, a0); a1 = mul2(cl, a1); }  // the last cost factor
+          if (isQ && final_cost) { const u64 cl = bc2(cstep[steps]); a0 = mul2(cl, a0); a1 = mul2(cl, a1); }  // the last cost factor
           upk2(a0, t[0], t[1]); upk2(a1, t[2], t[3]);
           if (ok) {
             float* drow = dst + (size_t)row * n + col;
@@ -245,7 +250,8 @@ ruiz_chain_kernel(const float* __restrict__ Qsrc, const float* __restrict__ Asrc
             }
           }
           rmax[u] = 0.f;
-        } else {
+        }
+        if (NORM) {
           upk2(a0, t[0], t[1]); upk2(a1, t[2], t[3]);
           float rm = 0.f;
 #pragma unroll
@@ -257,16 +263,16 @@ ruiz_chain_kernel(const float* __restrict__ Qsrc, const float* __restrict__ Asrc
           rmax[u] = rm;
         }
       }
-      if (!WRITE && !isQ) {
+      if (NORM && !isQ) {
         const float tot = warp_transpose_reduce<kRzUnroll, true>(rmax, lane);
         if ((lane & 3) == 0) rowpart[warp][rg + (lane >> 2)] = tot;
       }
     }
-    if (!WRITE && active) {
+    if (NORM && active) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) if (col + e < n) colpart[col + e] = cmax[e];
     }
-    if (!WRITE && !isQ) {
+    if (NORM && !isQ) {
       __syncthreads();
       for (int r = tid; r < R; r += kRzThreads) {
         float t = 0.f;
@@ -374,7 +380,7 @@ size_t ruiz_ws_floats(int B, int n, int m, int* R_out, int* cq_out, int* ca_out)
   int R = kd.rows_per_chunk > 128 ? 128 : kd.rows_per_chunk;
   const int cq = cdiv(n, R), ca = cdiv(m, R);
   if (R_out) { *R_out = R; *cq_out = cq; *ca_out = ca; }
-  const size_t hist = kRzMaxChain + 1;          // per-iteration diagonals for the chain passes
+  const size_t hist = kRzMaxHist + 1;           // per-iteration diagonals for the chain passes
   return hist * ((size_t)B * n + (size_t)B * m + B) + (size_t)B * m + (size_t)B * cq * n + (size_t)B * ca * n + 64 + 4 * 8;
 }
 
@@ -386,12 +392,12 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
   if (workspace_bytes < need) IADMM_FAIL(IADMM_EWORK, "ruiz workspace too small: %zu < %zu", workspace_bytes, need);
   float* base = static_cast<float*>(workspace);
   auto take = [&](size_t cnt) { float* q = base; base += (cnt + 3) / 4 * 4; return q; };
-  const size_t hist = kRzMaxChain + 1;
+  const size_t hist = kRzMaxHist + 1;
   W.B = B;
   W.sd = take(hist * (size_t)B * n); W.se = take(hist * (size_t)B * m); W.cprev = take(hist * (size_t)B); W.rowmax = take((size_t)B * m);
   W.partq = take((size_t)B * W.chunks_q * n); W.parta = take((size_t)B * W.chunks_a * n);
   const char* sw = dev_env("IADMM_RUIZ_CHAIN");                       // development switch: 0 = in-place form (round 1)
-  const bool chain = iterations <= kRzMaxChain && !(sw && sw[0] == '0');
+  const bool chain = iterations <= kRzMaxHist && !(sw && sw[0] == '0');
   W.hist_on = chain ? 1 : 0;
 
   IADMM_CUDA(cudaMemcpyAsync(ps, p, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -414,17 +420,32 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
   ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 1, -1, ps, zls, zus, d, e, c, W);
   IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
   if (chain) {
-    // iteration k: norms of the original matrices under the scale steps 0..k (read only), then the vector work
+    // Iteration k needs the norms of the matrices under the scale steps 0..k.  They are taken from the last MATERIALISED state
+    // (the originals, later Qs/A0s) by re-applying the steps since then in registers; every kRzPeriod-th iteration the pass also
+    // writes its result, which bounds the re-applied steps at kRzPeriod (more and the pass turns compute bound: measured 0.16
+    // ms per step and pass at config 2 against 0.33 ms of HBM time per read).  10 iterations: 12 reads + 4 writes instead of
+    // the 11 + 10.5 of the in-place form.
+    const float* qsrc = Q;
+    const float* asrc = A0;
+    int slot0 = 0;
     for (int k = 0; k < iterations; ++k) {
-      if (vec) ruiz_chain_kernel<false, true><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, k + 1, W);
-      else     ruiz_chain_kernel<false, false><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, k + 1, W);
+      const int steps = k - slot0 + 1;
+      const bool write = (steps == kRzPeriod) && (k + 1 < iterations);
+      if (write) {
+        if (vec) ruiz_chain_kernel<true, true, true><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, slot0, steps, 0, W);
+        else     ruiz_chain_kernel<true, true, false><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, slot0, steps, 0, W);
+      } else {
+        if (vec) ruiz_chain_kernel<true, false, true><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, nullptr, nullptr, n, m, slot0, steps, 0, W);
+        else     ruiz_chain_kernel<true, false, false><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, nullptr, nullptr, n, m, slot0, steps, 0, W);
+      }
       IADMM_LAUNCH_CHECK("ruiz_chain_kernel<norm>");
       ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 1, (k + 1 < iterations) ? 1 : 0, k, ps, zls, zus, d, e, c, W);
       IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+      if (write) { qsrc = Qs; asrc = A0s; slot0 = k + 1; }
     }
-    // the only write: all steps and the last cost factor applied to the original entries
-    if (vec) ruiz_chain_kernel<true, true><<<grid, kRzThreads, 0, st>>>(Q, A0, Qs, A0s, n, m, iterations, W);
-    else     ruiz_chain_kernel<true, false><<<grid, kRzThreads, 0, st>>>(Q, A0, Qs, A0s, n, m, iterations, W);
+    // the last write: the steps since the last materialised state and the last cost factor
+    if (vec) ruiz_chain_kernel<false, true, true><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, slot0, iterations - slot0, 1, W);
+    else     ruiz_chain_kernel<false, true, false><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, slot0, iterations - slot0, 1, W);
     IADMM_LAUNCH_CHECK("ruiz_chain_kernel<write>");
     return IADMM_OK;
   }

@@ -127,11 +127,68 @@ __global__ void __launch_bounds__(kSpThreads) sparse_fill_kernel(const float* __
     }
 }
 
+// Block occupancy of a dense batch: bit s of word g of instance b <-> rows 8g..8g+7, columns 128s..128s+127 hold a non-zero.
+// grid = (ceil(rows/8), B), 8 warps; warp w scans the slabs w, w+8, ...
+__global__ void __launch_bounds__(256) block_mask_kernel(const float* __restrict__ M, int rows, int n, int S,
+                                                         unsigned long long* __restrict__ blk, unsigned int* __restrict__ count) {
+  __shared__ unsigned long long word_s;
+  const int b = blockIdx.y, g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) word_s = 0ull;
+  __syncthreads();
+  unsigned long long mine = 0ull;
+  for (int s = warp; s < S; s += 8) {
+    bool nz = false;
+    const int col = s * 128 + lane * 4;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int row = g * 8 + u;
+      if (row < rows) {
+        const float* rp = M + ((size_t)b * rows + row) * n;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) nz |= (col + e < n) && (rp[col + e] != 0.0f);
+      }
+    }
+    if (__any_sync(kFullMask, nz)) mine |= 1ull << s;
+  }
+  if (lane == 0 && mine) atomicOr(&word_s, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    blk[(size_t)b * gridDim.x + g] = word_s;
+    if (count) atomicAdd(count + b, (unsigned int)__popcll(word_s));
+  }
+}
+
 }  // namespace iadmm
 
 using namespace iadmm;
 
 extern "C" {
+
+int iadmm_block_mask_bytes(int B, int rows, int n, size_t* bytes) {
+  if (B <= 0 || rows < 0 || n <= 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "block_mask_bytes: B=%d rows=%d n=%d", B, rows, n);
+  if (n > 64 * 128) IADMM_FAIL(IADMM_EMODE, "block masks cover at most 8192 columns (got %d)", n);
+  *bytes = align_up((size_t)B * ((rows + 7) / 8) * sizeof(unsigned long long), 256) + 256;
+  return IADMM_OK;
+}
+
+int iadmm_block_mask(const float* M, int B, int rows, int n, void* blocks, size_t blocks_bytes, unsigned int* nonempty, void* stream) {
+  size_t need = 0;
+  int rc = iadmm_block_mask_bytes(B, rows, n, &need);
+  if (rc) return rc;
+  if (B > 65535) IADMM_FAIL(IADMM_ESHAPE, "block_mask: batch %d > 65535", B);
+  if (!M || !blocks || !aligned16(blocks)) IADMM_FAIL(IADMM_EALIGN, "block_mask: NULL or unaligned pointer");
+  if (blocks_bytes < need) IADMM_FAIL(IADMM_EWORK, "block_mask: buffer too small: %zu < %zu", blocks_bytes, need);
+  int dev = 0, major = 0;
+  IADMM_CUDA(cudaGetDevice(&dev));
+  IADMM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) IADMM_FAIL(IADMM_EARCH, "device %d has compute capability %d.x; libiadmm_b200 needs sm_100 (B200)", dev, major);
+  if (rows == 0) return IADMM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nonempty) IADMM_CUDA(cudaMemsetAsync(nonempty, 0, (size_t)B * sizeof(unsigned int), st));
+  block_mask_kernel<<<dim3((rows + 7) / 8, B), 256, 0, st>>>(M, rows, n, cdiv(n, 128), static_cast<unsigned long long*>(blocks), nonempty);
+  IADMM_LAUNCH_CHECK("block_mask_kernel");
+  return IADMM_OK;
+}
 
 int iadmm_sparse_bytes(int B, int rows, int n, size_t cap, size_t* bytes) {
   if (B <= 0 || rows < 0 || n <= 0 || !bytes) IADMM_FAIL(IADMM_ESHAPE, "sparse_bytes: B=%d rows=%d n=%d", B, rows, n);

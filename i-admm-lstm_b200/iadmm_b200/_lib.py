@@ -39,7 +39,9 @@ SIGNATURES = {
     "iadmm_solve": ([_P] * 20 + [_I] * 8 + [_F, _I, _I, _P, _Z, _P], c_int),
     "iadmm_sparse_bytes": ([_I, _I, _I, _Z, POINTER(_Z)], c_int),
     "iadmm_sparse_pack": ([_P, _I, _I, _I, _Z, _P, _Z, _P, _P], c_int),
-    "iadmm_solve_sparse": ([_P, _P, _P, _Z, _P, _P, _P, _Z] + [_P] * 16 + [_I] * 8 + [_F, _I, _I, _P, _Z, _P], c_int),
+    "iadmm_block_mask_bytes": ([_I, _I, _I, POINTER(_Z)], c_int),
+    "iadmm_block_mask": ([_P, _I, _I, _I, _P, _Z, _P, _P], c_int),
+    "iadmm_solve_sparse": ([_P, _P, _P, _Z, _P, _P, _P, _P, _Z, _P] + [_P] * 16 + [_I] * 8 + [_F, _I, _I, _P, _Z, _P], c_int),
     "iadmm_residuals_workspace_bytes": ([_I, _I, _I, POINTER(_Z)], c_int),
     "iadmm_residuals": ([_P] * 8 + [_I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_build_kkt": ([_P] * 10 + [_I] * 7 + [_F, _P], c_int),

@@ -28,26 +28,40 @@ PARAM_ORDER = ("W_i", "U_i", "b_i", "W_f", "U_f", "b_f", "W_o", "U_o", "b_o",
 SPARSE_AUTO_DENSITY = 0.003
 
 
-class SparseBatch:
-    """A [B, rows, n] matrix batch in the library's bitmap-slab form (include/iadmm.h, iadmm_sparse_pack)."""
+BLOCK_AUTO_OCCUPANCY = 0.7     # "auto": dense matrix with block skipping when at most this share of its 8x128 blocks is non-empty
 
-    def __init__(self, buf, cap, shape, nnz):
-        self.buf, self.cap, self.shape, self.nnz = buf, cap, tuple(shape), nnz
+
+class SparseBatch:
+    """A [B, rows, n] matrix batch in one of the library's two sparse forms (include/iadmm.h):
+    kind "slabs"  -- bitmap slabs (iadmm_sparse_pack): masks + packed non-zero values, for unstructured patterns below ~0.3 %;
+    kind "blocks" -- the dense matrix plus one occupancy bit per 8-row x 128-column block (iadmm_block_mask): structured
+                     sparsity (diagonal, identity blocks, bands) at no decode cost."""
+
+    def __init__(self, kind, buf, cap, shape, nnz=None, nonempty=None):
+        self.kind, self.buf, self.cap, self.shape, self.nnz, self.nonempty = kind, buf, cap, tuple(shape), nnz, nonempty
 
     @property
     def density(self):
         return float(self.nnz.max()) / max(1, self.shape[1] * self.shape[2])
 
     @property
+    def occupancy(self):
+        """Share of non-empty 8x128 blocks (worst instance)."""
+        total = ((self.shape[1] + 7) // 8) * ((self.shape[2] + 127) // 128)
+        return float(self.nonempty.max()) / max(1, total)
+
+    @property
     def bytes_per_instance(self):
-        """What one streaming pass reads per instance (worst instance): 4 nnz + 20 bytes per row and 128-column slab."""
+        """What one streaming pass reads per instance (worst instance)."""
+        if self.kind == "blocks":
+            return 4096 * int(self.nonempty.max()) + 8 * ((self.shape[1] + 7) // 8)
         return 4 * int(self.nnz.max()) + 20 * self.shape[1] * ((self.shape[2] + 127) // 128)
 
     @staticmethod
     def pack(M, max_density=None, cap=None):
-        """Pack a dense CUDA batch.  Without `cap` the value capacity is the densest instance's non-zero count (one host
-        sync) and None is returned when `max_density` is given and exceeded.  With `cap` (e.g. the capacity of a previous
-        batch of the same family, or rows*n) nothing synchronises; check `nnz.max() <= cap` afterwards."""
+        """Bitmap-slab form of a dense CUDA batch.  Without `cap` the value capacity is the densest instance's non-zero count
+        (one host sync) and None is returned when `max_density` is given and exceeded.  With `cap` (e.g. the capacity of a
+        previous batch of the same family, or rows*n) nothing synchronises; check `nnz.max() <= cap` afterwards."""
         _lib.require_cuda(M)
         M = _lib.f32(M)
         B, rows, n = M.shape
@@ -63,7 +77,33 @@ class SparseBatch:
         buf = torch.empty(nbytes.value, dtype=torch.uint8, device=M.device)
         nnz = torch.empty((B,), dtype=torch.int32, device=M.device)
         torch.ops.iadmm.sparse_pack(M, buf, nnz, cap)
-        return SparseBatch(buf, cap, M.shape, nnz)
+        return SparseBatch("slabs", buf, cap, M.shape, nnz=nnz)
+
+    @staticmethod
+    def blocks(M, max_occupancy=None):
+        """Block-occupancy words of a dense CUDA batch (the matrix itself stays dense).  With `max_occupancy` the share of
+        non-empty blocks is read back (one host sync) and None is returned when it is exceeded."""
+        _lib.require_cuda(M)
+        M = _lib.f32(M)
+        B, rows, n = M.shape
+        if rows == 0 or n > 8192:
+            return None
+        nbytes = c_size_t()
+        _lib.check(_lib.lib().iadmm_block_mask_bytes(B, rows, n, byref(nbytes)))
+        buf = torch.empty(nbytes.value, dtype=torch.uint8, device=M.device)
+        nonempty = torch.empty((B,), dtype=torch.int32, device=M.device)
+        torch.ops.iadmm.block_mask(M, buf, nonempty)
+        sb = SparseBatch("blocks", buf, 0, M.shape, nonempty=nonempty)
+        if max_occupancy is not None and sb.occupancy > max_occupancy:
+            return None
+        return sb
+
+    @staticmethod
+    def auto(M):
+        """Selection by measured density / structure: bitmap slabs below SPARSE_AUTO_DENSITY, else block skipping when at most
+        BLOCK_AUTO_OCCUPANCY of the blocks are non-empty, else None (plain dense streaming)."""
+        sb = SparseBatch.pack(M, SPARSE_AUTO_DENSITY)
+        return sb if sb is not None else SparseBatch.blocks(M, BLOCK_AUTO_OCCUPANCY)
 
 
 @dataclass
@@ -182,10 +222,12 @@ class LSTM(nn.Module):
         on-chip-resident kernel (one persistent CTA per instance); `streaming=True` forces the HBM-streaming path.  `state=(x,y,z,xv,H,C)` or None for the zero state of main.py:837-843.
         `scaling` is the `Scaling` object that produced (Q,p,A0,zl,zu): with it the residuals of the
         un-scaled iterates on the original data (main.py:922-955) are traced too.
-        `sparse`: None = stream Q and A0 dense (the reference densifies every family, main.py:243-296); "auto" = re-lay each of
-        Q, A0 in the bitmap-slab form when its density is below SPARSE_AUTO_DENSITY (Random_QP / Equality_QP / SVM / QPLIB
-        families: the KKT passes then read only the stored bytes, results are bit-identical); True = always; or a pair
-        `(SparseBatch | None, SparseBatch | None)` packed by the caller.  One host sync per packed matrix."""
+        `sparse`: None = stream Q and A0 dense (the reference densifies every family, main.py:243-296); "auto" = per matrix,
+        by measured density / structure (SparseBatch.auto): bitmap slabs for unstructured patterns below 0.3 %, block skipping
+        on the dense layout when whole 8x128 blocks are empty (diagonal Q, identity blocks of SVM, banded QPLIB), else dense;
+        True / "slabs" = bitmap slabs always, "blocks" = block skipping always; or a pair `(SparseBatch | None, SparseBatch |
+        None)` prepared by the caller.  The KKT passes then read only the stored bytes; results are bit-identical to the
+        dense path.  One or two host syncs per matrix for "auto"."""
         L = _lib.lib()
         _lib.require_cuda(Q, p, A0, zl, zu, *[prm for prm in self.parameters()])
         dev = Q.device
@@ -221,13 +263,20 @@ class LSTM(nn.Module):
         if sparse is not None and sparse is not False:
             if isinstance(sparse, (tuple, list)):
                 q_sp, a_sp = sparse
+            elif sparse == "auto":
+                q_sp, a_sp = SparseBatch.auto(Q), SparseBatch.auto(A0)
+            elif sparse == "blocks":
+                q_sp, a_sp = SparseBatch.blocks(Q), SparseBatch.blocks(A0)
             else:
-                lim = SPARSE_AUTO_DENSITY if sparse == "auto" else None
-                q_sp, a_sp = SparseBatch.pack(Q, lim), SparseBatch.pack(A0, lim)
+                q_sp, a_sp = SparseBatch.pack(Q), SparseBatch.pack(A0)
             self.last_sparse = (q_sp, a_sp)
             if q_sp is not None or a_sp is not None:
-                torch.ops.iadmm.solve_sparse(packed, Q, q_sp.buf if q_sp else None, q_sp.cap if q_sp else 0, p,
-                                             A0, a_sp.buf if a_sp else None, a_sp.cap if a_sp else 0, zl, zu, sd, se, sc,
+                def form(sb):          # (slab buffer, capacity, block words)
+                    if sb is None:
+                        return None, 0, None
+                    return (sb.buf, sb.cap, None) if sb.kind == "slabs" else (None, 0, sb.buf)
+                (q_buf, q_cap, q_blk), (a_buf, a_cap, a_blk) = form(q_sp), form(a_sp)
+                torch.ops.iadmm.solve_sparse(packed, Q, q_buf, q_cap, q_blk, p, A0, a_buf, a_cap, a_blk, zl, zu, sd, se, sc,
                                              x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met, ws,
                                              int(num_ineq), int(num_eq), h, self.length, int(t0), int(K), float(sigma), mode, flags)
                 return SolveResult(x, y, z, xv, H, C, pri, dual, pri_u, dual_u, met)

@@ -79,8 +79,8 @@ def sparse_pack(M: Tensor, packed: Tensor, nnz: Tensor, cap: int) -> None:
 
 @torch.library.custom_op("iadmm::solve_sparse", mutates_args=("x", "y", "z", "xv", "H", "C", "pri", "dual", "pri_u", "dual_u",
                                                                "metrics", "workspace"), device_types="cuda")
-def solve_sparse(packed: Tensor, Q: Optional[Tensor], Q_sp: Optional[Tensor], q_cap: int, p: Tensor,
-                 A0: Optional[Tensor], A0_sp: Optional[Tensor], a_cap: int, zl: Tensor, zu: Tensor,
+def solve_sparse(packed: Tensor, Q: Optional[Tensor], Q_sp: Optional[Tensor], q_cap: int, Q_blk: Optional[Tensor], p: Tensor,
+                 A0: Optional[Tensor], A0_sp: Optional[Tensor], a_cap: int, A0_blk: Optional[Tensor], zl: Tensor, zu: Tensor,
                  sd: Optional[Tensor], se: Optional[Tensor], sc: Optional[Tensor],
                  x: Tensor, y: Tensor, z: Tensor, xv: Tensor, H: Tensor, C: Tensor,
                  pri: Optional[Tensor], dual: Optional[Tensor], pri_u: Optional[Tensor], dual_u: Optional[Tensor],
@@ -88,8 +88,16 @@ def solve_sparse(packed: Tensor, Q: Optional[Tensor], Q_sp: Optional[Tensor], q_
                  num_ineq: int, num_eq: int, h: int, length: int, t0: int, K: int, sigma: float, mode: int, flags: int) -> None:
     B, n = x.shape[0], x.shape[1]
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().iadmm_solve_sparse(_P(packed), _P(Q), _P(Q_sp), q_cap, _P(p), _P(A0), _P(A0_sp), a_cap, _P(zl), _P(zu),
+        _lib.check(_lib.lib().iadmm_solve_sparse(_P(packed), _P(Q), _P(Q_sp), q_cap, _P(Q_blk), _P(p), _P(A0), _P(A0_sp), a_cap, _P(A0_blk),
+                                                 _P(zl), _P(zu),
                                                  _P(sd), _P(se), _P(sc), _P(x), _P(y), _P(z), _P(xv), _P(H), _P(C),
                                                  _P(pri), _P(dual), _P(pri_u), _P(dual_u), _P(metrics),
                                                  B, n, num_ineq, num_eq, h, length, t0, K, sigma, mode, flags,
                                                  _P(workspace), workspace.numel(), _lib.stream_ptr()))
+
+
+@torch.library.custom_op("iadmm::block_mask", mutates_args=("blocks", "nonempty"), device_types="cuda")
+def block_mask(M: Tensor, blocks: Tensor, nonempty: Tensor) -> None:
+    B, rows, n = M.shape
+    with torch.cuda.device(M.device):
+        _lib.check(_lib.lib().iadmm_block_mask(_P(M), B, rows, n, _P(blocks), blocks.numel(), _P(nonempty), _lib.stream_ptr()))

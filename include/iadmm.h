@@ -149,13 +149,26 @@ int iadmm_solve(const void* packed_weights,
  * iadmm_solve_sparse = iadmm_solve with Q and/or A0 given in that form (pass NULL for the form not used; the dense
  * pointer of a matrix given in sparse form may be NULL).  Same kernels, same lane-to-column assignment and accumulation
  * order as the dense passes: results are bit-identical to the densified problem, the KKT passes read only the stored bytes.
- * Always runs the HBM-streaming variant. */
+ * Always runs the HBM-streaming variant.
+ *
+ * Second form, for STRUCTURED sparsity (diagonal Q of the QP family, the identity blocks of SVM, banded QPLIB matrices):
+ * the dense matrix stays as it is and iadmm_block_mask computes one bit per 8-row x 128-column block ("does it hold a
+ * non-zero"): blocks [B][ceil(rows/8)] 64-bit words, bit s of word g <-> rows 8g..8g+7, columns 128s..128s+127 (n <= 8192);
+ * `nonempty` (device, [B], may be NULL) receives the number of non-empty blocks per instance.  A warp's unit of work in the
+ * KKT passes IS such a block, so a clear bit skips its 4 KB of loads with a warp-uniform branch at no decode cost: HBM bytes
+ * = the non-empty blocks, results bit-identical.  Pass the words as Q_blocks / A0_blocks (with the dense Q / A0).  The
+ * bitmap-slab form wins below ~0.3 % density on unstructured patterns, block skipping whenever whole blocks are empty;
+ * unstructured 1-60 % dense matrices are fastest in plain dense form (the mask expansion is instruction bound). */
 int iadmm_sparse_bytes(int B, int rows, int n, size_t cap, size_t* bytes);
 int iadmm_sparse_pack(const float* M, int B, int rows, int n, size_t cap, void* packed, size_t packed_bytes, int* nnz,
                       void* stream);
+int iadmm_block_mask_bytes(int B, int rows, int n, size_t* bytes);
+int iadmm_block_mask(const float* M, int B, int rows, int n, void* blocks, size_t blocks_bytes, unsigned int* nonempty,
+                     void* stream);
 int iadmm_solve_sparse(const void* packed_weights,
-                       const float* Q, const void* Q_sparse, size_t q_cap, const float* p,
-                       const float* A0, const void* A0_sparse, size_t a_cap, const float* zl, const float* zu,
+                       const float* Q, const void* Q_sparse, size_t q_cap, const void* Q_blocks, const float* p,
+                       const float* A0, const void* A0_sparse, size_t a_cap, const void* A0_blocks,
+                       const float* zl, const float* zu,
                        const float* d, const float* e, const float* c,
                        float* x, float* y, float* z, float* xv, float* H, float* C,
                        float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,

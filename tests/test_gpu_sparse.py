@@ -14,6 +14,20 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+def _block_words(M):
+    """Host-side block occupancy (documents the layout: bit s of word g <-> rows 8g..8g+7, columns 128s..128s+127)."""
+    B, rows, n = M.shape
+    G, S = (rows + 7) // 8, (n + 127) // 128
+    out = np.zeros((B, G), dtype=np.uint64)
+    nz = M.cpu().numpy() != 0
+    for b in range(B):
+        for g in range(G):
+            for s_ in range(S):
+                if nz[b, 8 * g:8 * g + 8, 128 * s_:128 * s_ + 128].any():
+                    out[b, g] |= np.uint64(1) << np.uint64(s_)
+    return out
+
+
 def _unpack(sb):
     """Host-side decode of a SparseBatch (documents the layout of include/iadmm.h: mask | off | vals)."""
     B, rows, n = sb.shape
@@ -57,6 +71,26 @@ def test_pack_roundtrip(shape):
     assert sb.bytes_per_instance < 4 * rows * n * 1.05
 
 
+@pytest.mark.parametrize("shape", [(2, 37, 130), (1, 64, 1000), (3, 100, 260)])
+def test_block_mask(shape):
+    import iadmm_b200 as ia
+    B, rows, n = shape
+    g = torch.Generator().manual_seed(rows)
+    M = torch.zeros((B, rows, n))
+    for b in range(B):                       # a diagonal, a dense band of rows and a few scattered entries
+        for i in range(min(rows, n)):
+            M[b, i, i] = 1.0 + i
+        M[b, rows // 2:rows // 2 + 3, :] = torch.randn((min(3, rows - rows // 2), n), generator=g)
+        M[b, 0, n - 1] = -0.0                # a negative zero does not make a block non-empty
+    sb = ia.SparseBatch.blocks(M.to(DEV))
+    G = (rows + 7) // 8
+    words = sb.buf.cpu().numpy()[:B * G * 8].view(np.uint64).reshape(B, G)
+    ref = _block_words(M)
+    assert np.array_equal(words, ref)
+    assert np.array_equal(sb.nonempty.cpu().numpy(), np.array([sum(bin(int(w)).count("1") for w in ref[b]) for b in range(B)]))
+    assert 0 < sb.occupancy < 1 and sb.bytes_per_instance < 4 * rows * n
+
+
 def _families():
     from iadmm_b200 import data
     yield "Random_QP", data.generate_family_batch("Random_QP", 3, 100, num_ineq=50, seed=1, device=DEV)
@@ -64,6 +98,9 @@ def _families():
     yield "SVM", data.generate_family_batch("SVM", 2, 60, num_ineq=40, seed=3, device=DEV)
     yield "QPLIB-like 1 %", data.generate_family_batch("Random_QP", 2, 1100, num_ineq=300, seed=4, device=DEV, density=0.01)
     yield "ragged n", data.generate_family_batch("Random_QP", 2, 203, num_ineq=77, seed=5, device=DEV)
+    from bench import device_qp_batch
+    Q, p, A0, zl, zu = device_qp_batch(2, 300, 100, 60, 6, DEV)                     # the QP family: diagonal Q, dense A0
+    yield "QP (diagonal Q)", dict(Q=Q, p=p, A0=A0, zl=zl, zu=zu, num_var=300, num_ineq=100, num_eq=60)
 
 
 @pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16f8"])
@@ -85,11 +122,14 @@ def test_sparse_solve_is_bit_identical_to_the_densified_problem(mode):
         with torch.no_grad():
             dense = model.solve(K, mi, me, *data, 6e-6, scaling=sc, streaming=True)
             sparse = model.solve(K, mi, me, *data, 6e-6, scaling=sc, sparse=True)
+            blocks = model.solve(K, mi, me, *data, 6e-6, scaling=sc, sparse="blocks")
+            mixed = model.solve(K, mi, me, *data, 6e-6, scaling=sc, sparse=(ia.SparseBatch.blocks(data[0]), ia.SparseBatch.pack(data[2])))
             auto = model.solve(K, mi, me, *data, 6e-6, scaling=sc, sparse="auto")
         q_sp, a_sp = model.last_sparse
         print(name, mode, "density Q %.3f A0 %.3f" % (ia.SparseBatch.pack(data[0]).density, ia.SparseBatch.pack(data[2]).density),
-              "auto packed:", q_sp is not None, a_sp is not None)
-        for r in (sparse, auto):
+              "block occupancy Q %.2f A0 %.2f" % (ia.SparseBatch.blocks(data[0]).occupancy, ia.SparseBatch.blocks(data[2]).occupancy),
+              "auto:", q_sp.kind if q_sp else "dense", a_sp.kind if a_sp else "dense")
+        for r in (sparse, blocks, mixed, auto):
             for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual", "pri_unscaled", "dual_unscaled", "metrics"):
                 assert torch.equal(getattr(dense, k), getattr(r, k)), (name, mode, k)
         assert torch.isfinite(dense.x).all()
@@ -115,12 +155,13 @@ def test_sparse_only_pointers_and_errors():
         B, m = 2, mi
         st = [torch.zeros(s, device=DEV) for s in ((B, n, 1), (B, m, 1), (B, m, 1), (B, n + m, 1), (B, n + m, h), (B, n + m, h))]
         ws = model._workspace(B, n, m, model._mode(), torch.device(DEV))
-        torch.ops.iadmm.solve_sparse(model.packed_weights(), None, q_sp.buf, q_sp.cap, d["p"], None, a_sp.buf, a_sp.cap, d["zl"], d["zu"],
-                                     None, None, None, *st, None, None, None, None, None, ws, mi, 0, h, K, 0, K, 6e-6, model._mode(), 1)
+        torch.ops.iadmm.solve_sparse(model.packed_weights(), None, q_sp.buf, q_sp.cap, None, d["p"], None, a_sp.buf, a_sp.cap, None,
+                                     d["zl"], d["zu"], None, None, None, *st, None, None, None, None, None, ws, mi, 0, h, K, 0, K, 6e-6,
+                                     model._mode(), 1)
         for a, b in zip(st, (ref.x, ref.y, ref.z, ref.xv, ref.H, ref.C)):
             assert torch.equal(a, b)
         with pytest.raises(ia.IadmmError, match="neither matrix"):
-            torch.ops.iadmm.solve_sparse(model.packed_weights(), d["Q"], None, 0, d["p"], d["A0"], None, 0, d["zl"], d["zu"],
+            torch.ops.iadmm.solve_sparse(model.packed_weights(), d["Q"], None, 0, None, d["p"], d["A0"], None, 0, None, d["zl"], d["zu"],
                                          None, None, None, *st, None, None, None, None, None, ws, mi, 0, h, K, 0, K, 6e-6, model._mode(), 0)
 
 
