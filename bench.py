@@ -269,14 +269,14 @@ def run_reference(args):
         torch.cuda.set_device(dev)
         g = gpu_reference_solves_per_s(steps, max(1, warmup), args.gpu_ref_batch, args.iters, dev, n, h)
         if g is None:
-            print(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref is not in this snapshot (run build() in the build container)"}), flush=True)
+            emit({"impl": "reference-gpu", "unavailable": "baseline/_ref is not in this snapshot (run build() in the build container)"})
             return
         line = {"impl": "reference-gpu", "metric": METRIC, "value": g["value"], "unit": UNIT, "n_gpus": 1, "steps": steps,
                 "warmup": max(1, warmup), "ms_per_step": g["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "batch_per_step": args.gpu_ref_batch, "iters": args.iters},
                 "gpu_reference": g, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     val, ms, cores, sample, kind = cpu_reference_solves_per_s(steps, warmup, args.cpu_batch, args.iters, n, h)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
@@ -286,7 +286,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args):
@@ -775,6 +775,7 @@ def run_train(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    quiet_stdout()        # libraries (NCCL banner, MAGMA's batched-solve warning at n=5000) print to stdout from C: keep it to ONE JSON line
     if a.impl != "ours":
         run_reference(a)
     elif a.workload == "train":

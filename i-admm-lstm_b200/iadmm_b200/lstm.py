@@ -53,8 +53,8 @@ class SparseBatch:
     @property
     def bytes_per_instance(self):
         """What one streaming pass reads per instance (worst instance)."""
-        if self.kind == "blocks":
-            return 4096 * int(self.nonempty.max()) + 8 * ((self.shape[1] + 7) // 8)
+        if self.kind == "blocks":      # (edge blocks are smaller than 4 KB: never more than the dense matrix)
+            return min(4096 * int(self.nonempty.max()), 4 * self.shape[1] * self.shape[2]) + 8 * ((self.shape[1] + 7) // 8)
         return 4 * int(self.nnz.max()) + 20 * self.shape[1] * ((self.shape[2] + 127) // 128)
 
     @staticmethod
@@ -100,10 +100,12 @@ class SparseBatch:
 
     @staticmethod
     def auto(M):
-        """Selection by measured density / structure: bitmap slabs below SPARSE_AUTO_DENSITY, else block skipping when at most
-        BLOCK_AUTO_OCCUPANCY of the blocks are non-empty, else None (plain dense streaming)."""
-        sb = SparseBatch.pack(M, SPARSE_AUTO_DENSITY)
-        return sb if sb is not None else SparseBatch.blocks(M, BLOCK_AUTO_OCCUPANCY)
+        """Selection by measured structure / density.  Block skipping first -- it has no decode cost, so it wins whenever at most
+        BLOCK_AUTO_OCCUPANCY of the 8x128 blocks are non-empty (measured: diagonal Q at n = 1000 reads 3.5x more bytes as blocks
+        than as bitmap slabs and is still ~5x faster); bitmap slabs for unstructured patterns below SPARSE_AUTO_DENSITY; else
+        None (plain dense streaming)."""
+        sb = SparseBatch.blocks(M, BLOCK_AUTO_OCCUPANCY)
+        return sb if sb is not None else SparseBatch.pack(M, SPARSE_AUTO_DENSITY)
 
 
 @dataclass

@@ -88,7 +88,7 @@ def test_block_mask(shape):
     ref = _block_words(M)
     assert np.array_equal(words, ref)
     assert np.array_equal(sb.nonempty.cpu().numpy(), np.array([sum(bin(int(w)).count("1") for w in ref[b]) for b in range(B)]))
-    assert 0 < sb.occupancy < 1 and sb.bytes_per_instance < 4 * rows * n
+    assert 0 < sb.occupancy < 1 and sb.bytes_per_instance <= 4 * rows * n + 8 * G
 
 
 def _families():
