@@ -265,6 +265,7 @@ __device__ __forceinline__ void tile_pass_blocks(const TileArgs& a, float* smem)
   __syncthreads();
 
   const int nchunk = (n + kChunkCols - 1) / kChunkCols;
+  unsigned long long blkword = 0ull;
   for (int cc = 0; cc < nchunk; ++cc) {
     const int  col    = cc * kChunkCols + warp * kSlabCols + lane * 4;
     const bool active = col < n;
@@ -274,13 +275,18 @@ __device__ __forceinline__ void tile_pass_blocks(const TileArgs& a, float* smem)
     float4 cacc[NC > 0 ? NC : 1];
 #pragma unroll
     for (int c = 0; c < NC; ++c) cacc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the occupancy words of the CTA's row groups (R <= 64 -> at most 8), one load per CTA and warp instead of a dependent load
+    // per group: lane g holds word g; bit g of `mygroups` = this warp's slab is non-empty in row group g
+    if (cc == 0) {
+      const int g0 = a.r0 >> 3;                               // R and r0 are multiples of 8 (= kRowUnroll)
+      blkword = (lane < (R >> 3) && a.r0 + lane * 8 < a.rows_total) ? __ldg(a.blk + g0 + lane) : 0ull;
+    }
+    const unsigned mygroups = __ballot_sync(kFullMask, (blkword >> (cc * kKktWarps + warp)) & 1ull);
 
     for (int rg = 0; rg < R; rg += kRowUnroll) {
       float4 v[kRowUnroll];
       {
-        const int g = (a.r0 + rg) >> 3;                       // R and r0 are multiples of 8 (= kRowUnroll)
-        const unsigned long long word = (a.r0 + rg < a.rows_total) ? __ldg(a.blk + g) : 0ull;
-        if (!((word >> (cc * kKktWarps + warp)) & 1ull)) {
+        if (!((mygroups >> (rg >> 3)) & 1u)) {                 // this warp's slab holds no non-zero in rows rg..rg+7
           if (NR > 0) {
             constexpr int NV0 = kRowUnroll * (NR > 0 ? NR : 1);
             constexpr int kGroup0 = 32 / NV0;
