@@ -226,3 +226,47 @@ def test_recomputed_gates_give_identical_gradients(mode):
     for f, v in zip((0, 1), nb):
         _lib.check(_lib.lib().iadmm_window_workspace_bytes(32, 1000, 1000, 800, 100, f, ctypes.byref(v)))
     assert nb[1].value < 0.45 * nb[0].value          # 129 GB -> < 58 GB at config 3, batch 32
+
+
+def test_forward_under_autograd_returns_the_kkt_tuple():
+    """models/lstm.py:96 always returns A_tild, b_tild, rho_vec; the training path returns them too (detached), A_tild only
+    when `materialize_kkt` asks for the dense matrix."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h = 2, 12, 4, 5, 16
+    m = mi + me
+    qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=87).items()}
+    model = ia.LSTM(None, 2, h, 3, DEV)
+    gen = torch.Generator().manual_seed(88)
+    st = [torch.randn(s, generator=gen).to(DEV) for s in ((B, n, 1), (B, m, 1), (B, m, 1), (B, n + m, 1))]
+    H = torch.tanh(torch.randn((B, n + m, h), generator=gen)).to(DEV); C = torch.randn((B, n + m, h), generator=gen).to(DEV)
+    kw = dict(Q=qp["Q"], p=qp["p"], A0=qp["A0"], lb=None, ub=None, zl=qp["zl"], zu=qp["zu"])
+    with torch.no_grad():
+        ref = model(1, mi, me, *st, 6e-6, H, C, **kw)
+    out = model(1, mi, me, *st, 6e-6, H, C, **kw)                   # grad mode: parameters require grad -> autograd node
+    assert out[0].requires_grad and out[6] is not None
+    for a, b in zip(out[6:], ref[6:]):
+        assert torch.equal(a, b) and not a.requires_grad
+    model.materialize_kkt = False
+    out = model(1, mi, me, *st, 6e-6, H, C, **kw)
+    assert out[6] is None and torch.equal(out[7], ref[7]) and torch.equal(out[8], ref[8])
+
+
+def test_invalidate_packed_after_an_edit_through_param_data():
+    """The packed-weight cache is keyed by (data_ptr, _version); an edit through `.data` bumps neither:
+    `invalidate_packed()` is the documented way to make the kernels see it."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, K = 2, 16, 4, 4, 16, 3
+    qp = {k: v.to(DEV) for k, v in orc.qp_instances(B, n, mi, me, seed=89).items()}
+    args = (K, mi, me, qp["Q"], qp["p"], qp["A0"], qp["zl"], qp["zu"], 6e-6)
+    model = ia.LSTM(None, 2, h, K, DEV).eval()
+    with torch.no_grad():
+        a = model.solve(*args)
+        model.W_h.data.mul_(3.0)                                     # no version bump
+        model.invalidate_packed()
+        b = model.solve(*args)
+        model.W_h.mul_(1.0 / 3.0)                                    # in-place op: version bump, noticed automatically
+        c = model.solve(*args)
+    assert not torch.equal(a.x, b.x)
+    assert rel_err(c.x, a.x) < 1e-5
