@@ -95,6 +95,8 @@ def parse_args():
     ap.add_argument("--gpu-ref-batch", type=int, default=32, help="instances per step of the stock-PyTorch GPU arm")
     ap.add_argument("--tl", type=int, default=100, help="train: truncated_length of the window")
     ap.add_argument("--recompute", action="store_true", help="train: recompute the gate activations in the backward (3x less memory)")
+    ap.add_argument("--abi-allreduce", action="store_true", help="train, N > 1: issue the gradient all-reduce through the library's own "
+                                                                  "iadmm_allreduce_grads (raw NCCL communicator) instead of torch.distributed")
     ap.add_argument("--graph", action="store_true", help="train: capture scale_data + the window (forward, loss, backward) in ONE CUDA graph "
                                                           "and replay it per step (the library only enqueues on the caller's stream)")
     a = ap.parse_args()
@@ -611,6 +613,10 @@ def run_train(args):
     Q, p, A0, zl, zu = device_qp_batch(B, n, mi, me, 17 + rank, dev)
     scaling = ia.Scaling(n, m, RUIZ_ITS, dev)
     ar_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    comm = None
+    if world > 1 and args.abi_allreduce:
+        from iadmm_b200.dist import nccl_comm
+        comm = nccl_comm()
 
     def zero_state():
         return (torch.zeros((B, n, 1), device=dev), torch.zeros((B, m, 1), device=dev), torch.zeros((B, m, 1), device=dev),
@@ -625,7 +631,7 @@ def run_train(args):
         if world > 1:
             if timed_idx is not None:
                 ar_ev[timed_idx][0].record()
-            allreduce_gradients(model, local_batch=B)        # ONE NCCL all-reduce of the flat gradient buffer per window
+            allreduce_gradients(model, local_batch=B, comm=comm)   # ONE NCCL all-reduce of the flat gradient buffer per window
             if timed_idx is not None:
                 ar_ev[timed_idx][1].record()
         opt.step()
@@ -668,7 +674,7 @@ def run_train(args):
             if world > 1:
                 if timed_idx is not None:
                     ar_ev[timed_idx][0].record()
-                allreduce_gradients(model, local_batch=B)
+                allreduce_gradients(model, local_batch=B, comm=comm)
                 if timed_idx is not None:
                     ar_ev[timed_idx][1].record()
             opt.step()
@@ -747,8 +753,9 @@ def run_train(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "batch_per_gpu": B, "truncated_length": TL, "gate_mode": args.gate_mode,
                        "cache": "inputs larger than L2: saved states %.1f GB per window" % (2 * (TL + 1) * rows * h * 4 / 1e9),
-                       "parallelism": "data parallel over %d GPU(s): one NCCL all-reduce of the flat gradient buffer (%d floats) per window, "
-                                      "then the reference's Adam on every rank" % (world, sum(p_.numel() for p_ in model.parameters())),
+                       "parallelism": "data parallel over %d GPU(s): one NCCL all-reduce of the flat gradient buffer (%d floats) per window (%s), "
+                                      "then the reference's Adam on every rank" % (world, sum(p_.numel() for p_ in model.parameters()),
+                                                                                    "iadmm_allreduce_grads of the C ABI" if comm is not None else "torch.distributed"),
                        "weights_identical_across_ranks": same, "loss": loss_v, "peak_mem_GB": mem_gb,
                        "gate_activations": "recomputed in the backward" if getattr(model, "last_window_flags", 0) & 1 else "kept over the window",
                        "launch": "one CUDA graph per step (scale_data + window)" if graph is not None else "eager (the library enqueues ~60 launches per iteration)"},

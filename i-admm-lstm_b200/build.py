@@ -19,7 +19,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "iadmm_b200", "libiadmm_b200.so")
-SOURCES = ["api.cu", "pack.cu", "kkt.cu", "sparse.cu", "ruiz.cu", "gates_simt.cu", "gates_tc.cu", "gemm_tc.cu", "train.cu", "lu.cu", "resident.cu"]
+SOURCES = ["api.cu", "pack.cu", "kkt.cu", "sparse.cu", "ruiz.cu", "gates_simt.cu", "gates_tc.cu", "gemm_tc.cu", "train.cu", "lu.cu", "resident.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
               "-cudart", "static"]
@@ -66,7 +66,7 @@ def build(force=False, verbose=False, dev=None):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(target, objs):
-        cmd = [nvcc, "-shared", "-o", target] + objs + ["-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [nvcc, "-shared", "-o", target] + objs + ["-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         subprocess.check_call(cmd)
     return target
 

@@ -97,14 +97,37 @@ def gather_batch(local, batch, dim=0, group=None, sizes=None):
     return full.movedim(0, dim)
 
 
-def allreduce_gradients(module, group=None, local_batch=None):
+_COMMS = {}
+
+
+def nccl_comm(group=None):
+    """A raw NCCL communicator over the ranks of `group` for the library's own collective (`iadmm_allreduce_grads`): the
+    unique id is created on rank 0 and handed to the others through torch.distributed (plumbing), the communicator itself is
+    NCCL's.  Returns the ncclComm_t as an integer address (cached per group; the capsule that owns it is kept alive here)."""
+    import ctypes
+    import torch.cuda.nccl as tnccl
+    key = id(group) if group is not None else 0
+    if key not in _COMMS:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = [tnccl.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        capsule = tnccl.init_rank(world, uid[0], rank)
+        get = ctypes.pythonapi.PyCapsule_GetPointer
+        get.restype, get.argtypes = ctypes.c_void_p, [ctypes.py_object, ctypes.c_char_p]
+        _COMMS[key] = (capsule, get(capsule, b"torch.cuda.nccl.Communicator"))
+    return _COMMS[key][1]
+
+
+def allreduce_gradients(module, group=None, local_batch=None, comm=None):
     """Data-parallel training: combine the LSTM weight gradients of the ranks with ONE
     all-reduce of the flat gradient buffer (2,570,601 floats at h=800, K=100) per TBPTT window, then the
     unchanged Adam step runs on every rank.  Each rank's loss is the mean over ITS instances (main.py:347), so the
     gradient of the mean over the concatenated batch is sum_r (B_r / B) * grad_r: pass `local_batch` = B_r when the
     shards are unequal (`shard_range` remainders, `balance_by_rate`); without it equal shards are assumed (plain
     average).  The flat buffer covers EVERY parameter (zeros where `.grad` is None), so all ranks issue the same
-    collective whatever their local graph touched.  NCCL on GPUs, gloo in the CPU tests."""
+    collective whatever their local graph touched.  NCCL on GPUs, gloo in the CPU tests.
+    `comm` = `nccl_comm(group)`: the all-reduce is then issued by the library itself (`iadmm_allreduce_grads` of the C ABI:
+    ncclAllReduce on the current stream) instead of torch.distributed; same sum, same result."""
     world = dist.get_world_size(group)
     params = list(module.parameters())
     if not params or world == 1:
@@ -122,7 +145,12 @@ def allreduce_gradients(module, group=None, local_batch=None):
         off += k
     flat[:total] *= w
     flat[total] = w
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if comm is not None:
+        from . import _lib
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().iadmm_allreduce_grads(_lib.ptr(flat), flat.numel(), 1.0, comm, _lib.stream_ptr()))
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat[:total] /= flat[total]
     off = 0
     for p in params:

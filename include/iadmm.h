@@ -270,6 +270,13 @@ int iadmm_train_window(const void* packed_weights,
                        int B, int n, int num_ineq, int num_eq, int h, int length, int t0, int TL, float sigma,
                        float loss_scale, int mode, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- data-parallel training: the one collective of the path ------------------------------------------
+ * Replaces: nothing in the reference (single process); SURVEY.md section 8(b/e): one sum all-reduce of the flat gradient
+ * buffer of iadmm_train_window / iadmm_step_bwd over NCCL (NVLink / NVSwitch) per truncated-BPTT window, in place, followed
+ * by a multiplication with `scale` (1/world for equal shards; 1 when the caller weights the ranks itself).  `nccl_comm` is an
+ * ncclComm_t passed as void*; NCCL is looked up in the host process at the first call (no link-time dependency). */
+int iadmm_allreduce_grads(float* flat_grads, size_t count, float scale, void* nccl_comm, void* stream);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------
  * The reference times its solve with time.time() around model() (main.py:881-890, no device sync).
  * Between iadmm_profile_begin and iadmm_profile_end every iadmm_solve call records CUDA events on its

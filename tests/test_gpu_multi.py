@@ -117,7 +117,20 @@ def _nccl_worker(rank, world, port, out):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         if rank == 0:
             res[tag + "_identical"] = bool(lo == hi)
+    # the library's own collective (iadmm_allreduce_grads of the C ABI: ncclAllReduce on a raw communicator) against
+    # torch.distributed's: the same two-rank sum, bit for bit
+    from iadmm_b200.dist import nccl_comm
+    rows = slice(0, 3) if rank == 0 else slice(3, B)
+    m_a, _, b_a = window(rows)
+    m_b, _, _ = window(rows)
+    allreduce_gradients(m_a, local_batch=b_a)
+    allreduce_gradients(m_b, local_batch=b_a, comm=nccl_comm())
+    torch.cuda.synchronize()
+    same = all(torch.equal(pa.grad, pb.grad) for pa, pb in zip(m_a.parameters(), m_b.parameters()))
+    flag = torch.tensor([1.0 if same else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
+        res["abi_collective_identical"] = bool(flag.item() == 1.0)
         out.update(res)
     dist.barrier()
     dist.destroy_process_group()
@@ -130,6 +143,6 @@ def test_nccl_allreduced_gradient_equals_single_gpu_gradient():
     port = 29300 + (os.getpid() % 200)
     mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
     print("NCCL DP gradient vs single GPU:", dict(out))
-    assert out["equal_identical"] and out["unequal_identical"]
+    assert out["equal_identical"] and out["unequal_identical"] and out["abi_collective_identical"]
     # fp32 kernels: the per-instance adjoints are bit-identical, the only difference is the order of the sum over instances
     assert out["equal"] < 2e-5 and out["unequal"] < 2e-5
