@@ -6,14 +6,22 @@
 #include "common.cuh"
 
 #include <dlfcn.h>
+#include <string.h>
 
 namespace iadmm {
 
+struct NcclUid { char internal[128]; };             // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128), passed by value
 typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*NcclErrFn)(int);
+typedef int (*NcclGetUidFn)(NcclUid*);
+typedef int (*NcclInitRankFn)(void**, int, NcclUid, int);
+typedef int (*NcclDestroyFn)(void*);
 
 static NcclAllReduceFn g_allreduce = nullptr;
 static NcclErrFn g_errstr = nullptr;
+static NcclGetUidFn g_getuid = nullptr;
+static NcclInitRankFn g_initrank = nullptr;
+static NcclDestroyFn g_destroy = nullptr;
 
 static int load_nccl() {
   if (g_allreduce) return IADMM_OK;
@@ -22,6 +30,9 @@ static int load_nccl() {
   if (!h) h = dlopen("libnccl.so", RTLD_LAZY);
   if (!h) IADMM_FAIL(IADMM_ECUDA, "allreduce_grads: libnccl.so.2 is not loaded and cannot be found (%s)", dlerror());
   g_errstr = reinterpret_cast<NcclErrFn>(dlsym(h, "ncclGetErrorString"));
+  g_getuid = reinterpret_cast<NcclGetUidFn>(dlsym(h, "ncclGetUniqueId"));
+  g_initrank = reinterpret_cast<NcclInitRankFn>(dlsym(h, "ncclCommInitRank"));
+  g_destroy = reinterpret_cast<NcclDestroyFn>(dlsym(h, "ncclCommDestroy"));
   NcclAllReduceFn f = reinterpret_cast<NcclAllReduceFn>(dlsym(h, "ncclAllReduce"));
   if (!f) IADMM_FAIL(IADMM_ECUDA, "allreduce_grads: ncclAllReduce not found in libnccl");
   g_allreduce = f;
@@ -50,5 +61,39 @@ extern "C" int iadmm_allreduce_grads(float* flat_grads, size_t count, float scal
     scale_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(flat_grads, count, scale);
     IADMM_LAUNCH_CHECK("scale_kernel");
   }
+  return IADMM_OK;
+}
+
+// Communicator set-up for iadmm_allreduce_grads without going through the host framework: rank 0 creates the 128-byte unique id,
+// the caller hands it to the other ranks by any means (torch.distributed's store in iadmm_b200/dist.py), every rank joins.
+extern "C" int iadmm_nccl_unique_id(void* uid128) {
+  if (!uid128) IADMM_FAIL(IADMM_EALIGN, "nccl_unique_id: NULL pointer");
+  int rc = load_nccl();
+  if (rc) return rc;
+  if (!g_getuid) IADMM_FAIL(IADMM_ECUDA, "nccl_unique_id: ncclGetUniqueId not found in libnccl");
+  NcclUid u;
+  const int r = g_getuid(&u);
+  if (r != 0) IADMM_FAIL(IADMM_ECUDA, "ncclGetUniqueId failed: %s", g_errstr ? g_errstr(r) : "unknown NCCL error");
+  memcpy(uid128, &u, sizeof(u));
+  return IADMM_OK;
+}
+
+extern "C" int iadmm_nccl_comm_init(void** comm, int world, const void* uid128, int rank) {
+  if (!comm || !uid128 || world <= 0 || rank < 0 || rank >= world) IADMM_FAIL(IADMM_ESHAPE, "nccl_comm_init: world=%d rank=%d", world, rank);
+  int rc = load_nccl();
+  if (rc) return rc;
+  if (!g_initrank) IADMM_FAIL(IADMM_ECUDA, "nccl_comm_init: ncclCommInitRank not found in libnccl");
+  NcclUid u;
+  memcpy(&u, uid128, sizeof(u));
+  const int r = g_initrank(comm, world, u, rank);
+  if (r != 0) IADMM_FAIL(IADMM_ECUDA, "ncclCommInitRank failed: %s", g_errstr ? g_errstr(r) : "unknown NCCL error");
+  return IADMM_OK;
+}
+
+extern "C" int iadmm_nccl_comm_destroy(void* comm) {
+  if (!comm) return IADMM_OK;
+  int rc = load_nccl();
+  if (rc) return rc;
+  if (g_destroy) g_destroy(comm);
   return IADMM_OK;
 }

@@ -57,6 +57,9 @@ SIGNATURES = {
     "iadmm_residuals_fwd": ([_P] * 10 + [_I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_residuals_bwd": ([_P] * 11 + [_I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_allreduce_grads": ([_P, _Z, _F, _P, _P], c_int),
+    "iadmm_nccl_unique_id": ([_P], c_int),
+    "iadmm_nccl_comm_init": ([POINTER(c_void_p), _I, _P, _I], c_int),
+    "iadmm_nccl_comm_destroy": ([_P], c_int),
     "iadmm_profile_begin": ([_I], c_int),
     "iadmm_profile_end": ([POINTER(ctypes.c_double)] * 3 + [POINTER(_I)], c_int),
     "iadmm_profile_end_kinds": ([POINTER(ctypes.c_double), POINTER(_I), _I], c_int),

@@ -100,22 +100,28 @@ def gather_batch(local, batch, dim=0, group=None, sizes=None):
 _COMMS = {}
 
 
-def nccl_comm(group=None):
-    """A raw NCCL communicator over the ranks of `group` for the library's own collective (`iadmm_allreduce_grads`): the
-    unique id is created on rank 0 and handed to the others through torch.distributed (plumbing), the communicator itself is
-    NCCL's.  Returns the ncclComm_t as an integer address (cached per group; the capsule that owns it is kept alive here)."""
+def nccl_comm(group=None, device=None):
+    """A raw NCCL communicator over the ranks of `group` for the library's own collective (`iadmm_allreduce_grads`): rank 0
+    creates the unique id (`iadmm_nccl_unique_id`), torch.distributed only carries its 128 bytes to the other ranks (plumbing),
+    every rank joins on its current CUDA device (`iadmm_nccl_comm_init`).  Returns the ncclComm_t as an integer address
+    (cached per group)."""
     import ctypes
-    import torch.cuda.nccl as tnccl
+    from . import _lib
     key = id(group) if group is not None else 0
     if key not in _COMMS:
+        L = _lib.lib()
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        uid = [tnccl.unique_id() if rank == 0 else None]
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(L.iadmm_nccl_unique_id(buf))
+        uid = [bytes(buf.raw) if rank == 0 else None]
         dist.broadcast_object_list(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-        capsule = tnccl.init_rank(world, uid[0], rank)
-        get = ctypes.pythonapi.PyCapsule_GetPointer
-        get.restype, get.argtypes = ctypes.c_void_p, [ctypes.py_object, ctypes.c_char_p]
-        _COMMS[key] = (capsule, get(capsule, b"torch.cuda.nccl.Communicator"))
-    return _COMMS[key][1]
+        comm = ctypes.c_void_p()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
+            _lib.check(L.iadmm_nccl_comm_init(ctypes.byref(comm), world, ctypes.create_string_buffer(uid[0], 128), rank))
+        _COMMS[key] = comm.value
+    return _COMMS[key]
 
 
 def allreduce_gradients(module, group=None, local_batch=None, comm=None):

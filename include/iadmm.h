@@ -276,6 +276,11 @@ int iadmm_train_window(const void* packed_weights,
  * by a multiplication with `scale` (1/world for equal shards; 1 when the caller weights the ranks itself).  `nccl_comm` is an
  * ncclComm_t passed as void*; NCCL is looked up in the host process at the first call (no link-time dependency). */
 int iadmm_allreduce_grads(float* flat_grads, size_t count, float scale, void* nccl_comm, void* stream);
+/* Communicator set-up without the host framework: rank 0 fills a 128-byte unique id (ncclGetUniqueId), the caller carries it to
+ * the other ranks (any side channel), every rank joins with the CURRENT cuda device (ncclCommInitRank). */
+int iadmm_nccl_unique_id(void* uid128);
+int iadmm_nccl_comm_init(void** comm, int world, const void* uid128, int rank);
+int iadmm_nccl_comm_destroy(void* comm);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------
  * The reference times its solve with time.time() around model() (main.py:881-890, no device sync).
