@@ -67,6 +67,28 @@ def make_cell(mode):
         Ucat = torch.cat([prm[f"U_{g}"] for g in orc.GATES], dim=1)          # [h, 4h]
         mxu = float(Ucat.abs().max())
         us = 2.0 ** (12 - math.frexp(mxu)[1] + 1) if mxu > 0 else 1.0        # max|U| us in [2^12, 2^13)
+        if mode.startswith("i8x"):
+            # 16-bit FIXED-point operands split into bytes for tcgen05 kind::i8 (s32 accumulation, emulated exactly in float64):
+            # H16 = round(H 2^15), U16 = round(U su) with max|U| su in [2^14, 2^15); x = 256 hi + lo, hi signed, lo in [0, 255].
+            # i8x3 = hi hi + hi lo + lo hi (1.5 MMA units at the fp8 rate), i8x4 adds lo lo (the exact 16-bit product, 2 units).
+            su16 = 2.0 ** (15 - math.frexp(mxu)[1]) if mxu > 0 else 1.0
+            H16 = torch.round(H.double() * 32768.0).clamp(-32768, 32767)
+            U16 = torch.round(Ucat.double() * su16).clamp(-32768, 32767)
+            Hhi = torch.floor(H16 / 256.0); Hlo = H16 - 256.0 * Hhi
+            Uhi = torch.floor(U16 / 256.0); Ulo = U16 - 256.0 * Uhi
+            acc1 = Hhi @ Uhi
+            acc2 = Hhi @ Ulo + Hlo @ Uhi
+            prod = (acc1.float() * 65536.0) + (acc2.float() * 256.0)           # int32 -> fp32 in the epilogue
+            if mode == "i8x4":
+                prod = prod + (Hlo @ Ulo).float()
+            HU = prod / (32768.0 * su16)
+            h = H.shape[-1]
+            pre = {g: feats @ prm[f"W_{g}"] + HU[..., i * h:(i + 1) * h] + prm[f"b_{g}"] for i, g in enumerate(orc.GATES)}
+            gate_i = torch.sigmoid(pre["i"]); gate_f = torch.sigmoid(pre["f"]); gate_o = torch.sigmoid(pre["o"])
+            cand = torch.tanh(pre["u"])
+            C = gate_i * cand + gate_f * C
+            H = gate_o * torch.tanh(C)
+            return H, C, H @ prm["W_h"] + prm["b_h"]
         Hs = H * 16384.0
         if "_fb" in mode:                # temporal error feedback on the fp16 image of H (first-order noise shaping)
             carry = counter.get("carry")
