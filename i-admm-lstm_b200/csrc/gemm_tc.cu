@@ -177,6 +177,177 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 }
 
 // A_hi/A_lo: [M][lda], B_hi/B_lo: [N][ldb] fp16 K-major; lda, ldb multiples of 8; N multiple of 16; C fp32 [M][ldc], ldc % 4 == 0
+// ================================================================================================
+// CTA-pair variant (cta_group::2): tile = 256 rows x 256 columns over two SMs, the barrier protocol of
+// gates_tc_pair_kernel (gates_tc.cu): each CTA loads its own 128 rows of A and HALF of the B tile, the leader issues
+// M = 256 MMAs that read both halves; `full` lives in the leader and counts the TMA bytes of BOTH CTAs, `empty` and `tmem_full`
+// are signalled in both CTAs by multicast tcgen05.commit, `tmem_empty` lives in the leader and collects the epilogue warps of
+// both CTAs through the cluster window.  Per SM and K block 64 KB of operands feed 12 MMA-halves of 256x256x16 instead of 96 KB
+// for 12 MMAs of 128x256x16: the single-CTA form is L2->SM fill bound with 4-byte (hi + lo) operands.
+// ================================================================================================
+constexpr int kGpABytes = kTcBM * kGmBK * 2;            // 16 KB: this CTA's 128 rows of A (one of hi / lo)
+constexpr int kGpBBytes = (kGmBN / 2) * kGmBK * 2;      // 16 KB: this CTA's half of the B tile (one of hi / lo)
+constexpr int kGpStageBytes = 2 * (kGpABytes + kGpBBytes);   // 64 KB
+constexpr int kGpStages = 3;
+constexpr int kGpBoxRows = 64;                          // B halves are fetched in 64-row TMA boxes
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGmThreads, 1)
+tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const GemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kGpStages * kGpStageBytes);
+  uint64_t* full_bar = bars;                         // [stages]  (leader's copy is the live one)
+  uint64_t* empty_bar = bars + kGpStages;            // [stages]  both CTAs
+  uint64_t* tfull_bar = bars + 2 * kGpStages;        // [2]       both CTAs
+  uint64_t* tempty_bar = bars + 2 * kGpStages + 2;   // [2]       leader's copy is the live one
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGpStages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+    for (int s = 0; s < kGpStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull_bar[b]), 1); mbar_init(smem_u32(&tempty_bar[b]), 2 * kGmEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long pair = blockIdx.x / 2, num_pairs = gridDim.x / 2;
+  const long units = P.num_tiles * P.splits;          // num_tiles counts 256-row tiles here
+
+  if (warp == 0) {
+    // ===================== TMA producer (every CTA) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long unit = pair; unit < units; unit += num_pairs) {
+        const long tile = unit / P.splits;
+        const int sp = (int)(unit - tile * P.splits);
+        const int nt = (int)(tile % P.n_tiles);
+        const long mt = tile / P.n_tiles;
+        const int n_cols = (int)min((long)kGmBN, P.N - (long)nt * kGmBN);
+        const int row0 = (int)(mt * (2 * kTcBM)) + (int)rank * kTcBM;          // this CTA's 128 rows of A
+        const int col0 = nt * kGmBN + (int)rank * (n_cols / 2);                // first row of this CTA's half of the B tile
+        const int b_boxes = (n_cols / 2 + kGpBoxRows - 1) / kGpBoxRows;
+        const int kb_end = min(P.k_blocks, (sp + 1) * P.kb_per_split);
+        for (int kb = sp * P.kb_per_split; kb < kb_end; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb_local = smem_u32(&full_bar[stage]);
+          if (leader) mbar_expect_tx(fb_local, 2u * (2u * kGpABytes + (uint32_t)b_boxes * 2u * (kGpBoxRows * kGmBK * 2)));
+          const uint32_t fb = map_to_cta(fb_local, 0);
+          const uint32_t sb = smem_u32(smem + (size_t)stage * kGpStageBytes);
+          const int k0 = kb * kGmBK;
+          tma_load_2d_pair(sb, &map_a_hi, fb, k0, row0);
+          tma_load_2d_pair(sb + kGpABytes, &map_a_lo, fb, k0, row0);
+          for (int bx = 0; bx < b_boxes; ++bx) {
+            tma_load_2d_pair(sb + 2 * kGpABytes + (uint32_t)bx * (kGpBoxRows * 128), &map_b_hi, fb, k0, col0 + bx * kGpBoxRows);
+            tma_load_2d_pair(sb + 2 * kGpABytes + kGpBBytes + (uint32_t)bx * (kGpBoxRows * 128), &map_b_lo, fb, k0, col0 + bx * kGpBoxRows);
+          }
+          if (++stage == kGpStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      long it = 0;
+      for (long unit = pair; unit < units; unit += num_pairs, ++it) {
+        const long tile = unit / P.splits;
+        const int sp = (int)(unit - tile * P.splits);
+        const int nt = (int)(tile % P.n_tiles);
+        const int n_cols = (int)min((long)kGmBN, P.N - (long)nt * kGmBN);
+        const uint32_t idesc = make_idesc_f16(n_cols, 2 * kTcBM);
+        const int buf = (int)(it & 1);
+        const uint32_t use = (uint32_t)(it >> 1);
+        const int kb_end = min(P.k_blocks, (sp + 1) * P.kb_per_split);
+        mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1) ^ 1);     // both CTAs' epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kGmBN);
+        uint32_t acc = 0;
+        for (int kb = sp * P.kb_per_split; kb < kb_end; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + (size_t)stage * kGpStageBytes);
+          const long k_len = min((long)kGmBK, P.K - (long)kb * kGmBK);
+          const int k_steps = (int)((k_len + kTcUK - 1) / kTcUK);
+          for (int ks = 0; ks < k_steps; ++ks) {
+            const uint32_t koff = (uint32_t)(ks * kTcUK * 2);
+            const uint64_t a_hi = make_smem_desc_sw128(sb + koff);
+            const uint64_t a_lo = make_smem_desc_sw128(sb + kGpABytes + koff);
+            const uint64_t b_hi = make_smem_desc_sw128(sb + 2 * kGpABytes + koff);
+            const uint64_t b_lo = make_smem_desc_sw128(sb + 2 * kGpABytes + kGpBBytes + koff);
+            tc_mma_f16_pair(d_tmem, a_lo, b_hi, idesc, acc); acc = 1;
+            tc_mma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1);
+            tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+          }
+          tc_commit_pair(smem_u32(&empty_bar[stage]), (uint16_t)3);   // frees the stage in both CTAs when the MMAs retire
+          if (++stage == kGpStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(smem_u32(&tfull_bar[buf]), (uint16_t)3);       // accumulators complete in both CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = (ew >= 4) ? 1 : 0;
+    const float scale = *P.scale;
+    long it = 0;
+    for (long unit = pair; unit < units; unit += num_pairs, ++it) {
+      const long tile = unit / P.splits;
+      const int sp = (int)(unit - tile * P.splits);
+      const int nt = (int)(tile % P.n_tiles);
+      const long mt = tile / P.n_tiles;
+      const int buf = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      const long row = mt * (2 * kTcBM) + (long)rank * kTcBM + quarter * 32 + lane;
+      mbar_wait(smem_u32(&tfull_bar[buf]), use & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        const int chunk = half * 4 + cc;
+        const long col0 = (long)nt * kGmBN + chunk * 32;
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kGmBN + chunk * 32), v);
+        tc_wait_ld();
+        if (row < P.M) {
+          float* crow = P.C + ((size_t)sp * P.M + row) * P.ldc + col0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (col0 + q * 8 < P.N) {            // N % 8 == 0
+              float4 o0 = make_float4(__uint_as_float(v[q * 8 + 0]) * scale, __uint_as_float(v[q * 8 + 1]) * scale,
+                                      __uint_as_float(v[q * 8 + 2]) * scale, __uint_as_float(v[q * 8 + 3]) * scale);
+              float4 o1 = make_float4(__uint_as_float(v[q * 8 + 4]) * scale, __uint_as_float(v[q * 8 + 5]) * scale,
+                                      __uint_as_float(v[q * 8 + 6]) * scale, __uint_as_float(v[q * 8 + 7]) * scale);
+              *reinterpret_cast<float4*>(crow + q * 8) = o0;
+              *reinterpret_cast<float4*>(crow + q * 8 + 4) = o1;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[buf]), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // sum of the split-K partials in a fixed order (deterministic): C[i] = ((p0 + p1) + p2) + ...
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __restrict__ part, float4* __restrict__ C, size_t count4, int splits) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +364,12 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4* __rest
 // work units should fill whole waves of the persistent grid.  Picks the factor <= max_splits with the best wave efficiency
 // (ties: the smaller one); every split keeps at least 8 K blocks.
 int tc_gemm_pick_splits(long M, long N, long K, int num_sms, int max_splits) {
-  const long tiles = ((M + kTcBM - 1) / kTcBM) * ((N + kGmBN - 1) / kGmBN);
+  // (the pair kernel works on 256-row tiles with one unit per pair of SMs: same wave arithmetic on num_sms / 2 pairs)
+  const char* sw = dev_env("IADMM_GEMM_PAIR");
+  const bool pair = num_sms >= 2 && !(sw && sw[0] == '0') && (N % 16 == 0);
+  const long tile_rows = pair ? 2 * kTcBM : kTcBM;
+  if (pair) num_sms /= 2;
+  const long tiles = ((M + tile_rows - 1) / tile_rows) * ((N + kGmBN - 1) / kGmBN);
   const long k_blocks = (K + kGmBK - 1) / kGmBK;
   if (tiles >= 4L * num_sms) return 1;
   int best = 1;
@@ -227,8 +403,14 @@ int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi
   };
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
+  int num_sms = 0;
+  if ((rc = device_sm_count(&num_sms))) return rc;
+  // CTA pairs (256 x 256 tiles) when the tile halves are whole 8-row groups of B and there are two SMs; development switch
+  // IADMM_GEMM_PAIR=0 keeps the single-CTA kernel
+  const char* sw = dev_env("IADMM_GEMM_PAIR");
+  const bool pair = num_sms >= 2 && !(sw && sw[0] == '0') && (N % 16 == 0);
   if ((rc = mk(&ma_hi, A_hi, M, lda, kTcBM)) || (rc = mk(&ma_lo, A_lo, M, lda, kTcBM)) ||
-      (rc = mk(&mb_hi, B_hi, N, ldb, kGmBN)) || (rc = mk(&mb_lo, B_lo, N, ldb, kGmBN)))
+      (rc = mk(&mb_hi, B_hi, N, ldb, pair ? kGpBoxRows : kGmBN)) || (rc = mk(&mb_lo, B_lo, N, ldb, pair ? kGpBoxRows : kGmBN)))
     return rc;
   GemmParams P;
   if (splits < 1 || (splits > 1 && (!part || (M * ldc) % 4 != 0))) IADMM_FAIL(IADMM_ESHAPE, "tc_gemm: bad split-K arguments");
@@ -237,16 +419,24 @@ int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi
   P.k_blocks = (int)((K + kGmBK - 1) / kGmBK);
   P.splits = splits;
   P.kb_per_split = (P.k_blocks + splits - 1) / splits;
-  P.num_tiles = ((M + kTcBM - 1) / kTcBM) * P.n_tiles;
-  int num_sms = 0;
-  static PerDeviceOnce attr;
-  if ((rc = device_sm_count(&num_sms))) return rc;
-  if ((rc = ensure_dyn_smem(tc_gemm_nt_kernel, 220 * 1024, &attr))) return rc;
-  const size_t smem = 1024 + (size_t)kGmStages * kGmStageBytes + (2 * kGmStages + 4) * sizeof(uint64_t) + 16;
+  const int tile_rows = pair ? 2 * kTcBM : kTcBM;
+  P.num_tiles = ((M + tile_rows - 1) / tile_rows) * P.n_tiles;
+  static PerDeviceOnce attr, attr_pair;
   const long units = P.num_tiles * splits;
-  const long grid = units < num_sms ? units : num_sms;
-  tc_gemm_nt_kernel<<<(unsigned)grid, kGmThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
-  IADMM_LAUNCH_CHECK("tc_gemm_nt_kernel");
+  if (pair) {
+    if ((rc = ensure_dyn_smem(tc_gemm_nt_pair_kernel, 220 * 1024, &attr_pair))) return rc;
+    const size_t smem = 1024 + (size_t)kGpStages * kGpStageBytes + (2 * kGpStages + 4) * sizeof(uint64_t) + 16;
+    long clusters = num_sms / 2;
+    if (units < clusters) clusters = units;
+    tc_gemm_nt_pair_kernel<<<(unsigned)(2 * clusters), kGmThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+    IADMM_LAUNCH_CHECK("tc_gemm_nt_pair_kernel");
+  } else {
+    if ((rc = ensure_dyn_smem(tc_gemm_nt_kernel, 220 * 1024, &attr))) return rc;
+    const size_t smem = 1024 + (size_t)kGmStages * kGmStageBytes + (2 * kGmStages + 4) * sizeof(uint64_t) + 16;
+    const long grid = units < num_sms ? units : num_sms;
+    tc_gemm_nt_kernel<<<(unsigned)grid, kGmThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+    IADMM_LAUNCH_CHECK("tc_gemm_nt_kernel");
+  }
   if (splits > 1) {
     const size_t count4 = (size_t)(M * ldc) / 4;
     splitk_reduce_kernel<<<(unsigned)((count4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(part),
