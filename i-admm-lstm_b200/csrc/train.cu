@@ -142,9 +142,10 @@ static int launch_sgemm(const float* A, const float* Bm, float* C, long M, long 
 // rows per partial: 256 at large row counts (bounded partial buffer), down to 32 so that a few thousand rows still
 // fill the GPU; a function of the row count only
 static int cs_rows_per_part(size_t rows) {
-  size_t r = rows / 1024;
+  // ~512 parts: enough CTAs for the partial sums (4 column CTAs each at hidden_dim 800), few enough for the final sum
+  size_t r = rows / 512;
   r = (r + 7) / 8 * 8;
-  return (int)(r < 32 ? 32 : (r > 256 ? 256 : r));
+  return (int)(r < 32 ? 32 : (r > 512 ? 512 : r));
 }
 
 template <int NW>
@@ -152,44 +153,47 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
                                                              const float* __restrict__ w0, const float* __restrict__ w1,
                                                              const float* __restrict__ w2, float wscale,
                                                              float* __restrict__ part, int rows_per_part) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread = four consecutive columns (cols % 4 == 0: 128-bit loads, 8 rows in flight), one CTA row = one part of rows
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const long r0 = (long)blockIdx.y * rows_per_part;
   if (c >= cols) return;
   const long r1 = (r0 + rows_per_part < rows) ? r0 + rows_per_part : rows;
-  float acc[NW];
+  float4 acc[NW];
 #pragma unroll
-  for (int w = 0; w < NW; ++w) acc[w] = 0.f;
+  for (int w = 0; w < NW; ++w) acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* ws[3] = {w0, w1, w2};
 #pragma unroll 8
   for (long r = r0; r < r1; ++r) {
-    const float v = Mx[r * cols + c];
-    const float* ws[3] = {w0, w1, w2};
+    const float4 v = __ldg(reinterpret_cast<const float4*>(Mx + r * cols + c));
 #pragma unroll
-    for (int w = 0; w < NW; ++w) acc[w] = fmaf(v, ws[w] ? ws[w][r] * wscale : 1.0f, acc[w]);
+    for (int w = 0; w < NW; ++w) {
+      const float f = ws[w] ? __ldg(ws[w] + r) * wscale : 1.0f;
+      acc[w].x = fmaf(v.x, f, acc[w].x); acc[w].y = fmaf(v.y, f, acc[w].y);
+      acc[w].z = fmaf(v.z, f, acc[w].z); acc[w].w = fmaf(v.w, f, acc[w].w);
+    }
   }
 #pragma unroll
-  for (int w = 0; w < NW; ++w) part[((size_t)blockIdx.y * NW + w) * cols + c] = acc[w];
+  for (int w = 0; w < NW; ++w) *reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * NW + w) * cols + c) = acc[w];
 }
 
 // out_w[c] = sum over partials (fixed order: four interleaved groups of partials, then ((g0+g1)+g2)+g3).
-// block = 64 columns x 4 groups
+// block = 64 columns x 4 groups; grid = (ceil(cols/64), nw)
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int nparts, int nw, int cols,
                                                            float* __restrict__ out0, float* __restrict__ out1,
                                                            float* __restrict__ out2) {
   __shared__ float sh[4][64];
   const int t = threadIdx.x & 63, g = threadIdx.x >> 6;
   const int c = blockIdx.x * 64 + t;
-  float* outs[3] = {out0, out1, out2};
-  for (int w = 0; w < nw; ++w) {
-    float s = 0.f;
-    if (c < cols) {
+  const int w = blockIdx.y;
+  float* out = (w == 0) ? out0 : (w == 1) ? out1 : out2;
+  float s = 0.f;
+  if (c < cols) {
 #pragma unroll 8
-      for (int p = g; p < nparts; p += 4) s += part[((size_t)p * nw + w) * cols + c];
-    }
-    sh[g][t] = s;
-    __syncthreads();
-    if (g == 0 && c < cols) outs[w][c] = ((sh[0][t] + sh[1][t]) + sh[2][t]) + sh[3][t];
-    __syncthreads();
+    for (int p = g; p < nparts; p += 4) s += part[((size_t)p * nw + w) * cols + c];
   }
+  sh[g][t] = s;
+  __syncthreads();
+  if (g == 0 && c < cols) out[c] = ((sh[0][t] + sh[1][t]) + sh[2][t]) + sh[3][t];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -635,17 +639,17 @@ int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, c
   IADMM_LAUNCH_CHECK("cell_bwd_kernel");
   // 3. small parameter adjoints: W_h (weights s_bar = -Xbar over H'), b_h, and b, W rows over D
   {
-    const dim3 g1((unsigned)cdiv(h, 256), (unsigned)W.cs_parts);
+    const dim3 g1((unsigned)cdiv(h / 4, 256), (unsigned)W.cs_parts);
     colsum_partial_kernel<1><<<g1, 256, 0, st>>>(H_o, (long)rows, h, W.Xbar, nullptr, nullptr, -1.0f, W.cs_part, W.cs_rows);
     IADMM_LAUNCH_CHECK("colsum_partial_kernel<1>");
-    colsum_final_kernel<<<cdiv(h, 64), 256, 0, st>>>(W.cs_part, W.cs_parts, 1, h, W.whbar, nullptr, nullptr);
+    colsum_final_kernel<<<dim3(cdiv(h, 64), 1), 256, 0, st>>>(W.cs_part, W.cs_parts, 1, h, W.whbar, nullptr, nullptr);
     IADMM_LAUNCH_CHECK("colsum_final_kernel");
     negate_sum_kernel<<<1, 1024, 0, st>>>(W.Xbar, (long)rows, W.sbar_sum);
     IADMM_LAUNCH_CHECK("negate_sum_kernel");
-    const dim3 g3((unsigned)cdiv(h4, 256), (unsigned)W.cs_parts);
+    const dim3 g3((unsigned)cdiv(h4 / 4, 256), (unsigned)W.cs_parts);
     colsum_partial_kernel<3><<<g3, 256, 0, st>>>(W.D, (long)rows, h4, nullptr, xv, g_save, 1.0f, W.cs_part, W.cs_rows);
     IADMM_LAUNCH_CHECK("colsum_partial_kernel<3>");
-    colsum_final_kernel<<<cdiv(h4, 64), 256, 0, st>>>(W.cs_part, W.cs_parts, 3, h4, W.bbar, W.w0bar, W.w1bar);
+    colsum_final_kernel<<<dim3(cdiv(h4, 64), 3), 256, 0, st>>>(W.cs_part, W.cs_parts, 3, h4, W.bbar, W.w0bar, W.w1bar);
     IADMM_LAUNCH_CHECK("colsum_final_kernel");
   }
   prof_end(kProfTrainCell, st);
