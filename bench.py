@@ -7,7 +7,7 @@
 Workloads (`--workload`; the default `solve` is the headline BASELINE config 2, the line the driver records):
     solve     config 2: n=1000, 500+500, hidden_dim=800, --scaling, K=100, batch 256 per GPU
     config5   config 5: n=5000, 2500+2500, hidden_dim=800, K=100, batch 24 per GPU
-    hidden200 configs/QP.yaml's default hidden_dim (208 = 200 rounded up to the tensor-core tile granularity): HBM-bound regime
+    hidden200 configs/QP.yaml's default hidden_dim 200 (% 16 == 8: half-padded last operand group): HBM-bound regime
     train     config 3: one truncated-BPTT window (TL=100) forward + backward + NCCL gradient all-reduce + Adam per step
     sparse    a sparse family of generate_data.py:96-228 (--family Random_QP | Equality_QP | SVM) at n=1000: Q / A0 streamed in the
               bitmap-slab form (--sparse auto) or densified like main.py:243-296 (--sparse off)
@@ -103,7 +103,7 @@ def parse_args():
     if a.workload == "config5":
         a.nvar = 5000
     if a.workload == "hidden200":
-        a.hidden = 208
+        a.hidden = 200
     if a.batch is None:
         a.batch = {"solve": 256, "config5": 24, "hidden200": 256, "train": 2, "sparse": 128}[a.workload]
     return a

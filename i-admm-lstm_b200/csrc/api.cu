@@ -105,7 +105,8 @@ static int is_f16f8(int mode) { return mode == IADMM_GATES_TC_F16F8 || mode == I
 static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, void* base, SolveWs* ws) {
   if (mode != IADMM_GATES_SIMT_FP32 && !is_tc(mode)) IADMM_FAIL(IADMM_EMODE, "unknown gate mode %d", mode);
   if (is_tc(mode) && (h % 8 != 0)) IADMM_FAIL(IADMM_EMODE, "tensor-core gate modes need hidden_dim %% 8 == 0 (got %d)", h);
-  if (is_f16f8(mode) && (h % 16 != 0)) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0 (got %d)", h);
+  // (fp16+fp8 mode: hidden_dim % 16 == 8, e.g. configs/QP.yaml's 200, runs on the row-interleaved kernels only: the last 16-unit
+  // group of the e4m3 planes is half padding)
   ws->d = make_kkt_dims(B, n, m, num_ineq);
   const size_t rows = (size_t)B * (n + m);
   ws->tiles = is_tc(mode) ? tc_gate_tiles(h) : simt_gate_tiles(h);
@@ -123,7 +124,10 @@ static int plan_workspace(int B, int n, int m, int num_ineq, int h, int mode, vo
     ws->rows_p = il ? il_rows((long)rows) : (long)rows;
     const size_t rp = (size_t)ws->rows_p;
     const size_t hb = rp * (size_t)h * sizeof(__half);
-    const size_t lb = il ? (tc_lo_bytes((long)rows, h) > hb ? tc_lo_bytes((long)rows, h) : hb) : tc_lo_bytes((long)rows, h);
+    const size_t qb = il_q8_bytes((long)rp, h);                     // row-interleaved e4m3 planes [ceil(h/16)][2][rows_p][16]
+    size_t lb = tc_lo_bytes((long)rows, h);
+    if (il && hb > lb) lb = hb;
+    if (il && qb > lb) lb = qb;
     for (int i = 0; i < 2; ++i) {
       ws->tc.h_hi[i] = reinterpret_cast<__half*>(take(hb));
       ws->tc.h_lo[i] = reinterpret_cast<__half*>(take(lb));
@@ -243,17 +247,23 @@ static int solve_impl(const void* packed_weights, const float* Q, const float* p
   // Row-interleaved state for the fused F16F8 solve (K >= 2; a single step would only pay the layout conversion):
   // the epilogue of the gate kernel then touches whole 128-byte lines instead of one 32-byte sector per row.
   const char* il_sw = dev_env("IADMM_TC_INTERLEAVED");     // development switch: 0 = row-major state
-  const bool il = tc && nprod == 2 && K >= 2 && !(il_sw && il_sw[0] == '0') && ws.c_il != nullptr;
+  const bool il = tc && nprod == 2 && (K >= 2 || h % 16 != 0) && !(il_sw && il_sw[0] == '0') && ws.c_il != nullptr;
+  if (tc && nprod == 2 && h % 16 != 0 && !il) IADMM_FAIL(IADMM_EMODE, "hidden_dim %% 16 != 0 needs the row-interleaved fp16+fp8 kernels");
   TcIl ilp;
   ilp.rows_p = ws.rows_p; ilp.C_il = ws.c_il; ilp.C_rm_out = nullptr;
   ilp.drop_h_correction = (mode == IADMM_GATES_TC_F16F8U) ? 1 : 0;
   if (il) {
     const size_t hb = (size_t)ws.rows_p * h * sizeof(__half);
+    const size_t qb = il_q8_bytes(ws.rows_p, h);
+    // the padding half of a lone last half group (hidden_dim % 16 == 8) must read as zero in BOTH plane buffers: the epilogue
+    // rewrites it as zero every iteration, the entry conversion below only writes the valid halves
+    if (h % 16 != 0) IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[1], 0, qb, st));
     if (flags & IADMM_F_ZERO_STATE) {
       IADMM_CUDA(cudaMemsetAsync(ws.tc.h_hi[0], 0, hb, st));
-      IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[0], 0, hb, st));
+      IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[0], 0, qb, st));
       IADMM_CUDA(cudaMemsetAsync(ws.c_il, 0, (size_t)ws.rows_p * h * sizeof(float), st));
     } else {
+      if (h % 16 != 0) IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[0], 0, qb, st));
       if ((rc = launch_split_state_il(H, ws.tc.h_hi[0], ws.tc.h_lo[0], rows, h, st))) return rc;
       if ((rc = launch_c_to_il(C, ws.c_il, rows, h, st))) return rc;
     }

@@ -286,6 +286,9 @@ struct TcIl {
   int    drop_h_correction;   // IADMM_GATES_TC_F16F8U: the e4m3 product that corrects the fp16 rounding of H is not issued
 };
 static inline long il_rows(long rows) { return (rows + 127) / 128 * 128; }
+// bytes of one row-interleaved e4m3 plane pair [ceil(h/16)][residual | coarse][rows_p][16]; with hidden_dim % 16 == 8 the last
+// 16-unit group is half padding, which must read as zero (it is multiplied)
+static inline size_t il_q8_bytes(long rows_p, int h) { return (size_t)((h + 15) / 16) * 2 * (size_t)rows_p * 16; }
 int  launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, const float* g,
                      const __half* Hin_hi, const __half* Hin_lo, __half* Hout_hi, __half* Hout_lo,
                      float* H_out_f32 /* may be NULL */, float* C, float* head_part, long rows, int h,

@@ -368,7 +368,13 @@ __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const E
         if (P.c_rm_out) st_global_v8(P.c_rm_out + o, cnew);
         if (P.hout_f32) st_global_v8(P.hout_f32 + o, hnew);
         *reinterpret_cast<uint4*>(P.hout_hi + gi * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if ((cc & 1) == 0) {
+        if ((cc & 1) == 0 && unit0 + 8 >= P.h) {
+          // hidden_dim % 16 == 8: the last 16-unit group has no second half; its padding bytes are multiplied by the MMAs and
+          // are written as zero
+          uint8_t* q = reinterpret_cast<uint8_t*>(P.hout_lo) + ((size_t)(unit0 >> 4) * 2 * P.rows_p + R.row) * 16;
+          *reinterpret_cast<uint4*>(q)                         = make_uint4(res[0], res[1], 0u, 0u);
+          *reinterpret_cast<uint4*>(q + (size_t)P.rows_p * 16) = make_uint4(crs[0], crs[1], 0u, 0u);
+        } else if ((cc & 1) == 0) {
           res_st[0] = res[0]; res_st[1] = res[1]; crs_st[0] = crs[0]; crs_st[1] = crs[1];
         } else {
           // e4m3 planes [16-unit group][residual | coarse][row][16]
@@ -998,7 +1004,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   const bool pair = use_cta_pairs() && num_sms >= 2;
   const char* base = static_cast<const char*>(packed);
   if (nprod == 2 && !pair) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode runs on CTA pairs only");
-  if (nprod == 2 && h % 16 != 0) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0");
+  if (nprod == 2 && h % 16 != 0 && !il) IADMM_FAIL(IADMM_EMODE, "the fp16+fp8 gate mode needs hidden_dim %% 16 == 0 outside the row-interleaved kernels");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   const int b_box_rows = pair ? kPairBBoxRows : kTcBN;
   const int bk = pair ? kPairBK : kTcBK;
@@ -1007,9 +1013,9 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   if (il) {
     if (!pair || nprod != 2 || gates_out) IADMM_FAIL(IADMM_EMODE, "the row-interleaved layout is the F16F8 CTA-pair solve path only");
     if ((rc = get_map_il(&ma_hi, Hin_hi, (uint64_t)il->rows_p, h / 8, false, il_bk))) return rc;
-    if ((rc = get_map_il(&ma_lo, Hin_lo, (uint64_t)il->rows_p, h / 16, true, il_bk))) return rc;
+    if ((rc = get_map_il(&ma_lo, Hin_lo, (uint64_t)il->rows_p, (h + 15) / 16, true, il_bk))) return rc;
     if ((rc = get_map_il(&mb_hi, base + L.off_uhi_il, (uint64_t)4 * h, h / 8, false, il_bk))) return rc;
-    if ((rc = get_map_il(&mb_lo, base + L.off_uq8_il, (uint64_t)4 * h, h / 16, true, il_bk))) return rc;
+    if ((rc = get_map_il(&mb_lo, base + L.off_uq8_il, (uint64_t)4 * h, (h + 15) / 16, true, il_bk))) return rc;
   } else {
     if ((rc = get_map(&ma_hi, Hin_hi, (uint64_t)rows, h, kTcBM, 2, bk))) return rc;
     if ((rc = get_map(&mb_hi, base + L.off_uhi, (uint64_t)4 * h, h, b_box_rows, 2, bk))) return rc;

@@ -55,7 +55,9 @@ enum {
   IADMM_GATES_TC_1XFP16   = 2,  /* tcgen05, single fp16 MMA (TF32-class operands): opt-in fast mode     */
   IADMM_GATES_TC_F16F8    = 3,  /* tcgen05, fp16 main product + two fp8 (e4m3) correction products for  */
                                 /* the operand rounding residuals: ~16-bit operands at 2/3 of the cost  */
-                                /* of the 3-way split (needs hidden_dim % 16 == 0): THE DEFAULT          */
+                                /* of the 3-way split: THE DEFAULT.  hidden_dim % 8 == 0; with           */
+                                /* hidden_dim % 16 == 8 (configs/QP.yaml's 200) the solve pads the last */
+                                /* 16-unit operand group, training uses the 3-way split                  */
   IADMM_GATES_TC_F16F8U   = 4   /* opt-in: as F16F8 but only the rounding of the WEIGHTS U is corrected */
                                 /* (1.5 instead of 2 MMA units in the fused K >= 2 solve; single steps  */
                                 /* and training run F16F8).  The fp16 rounding of H then acts as fresh  */

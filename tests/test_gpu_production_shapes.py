@@ -189,14 +189,15 @@ def test_clip_gradient_at_an_exact_double_tie():
         assert rel_err(alt[3], ref[3]) > 1e-3      # a one-sided tie (0.5) is a different gradient than the double tie (0.25)
 
 
-def test_hidden208_k100_vs_fp32_path():
-    """configs/QP.yaml's default hidden_dim (200 -> 208, the tensor-core tile granularity): the 16-epilogue-warp kernel with the
-    shared-reciprocal activations (gates_tc_pair_kernel<2,2,9>, hidden_dim <= 256).  K=100 at n=1000, 500+500, --scaling against
-    the fp32 CUDA-core path on the same inputs and weights (which matches the reference's fp32 run to <= 2e-6, test_gpu_parity):
-    worst INSTANCE within north_star's 1e-4 on x, y, z, batch norm within 1e-4 on the residual traces."""
+@pytest.mark.parametrize("h", [200, 208])
+def test_hidden200_k100_vs_fp32_path(h):
+    """configs/QP.yaml's default hidden_dim 200 (% 16 == 8: half-padded last operand group) and 208: the 16-epilogue-warp kernel
+    with the shared-reciprocal activations (gates_tc_pair_kernel<2,2,9>, hidden_dim <= 256).  K=100 at n=1000, 500+500, --scaling
+    against the fp32 CUDA-core path on the same inputs and weights (which matches the reference's fp32 run to <= 2e-6,
+    test_gpu_parity): worst INSTANCE within north_star's 1e-4 on x, y, z, batch norm within 1e-4 on the residual traces."""
     from bench import device_qp_batch
     import iadmm_b200 as ia
-    B, n, mi, me, h, K = 4, 1000, 500, 500, 208, 100
+    B, n, mi, me, K = 4, 1000, 500, 500, 100
     Q, p, A0, zl, zu = device_qp_batch(B, n, mi, me, 21, DEV)
     sc = ia.Scaling(n, mi + me, 10, DEV)
     data = sc.scale_data(Q, p, A0, zl, zu)
@@ -209,6 +210,6 @@ def test_hidden208_k100_vs_fp32_path():
         r = model.solve(K, mi, me, *data, 6e-6, scaling=sc)
     worst = {k: max(rel_err(getattr(r, k)[i], getattr(ref, k)[i]) for i in range(B)) for k in ("x", "y", "z")}
     tr = {k: rel_err(getattr(r, k), getattr(ref, k)) for k in ("pri", "dual", "pri_unscaled", "dual_unscaled")}
-    print("hidden 208, K=100: worst instance", {k: f"{v:.1e}" for k, v in worst.items()}, "traces", {k: f"{v:.1e}" for k, v in tr.items()})
+    print(f"hidden {h}, K=100: worst instance", {k: f"{v:.1e}" for k, v in worst.items()}, "traces", {k: f"{v:.1e}" for k, v in tr.items()})
     for k, v in {**worst, **tr}.items():
         assert v <= 1e-4, (k, v)

@@ -59,7 +59,7 @@ def our_window(prm, qp, mi, me, h, TL, outer_T, state=None, mode="simt_fp32"):
 
 @pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16f8"])
 @pytest.mark.parametrize("shape", [(2, 12, 5, 7, 8, 4, 1.0), (3, 40, 12, 16, 32, 5, 3.0), (2, 100, 50, 50, 64, 6, 1.0),
-                                   (2, 24, 10, 0, 16, 4, 2.0)])
+                                   (2, 24, 10, 0, 16, 4, 2.0), (2, 30, 9, 8, 40, 4, 1.0)])
 def test_window_gradients_match_autograd(shape, mode):
     from oracle import iadmm_oracle as orc
     B, n, mi, me, h, TL, wscale = shape
