@@ -30,6 +30,7 @@ struct GemmParams {
   int n_tiles, k_blocks;
   int splits, kb_per_split;   // split-K: work unit = (tile, split), split s covers K blocks [s*kb_per_split, ...)
   long num_tiles;             // output tiles; work units = num_tiles * splits
+  int prod_mask;              // which of the products are issued: 1 = A_lo B_hi, 2 = A_hi B_lo, 4 = A_hi B_hi (7 = all)
 };
 
 __global__ void __launch_bounds__(kGmThreads, 1)
@@ -286,9 +287,9 @@ tc_gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
             const uint64_t a_lo = make_smem_desc_sw128(sb + kGpABytes + koff);
             const uint64_t b_hi = make_smem_desc_sw128(sb + 2 * kGpABytes + koff);
             const uint64_t b_lo = make_smem_desc_sw128(sb + 2 * kGpABytes + kGpBBytes + koff);
-            tc_mma_f16_pair(d_tmem, a_lo, b_hi, idesc, acc); acc = 1;
-            tc_mma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1);
-            tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+            if (P.prod_mask & 1) { tc_mma_f16_pair(d_tmem, a_lo, b_hi, idesc, acc); acc = 1; }
+            if (P.prod_mask & 2) { tc_mma_f16_pair(d_tmem, a_hi, b_lo, idesc, acc); acc = 1; }
+            tc_mma_f16_pair(d_tmem, a_hi, b_hi, idesc, acc); acc = 1;
           }
           tc_commit_pair(smem_u32(&empty_bar[stage]), (uint16_t)3);   // frees the stage in both CTAs when the MMAs retire
           if (++stage == kGpStages) { stage = 0; phase ^= 1; }
@@ -386,7 +387,7 @@ int tc_gemm_pick_splits(long M, long N, long K, int num_sms, int max_splits) {
 // splits > 1: `part` must hold splits * M * ldc floats; C then receives the fixed-order sum of the partials
 int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi, const __half* B_lo, float* C,
                       const float* scale, long M, long N, long K, long lda, long ldb, long ldc, cudaStream_t st,
-                      int splits, float* part) {
+                      int splits, float* part, int prod_mask) {
   if (N % 16 != 0 || lda % 8 != 0 || ldb % 8 != 0 || ldc % 4 != 0) IADMM_FAIL(IADMM_ESHAPE, "tc_gemm: unsupported leading dimensions");
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) IADMM_FAIL(IADMM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -418,6 +419,7 @@ int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi
   P.n_tiles = (int)((N + kGmBN - 1) / kGmBN);
   P.k_blocks = (int)((K + kGmBK - 1) / kGmBK);
   P.splits = splits;
+  P.prod_mask = prod_mask | 4;
   P.kb_per_split = (P.k_blocks + splits - 1) / splits;
   const int tile_rows = pair ? 2 * kTcBM : kTcBM;
   P.num_tiles = ((M + tile_rows - 1) / tile_rows) * P.n_tiles;

@@ -24,7 +24,7 @@ int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, co
 // gemm_tc.cu
 int launch_tc_gemm_nt(const __half* A_hi, const __half* A_lo, const __half* B_hi, const __half* B_lo, float* C,
                       const float* scale, long M, long N, long K, long lda, long ldb, long ldc, cudaStream_t st,
-                      int splits = 1, float* part = nullptr);
+                      int splits = 1, float* part = nullptr, int prod_mask = 7);
 int tc_gemm_pick_splits(long M, long N, long K, int num_sms, int max_splits);
 constexpr int kMaxSplitK = 16;
 int launch_absmax(const float* X, size_t count, float* out, cudaStream_t st);
@@ -670,13 +670,16 @@ int iadmm_step_bwd(const void* packed_weights, const float* Q, const float* p, c
     }
     if ((rc = launch_split_both(W.D, (long)rows, h4, W.rows_p, W.gscal + 4, W.d_hi, W.d_lo, W.dt_hi, W.dt_lo, st))) return rc;
     if ((rc = launch_split_both(H, (long)rows, h, W.rows_p, nullptr, nullptr, nullptr, W.ht_hi, W.ht_lo, st))) return rc;
-    if ((rc = launch_tc_gemm_nt(W.d_hi, W.d_lo, u32hi, u32lo, gH, W.gscal + 5, (long)rows, h, h4, h4, h4, h, st))) return rc;
+    const char* m1 = dev_env("IADMM_GEMM1_MASK");
+    const char* m2 = dev_env("IADMM_GEMM2_MASK");
+    if ((rc = launch_tc_gemm_nt(W.d_hi, W.d_lo, u32hi, u32lo, gH, W.gscal + 5, (long)rows, h, h4, h4, h4, h, st, 1, nullptr,
+                                m1 ? atoi(m1) : 7))) return rc;
     // U_bar = H^T D has 7 x 13 output tiles and K = rows: split K so that the (tile, split) units fill the 148 SMs
     int num_sms = 148;
     if ((rc = device_sm_count(&num_sms))) return rc;
     const int splits = tc_gemm_pick_splits(h, h4, (long)rows, num_sms, kMaxSplitK);
     if ((rc = launch_tc_gemm_nt(W.ht_hi, W.ht_lo, W.dt_hi, W.dt_lo, W.u32bar, W.gscal + 6, h, h4, (long)rows, W.rows_p, W.rows_p,
-                                h4, st, splits, W.u32bar_part))) return rc;
+                                h4, st, splits, W.u32bar_part, m2 ? atoi(m2) : 7))) return rc;
   } else {
     if ((rc = launch_sgemm<false, true>(W.D, u32, gH, (long)rows, h, h4, h4, h4, h, st))) return rc;
     if ((rc = launch_sgemm<true, false>(H, W.D, W.u32bar, h, h4, (long)rows, h, h4, h4, st))) return rc;
