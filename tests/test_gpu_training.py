@@ -28,7 +28,7 @@ def oracle_window(prm, qp, mi, me, h, TL, outer_T, state=None, dtype=torch.float
         pr, du, tot = orc.primal_dual_residuals(x, y, z, Q, p, A0)
         loss = loss + tot.mean() / outer_T
     loss.backward()
-    return float(loss), {k: v.grad for k, v in p64.items()}, [s.detach() for s in (x, y, z, xv, H, C)]
+    return float(loss.detach()), {k: v.grad for k, v in p64.items()}, [s.detach() for s in (x, y, z, xv, H, C)]
 
 
 def our_window(prm, qp, mi, me, h, TL, outer_T, state=None, mode="simt_fp32"):
@@ -73,8 +73,14 @@ def test_window_gradients_match_autograd(shape, mode):
     assert abs(loss - ref_loss) <= 2e-5 * abs(ref_loss)
     errs = {k: rel_err(g[k], ref_g[k]) for k in ref_g if float(ref_g[k].abs().max()) > 0}
     print(shape, mode, {k: f"{v:.1e}" for k, v in errs.items()})
+    # The bias gradients b_u and b_h are sums over all B*N coordinates and TL iterations that cancel to ~1e-3 of their terms:
+    # the REFERENCE's own fp32 autograd misses the float64 value by 1e-4 ... 3e-4 there.  That floor is measured here (the
+    # oracle in float32 against the oracle in float64, same inputs) and an fp32 implementation is held to the fixed bound or
+    # 3x the floor, whichever is larger.
+    _, g32, _ = oracle_window(prm, qp, mi, me, h, TL, outer_T, dtype=torch.float32)
+    floor = {k: rel_err(g32[k].double(), ref_g[k]) for k in errs}
     for k, v in errs.items():
-        assert v < (2e-4 if mode == "simt_fp32" else 5e-4), (k, v)
+        assert v < max(2e-4 if mode == "simt_fp32" else 5e-4, 3.0 * floor[k]), (k, v, floor[k])
     # rows >= TL of the schedule never receive gradient (main.py:338 restarts t at 0)
     assert float(g["rho"][TL:].abs().max()) == 0.0 and float(g["alpha"][TL:].abs().max()) == 0.0
     # fp32 state vs the fp64 run; y = y + rho (z~ - z) cancels catastrophically on equality rows, so its fp32
