@@ -64,6 +64,7 @@ struct TcParams {
   float*  head_part;      // [2*unit_tiles][rows]
   long rows;
   int  h, unit_tiles, k_blocks, stages, nprod;
+  int  skew;              // rotate the unit tiles of a row tile by the row-tile index (see tile_unit)
   int  exp;               // development experiments (IADMM_TC_EXP, row-interleaved kernel only, compiled into the EPI 4 instantiation;
                           // results are garbage): 1 = epilogue reads TMEM only,
                           // 2 = no TMA / MMA, 3 = no global traffic in the epilogue, 4 = no cell math, 5 = all rows alias 1024 rows (no DRAM),
@@ -193,6 +194,17 @@ __device__ __forceinline__ void lstm_epilogue_tile(const TcParams& P, const EpiR
   if (R.row_ok) P.head_part[((size_t)ut * 2 + half) * P.rows + R.row] = hp;
 }
 
+
+// Work unit `tile` of the persistent grids -> (row tile rt = tile / unit_tiles, unit tile).  The stride between the tiles of a
+// CTA (pair) is the number of CTAs (pairs): with 74 pairs and the 4 unit tiles of hidden_dim 200 / 208 a pair would only ever
+// see unit tiles {0, 2} or {1, 3}, and since the last unit tile is ragged (8 / 16 of 64 units: a fraction of the epilogue work)
+// the pairs on {0, 2} carried 108 full tiles against 54 + 54 ragged ones on the others and set the kernel's time.  Rotating the
+// unit tiles of a row tile by rt hands every pair all unit tiles in turn; the unit tiles of a row tile stay adjacent in the
+// schedule, so its operand rows are still fetched from HBM once and hit L2 for the other unit tiles.
+__device__ __forceinline__ int tile_unit(long tile, long rt, int unit_tiles, int skew) {
+  const int j = (int)(tile - rt * unit_tiles);
+  return skew ? (int)((j + rt) % unit_tiles) : j;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Packed-fp32 epilogue (EPI 1, 2).  Power measurements (profiles/r01_gate_power_experiments.json) show the gate
@@ -485,8 +497,8 @@ gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (long tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const int  ut = (int)(tile % unit_tiles);
         const long rt = tile / unit_tiles;
+        const int  ut = tile_unit(tile, rt, unit_tiles, P.skew);
         const int row0 = (int)(rt * kTcBM);
         const int col0 = ut * kTcBN;
         for (int kb = 0; kb < P.k_blocks; ++kb) {
@@ -513,7 +525,7 @@ gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       int stage = 0; uint32_t phase = 0;
       long it = 0;
       for (long tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
-        const int ut = (int)(tile % unit_tiles);
+        const int ut = tile_unit(tile, tile / unit_tiles, unit_tiles, P.skew);
         const int n_cols = min(kTcBN, h4 - ut * kTcBN);
         const uint32_t idesc = make_idesc_f16(n_cols);
         const int buf = (int)(it & 1);
@@ -559,8 +571,8 @@ gates_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const float dequant = P.scale[1];
     long it = 0;
     for (long tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
-      const int  ut = (int)(tile % unit_tiles);
       const long rt = tile / unit_tiles;
+      const int  ut = tile_unit(tile, rt, unit_tiles, P.skew);
       const int buf = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       float* sp = sparam + buf * kParamFloats;
@@ -687,8 +699,8 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       constexpr uint32_t kBBoxTotal = ((NPROD == 1) ? 1 : 2) * kPairBBoxRows * kPairBK * 2; // bytes of one 64-row box of every U operand
       long pit = 0;
       for (long tile = pair; tile < P.num_tiles; tile += num_pairs, ++pit) {
-        const int  ut = (int)(tile % unit_tiles);
         const long rt = tile / unit_tiles;
+        const int  ut = tile_unit(tile, rt, unit_tiles, P.skew);
         // this tile's epilogue parameters: one bulk copy into the buffer of its accumulator (no thread of the epilogue stages
         // anything, no CTA barrier).  Issued after the tile's first operand stages are in flight: the buffer frees up when the
         // epilogue of the tile two back is done, which is also what this tile's MMAs wait for.
@@ -759,7 +771,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       int stage = 0; uint32_t phase = 0;
       long it = 0;
       for (long tile = pair; tile < P.num_tiles; tile += num_pairs, ++it) {
-        const int ut = (int)(tile % unit_tiles);
+        const int ut = tile_unit(tile, tile / unit_tiles, unit_tiles, P.skew);
         const int n_cols = min(kTcBN, h4 - ut * kTcBN);
         const uint32_t idesc = make_idesc_f16(n_cols, 2 * kTcBM);
         const int buf = (int)(it & 1);
@@ -832,8 +844,8 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     const float dequant = P.scale[1];
     long it = 0;
     for (long tile = pair; tile < P.num_tiles; tile += num_pairs, ++it) {
-      const int  ut = (int)(tile % unit_tiles);
       const long rt = tile / unit_tiles;
+      const int  ut = tile_unit(tile, rt, unit_tiles, P.skew);
       const int buf = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       float* sp = sparam + buf * kParamFloats;
@@ -882,6 +894,17 @@ EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+// tile_unit's rotation is only needed when the grid stride and the number of unit tiles share a factor (74 pairs and the 4 unit
+// tiles of hidden_dim 200: every pair would see two of the four unit tiles); otherwise the schedule of rounds 1-2 is kept as
+// profiled (hidden_dim 800: 13 unit tiles).  Development switch IADMM_TC_SKEW = 0 / 1 forces it off / on.
+static int tile_skew_needed(long stride, int unit_tiles, int h) {
+  if (const char* e = dev_env("IADMM_TC_SKEW")) return atoi(e) != 0;
+  if (h % kTcUnits == 0) return 0;                 // no ragged unit tile: all tiles cost the same
+  long a = stride, b = unit_tiles;
+  while (b) { const long t = a % b; a = b; b = t; }
+  return a > 1;
 }
 
 // 2D row-major [rows_total][h] tensor of fp16 (elem_bytes 2, 64B swizzle) or e4m3 bytes (elem_bytes 1, 32B
@@ -1043,6 +1066,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   if (il) P.C = il->C_il;
   P.rows = rows; P.h = h; P.q8_pitch = q8_pitch(h);
   P.unit_tiles = cdiv(h, kTcUnits);
+  P.skew = 0;             // set at launch from the grid size (tile_unit)
   P.k_blocks = cdiv(h, il ? il_bk : bk);
   P.nprod = nprod;
   int exp_mode = 0, epi = 1;
@@ -1093,6 +1117,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
         clusters = n < num_sms / 4 ? n : num_sms / 4;
       }
       if (P.num_tiles < clusters) clusters = P.num_tiles;
+      P.skew = tile_skew_needed(clusters, P.unit_tiles, P.h);
       kernel<<<(unsigned)(cluster * clusters), threads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
       return IADMM_OK;
     };
@@ -1131,6 +1156,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
     return IADMM_OK;
   }
   const long grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
+  P.skew = tile_skew_needed(grid, P.unit_tiles, P.h);
   static PerDeviceOnce a3, a1;
   if (nprod == 3) {
     if ((rc = ensure_dyn_smem(gates_tc_kernel<3>, 220 * 1024, &a3))) return rc;
