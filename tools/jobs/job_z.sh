@@ -1,4 +1,4 @@
 export IADMM_B200_LIB=$PWD/i-admm-lstm_b200/iadmm_b200/libiadmm_b200_dev.so
-for hh in 208 256; do for ex in 0 1 2 3 4 5; do IADMM_TC_EXP=$ex timeout 300 python bench.py --hidden $hh --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-gpu-reference 2>/dev/null | python -c "
+for b in 2 8; do for w in 592 300 150 64; do IADMM_TRAIN_KKT_CTAS=$w python bench.py --workload train --batch $b --steps 2 --warmup 3 --graph 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('hidden $hh exp $ex', round(d['value'],1), {k:round(v,3) for k,v in d['phase_ms_per_iteration'].items()}, d['clocks']['sm_mhz'])" | tee -a gpurun_out/r02_h208_ablation.txt; done; done
+d=json.loads(sys.stdin.read()); print('batch $b want $w', round(d['value'],2), round(d['ms_per_step'],1))" | tee -a gpurun_out/r02_train_kkt_chunks.txt; done; done
