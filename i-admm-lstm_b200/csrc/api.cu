@@ -247,8 +247,14 @@ static int solve_impl(const void* packed_weights, const float* Q, const float* p
   // Row-interleaved state for the fused F16F8 solve (K >= 2; a single step would only pay the layout conversion):
   // the epilogue of the gate kernel then touches whole 128-byte lines instead of one 32-byte sector per row.
   const char* il_sw = dev_env("IADMM_TC_INTERLEAVED");     // development switch: 0 = row-major state
-  const bool il = tc && nprod == 2 && (K >= 2 || h % 16 != 0) && !(il_sw && il_sw[0] == '0') && ws.c_il != nullptr;
+  const bool keep = (flags & (IADMM_F_KEEP_PLANES | IADMM_F_RESUME)) != 0;
+  const bool il = tc && nprod == 2 && (K >= 2 || h % 16 != 0 || keep) && !(il_sw && il_sw[0] == '0') && ws.c_il != nullptr;
   if (tc && nprod == 2 && h % 16 != 0 && !il) IADMM_FAIL(IADMM_EMODE, "hidden_dim %% 16 != 0 needs the row-interleaved fp16+fp8 kernels");
+  // one iteration per call (main.py:874-887): the state stays in the planes the previous call left in this workspace
+  const bool resume = (flags & IADMM_F_RESUME) != 0;
+  if (resume && !il) IADMM_FAIL(IADMM_EMODE, "solve: IADMM_F_RESUME needs the row-interleaved fp16+fp8 path (iadmm_solve_state_resumable)");
+  if (resume && (flags & IADMM_F_ZERO_STATE)) IADMM_FAIL(IADMM_EMODE, "solve: IADMM_F_RESUME and IADMM_F_ZERO_STATE exclude each other");
+  if (resume && (flags & IADMM_F_RESUME_ODD)) cur = 1;
   TcIl ilp;
   ilp.rows_p = ws.rows_p; ilp.C_il = ws.c_il; ilp.C_rm_out = nullptr;
   ilp.drop_h_correction = (mode == IADMM_GATES_TC_F16F8U) ? 1 : 0;
@@ -257,8 +263,10 @@ static int solve_impl(const void* packed_weights, const float* Q, const float* p
     const size_t qb = il_q8_bytes(ws.rows_p, h);
     // the padding half of a lone last half group (hidden_dim % 16 == 8) must read as zero in BOTH plane buffers: the epilogue
     // rewrites it as zero every iteration, the entry conversion below only writes the valid halves
-    if (h % 16 != 0) IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[1], 0, qb, st));
-    if (flags & IADMM_F_ZERO_STATE) {
+    // (resume: nothing to convert, and both padding halves were zeroed by the call that started the sequence)
+    if (!resume && h % 16 != 0) IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[1], 0, qb, st));
+    if (resume) {
+    } else if (flags & IADMM_F_ZERO_STATE) {
       IADMM_CUDA(cudaMemsetAsync(ws.tc.h_hi[0], 0, hb, st));
       IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[0], 0, qb, st));
       IADMM_CUDA(cudaMemsetAsync(ws.c_il, 0, (size_t)ws.rows_p * h * sizeof(float), st));
@@ -307,6 +315,12 @@ static int solve_impl(const void* packed_weights, const float* Q, const float* p
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, nullptr, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
                                   dual_trace_u, sd, se, sc, K - 1, 1, st, metric_trace, zu, sched + (t0 + K - 1)))) return rc;
   }
+  return IADMM_OK;
+}
+
+int iadmm_solve_state_resumable(int n, int m, int h, int mode, int flags, int* yes) {
+  if (n <= 0 || m < 0 || h <= 0 || !yes) IADMM_FAIL(IADMM_ESHAPE, "solve_state_resumable: n=%d m=%d h=%d", n, m, h);
+  *yes = (is_f16f8(mode) && h % 8 == 0 && !resident_eligible(n, m, h, 2, flags)) ? 1 : 0;
   return IADMM_OK;
 }
 

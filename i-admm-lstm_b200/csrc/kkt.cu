@@ -999,34 +999,102 @@ int launch_tail(const KktDims& d, const float* head_part, int tiles, const float
 // ------------------------------------------------------------------------------------------------
 // dense K / rhs / rho_vec materialisation for API compatibility (models/lstm.py:61-62,67-69)
 // ------------------------------------------------------------------------------------------------
+// 64 x 64 tiles that never straddle a block boundary of K = [[Q + sigma I, A0^T], [A0, -diag(1/rho)]]: blockIdx.x / .y run over
+// the column / row tiles of the first n and then of the last m indices.  Every global access is a whole 128-byte line per warp;
+// the A0^T block goes through a shared-memory transpose (the first version read it with stride n: 1.8 TB/s).
+constexpr int kBkT = 64;
+template <bool VEC>
 __global__ void __launch_bounds__(256) build_kkt_kernel(int B, int n, int m, int num_ineq, const float* __restrict__ Q,
                                                         const float* __restrict__ p, const float* __restrict__ A0,
                                                         const float* __restrict__ x, const float* __restrict__ y,
                                                         const float* __restrict__ z, const Sched* __restrict__ sched,
                                                         float sigma, float* __restrict__ K, float* __restrict__ rhs,
                                                         float* __restrict__ rho_vec) {
+  __shared__ float tile[kBkT][kBkT + 1];
   const size_t N = (size_t)n + m;
   const size_t b = blockIdx.z;
-  const int r = blockIdx.y;                       // row of K
-  const float rho_r = (r >= n) ? ((r - n < num_ineq) ? sched->rho_ineq : sched->rho_eq) : 0.f;
-  const float inv_r = (r >= n) ? ((r - n < num_ineq) ? sched->inv_rho_ineq : sched->inv_rho_eq) : 0.f;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; K != nullptr && c < (int)N; c += gridDim.x * blockDim.x) {
-    float v;
-    if (r < n) {
-      if (c < n) { v = Q[(b * n + r) * n + c]; if (c == r) v = __fadd_rn(v, sigma); }
-      else       v = A0[(b * m + (c - n)) * n + r];
+  const int tn = (n + kBkT - 1) / kBkT;                       // tiles over the first n indices
+  const bool low = (int)blockIdx.y >= tn, right = (int)blockIdx.x >= tn;
+  const int r0 = low ? ((int)blockIdx.y - tn) * kBkT : (int)blockIdx.y * kBkT;      // origin inside the block
+  const int c0 = right ? ((int)blockIdx.x - tn) * kBkT : (int)blockIdx.x * kBkT;
+  const int rlim = low ? m : n, clim = right ? m : n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (K != nullptr) {
+    float* Kb = K + b * N * N;
+    if (!low && right) {
+      // A0^T block: K[r][n + j] = A0[j][r]
+      const float* Ab = A0 + b * (size_t)m * n;
+#pragma unroll
+      for (int i = 0; i < kBkT; i += 8) {
+        const int j = c0 + ty + i;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int r = r0 + tx + 32 * h2;
+          tile[ty + i][tx + 32 * h2] = (j < m && r < n) ? Ab[(size_t)j * n + r] : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kBkT; i += 8) {
+        const int r = r0 + ty + i;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int j = c0 + tx + 32 * h2;
+          if (r < n && j < m) Kb[(size_t)r * N + n + j] = tile[tx + 32 * h2][ty + i];
+        }
+      }
+    } else if (VEC) {
+      // n % 4 == 0 and m % 4 == 0: 128-bit accesses, 16 threads per 64-column row, all loads of a thread issued before its stores
+      const float* src = low ? A0 + b * (size_t)m * n : Q + b * (size_t)n * n;
+      const int c = c0 + 4 * (int)(threadIdx.x & 15), rr = r0 + (int)(threadIdx.x >> 4);
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rr + 16 * i;
+        v[i] = make_float4(-0.0f, -0.0f, -0.0f, -0.0f);          // -(1/rho) * 0 in the reference is -0.0
+        if (!right && r < rlim && c < clim) v[i] = *reinterpret_cast<const float4*>(src + (size_t)r * n + c);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rr + 16 * i;
+        if (r >= rlim || c >= clim) continue;
+        if (low == right && r >= c && r < c + 4) {                // the diagonal crosses this quad
+          float* e = reinterpret_cast<float*>(&v[i]) + (r - c);
+          *e = low ? -((r < num_ineq) ? sched->inv_rho_ineq : sched->inv_rho_eq) : __fadd_rn(*e, sigma);
+        }
+        *reinterpret_cast<float4*>(Kb + ((size_t)(low ? n : 0) + r) * N + (right ? n : 0) + c) = v[i];
+      }
     } else {
-      if (c < n) v = A0[(b * m + (r - n)) * n + c];
-      else       v = (c == r) ? -inv_r : -0.0f;     // -(1/rho) * 0 in the reference is -0.0
+      const float* src = low ? A0 + b * (size_t)m * n : Q + b * (size_t)n * n;
+#pragma unroll
+      for (int i = 0; i < kBkT; i += 8) {
+        const int r = r0 + ty + i;
+        if (r >= rlim) break;
+        const float inv_r = (low && right) ? ((r < num_ineq) ? sched->inv_rho_ineq : sched->inv_rho_eq) : 0.f;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int c = c0 + tx + 32 * h2;
+          if (c >= clim) continue;
+          float v;
+          if (!right) {
+            v = src[(size_t)r * n + c];
+            if (!low && c == r) v = __fadd_rn(v, sigma);
+          } else {
+            v = (c == r) ? -inv_r : -0.0f;        // -(1/rho) * 0 in the reference is -0.0
+          }
+          Kb[((size_t)(low ? n : 0) + r) * N + (right ? n : 0) + c] = v;
+        }
+      }
     }
-    K[(b * N + r) * N + c] = v;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (r < n) rhs[b * N + r] = __fsub_rn(__fmul_rn(sigma, x[b * n + r]), p[b * n + r]);
-    else {
-      const int i = r - n;
-      rhs[b * N + r] = __fsub_rn(z[b * m + i], __fmul_rn(inv_r, y[b * m + i]));
-      rho_vec[b * m + i] = rho_r;
+  if (blockIdx.x == 0 && threadIdx.x < kBkT) {
+    const int r = r0 + (int)threadIdx.x;
+    if (!low && r < n) rhs[b * N + r] = __fsub_rn(__fmul_rn(sigma, x[b * n + r]), p[b * n + r]);
+    if (low && r < m) {
+      const bool in = r < num_ineq;
+      const float inv_r = in ? sched->inv_rho_ineq : sched->inv_rho_eq;
+      rhs[b * N + n + r] = __fsub_rn(z[b * m + r], __fmul_rn(inv_r, y[b * m + r]));
+      rho_vec[b * m + r] = in ? sched->rho_ineq : sched->rho_eq;
     }
   }
 }
@@ -1034,9 +1102,11 @@ __global__ void __launch_bounds__(256) build_kkt_kernel(int B, int n, int m, int
 int launch_build_kkt(int B, int n, int m, int num_ineq, const float* Q, const float* p, const float* A0,
                      const float* x, const float* y, const float* z, const Sched* sched_t, float sigma,
                      float* K, float* rhs, float* rho_vec, cudaStream_t st) {
-  const int N = n + m;
-  const dim3 grid(K == nullptr ? 1 : (cdiv(N, 256) > 8 ? 8 : cdiv(N, 256)), N, B);
-  build_kkt_kernel<<<grid, 256, 0, st>>>(B, n, m, num_ineq, Q, p, A0, x, y, z, sched_t, sigma, K, rhs, rho_vec);
+  const int tiles = cdiv(n, kBkT) + cdiv(m, kBkT);
+  const dim3 grid(K == nullptr ? 1 : tiles, tiles, B);
+  const bool vec = n % 4 == 0 && m % 4 == 0 && K != nullptr && aligned16(K) && aligned16(Q) && (m == 0 || aligned16(A0));
+  if (vec) build_kkt_kernel<true><<<grid, 256, 0, st>>>(B, n, m, num_ineq, Q, p, A0, x, y, z, sched_t, sigma, K, rhs, rho_vec);
+  else     build_kkt_kernel<false><<<grid, 256, 0, st>>>(B, n, m, num_ineq, Q, p, A0, x, y, z, sched_t, sigma, K, rhs, rho_vec);
   IADMM_LAUNCH_CHECK("build_kkt_kernel");
   return IADMM_OK;
 }

@@ -23,6 +23,9 @@ GATE_MODES = {"simt_fp32": GATES_SIMT_FP32, "tc_3xfp16": GATES_TC_3XFP16, "tc_1x
 F_ZERO_STATE = 1
 F_SKIP_FINAL_RESID = 2
 F_STREAMING = 4
+F_KEEP_PLANES = 8
+F_RESUME = 16
+F_RESUME_ODD = 32
 TRAIN_RECOMPUTE_GATES = 1
 
 # every symbol include/iadmm.h declares, with its argument types
@@ -36,6 +39,7 @@ SIGNATURES = {
     "iadmm_ruiz_workspace_bytes": ([_I, _I, _I, POINTER(_Z)], c_int),
     "iadmm_ruiz": ([_P] * 13 + [_I, _I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_solve_workspace_bytes": ([_I, _I, _I, _I, _I, POINTER(_Z)], c_int),
+    "iadmm_solve_state_resumable": ([_I, _I, _I, _I, _I, POINTER(_I)], c_int),
     "iadmm_solve": ([_P] * 20 + [_I] * 8 + [_F, _I, _I, _P, _Z, _P], c_int),
     "iadmm_sparse_bytes": ([_I, _I, _I, _Z, POINTER(_Z)], c_int),
     "iadmm_sparse_pack": ([_P, _I, _I, _I, _Z, _P, _Z, _P, _P], c_int),

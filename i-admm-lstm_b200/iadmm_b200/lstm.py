@@ -6,7 +6,8 @@ H_t, C_t, **kwargs)` 9-tuple.  `forward` runs ONE iteration through the same CUD
 `solve`, which runs K iterations and the per-iteration residual evaluation of utils.py:68-71 in one
 call with no host synchronisation.
 """
-from ctypes import byref, c_size_t
+import weakref
+from ctypes import byref, c_int, c_size_t
 from dataclasses import dataclass
 from typing import Optional
 
@@ -148,7 +149,11 @@ class LSTM(nn.Module):
         self.RHO_EQ_OVER_RHO_INEQ = 1e03
         self.device = torch.device(device)
         self.gate_mode = gate_mode
-        self.materialize_kkt = True      # forward() returns dense A_tild/b_tild like the reference
+        # forward() returns the dense A_tild like the reference (a fresh [B,N,N] tensor per call, 16 MB per instance at
+        # n = m = 1000).  "shared": ONE buffer per (Q, A0, sigma) whose -1/rho_t diagonal is rewritten by every call -- the
+        # tensor returned by call t is only valid until call t+1 (main.py re-binds it every iteration and uses the last one).
+        # False: A_tild is None.
+        self.materialize_kkt = True
         dev = self.device
 
         def normal(*size):
@@ -169,6 +174,9 @@ class LSTM(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = None
+        self._chain = None               # record of the last `forward` call (see `_step`)
+        self.resumed_calls = 0           # how many `forward` calls took the resumed path (diagnostic)
+        self._kkt_shared = None          # `materialize_kkt = "shared"`: (key, weakrefs, buffer)
 
     def name(self):
         return 'lstm'
@@ -232,6 +240,7 @@ class LSTM(nn.Module):
         dense path.  One or two host syncs per matrix for "auto"."""
         L = _lib.lib()
         _lib.require_cuda(Q, p, A0, zl, zu, *[prm for prm in self.parameters()])
+        self._chain = None               # the workspace is about to be rewritten
         dev = Q.device
         Q, p, A0, zl, zu = (_lib.f32(t, dev) for t in (Q, p, A0, zl, zu))
         B, n = Q.shape[0], Q.shape[1]
@@ -346,12 +355,26 @@ class LSTM(nn.Module):
         B, n = Q.shape[0], Q.shape[1]
         m = num_ineq + num_eq
         N = n + m
-        A_tild = torch.empty((B, N, N), device=dev) if dense else None
+        shared = dense == "shared"
         b_tild = torch.empty((B, N, 1), device=dev)
         rho_vec = torch.empty((B, m, 1), device=dev)
         Qc, pc, Ac, xc, yc, zc = (_lib.f32(v, dev) for v in (Q, p, A0, x, y, z))
-        torch.ops.iadmm.build_kkt(self.packed_weights(), Qc, pc, Ac, xc, yc, zc, A_tild, b_tild, rho_vec,
+        A_tild, hit = None, False
+        if shared:
+            # the matrix depends on the iteration only through the -1/rho_t diagonal of its last block
+            key = (Qc.data_ptr(), Qc._version, Ac.data_ptr(), Ac._version, float(sigma), B, n, m)
+            rec = self._kkt_shared
+            hit = rec is not None and rec[0] == key and rec[1]() is not None and rec[2]() is not None
+            A_tild = rec[3] if hit else torch.empty((B, N, N), device=dev)
+            if not hit:
+                self._kkt_shared = None          # (drop the old buffer before keeping the new one)
+                self._kkt_shared = (key, weakref.ref(Qc), weakref.ref(Ac), A_tild)
+        elif dense:
+            A_tild = torch.empty((B, N, N), device=dev)
+        torch.ops.iadmm.build_kkt(self.packed_weights(), Qc, pc, Ac, xc, yc, zc, None if hit else A_tild, b_tild, rho_vec,
                                   int(num_ineq), int(num_eq), self.hidden_dim, self.length, int(t), float(sigma))
+        if hit and m > 0:
+            A_tild.diagonal(dim1=1, dim2=2)[:, n:].copy_(-(1.0 / rho_vec[:, :, 0]))
         return A_tild, b_tild, rho_vec
 
     # -- the reference's per-iteration interface -------------------------------------------------
@@ -374,7 +397,7 @@ class LSTM(nn.Module):
             # NOTE: forward and backward nodes share one workspace (`model._train_ws`): single-stream use only.
             with torch.no_grad():
                 kkt = self._kkt_tuple(int(t), num_ineq, num_eq, Q, p, A0, x.detach(), y.detach(), z.detach(), sigma,
-                                      dense=bool(self.materialize_kkt))
+                                      dense=self.materialize_kkt)
             return (*outs, *kkt)
         if not (0 <= int(t) < self.length):
             raise IndexError(f"index {t} is out of bounds for dimension 0 with size {self.length}")
@@ -384,7 +407,53 @@ class LSTM(nn.Module):
         B, n = Q.shape[0], Q.shape[1]
         m = num_ineq + num_eq
         A_tild, b_tild, rho_vec = self._kkt_tuple(int(t), num_ineq, num_eq, Q, p, A0, x, y, z, sigma,
-                                                  dense=bool(self.materialize_kkt))
-        r = self.solve(1, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state=(x, y, z, xv, H_t, C_t), t0=int(t),
-                       traces=False)
-        return r.x, r.y, r.z, r.xv, r.H, r.C, A_tild, b_tild, rho_vec
+                                                  dense=self.materialize_kkt)
+        out = self._step(int(t), int(num_ineq), int(num_eq), Q, p, A0, zl, zu, float(sigma), (x, y, z, xv, H_t, C_t))
+        return (*out, A_tild, b_tild, rho_vec)
+
+    def _step(self, t, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state):
+        """One iteration for `forward`, returning new state tensors like models/lstm.py:82-96 (the inputs are left untouched).
+        The reference's loops feed the returned H_t, C_t straight back (main.py:874-887, 338-345).  The kernels keep that state
+        in row-interleaved fp16 / e4m3 / fp32 operand planes inside the workspace, so when the H_t and C_t passed in ARE the
+        tensors the previous call returned (same storage, not modified since: `_version`), the call resumes from the planes
+        (IADMM_F_RESUME of include/iadmm.h) instead of converting 2 x [B, n+m, hidden_dim] floats on the way in and cloning
+        them for the way out.  Anything else -- a fresh state, an edited H, another batch, a `solve` in between -- takes the
+        converting path.  (An edit of H or C through `.data` is not seen, exactly as for `packed_weights`.)"""
+        L = _lib.lib()
+        dev = Q.device
+        B, n = Q.shape[0], Q.shape[1]
+        m, h, mode = num_ineq + num_eq, self.hidden_dim, self._mode()
+        yes = c_int(0)
+        _lib.check(L.iadmm_solve_state_resumable(n, m, h, mode, 0, byref(yes)))
+        if not yes.value:
+            r = self.solve(1, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state=state, t0=t, traces=False)
+            return r.x, r.y, r.z, r.xv, r.H, r.C
+        Q, p, A0, zl, zu = (_lib.f32(v, dev) for v in (Q, p, A0, zl, zu))
+        if A0.shape != (B, m, n):
+            raise ValueError(f"A0 has shape {tuple(A0.shape)}, expected {(B, m, n)}")
+        x, y, z, xv = (_lib.f32(v, dev).clone() for v in state[:4])
+        H_t, C_t = state[4], state[5]
+        packed = self.packed_weights()
+        ws = self._workspace(B, n, m, mode, dev)
+        dims = (ws.data_ptr(), B, n, m, h, mode, torch.cuda.current_stream(dev).cuda_stream)
+        ch, self._chain = self._chain, None
+
+        def same(v, ref, ptr, ver):
+            return (ref() is not None and v.data_ptr() == ptr and v._version == ver and v.dtype == torch.float32
+                    and tuple(v.shape) == (B, n + m, h) and v.is_contiguous())
+
+        flags = _lib.F_KEEP_PLANES
+        if ch is not None and ch["dims"] == dims and same(H_t, *ch["H"]) and same(C_t, *ch["C"]):
+            flags |= _lib.F_RESUME | (_lib.F_RESUME_ODD if ch["odd"] else 0)
+            odd = not ch["odd"]
+            self.resumed_calls += 1
+            H = torch.empty((B, n + m, h), device=dev)
+            C = torch.empty((B, n + m, h), device=dev)
+        else:
+            odd = True
+            H, C = _lib.f32(H_t, dev).clone(), _lib.f32(C_t, dev).clone()
+        torch.ops.iadmm.solve(packed, Q, p, A0, zl, zu, None, None, None, x, y, z, xv, H, C, None, None, None, None, None, ws,
+                              num_ineq, num_eq, h, self.length, t, 1, sigma, mode, flags)
+        self._chain = {"dims": dims, "odd": odd, "H": (weakref.ref(H), H.data_ptr(), H._version),
+                       "C": (weakref.ref(C), C.data_ptr(), C._version)}
+        return x, y, z, xv, H, C

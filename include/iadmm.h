@@ -69,7 +69,17 @@ enum {
 enum {
   IADMM_F_ZERO_STATE = 1,       /* H (and the other state) is known to be all-zero on entry (main.py:837-843) */
   IADMM_F_SKIP_FINAL_RESID = 2, /* do not run the trailing residual pass (traces row K-1 left untouched)      */
-  IADMM_F_STREAMING = 4         /* force the streaming (HBM) variant even where the on-chip-resident one applies  */
+  IADMM_F_STREAMING = 4,        /* force the streaming (HBM) variant even where the on-chip-resident one applies  */
+  /* The reference drives the path ONE iteration per call (main.py:874-887: model(t, ...) with the returned H, C fed
+   * back).  The next three flags let such a loop run without converting H and C between the caller's fp32 tensors
+   * and the kernels' row-interleaved operand planes on every call (iadmm_solve_state_resumable says when they apply): */
+  IADMM_F_KEEP_PLANES = 8,      /* keep the state in the row-interleaved planes of the workspace even for K = 1, so   */
+                                /* that the NEXT call on the same workspace can resume from them                      */
+  IADMM_F_RESUME = 16,          /* H and C on entry are NOT read: the state is taken from the planes the previous     */
+                                /* call (same workspace, B, n, m, h, mode; workspace untouched since) left behind.    */
+                                /* H and C are still fully written on exit.  Implies IADMM_F_KEEP_PLANES              */
+  IADMM_F_RESUME_ODD = 32       /* with IADMM_F_RESUME: the planes are in ping-pong buffer 1.  A call that runs K     */
+                                /* iterations from buffer c leaves them in buffer (c + K) & 1 (c = 0 without RESUME)  */
 };
 
 int         iadmm_abi_version(void);
@@ -130,6 +140,9 @@ int iadmm_ruiz(const float* Q, const float* p, const float* A0, const float* zl,
  * mode: IADMM_GATES_*; flags: IADMM_F_*.
  */
 int iadmm_solve_workspace_bytes(int B, int n, int m, int h, int mode, size_t* bytes);
+/* *yes = 1 when iadmm_solve honours IADMM_F_KEEP_PLANES / IADMM_F_RESUME for this shape and mode (the fp16+fp8 modes on the
+ * HBM-streaming path), else 0: the flags are then ignored and H, C are read on entry as usual. */
+int iadmm_solve_state_resumable(int n, int m, int h, int mode, int flags, int* yes);
 int iadmm_solve(const void* packed_weights,
                 const float* Q, const float* p, const float* A0, const float* zl, const float* zu,
                 const float* d, const float* e, const float* c,
