@@ -91,6 +91,7 @@ def parse_args():
     ap.add_argument("--nvar", type=int, default=N_VAR, help="variables per QP (the metric is quoted at 1000; 5000 = BASELINE config 5, "
                                                              "with num_ineq = num_eq = nvar/2)")
     ap.add_argument("--hidden", type=int, default=HIDDEN, help="hidden_dim (the metric is quoted at 800; 200 is configs/QP.yaml's default)")
+    ap.add_argument("--no-literal-loop", action="store_true", help="skip the reference's literal per-iteration loop through the drop-in modules")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the stock-PyTorch-on-this-GPU sample in our line")
     ap.add_argument("--gpu-ref-batch", type=int, default=32, help="instances per step of the stock-PyTorch GPU arm")
     ap.add_argument("--tl", type=int, default=100, help="train: truncated_length of the window")
@@ -566,6 +567,31 @@ def run_ours(args):
         if e2e:
             line["e2e"] = {"value": sum(shares) * steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms / steps}
+        if n_gpus == 1 and not args.no_literal_loop and not sparse_mode:
+            # the reference's LITERAL loop (main.py:837-843, 874-887, 955) through the drop-in modules: K Python-level calls of
+            # model(t, ...) with the returned state fed back + primal_dual_loss per iteration, nine fresh tensors per call
+            # (incl. the dense A_tild) -- what a user gets who only swaps the imports.  Informational; `value` is the fused call.
+            def literal():
+                Qs, ps, As, zls, zus = scaling.scale_data(Q, p, A0, zl, zu)
+                st = [torch.zeros((B, d_, w_), device=dev) for d_, w_ in ((n, 1), (m, 1), (m, 1), (N, 1), (N, h), (N, h))]
+                for t_ in range(K):
+                    st = list(model(t_, mi, me, st[0], st[1], st[2], st[3], SIGMA, st[4], st[5], Q=Qs, p=ps, A0=As, lb=None, ub=None,
+                                    zl=zls, zu=zus)[:6])
+                    ia.primal_dual_loss(st[0], st[1], st[2], Qs, ps, As)
+                return st
+            with torch.no_grad():
+                literal()
+                l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                l0.record()
+                st_l = literal()
+                l1.record()
+                torch.cuda.synchronize()
+            line["literal_loop"] = {"value": B / (l0.elapsed_time(l1) * 1e-3), "unit": UNIT, "ms_per_step": l0.elapsed_time(l1),
+                                    "resumed_calls": model.resumed_calls, "x_equals_fused": bool(torch.equal(st_l[0], r.x)),
+                                    "what": "K x { model(t, ...) ; primal_dual_loss(...) } as main.py:874-887,955 writes it, state fed "
+                                            "back, fresh dense A_tild per call; 1 timed run after 1 warm-up"}
+            del st_l
         if n_gpus == 1 and not args.no_gpu_reference and not sparse_mode:
             # stock PyTorch on the same B200: bounded sample, after our timed regions
             try:
