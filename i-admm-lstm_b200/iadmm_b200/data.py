@@ -65,7 +65,9 @@ def write_instance(path, instance):
 
 def load_batch(data_path, prob_type, ids, device, qplib_num=None, pin=True):
     """Instances `ids` as device tensors: Q [B,n,n] (doubled, main.py:298), p [B,n,1], A0 [B,m,n], zl, zu [B,m,1] and,
-    when present, G, c, A, b, lb, ub.  Also returns the sizes main.py derives (num_var, num_ineq, num_eq)."""
+    when present, G, c, A, b, lb, ub.  Also returns the sizes main.py derives (num_var, num_ineq, num_eq): the row counts of the
+    file's G and A entries (main.py:248-272), to be passed to `LSTM.forward` / `solve` unchanged -- they need not add up to the
+    rows of A0 (Random_QP: G = [A0; -A0]; SVM: G without the identity rows), see `iadmm_b200.lstm.row_classes`."""
     insts = [load_instance(instance_path(data_path, prob_type, i, qplib_num)) for i in ids]
     out = {}
     dev = torch.device(device)

@@ -32,6 +32,25 @@ SPARSE_AUTO_DENSITY = 0.003
 BLOCK_AUTO_OCCUPANCY = 0.7     # "auto": dense matrix with block skipping when at most this share of its 8x128 blocks is non-empty
 
 
+def row_classes(num_ineq, num_eq, m):
+    """(inequality rows, equality rows) the way the kernels take them -- the first rows of A0 are inequality rows, the rest
+    equality rows, together m = A0.shape[1] -- from the counts main.py hands to `model(t, num_ineq, num_eq, ...)`.  Those
+    are the row counts of the `G` and `A` entries of the instance FILE (main.py:248-272), and models/lstm.py:61-62 uses them
+    only as the slice `rho_vec[:, num_ineq:num_ineq+num_eq] *= 1e3` of a [B, m, 1] tensor, so they need not add up to m:
+    Random_QP files carry G = [A0; -A0] (num_ineq = 2m, generate_data.py:116), SVM files G without the identity rows of A0
+    (num_ineq < m, num_eq = 0, :202-207).  Rows outside the slice are inequality-class rows."""
+    num_ineq, num_eq, m = int(num_ineq), int(num_eq), int(m)
+    if num_ineq < 0 or num_eq < 0:
+        raise ValueError(f"negative row count: num_ineq={num_ineq} num_eq={num_eq}")
+    a, b = min(num_ineq, m), min(num_ineq + num_eq, m)
+    if a == b:
+        return m, 0
+    if b == m:
+        return a, m - a
+    raise ValueError(f"rows {a}..{b - 1} of the {m} rows of A0 are equality rows and inequality-class rows follow them: "
+                     "the kernels take inequality rows first, then equality rows (generate_data.py:74)")
+
+
 class SparseBatch:
     """A [B, rows, n] matrix batch in one of the library's two sparse forms (include/iadmm.h):
     kind "slabs"  -- bitmap slabs (iadmm_sparse_pack): masks + packed non-zero values, for unstructured patterns below ~0.3 %;
@@ -244,10 +263,11 @@ class LSTM(nn.Module):
         dev = Q.device
         Q, p, A0, zl, zu = (_lib.f32(t, dev) for t in (Q, p, A0, zl, zu))
         B, n = Q.shape[0], Q.shape[1]
-        m = num_ineq + num_eq
+        if A0.dim() != 3 or A0.shape[0] != B or A0.shape[2] != n:
+            raise ValueError(f"A0 has shape {tuple(A0.shape)}, expected {(B, 'm', n)}")
+        m = A0.shape[1]
+        num_ineq, num_eq = row_classes(num_ineq, num_eq, m)
         h = self.hidden_dim
-        if A0.shape != (B, m, n):
-            raise ValueError(f"A0 has shape {tuple(A0.shape)}, expected {(B, m, n)}")
         flags = _lib.F_STREAMING if streaming else 0
         if state is None:
             x = torch.zeros((B, n, 1), device=dev); y = torch.zeros((B, m, 1), device=dev)
@@ -313,7 +333,8 @@ class LSTM(nn.Module):
         dev = Q.device
         Q, p, A0, zl, zu = (_lib.f32(t, dev) for t in (Q, p, A0, zl, zu))
         B, n = Q.shape[0], Q.shape[1]
-        m = num_ineq + num_eq
+        m = A0.shape[1]
+        num_ineq, num_eq = row_classes(num_ineq, num_eq, m)
         h = self.hidden_dim
         x, y, z, xv, H, C = (_lib.f32(t.detach(), dev) if inplace else _lib.f32(t.detach(), dev).clone() for t in state)
         count, nbytes = c_size_t(), c_size_t()
@@ -353,7 +374,8 @@ class LSTM(nn.Module):
         """(A_tild, b_tild, rho_vec) of models/lstm.py:61-69 for the iterate BEFORE iteration t; A_tild is None unless `dense`."""
         dev = Q.device
         B, n = Q.shape[0], Q.shape[1]
-        m = num_ineq + num_eq
+        m = A0.shape[1]
+        num_ineq, num_eq = row_classes(num_ineq, num_eq, m)
         N = n + m
         shared = dense == "shared"
         b_tild = torch.empty((B, N, 1), device=dev)
@@ -382,6 +404,7 @@ class LSTM(nn.Module):
         """One iteration; returns (x, y, z, xv, H_t, C_t, A_tild, b_tild, rho_vec) like models/lstm.py:96.
         `lb`/`ub` are accepted and ignored, as in the reference (lstm.py:89-90 is commented out)."""
         Q, p, A0, zl, zu = (kwargs[k] for k in ("Q", "p", "A0", "zl", "zu"))
+        num_ineq, num_eq = row_classes(num_ineq, num_eq, A0.shape[1])
         if torch.is_grad_enabled() and (any(prm.requires_grad for prm in self.parameters())
                                         or any(v.requires_grad for v in (x, y, z, xv, H_t, C_t))):
             # training (main.py:336-358): one autograd node per iteration, fp32 forward + hand-written backward
@@ -403,9 +426,6 @@ class LSTM(nn.Module):
             raise IndexError(f"index {t} is out of bounds for dimension 0 with size {self.length}")
         L = _lib.lib()
         _lib.require_cuda(Q, p, A0, zl, zu, x, y, z, xv, H_t, C_t)
-        dev = Q.device
-        B, n = Q.shape[0], Q.shape[1]
-        m = num_ineq + num_eq
         A_tild, b_tild, rho_vec = self._kkt_tuple(int(t), num_ineq, num_eq, Q, p, A0, x, y, z, sigma,
                                                   dense=self.materialize_kkt)
         out = self._step(int(t), int(num_ineq), int(num_eq), Q, p, A0, zl, zu, float(sigma), (x, y, z, xv, H_t, C_t))
@@ -429,7 +449,7 @@ class LSTM(nn.Module):
             r = self.solve(1, num_ineq, num_eq, Q, p, A0, zl, zu, sigma, state=state, t0=t, traces=False)
             return r.x, r.y, r.z, r.xv, r.H, r.C
         Q, p, A0, zl, zu = (_lib.f32(v, dev) for v in (Q, p, A0, zl, zu))
-        if A0.shape != (B, m, n):
+        if tuple(A0.shape) != (B, m, n):
             raise ValueError(f"A0 has shape {tuple(A0.shape)}, expected {(B, m, n)}")
         x, y, z, xv = (_lib.f32(v, dev).clone() for v in state[:4])
         H_t, C_t = state[4], state[5]

@@ -104,11 +104,14 @@ def lstm_parameters(hidden: int, length: int, seed: int = 17, input_dim: int = 2
 # --------------------------------------------------------------------------------------------
 # one unrolled iteration
 # --------------------------------------------------------------------------------------------
-def penalty_schedule(prm, t: int, num_ineq: int, num_eq: int, batch: int):
+def penalty_schedule(prm, t: int, num_ineq: int, num_eq: int, batch: int, rows: Optional[int] = None):
     """models/lstm.py:60-63: rho_t = sigmoid(rho[t]); equality rows carry 1e3*rho_t;
-    alpha_t = 2*sigmoid(alpha[t]).  Returns (rho_vec [B,m,1], alpha [1])."""
+    alpha_t = 2*sigmoid(alpha[t]).  Returns (rho_vec [B,m,1], alpha [1]).
+    The reference sizes rho_vec by ``y.shape`` (lstm.py:61) and only SLICES it with the counts (:62); ``rows`` is that
+    row count (default: the counts add up to it, as for the QP family).  main.py takes the counts from the G / A entries
+    of the instance file (:248-272), which for Random_QP and SVM files do not add up to the rows of A0."""
     rho = torch.sigmoid(prm["rho"][t, :])
-    m = num_ineq + num_eq
+    m = num_ineq + num_eq if rows is None else rows
     rho_vec = torch.ones((batch, m, 1), dtype=rho.dtype) * rho
     rho_vec[:, num_ineq:num_ineq + num_eq, :] = rho_vec[:, num_ineq:num_ineq + num_eq, :] * RHO_EQ_OVER_RHO_INEQ
     alpha = 2 * torch.sigmoid(prm["alpha"][t, :])
@@ -179,7 +182,7 @@ def lstm_step(prm, t: int, num_ineq: int, num_eq: int, x, y, z, xv, sigma: float
     """One unrolled I-ADMM-LSTM iteration (models/lstm.py:47-96).
     Returns ``(x, y, z, xv, H, C, rho_vec)``; K and rhs of the reference's 9-tuple are available
     from :func:`kkt_system`."""
-    rho_vec, alpha = penalty_schedule(prm, t, num_ineq, num_eq, x.shape[0])
+    rho_vec, alpha = penalty_schedule(prm, t, num_ineq, num_eq, x.shape[0], rows=y.shape[1])
     grad = ls_gradient(Q, p, A0, x, y, z, xv, rho_vec, sigma, form)
     feats = torch.cat((xv, grad), dim=-1)
     H, C, step = lstm_cell(prm, feats, H, C)

@@ -148,3 +148,50 @@ def test_shared_kkt_buffer_equals_fresh_one():
         model.materialize_kkt = False
         assert call(model, 0, mi, me, zero_state(B, n, m, h), other)[6] is None
         torch.cuda.synchronize()
+
+
+# ---- dataset files written by the reference's own generate_data.py, with the counts main.py derives from them ------------
+FAMILY_DIRS = {"QP": "QP_12_5_4", "QP_RHS": "QP_RHS_12_5_4", "Random_QP": "Random_QP_10_6", "Equality_QP": "Equality_QP_10_4",
+               "SVM": "SVM_10_4"}
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16f8"])
+@pytest.mark.parametrize("family", list(FAMILY_DIRS))
+def test_dataset_files_through_the_dropin_modules(family, mode):
+    """load_batch (pinned staging -> device) + Scaling + the literal loop and the fused solve, called with main.py's
+    (num_ineq, num_eq) -- for Random_QP (12 + 0 vs 6 rows of A0) and SVM (4 + 0 vs 14 rows) they do not add up to the rows of
+    A0, and models/lstm.py:61-62 only slices with them -- against the reference's outputs on the same files
+    (tests/golden/dataset_<family>.npz, make_dataset_golden.py)."""
+    import os
+    import iadmm_b200 as ia
+    from iadmm_b200 import data
+    from helpers import load_golden, golden_params, rel_err
+    g = load_golden(f"dataset_{family}")
+    B, n, num_ineq, num_eq, m, h, K, ites = (int(v) for v in g["meta"])
+    prm = golden_params(g)
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "datasets", FAMILY_DIRS[family])
+    batch, sizes = data.load_batch(d, family, [0, 1, 2], DEV)
+    assert (sizes["num_ineq"], sizes["num_eq"]) == (num_ineq, num_eq)
+    model = ia.LSTM(None, 2, h, K, DEV, gate_mode=mode).eval()
+    with torch.no_grad():
+        for k, v in prm.items():
+            getattr(model, k).copy_(v.to(DEV))
+    sc = ia.Scaling(n, m, ites, DEV)
+    scaled = sc.scale_data(*(batch[k] for k in ("Q", "p", "A0", "zl", "zu")))
+    tol = {"simt_fp32": 2e-5, "tc_f16f8": 5e-5}[mode]
+    with torch.no_grad():
+        st, pri, dual = zero_state(B, n, m, h), [], []
+        for t in range(K):
+            out = call(model, t, num_ineq, num_eq, st, scaled)
+            st = list(out[:6])
+            pr, du, _ = ia.primal_dual_loss(st[0], st[1], st[2], scaled[0], scaled[1], scaled[2])
+            pri.append(pr.reshape(B)); dual.append(du.reshape(B))
+        fused = model.solve(K, num_ineq, num_eq, *scaled, float(g["sigma"]))
+        torch.cuda.synchronize()
+    for k, v in zip(STATE, st):
+        assert rel_err(v, g["out_" + k]) < tol, (k, rel_err(v, g["out_" + k]))
+        assert rel_err(getattr(fused, k), g["out_" + k]) < tol, ("fused", k)
+    assert rel_err(torch.stack(pri), g["out_pri"]) < tol and rel_err(torch.stack(dual), g["out_dual"]) < tol
+    assert rel_err(fused.pri, g["out_pri"]) < tol and rel_err(fused.dual, g["out_dual"]) < tol
+    assert rel_err(out[8], g["out_rho_vec"]) < 1e-6
+    assert rel_err(out[6], g["out_K"]) < 1e-5 and rel_err(out[7], g["out_rhs"]) < 1e-4

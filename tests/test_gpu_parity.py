@@ -532,8 +532,13 @@ def test_error_behaviour():
             model.solve(K + 1, mi, me, *args)
         with pytest.raises(ia.IadmmError, match="schedule length"):
             model.solve(2, mi, me, *args, t0=2)
-        with pytest.raises(ValueError):                                        # A0 does not match num_ineq + num_eq
-            model.solve(K, mi + 1, me, *args)
+        # counts that do not add up to the rows of A0 are a SLICE of rho_vec in the reference (lstm.py:61-62; main.py takes them
+        # from the G / A entries of the file): clipped like a torch slice, an error only when the kernels' row order cannot hold it
+        assert torch.equal(model.solve(K, mi + 1, me, *args).x, model.solve(K, mi + 1, me - 1, *args).x)
+        with pytest.raises(ValueError, match="equality rows"):
+            model.solve(K, mi - 1, me - 1, *args)
+        with pytest.raises(ValueError, match="A0 has shape"):
+            model.solve(K, mi, me, qp["Q"], qp["p"], qp["A0"][:, :, :-1], qp["zl"], qp["zu"], 6e-6)
         with pytest.raises(ia.IadmmError, match="contiguous"):
             _lib.ptr(qp["A0"].transpose(1, 2))
         r = model.solve(0, mi, me, *args)                                      # K = 0 is a no-op
