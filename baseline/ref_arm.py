@@ -24,13 +24,14 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 REF_FILES = ("models/lstm.py", "models/lu.py", "methods/scaling.py", "utils.py")
+DRIVER_FILES = ("main.py",)      # the reference's driver script, run UNMODIFIED on the drop-in modules by tests/test_gpu_main_py.py
 SIGMA = 6e-6          # configs/QP.yaml:14
 
 
 def install(src="/root/reference"):
     """Copy the reference's files of the path into baseline/_ref (build container only).  Returns True if present after."""
     if os.path.isdir(src):
-        for rel in REF_FILES:
+        for rel in REF_FILES + DRIVER_FILES:
             dst = os.path.join(REF_DIR, rel)
             os.makedirs(os.path.dirname(dst), exist_ok=True)
             shutil.copyfile(os.path.join(src, rel), dst)

@@ -1,1 +1,1 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -8 | tee gpurun_out/r02_gpu_suite.log
+python -m pytest tests/test_gpu_main_py.py -x -q -m gpu -s 2>&1 | grep -v Warning | tail -40 | tee gpurun_out/r02_main_py_test.log
