@@ -119,10 +119,12 @@ def _arm_modules(arm, ref_root, init_prm=None):
     return mods
 
 
-def run_main_py(family, arm, ref_root, workdir, prm, h, K, device, scaling=True, feas_rest=0, batch=3, train=None):
+def run_main_py(family, arm, ref_root, workdir, prm, h, K, device, scaling=True, feas_rest=0, batch=3, train=None, case=None,
+                data_size=3):
     """One `python main.py ... --test --save_sol` run; returns (results dict, captured stdout).  With `train`: one training
-    run, returns (saved checkpoint, captured stdout)."""
-    case = CASES[family]
+    run, returns (saved checkpoint, captured stdout).  `case` overrides the CASES entry (a dataset the caller has already put
+    below `workdir/datasets/`, tools/main_py_speed.py)."""
+    case = case or CASES[family]
     os.makedirs(os.path.join(workdir, "datasets"), exist_ok=True)
     dst = os.path.join(workdir, "datasets", case["dir"])
     if not os.path.isdir(dst):
@@ -132,7 +134,7 @@ def run_main_py(family, arm, ref_root, workdir, prm, h, K, device, scaling=True,
     if not train:
         torch.save({k: v.clone() for k, v in prm.items()}, os.path.join(params_dir, case["ckpt"].format(K=K, h=h)))
     argv = ["main.py", "--model_name", "LSTM", "--prob_type", family, *case["sizes"], "--input_dim", "2", "--hidden_dim", str(h),
-            "--outer_T", str(K), "--test_outer_T", str(K), "--truncated_length", str(K), "--sigma", "0.000006", "--data_size", "3",
+            "--outer_T", str(K), "--test_outer_T", str(K), "--truncated_length", str(K), "--sigma", "0.000006", "--data_size", str(data_size),
             "--val_frac", "0", "--test_frac", "1", "--batch_size", str(batch), "--test_batch_size", str(batch), "--device", device,
             "--save_dir", "./results/", "--seed", "17", "--test", "--save_sol", "--eq_tol", "0.2", "--ineq_tol", "0.2"]
     if train:
