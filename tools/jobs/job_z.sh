@@ -1,3 +1,2 @@
-python tools/main_py_speed.py 16 16 800 100 1000 2>gpurun_out/r02_mps.err | tee gpurun_out/r02_main_py_speed.jsonl
-python tools/main_py_speed.py 16 16 200 100 1000 2>>gpurun_out/r02_mps.err | tee -a gpurun_out/r02_main_py_speed.jsonl
-tail -5 gpurun_out/r02_mps.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --workload config5 --gpus 8 --steps 2 --warmup 3 2>gpurun_out/r02_n8c5.err | tee gpurun_out/r02_bench_config5_n8.json
+tail -3 gpurun_out/r02_n8c5.err
