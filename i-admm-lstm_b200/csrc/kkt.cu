@@ -17,6 +17,7 @@
 // Column partials of different row chunks are summed in a fixed order by the combine kernels, so results
 // are bit-reproducible run to run.  HBM-bound by design: 8 independent 128-bit loads in flight per lane.
 #include "common.cuh"
+#include "tc_ptx.cuh"      // mbarrier / cp.async.bulk wrappers (the bulk-copy-staged variant of the dense pass)
 
 #include <string.h>
 
@@ -232,6 +233,159 @@ __device__ __forceinline__ void tile_pass(const TileArgs& a, float* smem) {
         rowacc[i] += s;
       }
       __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NR; ++k)
+    for (int r = tid; r < R; r += kKktThreads) {
+      const int row = a.r0 + r;
+      if (row < a.rows_total) a.rout[k][row] = rowacc[r * NR + k];
+    }
+}
+
+// The same dense pass with the matrix bytes moved by the copy engine instead of by load instructions (north_star: "stream from
+// HBM once per iteration, through TMA into shared memory, with warp-shuffle reductions").  A ninth warp issues, per 8-row group and
+// 1024-column chunk, eight `cp.async.bulk` copies of one row segment each (<= 4 KB, whole 16-byte lines) into a ring of
+// kTmaStages x 32 KB stages guarded by full / empty mbarriers; the eight consumer warps read their 128-column slab of a stage
+// into the SAME registers the load-instruction version fills, release the stage and do the same arithmetic in the same order:
+// results are bit-identical (all-zero padding row groups of a ragged last chunk are skipped; they add exact zeros).  Row-major
+// matrices with n % 4 == 0 only (16-byte aligned segments).  smem: tile_smem_bytes(R) | stages | barriers.
+constexpr int kTmaStages     = 3;
+constexpr int kTmaStageBytes = kRowUnroll * kChunkCols * 4;      // 32 KB
+constexpr int kKktTmaThreads = kKktThreads + 32;
+
+__device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kKktThreads) : "memory"); }
+
+static size_t tile_smem_bytes_tma(int R) {
+  return align_up((size_t)(4 * R + kKktWarps * R * 2) * sizeof(float), 128) + 128 + (size_t)kTmaStages * kTmaStageBytes +
+         2 * kTmaStages * sizeof(uint64_t);
+}
+
+template <int NR, int NC>
+__device__ __forceinline__ void tile_pass_tma(const TileArgs& a, float* smem) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = a.R, n = a.n;
+  float* rowscal = smem;
+  float* rowacc  = smem + 2 * R;
+  float* rowpart = smem + 4 * R;
+  // the stages start at the next 128-byte boundary behind the row arrays (the launch reserves the slack)
+  const uint32_t nominal = smem_u32(smem) + (uint32_t)(4 * R + kKktWarps * R * 2) * 4u;
+  unsigned char* stages = reinterpret_cast<unsigned char*>(smem) + (((nominal + 127u) & ~127u) - smem_u32(smem));
+  const uint32_t stage0 = smem_u32(stages);
+  const uint32_t full0  = smem_u32(stages + (size_t)kTmaStages * kTmaStageBytes);
+  const uint32_t empty0 = full0 + 8 * kTmaStages;
+  const int nchunk = (n + kChunkCols - 1) / kChunkCols;
+  const int rows_valid = (a.rows_total - a.r0 < R) ? a.rows_total - a.r0 : R;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kKktWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp < kKktWarps) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      for (int r = tid; r < R; r += kKktThreads) {
+        const int row = a.r0 + r;
+        rowscal[c * R + r] = (row < a.rows_total) ? __ldg(a.crhs[c] + row) : 0.f;
+      }
+    for (int i = tid; i < R * NR; i += kKktThreads) rowacc[i] = 0.f;
+    // (row groups beyond the valid rows are never computed: their row partials must still be finite zeros for the chunk sums)
+    for (int i = tid; i < kKktWarps * R * (NR > 0 ? NR : 1); i += kKktThreads) rowpart[i] = 0.f;
+  }
+  __syncthreads();
+
+  if (warp == kKktWarps) {
+    // ---- producer: one thread feeds the ring ----------------------------------------------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int cc = 0; cc < nchunk; ++cc) {
+        const int col0 = cc * kChunkCols;
+        const uint32_t seg = (uint32_t)(((n - col0 < kChunkCols) ? n - col0 : kChunkCols) * 4);
+        for (int rg = 0; rg < rows_valid; rg += kRowUnroll, ++it) {
+          const int st = it % kTmaStages;
+          if (it >= kTmaStages) mbar_wait(empty0 + 8 * st, ((it / kTmaStages) & 1) ^ 1);
+          const int nrow = (rows_valid - rg < kRowUnroll) ? rows_valid - rg : kRowUnroll;
+          mbar_expect_tx(full0 + 8 * st, seg * (uint32_t)nrow);
+          for (int u = 0; u < nrow; ++u)
+            bulk_load(stage0 + (uint32_t)st * kTmaStageBytes + (uint32_t)u * (kChunkCols * 4),
+                      a.mat + (size_t)(a.r0 + rg + u) * n + col0, seg, full0 + 8 * st);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: tile_pass with the loads taken from the ring ------------------------------------------------------
+  int it = 0;
+  for (int cc = 0; cc < nchunk; ++cc) {
+    const int  col    = cc * kChunkCols + warp * kSlabCols + lane * 4;
+    const bool active = col < n;
+    float4 rv[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) rv[k] = load_vec4<true>(a.rrhs[k], col, n);
+    float4 cacc[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cacc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int rg = 0; rg < rows_valid; rg += kRowUnroll, ++it) {
+      const int st = it % kTmaStages;
+      mbar_wait(full0 + 8 * st, (it / kTmaStages) & 1);
+      const float4* src = reinterpret_cast<const float4*>(stages + (size_t)st * kTmaStageBytes) + warp * (kSlabCols / 4) + lane;
+      float4 v[kRowUnroll];
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u)
+        v[u] = (active && rg + u < rows_valid) ? src[u * (kChunkCols / 4)] : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * st);          // this warp has read its slab of the stage
+      if (NC > 0) {
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const float sc = rowscal[c * R + rg + u];
+            cacc[c].x = fmaf(v[u].x, sc, cacc[c].x);
+            cacc[c].y = fmaf(v[u].y, sc, cacc[c].y);
+            cacc[c].z = fmaf(v[u].z, sc, cacc[c].z);
+            cacc[c].w = fmaf(v[u].w, sc, cacc[c].w);
+          }
+        }
+      }
+      if (NR > 0) {
+        float rp[kRowUnroll * (NR > 0 ? NR : 1)];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+          for (int k = 0; k < NR; ++k) {
+            float t = v[u].x * rv[k].x;
+            t = fmaf(v[u].y, rv[k].y, t);
+            t = fmaf(v[u].z, rv[k].z, t);
+            t = fmaf(v[u].w, rv[k].w, t);
+            rp[u * NR + k] = t;
+          }
+        }
+        constexpr int NV = kRowUnroll * (NR > 0 ? NR : 1);
+        const float tot = warp_transpose_reduce<NV>(rp, lane);
+        constexpr int kGroup = 32 / NV;
+        if ((lane % kGroup) == 0) {
+          const int idx = lane / kGroup;
+          rowpart[warp * (R * NR) + rg * NR + idx] = tot;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) store_cols4<true>(a.cpart[c], col, n, cacc[c]);
+
+    if (NR > 0) {
+      consumers_sync();
+      for (int i = tid; i < R * NR; i += kKktThreads) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kKktWarps; ++w) sacc += rowpart[w * (R * NR) + i];
+        rowacc[i] += sacc;
+      }
+      consumers_sync();
     }
   }
 #pragma unroll
@@ -513,7 +667,7 @@ __device__ __forceinline__ void tile_pass_sparse(const TileArgs& a, float* smem)
     }
 }
 
-static size_t tile_smem_bytes(int R, bool sparse = false) {
+static size_t tile_smem_bytes(int R, bool sparse) {
   return (size_t)(4 * R + kKktWarps * R * 2) * sizeof(float) + (sparse ? (size_t)kKktWarps * R * 20 : 0);
 }
 
@@ -597,6 +751,66 @@ __global__ void __launch_bounds__(kKktThreads, (MQ == 1 || MA == 1) ? 3 : 0) kkt
   }
 }
 
+// bulk-copy-staged forms of the two dense passes (tile_pass_tma): 8 consumer warps + 1 producer warp, 2 CTAs per SM
+__global__ void __launch_bounds__(kKktTmaThreads, 2) kkt_pass1_tma_kernel(const Pass1Args P) {
+  extern __shared__ float smem[];
+  const KktDims& d = P.d;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const size_t n = d.n, m = d.m;
+  TileArgs a;
+  a.n = d.n; a.R = d.rows_per_chunk; a.inst = b; a.blk = nullptr;
+  a.rrhs[0] = P.xt + (size_t)b * P.xt_stride;
+  a.rrhs[1] = P.x + b * n;
+  if (chunk < d.chunks_q) {
+    a.mat = P.Q + b * n * n; a.rows_total = d.n; a.r0 = chunk * a.R;
+    a.rout[0] = P.s.qxt + b * n; a.rout[1] = P.s.qx + b * n;
+    a.crhs[0] = a.crhs[1] = nullptr; a.cpart[0] = a.cpart[1] = nullptr;
+    tile_pass_tma<2, 0>(a, smem);
+  } else {
+    const int ca = chunk - d.chunks_q;
+    a.mat = P.A0 + b * m * n; a.rows_total = d.m; a.r0 = ca * a.R;
+    a.rout[0] = P.s.axt + b * m; a.rout[1] = P.s.ax + b * m;
+    a.crhs[0] = P.v + (size_t)b * P.v_stride; a.crhs[1] = P.y + b * m;
+    float* part = P.s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
+    a.cpart[0] = part; a.cpart[1] = part + n;
+    tile_pass_tma<2, 2>(a, smem);
+  }
+}
+
+__global__ void __launch_bounds__(kKktTmaThreads, 2) kkt_pass2_tma_kernel(const KktDims d, const float* __restrict__ Q,
+                                                                          const float* __restrict__ A0, const KktScratch s) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const size_t n = d.n, m = d.m, N = n + m;
+  TileArgs a;
+  a.n = d.n; a.R = d.rows_per_chunk; a.inst = b; a.blk = nullptr;
+  const float* w1 = s.w + b * N;
+  const float* w2 = w1 + n;
+  a.rrhs[1] = nullptr; a.rout[1] = nullptr; a.crhs[1] = nullptr; a.cpart[1] = nullptr;
+  if (chunk < d.chunks_q) {
+    a.mat = Q + b * n * n; a.rows_total = d.n; a.r0 = chunk * a.R;
+    a.rrhs[0] = nullptr; a.rout[0] = nullptr;
+    a.crhs[0] = w1; a.cpart[0] = s.part_q + ((size_t)b * d.chunks_q + chunk) * n;
+    tile_pass_tma<0, 1>(a, smem);
+  } else {
+    const int ca = chunk - d.chunks_q;
+    a.mat = A0 + b * m * n; a.rows_total = d.m; a.r0 = ca * a.R;
+    a.rrhs[0] = w1; a.rout[0] = s.aw1 + b * m;
+    a.crhs[0] = w2; a.cpart[0] = s.part_a + ((size_t)b * d.chunks_a + ca) * 2 * n;
+    tile_pass_tma<1, 1>(a, smem);
+  }
+}
+
+// Which calls take the bulk-copy-staged kernels: dense row-major matrices with 16-byte aligned rows in the solve's 32- / 64-row
+// chunks (training's small chunks and the sparse forms keep the load-instruction kernels).  Same-box A/B, bit-identical results
+// (tools/kkt_tma_ab.py, profiles/r02_kkt_tma_ab.jsonl): KKT phase 0.660 -> 0.646 ms at the headline size, 1.660 -> 1.522 ms
+// at n = 5000 (5.78 -> 6.31 TB/s).
+static bool use_tma_pass(const KktDims& d, bool vec, int mq, int ma) {
+  if (!vec || mq || ma || d.rows_per_chunk < 32 || d.rows_per_chunk % kRowUnroll) return false;
+  const char* e = dev_env("IADMM_KKT_TMA");              // development switch: 0 = load-instruction kernels
+  return !(e && e[0] == '0');
+}
+
 static int sp_mode(const SpMat* m) { return !m ? 0 : (m->vals ? 1 : (m->blk ? 2 : 0)); }
 
 static bool can_vectorise(const KktDims& d, const void* Q, const void* A0, const KktSparse* sp) {
@@ -626,8 +840,14 @@ static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t s
   if ((mq || ma) && (d.rows_per_chunk > 64 || d.rows_per_chunk % 8)) IADMM_FAIL(IADMM_EMODE, "sparse KKT pass: row chunks must be 8..64 rows");
   if ((mq == 2 || ma == 2) && d.n > 64 * 128) IADMM_FAIL(IADMM_EMODE, "block-skip KKT pass: at most 8192 columns");
   const size_t smem = tile_smem_bytes(d.rows_per_chunk, mq == 1 || ma == 1);
-  if (can_vectorise(d, P.Q, P.A0, sp)) launch_pass1_variant<true>(P, mq, ma, grid, smem, st);
-  else                                 launch_pass1_variant<false>(P, mq, ma, grid, smem, st);
+  const bool vec = can_vectorise(d, P.Q, P.A0, sp);
+  if (use_tma_pass(d, vec, mq, ma)) {
+    static PerDeviceOnce once;
+    int rc;
+    if ((rc = ensure_dyn_smem(kkt_pass1_tma_kernel, (int)tile_smem_bytes_tma(d.rows_per_chunk), &once))) return rc;
+    kkt_pass1_tma_kernel<<<grid, kKktTmaThreads, tile_smem_bytes_tma(d.rows_per_chunk), st>>>(P);
+  } else if (vec) launch_pass1_variant<true>(P, mq, ma, grid, smem, st);
+  else            launch_pass1_variant<false>(P, mq, ma, grid, smem, st);
   IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
   return IADMM_OK;
 }
@@ -680,8 +900,14 @@ int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const Kk
   memset(&q, 0, sizeof(q)); memset(&a, 0, sizeof(a));
   if (mq) q = sp->q;
   if (ma) a = sp->a;
-  if (can_vectorise(d, Q, A0, sp)) launch_pass2_variant<true>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
-  else                             launch_pass2_variant<false>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
+  const bool vec = can_vectorise(d, Q, A0, sp);
+  if (use_tma_pass(d, vec, mq, ma)) {
+    static PerDeviceOnce once;
+    int rc;
+    if ((rc = ensure_dyn_smem(kkt_pass2_tma_kernel, (int)tile_smem_bytes_tma(d.rows_per_chunk), &once))) return rc;
+    kkt_pass2_tma_kernel<<<grid, kKktTmaThreads, tile_smem_bytes_tma(d.rows_per_chunk), st>>>(d, Q, A0, s);
+  } else if (vec) launch_pass2_variant<true>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
+  else            launch_pass2_variant<false>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
   IADMM_LAUNCH_CHECK("kkt_pass2_kernel");
   return IADMM_OK;
 }
