@@ -200,6 +200,17 @@ class LSTM(nn.Module):
     def name(self):
         return 'lstm'
 
+    _TRANSIENT = ("_packed", "_packed_key", "_ws", "_chain", "_kkt_shared", "_window_ws", "_train_ws")
+
+    def __getstate__(self):
+        """Pickling / `copy.deepcopy` / `torch.save(model)` carry the parameters, not the device workspaces, packed weight images
+        and per-call records (which hold weak references): those are rebuilt on the next call."""
+        state = self.__dict__.copy()
+        for k in self._TRANSIENT:
+            if k in state:
+                state[k] = None
+        return state
+
     # -- packed weights ----------------------------------------------------------------------
     def _mode(self):
         mode = self.gate_mode

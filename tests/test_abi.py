@@ -150,3 +150,28 @@ def test_gate_mode_table_matches_header():
     src = open(os.path.join(ROOT, "include", "iadmm.h")).read()
     enum = dict((k.lower(), int(v)) for k, v in re.findall(r"IADMM_GATES_([A-Z0-9_]+)\s*=\s*(\d+)", src))
     assert enum == _lib.GATE_MODES
+
+
+def test_model_pickles_and_deepcopies_without_its_device_scratch():
+    """`torch.save(model)` / `copy.deepcopy(model)` (EarlyStopping-style checkpointing of whole modules) carry the 16 parameters;
+    workspaces, packed weights and the per-call records of `forward` (weak references) are dropped and rebuilt lazily."""
+    import copy
+    import io
+    import weakref
+    import iadmm_b200 as ia
+    m = ia.LSTM(None, 2, 8, 3, "cpu")
+    t = torch.zeros(3)
+    m._chain = {"dims": (1,), "odd": True, "H": (weakref.ref(t), 0, 0), "C": (weakref.ref(t), 0, 0)}
+    m._kkt_shared = ((1,), weakref.ref(t), weakref.ref(t), t)
+    m._ws = torch.zeros(4, dtype=torch.uint8)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    m3 = copy.deepcopy(m)
+    for other in (m2, m3):
+        assert other._chain is None and other._kkt_shared is None and other._ws is None and other._packed is None
+        assert list(other.state_dict().keys()) == list(m.state_dict().keys())
+        for k, v in m.state_dict().items():
+            assert torch.equal(other.state_dict()[k], v)
+    assert m._chain is not None and m._ws is not None            # the original keeps its own
