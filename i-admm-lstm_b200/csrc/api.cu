@@ -282,15 +282,22 @@ static int solve_impl(const void* packed_weights, const float* Q, const float* p
     // the other ping-pong buffer: padding bytes of the packed e4m3 rows must be finite (never multiplied, but loaded)
     if (nprod == 2 && K > 1) IADMM_CUDA(cudaMemsetAsync(ws.tc.h_lo[1], 0, tc_lo_bytes(rows, h), st));
   }
+  // programmatic dependent launches inside the KKT phase (common.cuh): measured, bit-identical and NOT faster (KKT phase 0.652 vs
+  // 0.652 ms, 1.528 vs 1.522 ms at n = 5000, profiles/r02_kkt_pdl_ab.jsonl: the kernel boundaries are not where the phase loses
+  // time), so plain launches stay the default and this is a development switch.  Pass 1 of iteration k > 0 follows this call's
+  // own tail kernel, so nothing it reads before its wait (Q, A0) was written by its predecessor; iteration 0 is always launched
+  // normally (the kernel before it may be the Ruiz scaling that wrote Q and A0).
+  const char* pdl_sw = dev_env("IADMM_PDL");               // development switch: 1 = programmatic dependent launches
+  const bool pdl = pdl_sw && pdl_sw[0] == '1';
   for (int k = 0; k < K; ++k) {
     const Sched* sk = sched + (t0 + k);
     prof_begin(kProfKkt, st);
-    if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st, sp))) return rc;
+    if ((rc = launch_kkt_pass1(ws.d, Q, A0, xv, x, y, ws.s, st, sp, pdl && k > 0))) return rc;
     if ((rc = launch_kkt_combine1(ws.d, p, xv, x, y, z, sk, sigma, ws.s, pri_trace, dual_trace, pri_trace_u,
                                   dual_trace_u, sd, se, sc, (k > 0 && want_trace) ? k - 1 : -1, 0, st, metric_trace, zu,
-                                  k > 0 ? sk - 1 : nullptr))) return rc;
-    if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st, sp))) return rc;
-    if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st))) return rc;
+                                  k > 0 ? sk - 1 : nullptr, pdl))) return rc;
+    if ((rc = launch_kkt_pass2(ws.d, Q, A0, ws.s, st, sp, pdl))) return rc;
+    if ((rc = launch_kkt_combine2(ws.d, sk, sigma, ws.s, st, pdl))) return rc;
     prof_end(kProfKkt, st);
     prof_begin(kProfGates, st);
     if (tc) {

@@ -241,21 +241,42 @@ struct SpMat {
 struct KktSparse { SpMat q, a; };
 int sparse_view(const void* packed, int B, int rows, int n, size_t cap, SpMat* out);   // carve a packed buffer
 
-// pass 1: qxt,qx,axt,ax and column partials of A0^T v, A0^T y
+// Programmatic dependent launch (PDL) inside one iteration of the solve: a kernel launched with `pdl` may become resident while
+// the kernel before it in the stream drains (that kernel executes `pdl_trigger()` first thing), runs its prologue, and blocks in
+// `pdl_wait()` until the predecessor has completed and its writes are visible -- BEFORE its first read of anything a predecessor
+// wrote and before its first global write.  Kernels carry both instructions unconditionally (no-ops in a normal launch).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
+// pass 1: qxt,qx,axt,ax and column partials of A0^T v, A0^T y.  `pdl`: see above; only valid when NOTHING the pass reads
+// (incl. Q and A0, which its copy-engine producer streams without waiting) was written by the kernel before it in the stream.
 int launch_kkt_pass1(const KktDims& d, const float* Q, const float* A0, const float* xv, const float* x,
-                     const float* y, const KktScratch& s, cudaStream_t st, const KktSparse* sp = nullptr);
+                     const float* y, const KktScratch& s, cudaStream_t st, const KktSparse* sp = nullptr, bool pdl = false);
 // combine 1: w = K xv - rhs ; residual norms of (x,y,z) into trace row `trace_row` (skipped when < 0)
 int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const float* x, const float* y,
                         const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
                         float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
                         const float* sd, const float* se, const float* sc, int trace_row, int residual_only,
                         cudaStream_t st, float* metric_trace = nullptr, const float* zu = nullptr,
-                        const Sched* sched_prev = nullptr);
+                        const Sched* sched_prev = nullptr, bool pdl = false);
 // pass 2: column partials of Q^T w1, A0^T w2 and rows A0 w1
 int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st,
-                     const KktSparse* sp = nullptr);
+                     const KktSparse* sp = nullptr, bool pdl = false);
 // combine 2: g = K^T w
-int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, const KktScratch& s, cudaStream_t st);
+int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, const KktScratch& s, cudaStream_t st, bool pdl = false);
 
 // LSTM cell on every coordinate (fp32 SIMT path): reads H_in, writes H_out, updates C in place,
 // writes per-unit-tile partial sums of the output head into head_part [tiles][rows].

@@ -277,6 +277,7 @@ __device__ __forceinline__ void tile_pass_tma(const TileArgs& a, float* smem) {
   const int nchunk = (n + kChunkCols - 1) / kChunkCols;
   const int rows_valid = (a.rows_total - a.r0 < R) ? a.rows_total - a.r0 : R;
 
+  pdl_trigger();
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kTmaStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kKktWarps); }
@@ -284,6 +285,8 @@ __device__ __forceinline__ void tile_pass_tma(const TileArgs& a, float* smem) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp < kKktWarps) {
+    // PDL: the vectors come from the kernel before this one; the producer warp below streams the (constant) matrix meanwhile
+    pdl_wait();
 #pragma unroll
     for (int c = 0; c < NC; ++c)
       for (int r = tid; r < R; r += kKktThreads) {
@@ -831,7 +834,7 @@ static void launch_pass1_variant(const Pass1Args& P, int mq, int ma, dim3 grid, 
   else              launch_pass1_a<VEC, 0>(P, ma, grid, smem, st);
 }
 
-static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t st) {
+static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t st, bool pdl = false) {
   const KktDims& d = P.d;
   const int mq = sp_mode(sp ? &sp->q : nullptr), ma = d.m > 0 ? sp_mode(sp ? &sp->a : nullptr) : 0;
   if (mq) P.spq = sp->q;
@@ -845,7 +848,7 @@ static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t s
     static PerDeviceOnce once;
     int rc;
     if ((rc = ensure_dyn_smem(kkt_pass1_tma_kernel, (int)tile_smem_bytes_tma(d.rows_per_chunk), &once))) return rc;
-    kkt_pass1_tma_kernel<<<grid, kKktTmaThreads, tile_smem_bytes_tma(d.rows_per_chunk), st>>>(P);
+    launch_kernel_pdl(pdl, kkt_pass1_tma_kernel, grid, dim3(kKktTmaThreads), tile_smem_bytes_tma(d.rows_per_chunk), st, P);
   } else if (vec) launch_pass1_variant<true>(P, mq, ma, grid, smem, st);
   else            launch_pass1_variant<false>(P, mq, ma, grid, smem, st);
   IADMM_LAUNCH_CHECK("kkt_pass1_kernel");
@@ -853,14 +856,14 @@ static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t s
 }
 
 int launch_kkt_pass1(const KktDims& d, const float* Q, const float* A0, const float* xv, const float* x,
-                     const float* y, const KktScratch& s, cudaStream_t st, const KktSparse* sp) {
+                     const float* y, const KktScratch& s, cudaStream_t st, const KktSparse* sp, bool pdl) {
   Pass1Args P;
   memset(&P.spq, 0, sizeof(SpMat)); memset(&P.spa, 0, sizeof(SpMat));
   P.d = d; P.Q = Q; P.A0 = A0;
   P.xt = xv; P.xt_stride = d.n + d.m;
   P.v = xv + d.n; P.v_stride = d.n + d.m;
   P.x = x; P.y = y; P.s = s;
-  return launch_pass1_common(P, sp, st);
+  return launch_pass1_common(P, sp, st, pdl);
 }
 
 // primal_dual_loss on its own (utils.py:68-71): x plays x~ and y plays v, the second product pair is unused
@@ -890,7 +893,8 @@ static void launch_pass2_variant(const KktDims& d, const float* Q, const float* 
   else              launch_pass2_a<VEC, 0>(d, Q, A0, s, q, a, ma, grid, smem, st);
 }
 
-int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st, const KktSparse* sp) {
+int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const KktScratch& s, cudaStream_t st, const KktSparse* sp,
+                     bool pdl) {
   const dim3 grid(d.chunks_q + d.chunks_a, d.B);
   const int mq = sp_mode(sp ? &sp->q : nullptr), ma = d.m > 0 ? sp_mode(sp ? &sp->a : nullptr) : 0;
   if ((mq || ma) && (d.rows_per_chunk > 64 || d.rows_per_chunk % 8)) IADMM_FAIL(IADMM_EMODE, "sparse KKT pass: row chunks must be 8..64 rows");
@@ -905,7 +909,7 @@ int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const Kk
     static PerDeviceOnce once;
     int rc;
     if ((rc = ensure_dyn_smem(kkt_pass2_tma_kernel, (int)tile_smem_bytes_tma(d.rows_per_chunk), &once))) return rc;
-    kkt_pass2_tma_kernel<<<grid, kKktTmaThreads, tile_smem_bytes_tma(d.rows_per_chunk), st>>>(d, Q, A0, s);
+    launch_kernel_pdl(pdl, kkt_pass2_tma_kernel, grid, dim3(kKktTmaThreads), tile_smem_bytes_tma(d.rows_per_chunk), st, d, Q, A0, s);
   } else if (vec) launch_pass2_variant<true>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
   else            launch_pass2_variant<false>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
   IADMM_LAUNCH_CHECK("kkt_pass2_kernel");
@@ -960,6 +964,8 @@ __device__ __forceinline__ double block_max_double(double v, double* sh) {
 
 __global__ void __launch_bounds__(kCombThreads) kkt_combine1_kernel(const Combine1Args A) {
   __shared__ double sh[kCombThreads / 32];
+  pdl_trigger();
+  pdl_wait();
   const KktDims& d = A.d;
   const int b = blockIdx.x;
   const size_t n = d.n, m = d.m, N = n + m;
@@ -1103,7 +1109,7 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
                         const float* z, const Sched* sched_t, float sigma, const KktScratch& s,
                         float* pri_trace, float* dual_trace, float* pri_trace_u, float* dual_trace_u,
                         const float* sd, const float* se, const float* sc, int trace_row, int residual_only,
-                        cudaStream_t st, float* metric_trace, const float* zu, const Sched* sched_prev) {
+                        cudaStream_t st, float* metric_trace, const float* zu, const Sched* sched_prev, bool pdl) {
   Combine1Args A;
   A.d = d; A.p = p; A.x = x; A.y = y; A.z = z;
   A.xt = xv; A.v = xv ? xv + d.n : nullptr; A.xt_stride = A.v_stride = d.n + d.m;
@@ -1122,7 +1128,7 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
     if (rc) return rc;
     A.d.sum_a = 1;
   }
-  kkt_combine1_kernel<<<d.B, kCombThreads, 0, st>>>(A);
+  launch_kernel_pdl(pdl, kkt_combine1_kernel, dim3(d.B), dim3(kCombThreads), 0, st, A);
   IADMM_LAUNCH_CHECK("kkt_combine1_kernel");
   return IADMM_OK;
 }
@@ -1132,6 +1138,8 @@ int launch_kkt_combine1(const KktDims& d, const float* p, const float* xv, const
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kkt_combine2_kernel(const KktDims d, const Sched* __restrict__ sched,
                                                            float sigma, const KktScratch s) {
+  pdl_trigger();
+  pdl_wait();
   const size_t n = d.n, m = d.m, N = n + m;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)d.B * N) return;
@@ -1152,7 +1160,7 @@ __global__ void __launch_bounds__(256) kkt_combine2_kernel(const KktDims d, cons
   }
 }
 
-int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, const KktScratch& s, cudaStream_t st) {
+int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, const KktScratch& s, cudaStream_t st, bool pdl) {
   const size_t total = (size_t)d.B * (d.n + d.m);
   KktDims d2 = d;
   int rc;
@@ -1161,7 +1169,7 @@ int launch_kkt_combine2(const KktDims& d, const Sched* sched_t, float sigma, con
     if ((rc = fold_partials(s.part_a, d.B, d.chunks_a, 2, 1, d.n, st))) return rc;
     d2.sum_a = 1;
   }
-  kkt_combine2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d2, sched_t, sigma, s);
+  launch_kernel_pdl(pdl, kkt_combine2_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, d2, sched_t, sigma, s);
   IADMM_LAUNCH_CHECK("kkt_combine2_kernel");
   return IADMM_OK;
 }
@@ -1178,6 +1186,7 @@ __global__ void __launch_bounds__(256) tail_kernel(const KktDims d, const float*
                                                    float* __restrict__ x, float* __restrict__ y, float* __restrict__ z,
                                                    float* __restrict__ xv, float* __restrict__ x_old,
                                                    float* __restrict__ y_old, float* __restrict__ z_old) {
+  pdl_trigger();            // (the next iteration's pass 1 may be a programmatic dependent of this kernel)
   const size_t n = d.n, m = d.m, N = n + m;
   const size_t rows = (size_t)d.B * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

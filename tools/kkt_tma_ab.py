@@ -3,7 +3,7 @@
 Checks that every output of a K-iteration solve is bit-identical, then times the KKT phase inside the solve through the library's
 profile spans (the number bench.py reports as roofline_kkt).
 
-    IADMM_B200_LIB=.../libiadmm_b200_dev.so python tools/kkt_tma_ab.py
+    IADMM_B200_LIB=.../libiadmm_b200_dev.so python tools/kkt_tma_ab.py [IADMM_KKT_TMA | IADMM_PDL]
 """
 import json
 import os
@@ -17,10 +17,11 @@ import iadmm_b200 as ia
 from bench import device_qp_batch, SIGMA
 
 dev = torch.device("cuda", 0)
+SWITCH = sys.argv[1] if len(sys.argv) > 1 else "IADMM_KKT_TMA"      # or IADMM_PDL: programmatic dependent launches in the KKT phase
 
 
 def run(tma, B, n, mi, me, h, K, seed, time_it):
-    os.environ["IADMM_KKT_TMA"] = "1" if tma else "0"
+    os.environ[SWITCH] = "1" if tma else "0"
     torch.manual_seed(seed)
     model = ia.LSTM(None, 2, h, K, dev).eval()
     Q, p, A0, zl, zu = device_qp_batch(B, n, mi, me, seed, dev)
@@ -52,7 +53,7 @@ def main():
         byts = 8.0 * B * (n * n + (mi + me) * n)
         row = {"B": B, "n": n, "m": mi + me, "hidden_dim": h, "K": K, "bit_identical": same}
         if time_it:
-            row.update(kkt_ms_ldg=round(ta, 4), kkt_ms_tma=round(tb, 4), tbs_ldg=round(byts / ta / 1e9, 3), tbs_tma=round(byts / tb / 1e9, 3))
+            row.update(switch=SWITCH, kkt_ms_off=round(ta, 4), kkt_ms_on=round(tb, 4), tbs_off=round(byts / ta / 1e9, 3), tbs_on=round(byts / tb / 1e9, 3))
         print(json.dumps(row), flush=True)
 
 
