@@ -616,3 +616,39 @@ def test_k100_at_config2_shape_vs_oracle():
     print("K=100 config-2 shape", {k: f"{v:.1e}" for k, v in errs.items()})
     for k, v in errs.items():
         assert v <= 1e-4, (k, v)
+
+
+@pytest.mark.parametrize("shape", [(3, 1000, 500, 500, 64, 3), (2, 5000, 72, 40, 64, 2), (4, 132, 64, 36, 64, 4), (2, 68, 0, 0, 64, 3)])
+def test_bulk_copy_and_load_instruction_passes_agree_bit_for_bit(shape):
+    """The dense KKT passes exist twice: staged by `cp.async.bulk` into a shared-memory ring (`kkt_pass*_tma_kernel`: 16-byte
+    aligned matrices with n % 4 == 0 -- the default) and with load instructions (`kkt_pass*_kernel`: everything else).  The same
+    data given once 16-byte aligned and once as a view that starts 4 bytes into a buffer takes the one and the other; every
+    output of the solve, traces included, must be identical (same lane-to-column assignment, same accumulation order)."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me, h, K = shape
+    m = mi + me
+    g = torch.Generator(device="cpu").manual_seed(5)
+    Q = torch.randn((B, n, n), generator=g) * (torch.rand((B, n, n), generator=g) < 0.3)
+    Q = (Q + Q.mT).to(DEV)
+    A0 = torch.randn((B, m, n), generator=g).to(DEV)
+    p = torch.randn((B, n, 1), generator=g).to(DEV)
+    zl = -torch.rand((B, m, 1), generator=g).to(DEV)
+    zu = torch.rand((B, m, 1), generator=g).to(DEV)
+
+    def shifted(t):                                   # same values, storage offset 1 float: not 16-byte aligned
+        buf = torch.empty(t.numel() + 1, device=DEV)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.data_ptr() % 16 != 0 and v.is_contiguous()
+        return v
+
+    model = make_model(orc.lstm_parameters(h, K, seed=2), h, K, "tc_f16f8")
+    with torch.no_grad():
+        a = model.solve(K, mi, me, Q, p, A0, zl, zu, 6e-6, streaming=True)
+        b = model.solve(K, mi, me, shifted(Q), p, shifted(A0) if m else A0, zl, zu, 6e-6, streaming=True)
+        torch.cuda.synchronize()
+    assert Q.data_ptr() % 16 == 0
+    for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual", "metrics"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert bool(torch.isfinite(a.x).all())
