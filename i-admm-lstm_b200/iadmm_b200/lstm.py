@@ -32,6 +32,12 @@ SPARSE_AUTO_DENSITY = 0.003
 BLOCK_AUTO_OCCUPANCY = 0.7     # "auto": dense matrix with block skipping when at most this share of its 8x128 blocks is non-empty
 
 
+def _version(t):
+    """`t._version`, or None for inference tensors (`torch.inference_mode()`), which do not track in-place edits: anything keyed
+    on a version then simply does not match and the converting / rebuilding path runs."""
+    return None if t.is_inference() else t._version
+
+
 def row_classes(num_ineq, num_eq, m):
     """(inequality rows, equality rows) the way the kernels take them -- the first rows of A0 are inequality rows, the rest
     equality rows, together m = A0.shape[1] -- from the counts main.py hands to `model(t, num_ineq, num_eq, ...)`.  Those
@@ -395,9 +401,10 @@ class LSTM(nn.Module):
         A_tild, hit = None, False
         if shared:
             # the matrix depends on the iteration only through the -1/rho_t diagonal of its last block
-            key = (Qc.data_ptr(), Qc._version, Ac.data_ptr(), Ac._version, float(sigma), B, n, m)
+            key = (Qc.data_ptr(), _version(Qc), Ac.data_ptr(), _version(Ac), float(sigma), B, n, m)
             rec = self._kkt_shared
-            hit = rec is not None and rec[0] == key and rec[1]() is not None and rec[2]() is not None
+            hit = (rec is not None and rec[0] == key and rec[1]() is not None and rec[2]() is not None
+                   and key[1] is not None and key[3] is not None)
             A_tild = rec[3] if hit else torch.empty((B, N, N), device=dev)
             if not hit:
                 self._kkt_shared = None          # (drop the old buffer before keeping the new one)
@@ -470,8 +477,8 @@ class LSTM(nn.Module):
         ch, self._chain = self._chain, None
 
         def same(v, ref, ptr, ver):
-            return (ref() is not None and v.data_ptr() == ptr and v._version == ver and v.dtype == torch.float32
-                    and tuple(v.shape) == (B, n + m, h) and v.is_contiguous())
+            return (ref() is not None and ver is not None and v.data_ptr() == ptr and _version(v) == ver
+                    and v.dtype == torch.float32 and tuple(v.shape) == (B, n + m, h) and v.is_contiguous())
 
         flags = _lib.F_KEEP_PLANES
         if ch is not None and ch["dims"] == dims and same(H_t, *ch["H"]) and same(C_t, *ch["C"]):
@@ -485,6 +492,6 @@ class LSTM(nn.Module):
             H, C = _lib.f32(H_t, dev).clone(), _lib.f32(C_t, dev).clone()
         torch.ops.iadmm.solve(packed, Q, p, A0, zl, zu, None, None, None, x, y, z, xv, H, C, None, None, None, None, None, ws,
                               num_ineq, num_eq, h, self.length, t, 1, sigma, mode, flags)
-        self._chain = {"dims": dims, "odd": odd, "H": (weakref.ref(H), H.data_ptr(), H._version),
-                       "C": (weakref.ref(C), C.data_ptr(), C._version)}
+        self._chain = {"dims": dims, "odd": odd, "H": (weakref.ref(H), H.data_ptr(), _version(H)),
+                       "C": (weakref.ref(C), C.data_ptr(), _version(C))}
         return x, y, z, xv, H, C

@@ -195,3 +195,32 @@ def test_dataset_files_through_the_dropin_modules(family, mode):
     assert rel_err(fused.pri, g["out_pri"]) < tol and rel_err(fused.dual, g["out_dual"]) < tol
     assert rel_err(out[8], g["out_rho_vec"]) < 1e-6
     assert rel_err(out[6], g["out_K"]) < 1e-5 and rel_err(out[7], g["out_rhs"]) < 1e-4
+
+
+def test_forward_under_inference_mode_takes_the_converting_path():
+    """Inference tensors have no version counter, so an in-place edit between two calls could not be noticed: `forward` then
+    never resumes, and still equals the fused solve."""
+    h, n, mi, me, B, K = 320, 48, 16, 16, 2, 3
+    m = mi + me
+    model, _ = make(h, K)
+    data = scaled_qp(B, n, mi, me, seed=12)
+    with torch.no_grad():
+        fused = model.solve(K, mi, me, *data, SIGMA, traces=False)
+    import iadmm_b200 as ia
+    with torch.inference_mode():
+        data_i = scaled_qp(B, n, mi, me, seed=12)                 # Scaling, too, on inference tensors
+        st = zero_state(B, n, m, h)
+        model.materialize_kkt = "shared"
+        for t in range(K):
+            out = call(model, t, mi, me, st, data_i)
+            st = list(out[:6])
+            pri, dual, tot = ia.primal_dual_loss(st[0], st[1], st[2], data_i[0], data_i[1], data_i[2])
+        fused_i = model.solve(K, mi, me, *data_i, SIGMA)
+        torch.cuda.synchronize()
+    assert model.resumed_calls == 0
+    for a, b in zip(data, data_i):
+        assert torch.equal(a, b)
+    for k, a in zip(STATE, st):
+        assert torch.equal(a, getattr(fused, k)), k
+        assert torch.equal(getattr(fused_i, k), getattr(fused, k)), k
+    assert torch.allclose(pri.reshape(-1), fused_i.pri[-1], rtol=1e-6) and torch.allclose(dual.reshape(-1), fused_i.dual[-1], rtol=1e-6)
