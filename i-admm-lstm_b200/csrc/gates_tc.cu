@@ -621,7 +621,10 @@ constexpr int kPairBBoxRows = 64;                         // U tiles are fetched
 // the time of its epilogue).  20 warps (five per scheduler, so 96 registers per thread; the two-chunk epilogue needs 90): warps 0-3 =
 // TMA producer, MMA issuer and two idle warps, warps 4-19 = epilogue (lane quarter = warp % 4).
 constexpr int pair_threads(int epi) { return (epi == 7 || epi == 9) ? 640 : kTcThreads; }
-constexpr int kEpi16MaxHidden = 256;   // measured: 16 warps win at hidden_dim 208 (0.667 vs 0.739 ms), lose at 400 and 800 (power-capped regime)
+// measured (profiles/r02_epi_warps_sweep.jsonl, same box, gate kernel per launch at the headline problem size): 16 warps win at
+// hidden_dim 208 (0.667 vs 0.739 ms), 320 (0.955 vs 1.137), 352 (1.215 vs 1.399) and 384 (1.314 vs 1.510); tie at 400 (1.50);
+// 8 warps win from 512 on (2.06 vs 2.13, 640: 3.09 vs 3.11, 800: the power-capped regime)
+constexpr int kEpi16MaxHidden = 384;
 
 template <int NPROD, int CL, int EPI>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(pair_threads(EPI), 1)

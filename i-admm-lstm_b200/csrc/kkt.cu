@@ -808,8 +808,9 @@ __global__ void __launch_bounds__(kKktTmaThreads, 2) kkt_pass2_tma_kernel(const 
 // chunks (training's small chunks and the sparse forms keep the load-instruction kernels).  Same-box A/B, bit-identical results
 // (tools/kkt_tma_ab.py, profiles/r02_kkt_tma_ab.jsonl): KKT phase 0.660 -> 0.646 ms at the headline size, 1.660 -> 1.522 ms
 // at n = 5000 (5.78 -> 6.31 TB/s).
+constexpr int kMaxRowsPerChunk = 64;          // make_kkt_dims / make_kkt_dims_train never exceed it
 static bool use_tma_pass(const KktDims& d, bool vec, int mq, int ma) {
-  if (!vec || mq || ma || d.rows_per_chunk < 32 || d.rows_per_chunk % kRowUnroll) return false;
+  if (!vec || mq || ma || d.rows_per_chunk < 32 || d.rows_per_chunk > kMaxRowsPerChunk || d.rows_per_chunk % kRowUnroll) return false;
   const char* e = dev_env("IADMM_KKT_TMA");              // development switch: 0 = load-instruction kernels
   return !(e && e[0] == '0');
 }
@@ -847,7 +848,8 @@ static int launch_pass1_common(Pass1Args& P, const KktSparse* sp, cudaStream_t s
   if (use_tma_pass(d, vec, mq, ma)) {
     static PerDeviceOnce once;
     int rc;
-    if ((rc = ensure_dyn_smem(kkt_pass1_tma_kernel, (int)tile_smem_bytes_tma(d.rows_per_chunk), &once))) return rc;
+    // (the opt-in is made once per device: ask for the largest row chunk there is, not for this call's)
+    if ((rc = ensure_dyn_smem(kkt_pass1_tma_kernel, (int)tile_smem_bytes_tma(kMaxRowsPerChunk), &once))) return rc;
     launch_kernel_pdl(pdl, kkt_pass1_tma_kernel, grid, dim3(kKktTmaThreads), tile_smem_bytes_tma(d.rows_per_chunk), st, P);
   } else if (vec) launch_pass1_variant<true>(P, mq, ma, grid, smem, st);
   else            launch_pass1_variant<false>(P, mq, ma, grid, smem, st);
@@ -908,7 +910,7 @@ int launch_kkt_pass2(const KktDims& d, const float* Q, const float* A0, const Kk
   if (use_tma_pass(d, vec, mq, ma)) {
     static PerDeviceOnce once;
     int rc;
-    if ((rc = ensure_dyn_smem(kkt_pass2_tma_kernel, (int)tile_smem_bytes_tma(d.rows_per_chunk), &once))) return rc;
+    if ((rc = ensure_dyn_smem(kkt_pass2_tma_kernel, (int)tile_smem_bytes_tma(kMaxRowsPerChunk), &once))) return rc;
     launch_kernel_pdl(pdl, kkt_pass2_tma_kernel, grid, dim3(kKktTmaThreads), tile_smem_bytes_tma(d.rows_per_chunk), st, d, Q, A0, s);
   } else if (vec) launch_pass2_variant<true>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);
   else            launch_pass2_variant<false>(d, Q, A0, s, q, a, mq, ma, grid, smem, st);

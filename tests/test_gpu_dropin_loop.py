@@ -50,9 +50,9 @@ def call(model, t, mi, me, st, data):
     return model(t, mi, me, st[0], st[1], st[2], st[3], SIGMA, st[4], st[5], Q=Q, p=p, A0=A0, lb=None, ub=None, zl=zl, zu=zu)
 
 
-# hidden_dim 320: the 8-warp production kernel <2,2,4>; 200: the padded last operand group (hidden_dim % 16 == 8); 64 with
-# n + m > 256: the 16-warp kernel on the streaming path
-@pytest.mark.parametrize("h,n,mi,me", [(320, 70, 13, 29), (200, 64, 32, 32), (64, 200, 60, 60)])
+# hidden_dim 400: the 8-warp production kernel <2,2,4> (hidden_dim > 384); 320: the 16-warp kernel <2,2,9>; 200: its padded last
+# operand group (hidden_dim % 16 == 8); 64 with n + m > 256: the 16-warp kernel on the streaming path
+@pytest.mark.parametrize("h,n,mi,me", [(400, 70, 13, 29), (320, 48, 16, 16), (200, 64, 32, 32), (64, 200, 60, 60)])
 def test_forward_loop_equals_fused_solve(h, n, mi, me):
     B, K, m = 3, 6, mi + me
     model, prm = make(h, K)

@@ -652,3 +652,28 @@ def test_bulk_copy_and_load_instruction_passes_agree_bit_for_bit(shape):
     for k in ("x", "y", "z", "xv", "H", "C", "pri", "dual", "metrics"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
     assert bool(torch.isfinite(a.x).all())
+
+
+def test_small_row_chunks_first_then_large_ones_in_a_fresh_process():
+    """The > 48 KB dynamic-shared-memory opt-in of the bulk-copy-staged KKT passes is made once per device and process: it has to
+    cover the largest row chunk (64 rows), not the chunk size of the first call (a 32-row first call used to make every later
+    64-row launch fail with `invalid argument`).  Fresh interpreter: 32-row chunks (max(n, m) < 64) first, then 64-row chunks."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import torch, iadmm_b200 as ia\n"
+        "from oracle import iadmm_oracle as orc\n"
+        "dev = 'cuda:0'\n"
+        "model = ia.LSTM(None, 2, 64, 3, dev).eval()\n"
+        "for n, mi, me in ((48, 16, 16), (64, 32, 32), (1000, 52, 48)):\n"
+        "    qp = orc.qp_instances(2, n, mi, me, seed=1)\n"
+        "    with torch.no_grad():\n"
+        "        r = model.solve(3, mi, me, *(qp[k].to(dev) for k in ('Q', 'p', 'A0', 'zl', 'zu')), 6e-6, streaming=True)\n"
+        "    torch.cuda.synchronize()\n"
+        "    assert bool(torch.isfinite(r.x).all()) and bool(torch.isfinite(r.pri).all())\n"
+        "print('ok')\n" % (root, os.path.join(root, "i-admm-lstm_b200")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
