@@ -189,10 +189,11 @@ def test_clip_gradient_at_an_exact_double_tie():
         assert rel_err(alt[3], ref[3]) > 1e-3      # a one-sided tie (0.5) is a different gradient than the double tie (0.25)
 
 
-@pytest.mark.parametrize("h", [200, 208])
+@pytest.mark.parametrize("h", [200, 208, 384, 400])
 def test_hidden200_k100_vs_fp32_path(h):
-    """configs/QP.yaml's default hidden_dim 200 (% 16 == 8: half-padded last operand group) and 208: the 16-epilogue-warp kernel
-    with the shared-reciprocal activations (gates_tc_pair_kernel<2,2,9>, hidden_dim <= 256).  K=100 at n=1000, 500+500, --scaling
+    """configs/QP.yaml's default hidden_dim 200 (% 16 == 8: half-padded last operand group), 208 and 384: the 16-epilogue-warp
+    kernel with the shared-reciprocal activations (gates_tc_pair_kernel<2,2,9>, hidden_dim <= 384); 400 (scripts/Synthetic.sh's
+    QP_RHS size): the first size on the 8-warp kernel <2,2,4>.  K=100 at n=1000, 500+500, --scaling
     against the fp32 CUDA-core path on the same inputs and weights (which matches the reference's fp32 run to <= 2e-6,
     test_gpu_parity): worst INSTANCE within north_star's 1e-4 on x, y, z, batch norm within 1e-4 on the residual traces."""
     from bench import device_qp_batch
