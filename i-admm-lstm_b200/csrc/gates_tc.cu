@@ -1127,7 +1127,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
     static PerDeviceOnce a34, a24, a14, a32, a22, a12, e0, e2, s2, s3, s1, i4, i5, i6, i7, i8;
     if (il && epi_warps == 16) {
       threads = pair_threads(7);
-      // hidden_dim <= 256: the special-function unit paces the epilogue (ncu: XU 47 % busy), and one shared reciprocal for the
+      // hidden_dim <= kEpi16MaxHidden: the special-function unit paces the epilogue (ncu: XU 47 % busy), and one shared reciprocal for the
       // four activations of a unit (4 ex2 + 1 rcp instead of 4 + 4) is 10 % faster (0.649 -> 0.586 ms at hidden_dim 208,
       // profiles/r02_gate_shared_rcp_ab.jsonl); in the power-capped 8-warp regime the same change is 1 % SLOWER (more ALU
       // instructions), so it stays a development switch there.  IADMM_TC_EPI=1 forces the separate reciprocals here.
