@@ -50,6 +50,7 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
               void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_kkt_pass1_plain(const KktDims& d, const float* Q, const float* A0, const float* x, const float* y,
                            const KktScratch& s, cudaStream_t st);
+int launch_kkt_penalty_diag(int B, int n, int m, int num_ineq, const Sched* sched_t, float* K, cudaStream_t st);
 int launch_build_kkt(int B, int n, int m, int num_ineq, const float* Q, const float* p, const float* A0,
                      const float* x, const float* y, const float* z, const Sched* sched_t, float sigma, float* K,
                      float* rhs, float* rho_vec, cudaStream_t st);
@@ -446,6 +447,18 @@ int iadmm_residuals(const float* x, const float* y, const float* z, const float*
   if ((rc = launch_kkt_pass1_plain(d, Q, A0, x, y, s, st))) return rc;
   return launch_kkt_combine1(d, p, nullptr, x, y, z, nullptr, 0.f, s, pri, dual, nullptr, nullptr, nullptr, nullptr,
                              nullptr, 0, 1, st);
+}
+
+int iadmm_kkt_penalty_diagonal(const void* packed_weights, float* Kmat, int B, int n, int num_ineq, int num_eq, int h,
+                               int length, int t, void* stream) {
+  const int m = num_ineq + num_eq;
+  if (B <= 0 || n <= 0 || m < 0 || t < 0 || t >= length) IADMM_FAIL(IADMM_ESHAPE, "kkt_penalty_diagonal: B=%d n=%d m=%d t=%d length=%d", B, n, m, t, length);
+  if (!packed_weights || !Kmat) IADMM_FAIL(IADMM_EALIGN, "kkt_penalty_diagonal: NULL pointer");
+  int rc = check_device();
+  if (rc) return rc;
+  const WeightLayout L = weight_layout(h, length);
+  const Sched* sched = reinterpret_cast<const Sched*>(static_cast<const char*>(packed_weights) + L.off_sched) + t;
+  return launch_kkt_penalty_diag(B, n, m, num_ineq, sched, Kmat, static_cast<cudaStream_t>(stream));
 }
 
 int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, const float* A0, const float* x,

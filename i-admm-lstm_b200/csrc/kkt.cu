@@ -1348,4 +1348,21 @@ int launch_build_kkt(int B, int n, int m, int num_ineq, const float* Q, const fl
   return IADMM_OK;
 }
 
+// the -(1/rho_t) diagonal of the last m rows of a dense K (the only entries of K that depend on the iteration)
+__global__ void __launch_bounds__(256) kkt_penalty_diag_kernel(int B, int n, int m, int num_ineq, const Sched* __restrict__ sched,
+                                                               float* __restrict__ K) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * m) return;
+  const size_t b = idx / m, N = (size_t)n + m;
+  const int i = (int)(idx - b * m);
+  K[(b * N + n + i) * N + n + i] = -((i < num_ineq) ? sched->inv_rho_ineq : sched->inv_rho_eq);
+}
+
+int launch_kkt_penalty_diag(int B, int n, int m, int num_ineq, const Sched* sched_t, float* K, cudaStream_t st) {
+  if (m == 0) return IADMM_OK;
+  kkt_penalty_diag_kernel<<<(unsigned)(((size_t)B * m + 255) / 256), 256, 0, st>>>(B, n, m, num_ineq, sched_t, K);
+  IADMM_LAUNCH_CHECK("kkt_penalty_diag_kernel");
+  return IADMM_OK;
+}
+
 }  // namespace iadmm

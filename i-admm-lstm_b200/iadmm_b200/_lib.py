@@ -49,6 +49,7 @@ SIGNATURES = {
     "iadmm_residuals_workspace_bytes": ([_I, _I, _I, POINTER(_Z)], c_int),
     "iadmm_residuals": ([_P] * 8 + [_I, _I, _I, _P, _Z, _P], c_int),
     "iadmm_build_kkt": ([_P] * 10 + [_I] * 7 + [_F, _P], c_int),
+    "iadmm_kkt_penalty_diagonal": ([_P, _P] + [_I] * 7 + [_P], c_int),
     "iadmm_lu_factor": ([_P] * 4 + [_I, _I, _P], c_int),
     "iadmm_lu_solve": ([_P] * 3 + [_I, _I, _P], c_int),
     "iadmm_param_count": ([_I, _I, POINTER(_Z)], c_int),

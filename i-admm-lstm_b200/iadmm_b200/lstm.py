@@ -414,7 +414,8 @@ class LSTM(nn.Module):
         torch.ops.iadmm.build_kkt(self.packed_weights(), Qc, pc, Ac, xc, yc, zc, None if hit else A_tild, b_tild, rho_vec,
                                   int(num_ineq), int(num_eq), self.hidden_dim, self.length, int(t), float(sigma))
         if hit and m > 0:
-            A_tild.diagonal(dim1=1, dim2=2)[:, n:].copy_(-(1.0 / rho_vec[:, :, 0]))
+            torch.ops.iadmm.kkt_penalty_diagonal(self.packed_weights(), A_tild, n, int(num_ineq), int(num_eq), self.hidden_dim,
+                                                 self.length, int(t))
         return A_tild, b_tild, rho_vec
 
     # -- the reference's per-iteration interface -------------------------------------------------

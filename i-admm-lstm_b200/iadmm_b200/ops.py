@@ -4,6 +4,7 @@
     torch.ops.iadmm.ruiz        -> iadmm_ruiz         (Scaling.scale_data)
     torch.ops.iadmm.residuals   -> iadmm_residuals    (primal_dual_loss)
     torch.ops.iadmm.build_kkt   -> iadmm_build_kkt    (A_tild / b_tild / rho_vec of LSTM.forward's return tuple)
+    torch.ops.iadmm.kkt_penalty_diagonal -> iadmm_kkt_penalty_diagonal (the t-dependent diagonal of a kept A_tild)
     torch.ops.iadmm.sparse_pack / solve_sparse -> iadmm_sparse_pack / iadmm_solve_sparse (sparse problem families)
 
 Each op is a few lines: it turns tensors into device pointers and calls the library on the current CUDA stream of the
@@ -68,6 +69,13 @@ def build_kkt(packed: Tensor, Q: Tensor, p: Tensor, A0: Tensor, x: Tensor, y: Te
     with torch.cuda.device(Q.device):
         _lib.check(_lib.lib().iadmm_build_kkt(_P(packed), _P(Q), _P(p), _P(A0), _P(x), _P(y), _P(z), _P(Kmat), _P(rhs),
                                               _P(rho_vec), B, n, num_ineq, num_eq, h, length, t, sigma, _lib.stream_ptr()))
+
+
+@torch.library.custom_op("iadmm::kkt_penalty_diagonal", mutates_args=("Kmat",), device_types="cuda")
+def kkt_penalty_diagonal(packed: Tensor, Kmat: Tensor, n: int, num_ineq: int, num_eq: int, h: int, length: int, t: int) -> None:
+    with torch.cuda.device(Kmat.device):
+        _lib.check(_lib.lib().iadmm_kkt_penalty_diagonal(_P(packed), _P(Kmat), Kmat.shape[0], n, num_ineq, num_eq, h, length, t,
+                                                         _lib.stream_ptr()))
 
 
 @torch.library.custom_op("iadmm::sparse_pack", mutates_args=("packed", "nnz"), device_types="cuda")

@@ -210,6 +210,11 @@ int iadmm_build_kkt(const void* packed_weights, const float* Q, const float* p, 
                     float* Kmat, float* rhs, float* rho_vec,
                     int B, int n, int num_ineq, int num_eq, int h, int length, int t, float sigma,
                     void* stream);
+/* Rewrites the -(1/rho_t) diagonal of the last m rows of a Kmat that iadmm_build_kkt produced for the same Q, A0 and sigma at
+ * another iteration: the only entries of A_tild that depend on t (models/lstm.py:60-62, :68).  Lets a caller keep ONE dense
+ * A_tild per problem batch over the per-iteration loop of main.py:874-887 instead of writing 4(n+m)^2 bytes per call. */
+int iadmm_kkt_penalty_diagonal(const void* packed_weights, float* Kmat, int B, int n, int num_ineq, int num_eq,
+                               int h, int length, int t, void* stream);
 
 /* ---- Stage II (feasibility restoration): batched dense LU --------------------------------------------
  * Replaces: `torch.lu(A_tild, pivot=True)` (models/lu.py:30) -- LAPACK getrf semantics, partial pivoting,

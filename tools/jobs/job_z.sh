@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_production_shapes.py -x -q -m gpu -s -k "hidden200" 2>&1 | grep "hidden \|passed\|failed" | tee gpurun_out/r02_k100_hidden_sizes.txt
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/r02_gpu_suite_final.log
