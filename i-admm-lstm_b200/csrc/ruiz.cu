@@ -48,6 +48,7 @@ struct RuizWs {            // per-instance vectors, fp32
   float* partq;            // [B,chunks_q,n] column inf-norm partials of the current (pre-cost) Q
   float* parta;            // [B,chunks_a,n]
   int R, chunks_q, chunks_a;
+  int scan_q, scan_a;      // chunk partials ruiz_vec_kernel still has to fold per column (1 after ruiz_fold_max_kernel)
 };
 
 enum { kRzNorm = 0, kRzScale = 1, kRzCost = 2 };
@@ -337,7 +338,7 @@ ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, int k, float* _
     float pmax = 0.f;
     for (int j = tid; j < n; j += kRzVecThreads) {
       float cq = 0.f;
-      for (int ch = 0; ch < W.chunks_q; ++ch) cq = fmaxf(cq, partq[(size_t)ch * n + j]);
+      for (int ch = 0; ch < W.scan_q; ++ch) cq = fmaxf(cq, partq[(size_t)ch * n + j]);
       colsum += (double)cq;
       const float pj = __fmul_rn(sd[j], p[j]);
       p[j] = pj;
@@ -365,8 +366,8 @@ ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, int k, float* _
     // scaling.py:66-69 on the matrix as it stands (Q carries the pending factor cprev)
     for (int j = tid; j < n; j += kRzVecThreads) {
       float cq = 0.f, ca = 0.f;
-      for (int ch = 0; ch < W.chunks_q; ++ch) cq = fmaxf(cq, partq[(size_t)ch * n + j]);
-      for (int ch = 0; ch < W.chunks_a; ++ch) ca = fmaxf(ca, parta[(size_t)ch * n + j]);
+      for (int ch = 0; ch < W.scan_q; ++ch) cq = fmaxf(cq, partq[(size_t)ch * n + j]);
+      for (int ch = 0; ch < W.scan_a; ++ch) ca = fmaxf(ca, parta[(size_t)ch * n + j]);
       const float nrm = fmaxf(__fmul_rn(cprev, cq), ca);
       sd_next[j] = __frcp_rn(__fsqrt_rn(limit_scaling(nrm)));   // reciprocal(sqrt(.)), two roundings like scaling.py:68-69
     }
@@ -374,6 +375,30 @@ ruiz_vec_kernel(int n, int m, int finish_prev, int prepare_next, int k, float* _
     for (int i = tid; i < m; i += kRzVecThreads) se_next[i] = __frcp_rn(__fsqrt_rn(limit_scaling(rowmax[i])));
   }
 }
+
+// With many row chunks (n = 5000: 79 + 79) the one-CTA-per-instance vector kernel above spent 370 us per call walking the chunk
+// partials of its columns (24 instances = 24 CTAs on 148 SMs, a dependent strided load per chunk).  This folds them first with
+// one thread per (instance, column) over the whole GPU, into chunk 0 -- a maximum, so the order is immaterial and the result
+// bit-identical -- and the vector kernel reads one value per column.
+__global__ void __launch_bounds__(256) ruiz_fold_max_kernel(float* __restrict__ partq, int chunks_q, float* __restrict__ parta,
+                                                            int chunks_a, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const size_t b = blockIdx.y;
+  float* pq = partq + b * chunks_q * n + j;
+  float cq = 0.f;
+#pragma unroll 8
+  for (int ch = 0; ch < chunks_q; ++ch) cq = fmaxf(cq, pq[(size_t)ch * n]);
+  pq[0] = cq;
+  if (chunks_a > 0) {
+    float* pa = parta + b * chunks_a * n + j;
+    float ca = 0.f;
+#pragma unroll 8
+    for (int ch = 0; ch < chunks_a; ++ch) ca = fmaxf(ca, pa[(size_t)ch * n]);
+    pa[0] = ca;
+  }
+}
+constexpr int kRzFoldChunks = 24;      // fold first when an instance has at least this many chunk partials per column
 
 size_t ruiz_ws_floats(int B, int n, int m, int* R_out, int* cq_out, int* ca_out) {
   const KktDims kd = make_kkt_dims(B, n, m, 0);
@@ -399,6 +424,22 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
   const char* sw = dev_env("IADMM_RUIZ_CHAIN");                       // development switch: 0 = in-place form (round 1)
   const bool chain = iterations <= kRzMaxHist && !(sw && sw[0] == '0');
   W.hist_on = chain ? 1 : 0;
+  W.scan_q = W.chunks_q; W.scan_a = W.chunks_a;
+  // the vector stage after a matrix pass (its column partials are fresh): fold them GPU-wide first when there are many
+  const char* swf = dev_env("IADMM_RUIZ_FOLD");                       // development switch: 0 = the vector kernel walks the partials
+  const bool fold = W.chunks_q + W.chunks_a >= kRzFoldChunks && !(swf && swf[0] == '0');
+  auto launch_vec = [&](int finish_prev, int prepare_next, int k) -> int {
+    RuizWs Wv = W;
+    if ((finish_prev || prepare_next) && fold) {
+      ruiz_fold_max_kernel<<<dim3(cdiv(n, 256), B), 256, 0, st>>>(W.partq, W.chunks_q, W.parta, m > 0 ? W.chunks_a : 0, n);
+      IADMM_LAUNCH_CHECK("ruiz_fold_max_kernel");
+      Wv.scan_q = 1; Wv.scan_a = (m > 0 && W.chunks_a > 0) ? 1 : 0;
+    }
+    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, finish_prev, prepare_next, k, ps, zls, zus, d, e, c, Wv);
+    IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+    return IADMM_OK;
+  };
+  int rcv;
 
   IADMM_CUDA(cudaMemcpyAsync(ps, p, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (m > 0) {
@@ -410,15 +451,12 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
   if (iterations == 0) {
     IADMM_CUDA(cudaMemcpyAsync(Qs, Q, (size_t)B * n * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (m > 0) IADMM_CUDA(cudaMemcpyAsync(A0s, A0, (size_t)B * m * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 0, -1, ps, zls, zus, d, e, c, W);
-    IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
-    return IADMM_OK;
+    return launch_vec(0, 0, -1);
   }
   if (vec) ruiz_pass_kernel<kRzNorm, true><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, W);
   else     ruiz_pass_kernel<kRzNorm, false><<<grid, kRzThreads, 0, st>>>(Q, A0, nullptr, nullptr, n, m, W);
   IADMM_LAUNCH_CHECK("ruiz_pass_kernel<norm>");
-  ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 0, 1, -1, ps, zls, zus, d, e, c, W);
-  IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+  if ((rcv = launch_vec(0, 1, -1))) return rcv;
   if (chain) {
     // Iteration k needs the norms of the matrices under the scale steps 0..k.  They are taken from the last MATERIALISED state
     // (the originals, later Qs/A0s) by re-applying the steps since then in registers; every kRzPeriod-th iteration the pass also
@@ -439,8 +477,7 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
         else     ruiz_chain_kernel<true, false, false><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, nullptr, nullptr, n, m, slot0, steps, 0, W);
       }
       IADMM_LAUNCH_CHECK("ruiz_chain_kernel<norm>");
-      ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 1, (k + 1 < iterations) ? 1 : 0, k, ps, zls, zus, d, e, c, W);
-      IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+      if ((rcv = launch_vec(1, (k + 1 < iterations) ? 1 : 0, k))) return rcv;
       if (write) { qsrc = Qs; asrc = A0s; slot0 = k + 1; }
     }
     // the last write: the steps since the last materialised state and the last cost factor
@@ -455,8 +492,7 @@ int ruiz_impl(const float* Q, const float* p, const float* A0, const float* zl, 
     if (vec) ruiz_pass_kernel<kRzScale, true><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, W);
     else     ruiz_pass_kernel<kRzScale, false><<<grid, kRzThreads, 0, st>>>(qsrc, asrc, Qs, A0s, n, m, W);
     IADMM_LAUNCH_CHECK("ruiz_pass_kernel<scale>");
-    ruiz_vec_kernel<<<B, kRzVecThreads, 0, st>>>(n, m, 1, (k + 1 < iterations) ? 1 : 0, k, ps, zls, zus, d, e, c, W);
-    IADMM_LAUNCH_CHECK("ruiz_vec_kernel");
+    if ((rcv = launch_vec(1, (k + 1 < iterations) ? 1 : 0, k))) return rcv;
   }
   if (vec) ruiz_pass_kernel<kRzCost, true><<<grid, kRzThreads, 0, st>>>(Qs, A0s, Qs, A0s, n, m, W);
   else     ruiz_pass_kernel<kRzCost, false><<<grid, kRzThreads, 0, st>>>(Qs, A0s, Qs, A0s, n, m, W);

@@ -104,6 +104,69 @@ def test_ruiz_last_bit():
         assert ulps(a, b) <= 4, (k, ulps(a, b))
 
 
+@pytest.mark.parametrize("shape", [(2, 1600, 500, 420), (3, 1100, 0, 500), (2, 1537, 0, 0), (2, 700, 300, 212)])
+def test_ruiz_many_row_chunks(shape):
+    """scale_data (methods/scaling.py:50-119) where an instance has 24 or more 64-row chunks (n + m >= 1536, i.e. also the
+    headline size): the column inf-norm partials of the chunks are folded GPU-wide by ruiz_fold_max_kernel before the
+    per-instance vector stage reads them.  A maximum has no rounding, so the bars are those of the small cases: after one
+    iteration the diagonals within 4 ulp of the oracle and every matrix / vector output bit-equal to the reference's product
+    chain evaluated with those diagonals; after ten iterations rel 1e-6.  Dense non-symmetric Q, -inf bounds, a zero row and a
+    zero column; n = 1537 is the unaligned path, m = 0 has no constraint partials; (700, 512) stays below the threshold."""
+    import iadmm_b200 as ia
+    from oracle import iadmm_oracle as orc
+    B, n, mi, me = shape
+    m = mi + me
+    g = torch.Generator().manual_seed(23)
+    Q = torch.diag_embed(torch.rand((B, n), generator=g)) + 0.05 * torch.randn((B, n, n), generator=g)
+    A0 = torch.randn((B, m, n), generator=g) * torch.logspace(-3, 2, m).reshape(1, m, 1) if m else torch.zeros((B, 0, n))
+    Q[0, :, 5] = 0.0; Q[0, 5, :] = 0.0
+    if m:
+        A0[0, :, 5] = 0.0; A0[1, 7, :] = 0.0
+    p = torch.rand((B, n, 1), generator=g)
+    bnd = torch.rand((B, m, 1), generator=g)
+    zl = torch.cat((torch.full((B, mi, 1), float("-inf")), bnd[:, mi:]), 1)
+    zu = torch.cat((bnd[:, :mi] + 1.0, bnd[:, mi:]), 1)
+    cpu = (Q, p, A0, zl, zu)
+    on_dev = tuple(v.to(DEV) for v in cpu)
+
+    def ulps(a, b):
+        a, b = a.cpu().contiguous(), b.contiguous()
+        fin = torch.isfinite(b)
+        assert torch.equal(a[~fin], b[~fin])
+        return int((a[fin].view(torch.int32).long() - b[fin].view(torch.int32).long()).abs().max()) if fin.any() else 0
+
+    for ites in (1, 10):
+        sc = ia.Scaling(n, m, ites, DEV)
+        out = [v.cpu() for v in sc.scale_data(*on_dev)]
+        torch.cuda.synchronize()
+        ref = orc.ruiz_equilibrate(*cpu, ites)
+        so = ref[5]
+        d, e, c = sc.d.cpu(), sc.e.cpu(), sc.c_vec.cpu()
+        pairs = dict(Q=(out[0], ref[0]), p=(out[1], ref[1]), A0=(out[2], ref[2]), zl=(out[3], ref[3]), zu=(out[4], ref[4]),
+                     d=(d, so.d), e=(e, so.e), c=(c, so.c.reshape(-1)))
+        for k, (a, b) in pairs.items():
+            assert a.shape == b.shape, (k, a.shape, b.shape)
+            if b.numel() == 0:
+                continue
+            if ites == 1:
+                # diagonals: torch's CPU sqrt is 1 ulp off now and then and the cost factor hangs on the order of one fp32 mean
+                # (test_ruiz_last_bit); a matrix entry is a product of up to three such factors
+                assert ulps(a, b) <= (4 if k in "dec" else 8), (shape, k, ulps(a, b))
+            else:
+                fin = torch.isfinite(b)
+                assert torch.equal(a[~fin], b[~fin])
+                assert rel_err(a[fin], b[fin]) < 1e-6, (shape, k, rel_err(a[fin], b[fin]))
+        if ites == 1:
+            # sharper than any ulp bar and independent of the sqrt: with the kernel's OWN diagonals every output of one iteration
+            # is the reference's chain of singly rounded fp32 products (scaling.py:80-84, :103-105), bit for bit
+            cc = c.reshape(B, 1, 1)
+            assert torch.equal(out[0], cc * (d.unsqueeze(2) * (Q * d.unsqueeze(1))))
+            assert torch.equal(out[1], cc * (d.unsqueeze(2) * p))
+            if m:
+                assert torch.equal(out[2], e.unsqueeze(2) * (A0 * d.unsqueeze(1)))
+                assert torch.equal(out[3], e.unsqueeze(2) * zl) and torch.equal(out[4], e.unsqueeze(2) * zu)
+
+
 @pytest.mark.parametrize("shape", [(3, 12, 5, 7), (2, 10, 6, 0), (2, 37, 11, 9), (2, 1100, 130, 70)])
 def test_primal_dual_loss_vs_oracle(shape):
     """primal_dual_loss (utils.py:68-71); n=37 takes the unaligned path, n=1100 spans two column chunks."""

@@ -25,5 +25,6 @@ h = hashlib.sha256()
 for t in list(out) + [sc.d, sc.e, sc.c_vec]:
     h.update(t.cpu().numpy().tobytes())
 mat = 4.0 * B * (n * n + (mi + me) * n)
-print(json.dumps({"form": "in-place (round 1)" if os.environ.get("IADMM_RUIZ_CHAIN") == "0" else "chain", "B": B, "n": n, "ms": ms,
+print(json.dumps({"form": ("in-place (round 1)" if os.environ.get("IADMM_RUIZ_CHAIN") == "0" else "chain")
+                  + (", vector kernel walks the chunk partials" if os.environ.get("IADMM_RUIZ_FOLD") == "0" else ""), "B": B, "n": n, "ms": ms,
                   "passes_equivalent_at_6559GBps": ms * 1e-3 * 6559.4e9 / mat, "algorithmic_passes": 11, "sha256": h.hexdigest()}))
