@@ -519,6 +519,11 @@ def run_ours(args):
         iter_bytes = kkt_bytes + 16.0 * rows * h + 64.0 * rows       # SURVEY section 8(d) bytes per iteration
         step_s = ms / steps * 1e-3
         hbm_frac_whole = (iter_bytes * K / step_s / 1e9) / hbm_gbs
+        # the step also runs scale_data and the trailing residual pass; SURVEY section 8(d) counts their algorithmic bytes per solve
+        # (Ruiz: RUIZ_ITS read passes + one write pass of the dense Q and A0 = its 11 x 4 (n^2 + mn); one more read pass for the residuals of
+        # the last iterate)
+        solve_bytes = iter_bytes * K + (RUIZ_ITS + 1) * 4.0 * B * (n * n + m * n) + kkt_bytes / 2
+        hbm_frac_solve = (solve_bytes / step_s / 1e9) / hbm_gbs
         launches_per_step = K * 6 + 2 + (3 + 2 * RUIZ_ITS)
         line = {
             "metric": METRIC, "value": sum(shares) * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
@@ -561,6 +566,7 @@ def run_ours(args):
                              "ms_per_iteration": kkt_avg_ms,
                              "share_of_step": kkt_ms.value / ms, "peak_kind": "%s hbm_gbs" % peak_kind},
             "hbm_roofline_frac_whole_path": hbm_frac_whole,
+            "hbm_roofline_frac_whole_solve": hbm_frac_solve,     # same, with the algorithmic bytes of scale_data and the trailing residual pass
             "phase_ms_per_iteration": {"kkt": kkt_avg_ms, "gates": gate_avg_ms, "tail": tail_ms.value / nit_v},
             "clocks": clocks,
         }
