@@ -620,7 +620,7 @@ constexpr int kPairBBoxRows = 64;                         // U tiles are fetched
 // regime where the cell epilogue, not the MMAs or the power cap, sets the pace (hidden_dim <~ 400: a tile's MMAs take a quarter of
 // the time of its epilogue).  20 warps (five per scheduler, so 96 registers per thread; the two-chunk epilogue needs 90): warps 0-3 =
 // TMA producer, MMA issuer and two idle warps, warps 4-19 = epilogue (lane quarter = warp % 4).
-constexpr int pair_threads(int epi) { return (epi == 7 || epi == 9) ? 640 : kTcThreads; }
+constexpr int pair_threads(int epi) { return (epi == 7 || epi == 9 || epi == 10) ? 640 : kTcThreads; }
 // measured (profiles/r02_epi_warps_sweep.jsonl, same box, gate kernel per launch at the headline problem size): 16 warps win at
 // hidden_dim 208 (0.667 vs 0.739 ms), 320 (0.955 vs 1.137), 352 (1.215 vs 1.399) and 384 (1.314 vs 1.510); tie at 400 (1.50);
 // 8 warps win from 512 on (2.06 vs 2.13, 640: 3.09 vs 3.11, 800: the power-capped regime)
@@ -642,8 +642,9 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
   // slower (same box: 4.74 vs 4.59 ms per launch); declaring a larger block only offers 128 registers with spills.
   constexpr bool ABL = (EPI == 4 || EPI == 8);   // EPI 8: as 4 with one shared reciprocal per unit (measured, not adopted: DESIGN.md)
   const int ex = ABL ? P.exp : 0;
-  constexpr int kEpiWarps = (EPI == 7 || EPI == 9) ? 16 : kTcEpiWarps;     // EPI 9: as 7 with one shared reciprocal per unit
-  constexpr int kFirstEpiWarp = (EPI == 7 || EPI == 9) ? 4 : 2;
+  constexpr bool E16 = (EPI == 7 || EPI == 9 || EPI == 10);                // EPI 9: as 7 with one shared reciprocal per unit; 10: as 9 with the exp-only tanh
+  constexpr int kEpiWarps = E16 ? 16 : kTcEpiWarps;
+  constexpr int kFirstEpiWarp = E16 ? 4 : 2;
   constexpr int kIlBK = (EPI == 5) ? 32 : 64;
   constexpr uint32_t kIlSub = kIlBK * 256;            // bytes of one operand box: [K groups][128 rows][16 B]
   constexpr int kStageBytes = IL ? 4 * (int)kIlSub : (NPROD == 1) ? (kPairABytes + kPairBBytes) : 2 * (kPairABytes + kPairBBytes);
@@ -865,7 +866,7 @@ gates_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
       } else if (EPI == 0) {
         if constexpr (NCH == kChunksPerHalf) lstm_epilogue_tile<NPROD>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
       } else {
-        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6, EPI == 3, IL, NCH, ABL, EPI == 8 || EPI == 9>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
+        lstm_epilogue_tile_x2<NPROD, EPI == 2 || EPI == 6 || EPI == 10, EPI == 3, IL, NCH, ABL, EPI == 8 || EPI == 9 || EPI == 10>(P, R, sp, tmem_base, buf, quarter, part, ut, dequant);
       }
       tc_fence_before();
       __syncwarp();
@@ -1131,9 +1132,10 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
       // four activations of a unit (4 ex2 + 1 rcp instead of 4 + 4) is 10 % faster (0.649 -> 0.586 ms at hidden_dim 208,
       // profiles/r02_gate_shared_rcp_ab.jsonl); in the power-capped 8-warp regime the same change is 1 % SLOWER (more ALU
       // instructions), so it stays a development switch there.  IADMM_TC_EPI=1 forces the separate reciprocals here.
-      static PerDeviceOnce i9;
-      if (dev_env("IADMM_TC_EPI") && epi == 1) rc = launch(gates_tc_pair_kernel<2, 2, 7>, &i7, 2);
-      else                                     rc = launch(gates_tc_pair_kernel<2, 2, 9>, &i9, 2);
+      static PerDeviceOnce i9, i10;
+      if (dev_env("IADMM_TC_EPI") && epi == 1)      rc = launch(gates_tc_pair_kernel<2, 2, 7>, &i7, 2);
+      else if (dev_env("IADMM_TC_EPI") && epi == 2) rc = launch(gates_tc_pair_kernel<2, 2, 10>, &i10, 2);
+      else                                          rc = launch(gates_tc_pair_kernel<2, 2, 9>, &i9, 2);
     } else if (il) {
       if (epi == 3)         rc = launch(gates_tc_pair_kernel<2, 2, 8>, &i8, 2);
       else if (epi == 2)    rc = launch(gates_tc_pair_kernel<2, 2, 6>, &i6, 2);
