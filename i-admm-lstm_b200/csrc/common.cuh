@@ -103,11 +103,19 @@ struct WeightLayout {
                       //                64 B of the coarse copy fp16(U*2^s) * 2^-5   (F16F8 mode; one 128-byte TMA row)
   size_t off_tilep;   // fp32 [ceil(h/64)][832]: per 64-unit tile the W row 0 | W row 1 | bias (256 gate columns each) | W_h (64) block the
                       //                gate kernel's epilogue reads, contiguous so ONE bulk copy stages it in shared memory
+  size_t off_tilep_il;// the same blocks with the gate columns in the order of the row-interleaved kernels (il_gate_col)
   size_t off_uhi_il;  // fp16 [h/8][4h][8]: row-interleaved image of fp16(U*2^s) (16-byte K groups of consecutive gate columns adjacent;
                       //                the no-swizzle UMMA core-matrix order, see gates_tc.cu "row-interleaved layout")
   size_t off_uq8_il;  // e4m3 [ceil(h/16)][2][4h][16]: residual plane, coarse plane per 16-wide K group
   size_t total;
 };
+// Gate-column order of the row-interleaved gate kernels.  Everywhere else column c = 4 * unit + gate (i, f, o, u).  The
+// row-interleaved U images and parameter blocks keep, within every 8 columns (two hidden units), the same gate of the two
+// units adjacent: (i0 i1 f0 f1 o0 o1 u0 u1).  The accumulator columns a thread reads from tensor memory are then already the
+// operand pairs of the epilogue's two-wide fp32 instructions (one pair = one gate of two units), for every activation and the
+// state update alike, instead of (i, f) / (o, u) pairs of one unit that have to be re-paired by register moves.
+__host__ __device__ __forceinline__ int il_gate_col(int c)     { return (c & ~7) | ((c & 3) << 1) | ((c >> 2) & 1); }
+__host__ __device__ __forceinline__ int il_gate_col_inv(int q) { return (q & ~7) | ((q & 1) << 2) | ((q >> 1) & 3); }
 WeightLayout weight_layout(int h, int length);
 
 struct Sched {  // one schedule row, already in fp32 exactly as models/lstm.py:60-63 rounds it

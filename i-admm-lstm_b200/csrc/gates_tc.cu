@@ -277,6 +277,21 @@ __device__ __forceinline__ u64 tanh2(float x0, float x1, float big0, float big1)
   return pk2((fabsf(x0) < 0.55f) ? s0 : big0, (fabsf(x1) < 0.55f) ? s1 : big1);
 }
 
+// the same on packed operands (X = the two arguments, BIG = 1 - 2/(e^{2x}+1) of both): nothing is re-paired
+template <bool FAST>
+__device__ __forceinline__ u64 tanh2p(u64 X, u64 BIG) {
+  if (FAST) return BIG;
+  const u64 T = mul2(X, X);
+  u64 Q = fma2(T, bc2(0.016433170300270403f), bc2(-0.052669384762106176f));
+  Q = fma2(Q, T, bc2(0.133206865150314f));
+  Q = fma2(Q, T, bc2(-0.33332945121698027f));
+  float s0, s1, x0, x1, b0, b1;
+  upk2(fma2(mul2(X, T), Q, X), s0, s1);
+  upk2(X, x0, x1);
+  upk2(BIG, b0, b1);
+  return pk2((fabsf(x0) < 0.55f) ? s0 : b0, (fabsf(x1) < 0.55f) ? s1 : b1);
+}
+
 template <int NPROD, bool FAST, bool SAVE, bool IL, int NCH = kChunksPerHalf, bool ABL = false, bool SHR = false>
 __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const EpiRowT<NCH>& R, const float* sp, uint32_t tmem_base, int buf,
                                                       int quarter, int half, int ut, float dequant) {
@@ -312,62 +327,121 @@ __device__ __forceinline__ void lstm_epilogue_tile_x2(const TcParams& P, const E
           hn2[u >> 1] = pk2(hnew[u], hnew[u + 1]);
           continue;
         }
-        u64 pif[2], pou[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float4 a0 = w0[u + j], a1 = w1[u + j], ab = bb[u + j];
-          const int b = (u + j) * 4;
-          // pre_g = xv*W0 + grad*W1 + (H@U) + b   (models/lstm.py:74-77), gates (i,f) and (o,u) as pairs
-          pif[j] = fma2(pk2(__uint_as_float(v[b]), __uint_as_float(v[b + 1])), dq2,
-                        fma2(gr2, pk2(a1.x, a1.y), fma2(xr2, pk2(a0.x, a0.y), pk2(ab.x, ab.y))));
-          pou[j] = fma2(pk2(__uint_as_float(v[b + 2]), __uint_as_float(v[b + 3])), dq2,
-                        fma2(gr2, pk2(a1.z, a1.w), fma2(xr2, pk2(a0.z, a0.w), pk2(ab.z, ab.w))));
-        }
-        float gi[2], gf[2], go[2], bigu[2], pu[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float ru, po_unused;
+        float gi[2], gf[2], gu[2];
+        u64 GO;                                          // sigmoid(p_o) of the two units
+        if constexpr (IL) {
+          // Row-interleaved kernels: the eight accumulator columns of a unit pair arrive as (i0 i1 f0 f1 o0 o1 u0 u1)
+          // (il_gate_col, common.cuh), the parameter block in the same order: every pair below is one gate of the two units.
+          // Lane by lane the same IEEE operations in the same order as the (i, f) / (o, u) pairing of the row-major kernels.
+          const float4 a0 = w0[u], a1 = w1[u], ab = bb[u];                    // columns i0 i1 f0 f1
+          const float4 c0 = w0[u + 1], c1 = w1[u + 1], cb = bb[u + 1];        // columns o0 o1 u0 u1
+          const int b = u * 4;
+          // pre_g = xv*W0 + grad*W1 + (H@U) + b   (models/lstm.py:74-77)
+          const u64 PI = fma2(pk2(__uint_as_float(v[b]), __uint_as_float(v[b + 1])), dq2,
+                              fma2(gr2, pk2(a1.x, a1.y), fma2(xr2, pk2(a0.x, a0.y), pk2(ab.x, ab.y))));
+          const u64 PF = fma2(pk2(__uint_as_float(v[b + 2]), __uint_as_float(v[b + 3])), dq2,
+                              fma2(gr2, pk2(a1.z, a1.w), fma2(xr2, pk2(a0.z, a0.w), pk2(ab.z, ab.w))));
+          const u64 PO = fma2(pk2(__uint_as_float(v[b + 4]), __uint_as_float(v[b + 5])), dq2,
+                              fma2(gr2, pk2(c1.x, c1.y), fma2(xr2, pk2(c0.x, c0.y), pk2(cb.x, cb.y))));
+          const u64 PU = fma2(pk2(__uint_as_float(v[b + 6]), __uint_as_float(v[b + 7])), dq2,
+                              fma2(gr2, pk2(c1.z, c1.w), fma2(xr2, pk2(c0.z, c0.w), pk2(cb.z, cb.w))));
+          u64 RU;                                        // 1/(e^{2 p_u}+1)
           if (SHR) {
-            // one reciprocal for the four activations of a unit (gate_math.cuh, gates4_shared_rcp_x2): 4 ex2 + 1 rcp
-            float t0, t1, t2, t3, a, b, c, d;
-            upk2(mul2(pif[j], k_if), t0, t1);
-            upk2(mul2(pou[j], k_ou), t2, t3);
-            upk2(add2(pk2(ex2_approx(fminf(t0, 30.0f)), ex2_approx(fminf(t1, 30.0f))), bc2(1.0f)), a, b);
-            upk2(add2(pk2(ex2_approx(fminf(t2, 30.0f)), ex2_approx(fminf(t3, 30.0f))), bc2(1.0f)), c, d);
-            const float ab = a * b, cd = c * d;
-            const float r = rcp_approx(ab * cd);
-            float rab, rcd;
-            upk2(mul2(bc2(r), pk2(cd, ab)), rab, rcd);
-            upk2(mul2(bc2(rab), pk2(b, a)), gi[j], gf[j]);
-            upk2(mul2(bc2(rcd), pk2(d, c)), go[j], ru);
+            // one reciprocal for the four activations of a unit (gate_math.cuh, gates4_shared_rcp_x2): 4 ex2 + 1 rcp per unit
+            float t0, t1;
+            upk2(mul2(PI, k_if), t0, t1);
+            const u64 A = add2(pk2(ex2_approx(fminf(t0, 30.0f)), ex2_approx(fminf(t1, 30.0f))), bc2(1.0f));
+            upk2(mul2(PF, k_if), t0, t1);
+            const u64 B = add2(pk2(ex2_approx(fminf(t0, 30.0f)), ex2_approx(fminf(t1, 30.0f))), bc2(1.0f));
+            upk2(mul2(PO, k_if), t0, t1);
+            const u64 C = add2(pk2(ex2_approx(fminf(t0, 30.0f)), ex2_approx(fminf(t1, 30.0f))), bc2(1.0f));
+            upk2(mul2(PU, k_t), t0, t1);
+            const u64 D = add2(pk2(ex2_approx(fminf(t0, 30.0f)), ex2_approx(fminf(t1, 30.0f))), bc2(1.0f));
+            const u64 AB = mul2(A, B), CD = mul2(C, D);
+            float q0, q1;
+            upk2(mul2(AB, CD), q0, q1);
+            const u64 RR = pk2(rcp_approx(q0), rcp_approx(q1));
+            const u64 RAB = mul2(RR, CD), RCD = mul2(RR, AB);
+            upk2(mul2(RAB, B), gi[0], gi[1]);
+            upk2(mul2(RAB, A), gf[0], gf[1]);
+            GO = mul2(RCD, D);
+            RU = mul2(RCD, C);
           } else {
-            rcp1p_ex2_2(mul2(pif[j], k_if), gi[j], gf[j]);           // sigmoid(p_i), sigmoid(p_f)
-            rcp1p_ex2_2(mul2(pou[j], k_ou), go[j], ru);              // sigmoid(p_o), 1/(e^{2 p_u}+1)
+            float g0, g1;
+            rcp1p_ex2_2(mul2(PI, k_if), gi[0], gi[1]);               // sigmoid(p_i)
+            rcp1p_ex2_2(mul2(PF, k_if), gf[0], gf[1]);               // sigmoid(p_f)
+            rcp1p_ex2_2(mul2(PO, k_if), g0, g1);                     // sigmoid(p_o)
+            GO = pk2(g0, g1);
+            rcp1p_ex2_2(mul2(PU, k_t), g0, g1);                      // 1/(e^{2 p_u}+1)
+            RU = pk2(g0, g1);
           }
-          upk2(pou[j], po_unused, pu[j]);
-          bigu[j] = fmaf(-2.0f, ru, 1.0f);
+          upk2(tanh2p<FAST>(PU, fma2(RU, bc2(-2.0f), bc2(1.0f))), gu[0], gu[1]);
+        } else {
+          u64 pif[2], pou[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float4 a0 = w0[u + j], a1 = w1[u + j], ab = bb[u + j];
+            const int b = (u + j) * 4;
+            // pre_g = xv*W0 + grad*W1 + (H@U) + b   (models/lstm.py:74-77), gates (i,f) and (o,u) as pairs
+            pif[j] = fma2(pk2(__uint_as_float(v[b]), __uint_as_float(v[b + 1])), dq2,
+                          fma2(gr2, pk2(a1.x, a1.y), fma2(xr2, pk2(a0.x, a0.y), pk2(ab.x, ab.y))));
+            pou[j] = fma2(pk2(__uint_as_float(v[b + 2]), __uint_as_float(v[b + 3])), dq2,
+                          fma2(gr2, pk2(a1.z, a1.w), fma2(xr2, pk2(a0.z, a0.w), pk2(ab.z, ab.w))));
+          }
+          float go[2], bigu[2], pu[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float ru, po_unused;
+            if (SHR) {
+              // one reciprocal for the four activations of a unit (gate_math.cuh, gates4_shared_rcp_x2): 4 ex2 + 1 rcp
+              float t0, t1, t2, t3, a, b, c, d;
+              upk2(mul2(pif[j], k_if), t0, t1);
+              upk2(mul2(pou[j], k_ou), t2, t3);
+              upk2(add2(pk2(ex2_approx(fminf(t0, 30.0f)), ex2_approx(fminf(t1, 30.0f))), bc2(1.0f)), a, b);
+              upk2(add2(pk2(ex2_approx(fminf(t2, 30.0f)), ex2_approx(fminf(t3, 30.0f))), bc2(1.0f)), c, d);
+              const float ab = a * b, cd = c * d;
+              const float r = rcp_approx(ab * cd);
+              float rab, rcd;
+              upk2(mul2(bc2(r), pk2(cd, ab)), rab, rcd);
+              upk2(mul2(bc2(rab), pk2(b, a)), gi[j], gf[j]);
+              upk2(mul2(bc2(rcd), pk2(d, c)), go[j], ru);
+            } else {
+              rcp1p_ex2_2(mul2(pif[j], k_if), gi[j], gf[j]);           // sigmoid(p_i), sigmoid(p_f)
+              rcp1p_ex2_2(mul2(pou[j], k_ou), go[j], ru);              // sigmoid(p_o), 1/(e^{2 p_u}+1)
+            }
+            upk2(pou[j], po_unused, pu[j]);
+            bigu[j] = fmaf(-2.0f, ru, 1.0f);
+          }
+          upk2(tanh2<FAST>(pu[0], pu[1], bigu[0], bigu[1]), gu[0], gu[1]);
+          GO = pk2(go[0], go[1]);
         }
-        float gu[2];
-        upk2(tanh2<FAST>(pu[0], pu[1], bigu[0], bigu[1]), gu[0], gu[1]);
         float cn[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j)
           cn[j] = __fadd_rn(__fmul_rn(gi[j], gu[j]), __fmul_rn(gf[j], R.c[cc][u + j]));   // lstm.py:78
         float rt0, rt1;
-        rcp1p_ex2_2(mul2(pk2(cn[0], cn[1]), k_t), rt0, rt1);
-        float bt0, bt1;
-        upk2(fma2(pk2(rt0, rt1), bc2(-2.0f), bc2(1.0f)), bt0, bt1);
-        const u64 HN = mul2(pk2(go[0], go[1]), tanh2<FAST>(cn[0], cn[1], bt0, bt1));      // lstm.py:79
+        const u64 CN = pk2(cn[0], cn[1]);
+        rcp1p_ex2_2(mul2(CN, k_t), rt0, rt1);
+        u64 HN;                                                                           // lstm.py:79
+        if constexpr (IL) {
+          HN = mul2(GO, tanh2p<FAST>(CN, fma2(pk2(rt0, rt1), bc2(-2.0f), bc2(1.0f))));
+        } else {
+          float bt0, bt1;
+          upk2(fma2(pk2(rt0, rt1), bc2(-2.0f), bc2(1.0f)), bt0, bt1);
+          HN = mul2(GO, tanh2<FAST>(cn[0], cn[1], bt0, bt1));
+        }
         upk2(HN, hnew[u], hnew[u + 1]);
         hn2[u >> 1] = HN;
         cnew[u] = cn[0]; cnew[u + 1] = cn[1];
         const float2 whp = wh[u >> 1];
         hp2 = fma2(HN, pk2(whp.x, whp.y), hp2);                                           // lstm.py:80 (partial)
         if (SAVE) {           // training forward: keep the activations for the hand-written backward
+          float go_s[2];
+          upk2(GO, go_s[0], go_s[1]);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             *reinterpret_cast<float4*>(P.gates_out + (size_t)R.row * 4 * P.h + 4 * (size_t)(unit0 + u + j)) =
-                make_float4(gi[j], gf[j], go[j], gu[j]);
+                make_float4(gi[j], gf[j], go_s[j], gu[j]);
         }
       }
       if (ex == 3) { hp2 = add2(hp2, pk2(cnew[0] + cnew[7], hnew[3])); continue; }
@@ -1062,7 +1136,7 @@ int launch_gates_tc(const void* packed, const WeightLayout& L, const float* xv, 
   P.bias = reinterpret_cast<const float*>(base + L.off_bias);
   P.wh = reinterpret_cast<const float*>(base + L.off_wh);
   P.scale = reinterpret_cast<const float*>(base + L.off_scale);
-  P.tilep = reinterpret_cast<const float*>(base + L.off_tilep);
+  P.tilep = reinterpret_cast<const float*>(base + (il ? L.off_tilep_il : L.off_tilep));
   P.xv = xv; P.g = g;
   P.hout_hi = Hout_hi; P.hout_lo = Hout_lo; P.hout_f32 = H_out_f32; P.C = C; P.head_part = head_part;
   P.gates_out = gates_out; P.exp = 0; P.wait_ns = IADMM_MBAR_SUSPEND_NS;

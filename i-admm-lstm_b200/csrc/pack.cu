@@ -33,6 +33,7 @@ WeightLayout weight_layout(int h, int length) {
   L.off_u32lo = take(4 * H * H * sizeof(__half));
   L.off_uq8   = take(4 * H * q8_pitch(h));
   L.off_tilep = take((size_t)((h + 63) / 64) * 832 * sizeof(float));
+  L.off_tilep_il = take((size_t)((h + 63) / 64) * 832 * sizeof(float));
   L.off_uhi_il = take((size_t)((h + 7) / 8) * 4 * H * 8 * sizeof(__half));
   L.off_uq8_il = take((size_t)((h + 15) / 16) * 2 * 4 * H * 16);
   L.total = off;
@@ -49,22 +50,30 @@ struct PackSrc {
 __global__ void __launch_bounds__(256) pack_small_kernel(PackSrc S, int h, int length, float* __restrict__ wc,
                                                          float* __restrict__ bias, float* __restrict__ wh,
                                                          float* __restrict__ bh, float* __restrict__ sched,
-                                                         float* __restrict__ scale, float* __restrict__ tilep) {
+                                                         float* __restrict__ scale, float* __restrict__ tilep,
+                                                         float* __restrict__ tilep_il) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
   // per-tile parameter blocks of the tensor-core gate kernel (zero padded past 4h / h)
   const int tiles = (h + 63) / 64;
   for (int i = tid; i < tiles * 832; i += stride) {
     const int t = i / 832, o = i - t * 832;
-    float v = 0.f;
+    float v = 0.f, vil = 0.f;
     if (o < 768) {
       const int a = o >> 8, c = t * 256 + (o & 255);
-      if (c < 4 * h) { const int j = c >> 2, g = c & 3; v = (a == 0) ? S.W[g][j] : (a == 1) ? S.W[g][h + j] : S.b[g][j]; }
+      if (c < 4 * h) {
+        const int j = c >> 2, g = c & 3;
+        v = (a == 0) ? S.W[g][j] : (a == 1) ? S.W[g][h + j] : S.b[g][j];
+        const int ci = il_gate_col_inv(c);                  // the column that sits at position c of the row-interleaved order
+        const int ji = ci >> 2, gi = ci & 3;
+        vil = (a == 0) ? S.W[gi][ji] : (a == 1) ? S.W[gi][h + ji] : S.b[gi][ji];
+      }
     } else {
       const int u = t * 64 + (o - 768);
-      if (u < h) v = S.W_h[u];
+      if (u < h) v = vil = S.W_h[u];
     }
     tilep[i] = v;
+    tilep_il[i] = vil;
   }
   for (int i = tid; i < 4 * h; i += stride) {
     const int j = i >> 2, g = i & 3;
@@ -138,10 +147,11 @@ __global__ void __launch_bounds__(256) pack_u_kernel(PackSrc S, int h, float* __
     uint8_t* q = uq8 + (size_t)c * q8_pitch_dev(h) + (size_t)(k >> 6) * 128 + (k & 63);
     q[0]  = to_e4m3(ldexpf(vs - __half2float(hi), kQ8ULoShift));      // residual
     q[64] = to_e4m3(ldexpf(__half2float(hi), kQ8UHiShift));           // coarse copy
-    // row-interleaved images: [K group][gate column][16 bytes]
+    // row-interleaved images: [K group][gate column in the order of il_gate_col][16 bytes]
     const size_t c4 = (size_t)4 * h;
-    uhi_il[((size_t)(k >> 3) * c4 + c) * 8 + (k & 7)] = hi;
-    uint8_t* qi = uq8_il + ((size_t)(k >> 4) * 2 * c4 + c) * 16 + (k & 15);
+    const size_t ci = (size_t)il_gate_col(c);
+    uhi_il[((size_t)(k >> 3) * c4 + ci) * 8 + (k & 7)] = hi;
+    uint8_t* qi = uq8_il + ((size_t)(k >> 4) * 2 * c4 + ci) * 16 + (k & 15);
     qi[0]       = q[0];
     qi[c4 * 16] = q[64];
   }
@@ -159,7 +169,8 @@ int pack_weights_impl(const float* const W[4], const float* const U[4], const fl
   pack_small_kernel<<<cdiv(4 * h > length ? 4 * h : length, 256), 256, 0, st>>>(
       S, h, length, reinterpret_cast<float*>(base + L.off_wc), reinterpret_cast<float*>(base + L.off_bias),
       reinterpret_cast<float*>(base + L.off_wh), reinterpret_cast<float*>(base + L.off_bh),
-      reinterpret_cast<float*>(base + L.off_sched), scale, reinterpret_cast<float*>(base + L.off_tilep));
+      reinterpret_cast<float*>(base + L.off_sched), scale, reinterpret_cast<float*>(base + L.off_tilep),
+      reinterpret_cast<float*>(base + L.off_tilep_il));
   IADMM_LAUNCH_CHECK("pack_small_kernel");
   const size_t total = (size_t)4 * h * h;
   const int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
