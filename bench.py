@@ -319,7 +319,7 @@ def measured_peaks():
     return 6650.0, 1400.0, 1590.0, "fallback"
 
 
-def ncu_traffic(kind, batch, mode, headline=True):
+def ncu_traffic(kind, batch, mode, headline=True, suffix=""):
     """DRAM bytes per launch from the committed ncu --set full capture of this config, if any."""
     if not headline:
         return None
@@ -327,7 +327,7 @@ def ncu_traffic(kind, batch, mode, headline=True):
     if os.path.exists(path):
         try:
             d = json.load(open(path))
-            return d.get(f"{kind}:{mode}:B{batch}")
+            return d.get(f"{kind}:{mode}:B{batch}{suffix}")
         except Exception:
             return None
     return None
@@ -503,6 +503,7 @@ def run_ours(args):
         kkt_avg_ms = kkt_ms.value / nit_v
         gate_flops = 8.0 * rows * h * h                      # logical fp32 flops of H@U (no credit for the 3-way split)
         gate_tflops = gate_flops / (gate_avg_ms * 1e-3) / 1e12 if gate_avg_ms > 0 else 0.0
+        gate_gbs = 16.0 * rows * h / (gate_avg_ms * 1e-3) / 1e9 if gate_avg_ms > 0 else 0.0      # H and C read once, written once
         kkt_bytes = 8.0 * B * (n * n + m * n)                # Q and A0 streamed once per pass, two passes
         kkt_dense_bytes = kkt_bytes
         sparse_info = None
@@ -545,12 +546,18 @@ def run_ours(args):
                                        % (n_gpus, args.batch, n_gpus, " in proportion to each GPU's measured warm-up rate" if balance else "")),
                        "results_finite": finite},
             "gpu_launches": steps * launches_per_step,
+            # the gate kernel against the roofline that binds it: tensor at hidden_dim 800 (8 h^2 flops per row against 16 h bytes of
+            # state), HBM for hidden_dim <~ 256; both fractions are in the line, `bound` names the larger
             "roofline": {"kernel": "gates_tc_pair_kernel" if args.gate_mode != "simt_fp32" else "gates_simt_kernel",
-                         "bound": "tensor", "achieved": gate_tflops, "peak": tf_sus, "unit": "TFLOP/s",
-                         "frac": gate_tflops / tf_sus, "traffic": ncu_traffic("gates", B, args.gate_mode, h == HIDDEN and n == N_VAR),
+                         **({"bound": "tensor", "achieved": gate_tflops, "peak": tf_sus, "unit": "TFLOP/s", "frac": gate_tflops / tf_sus}
+                            if gate_tflops / tf_sus >= gate_gbs / hbm_gbs else
+                            {"bound": "hbm", "achieved": gate_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gate_gbs / hbm_gbs}),
+                         "tensor_frac": gate_tflops / tf_sus, "hbm_frac": gate_gbs / hbm_gbs, "state_bytes_per_launch": 16.0 * rows * h,
+                         "traffic": ncu_traffic("gates", B, args.gate_mode, (h == HIDDEN or h == 200) and n == N_VAR, "" if h == HIDDEN else ":h%d" % h),
                          "traffic_source": "profiles/roofline_traffic.json: dram__bytes_read+write of one committed ncu --set full "
                                            "capture of this kernel at this shape (not measured in this run)",
-                         "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,
+                         "peak_kind": ("%s bf16_tflops_sustained (kernel timed inside a long step)" if gate_tflops / tf_sus >= gate_gbs / hbm_gbs
+                                       else "%s hbm_gbs") % peak_kind,
                          "flops_per_launch": gate_flops, "ms_per_launch": gate_avg_ms,
                          "share_of_step": gate_ms.value / ms,
                          "issued_frac": gate_tflops * {"tc_3xfp16": 3, "tc_f16f8": 2}.get(args.gate_mode, 1) / tf_sus,
